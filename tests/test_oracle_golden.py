@@ -1,0 +1,120 @@
+"""Pin the oracle against every known-answer vector the reference holds for the path
+(SURVEY.md section 8c).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+
+
+@pytest.mark.parametrize('key', ['fusion', 'rgb', 'depth'])
+def test_score_measures_match_stored_run_868(exp868, key):
+    """base_model.py:315-329 recomputed from the stored matrices reproduces the stored
+    measures (scalars to the last bit, arrays to their printed 8 digits)."""
+    m = oracle.score_measures(exp868['cm_test_%s' % key])
+    for scalar in ('mean_IoU', 'total_accuracy', 'mean_F1'):
+        assert m[scalar] == float(exp868['%s_%s' % (key, scalar)]), scalar
+    for arr in ('IoU', 'F1', 'precision', 'recall'):
+        np.testing.assert_allclose(m[arr], exp868['%s_%s' % (key, arr)], rtol=0, atol=5e-9)
+
+
+def test_published_numbers(exp868):
+    assert float(exp868['fusion_mean_IoU']) == 0.6877204624612501
+    assert float(exp868['fusion_total_accuracy']) == 0.920302592013555
+    # 149 frames of 768x384 in the measure set
+    assert exp868['cm_measure_rgb'].sum() == exp868['cm_measure_depth'].sum() == 43941888
+
+
+def test_bayes_fusion_consistent_with_decision_matrix(exp868):
+    """The two reference statements of the rule (bayes_mix.py:12-58 per pixel, :61-112 as a
+    C^M lookup table) agree on the real matrices of run 868 for every label pair."""
+    cms64 = [exp868['cm_measure_rgb'].T, exp868['cm_measure_depth'].T]
+    c = 12
+    a, b = np.meshgrid(np.arange(c), np.arange(c), indexing='ij')
+    for prior in ('data', 'uniform', 0.3):
+        lut = oracle.bayes_decision_matrix(cms64, prior)
+        score, lls, conds = oracle.bayes_fusion([a[None], b[None]], cms64, prior)
+        assert score.shape == (1, c, c, c)
+        np.testing.assert_array_equal(oracle.argmax_first(score)[0], lut)
+        assert len(lls) == 2 and conds[0].shape == (1, c, c, c)
+    # float32 tables as BayesFusion builds them (bayes_mix.py:141)
+    cms32 = [m.astype('float32') for m in cms64]
+    score32, _, _ = oracle.bayes_fusion([a[None], b[None]], cms32, 'data')
+    assert score32.dtype == np.float32
+    assert (oracle.argmax_first(score32)[0] == oracle.bayes_decision_matrix(cms64)).mean() > 0.97
+
+
+def test_bayes_zero_count_class_is_never_selected():
+    rng = np.random.default_rng(0)
+    cm = rng.integers(1, 50, size=(6, 6)).astype('float32')
+    cm[:, 2] = 0            # gt class 2 never observed -> conditional nan->0, prior 0
+    lut = oracle.bayes_decision_matrix([cm, cm])
+    assert not (lut == 2).any()
+
+
+def test_bilinear_kernel_closed_form():
+    np.testing.assert_allclose(oracle.bilinear_kernel_1d(4), [.25, .75, .75, .25])
+    k16 = oracle.bilinear_kernel_1d(16)
+    np.testing.assert_allclose(k16[:8], (2 * np.arange(8) + 1) / 16.0)
+    np.testing.assert_allclose(k16, k16[::-1])
+    w = oracle.bilinear_filter((4, 4, 3, 3))
+    assert w.shape == (4, 4, 3, 3) and w[1, 2, 0, 0] == np.float32(.75 * .75)
+    assert w[:, :, 0, 1].sum() == 0
+
+
+def test_weight_key_list_matches_reference_printout():
+    keys = json.load(open(os.path.join(GOLDEN, 'fcn_weight_keys.json')))
+    for prefix, cin in (('rgb', 3), ('depth', 1)):
+        shapes = oracle.fcn_param_shapes(prefix, cin, 64, 12)
+        assert list(shapes) == keys[prefix]
+        assert len(shapes) == 34
+    assert oracle.fcn_param_shapes('rgb', 3, 64, 12)['rgb/upscore/kernel'] == (16, 16, 64, 64)
+
+
+def test_dirichlet_fit_matches_reference_outputs(dirichlet_golden):
+    g = dirichlet_golden
+    for i in g['fit_cases']:
+        delta, beta = g['fit%d_delta_beta' % i]
+        c = len(g['fit%d_ss' % i])
+        alpha = oracle.find_dirichlet_priors(g['fit%d_ss' % i], g['fit%d_neg_ss' % i],
+                                             np.ones(c), max_iter=10000, delta=delta,
+                                             beta=beta)
+        np.testing.assert_allclose(np.asarray(alpha, np.float64), g['fit%d_alpha' % i],
+                                   rtol=1e-12, atol=0)
+
+
+def test_fastfit_pieces_match_reference_outputs(dirichlet_golden):
+    g = dirichlet_golden
+    np.testing.assert_allclose(oracle.init_a_moments(g['ff_D']), g['ff_init_a'], rtol=1e-13)
+    np.testing.assert_allclose(oracle.ipsi(g['ff_ipsi_y']), g['ff_ipsi_x'], rtol=1e-13)
+    np.testing.assert_allclose(oracle.fixedpoint_fit(g['ff_D']), g['ff_fixedpoint'],
+                               rtol=1e-12)
+
+
+def test_confusion_matrix_ignores_negative_labels():
+    labels = np.array([[0, 1, -1, 2], [2, 2, -5, 1]])
+    pred = np.array([[0, 2, 1, 2], [2, 0, 0, 1]])
+    cm = oracle.confusion_matrix(labels, pred, 3)
+    assert cm.dtype == np.int64 and cm.sum() == 6
+    np.testing.assert_array_equal(cm, [[1, 0, 0], [0, 1, 1], [1, 0, 2]])
+
+
+def test_fcn_shapes_and_relu_identity_of_bilinear_upscore():
+    rng = np.random.default_rng(1)
+    params = oracle.glorot_fcn_params('rgb', 3, 8, 5, rng)
+    x = rng.uniform(0, 1, size=(1, 32, 48, 3)).astype(np.float32)
+    out = oracle.test_pipeline(x, params, 'rgb', 8, 5)
+    assert out['fused'].shape == (1, 4, 6, 8)
+    assert out['score'].shape == (1, 32, 48, 5)
+    assert out['classification'].dtype == np.int64
+    np.testing.assert_allclose(out['prob'].sum(-1), 1, rtol=1e-5)
+    # the decoder is linear in `fused` for the bilinear kernel: score 1x1 and x8 upscore commute
+    lowres = oracle.conv2d(out['fused'], params, 'rgb/score', activation=False)
+    p2 = dict(params)
+    p2['rgb/upscore/kernel'] = oracle.bilinear_filter((16, 16, 5, 5))
+    up = oracle.deconv2d(lowres - params['rgb/score/bias'], p2, 'rgb/upscore', 8,
+                         activation=False) + params['rgb/score/bias']
+    np.testing.assert_allclose(up, out['score'], rtol=1e-4, atol=1e-5)
