@@ -1,0 +1,165 @@
+/* xview_b200 - C ABI of the B200-native inference + fusion + score() hot path of
+ * ethz-asl/modular_semantic_segmentation.
+ *
+ * This is the drop-in boundary: the reference reaches its compute through TensorFlow ops
+ * called from xview/models/*.py; a maintainer replaces those call sites by ctypes bindings to
+ * the functions below.  Each entry point cites the reference statement it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; xv_last_error() returns a
+ *     thread-local message.  No C++ exception crosses this boundary.
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - activations are NHWC float32 at the boundary (the reference layout/dtype); kernels are
+ *     HWIO ([kh,kw,Cin,Cout]); transposed-conv kernels are [kh,kw,Cout,Cin].
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     stream-ordered and asynchronous unless stated otherwise.
+ *   - label tensors are int64 (`label_bytes` = 8, the reference's tf.argmax dtype) or uint8
+ *     (`label_bytes` = 1, the compact internal form).
+ *   - one handle is used from one host thread at a time.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef XVIEW_B200_H_
+#define XVIEW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XV_ABI_VERSION 1
+
+/* ---- library / device ------------------------------------------------------------- */
+int xv_abi_version(void);
+const char* xv_last_error(void);
+/* Binds the calling thread to `device`, queries SM count / shared-memory limits and resolves
+ * the driver entry point used to build TMA descriptors.  (tf.Session creation,
+ * xview/models/base_model.py:166-172) */
+int xv_init(int device);
+int xv_device_sm_count(int* out);
+
+/* ---- plain memory / stream helpers (session feed/fetch, base_model.py:263-313) ----- */
+int xv_malloc(void** out, size_t bytes);
+int xv_free(void* p);
+int xv_malloc_host(void** out_host, size_t bytes);       /* pinned */
+int xv_free_host(void* p_host);
+int xv_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stream);
+int xv_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream);
+int xv_memset(void* dst, int value, size_t bytes, void* stream);
+int xv_stream_sync(void* stream);
+
+/* ---- FCN expert (xview/models/simple_fcn.py:137-170 `fcn`, :10-87 encoder, :90-134 decoder) */
+typedef struct xv_fcn xv_fcn;
+
+#define XV_PRECISION_BF16 0 /* tcgen05 bf16 implicit-GEMM convolutions, fp32 accumulate   */
+#define XV_PRECISION_FP32 1 /* validation mode: fp32 CUDA-core kernels, reference op order */
+
+/* dropout sites, simple_fcn.py:51-53,61-63,72-78,124-126 */
+#define XV_DROP_POOL3 1u    /* also enables pool4 dropout: reference quirk simple_fcn.py:61 */
+#define XV_DROP_CONV4_3 2u
+#define XV_DROP_CONV5_3 4u
+#define XV_DROP_FEATURES 8u
+
+typedef struct xv_dropout_cfg {
+  float rate;                 /* tf.layers.dropout rate; survivors are scaled by 1/(1-rate)  */
+  uint32_t sites;             /* OR of XV_DROP_*                                             */
+  int32_t num_samples;        /* T >= 1 Monte-Carlo samples sharing one weight load          */
+  uint64_t seed;              /* Philox key of the fused dropout masks                       */
+  /* optional external keep-masks (uint8, one byte per element of the [T*N,h,w,c] activation):
+   * order pool3, pool4, conv4_3, conv5_3, features.  NULL = fused Philox.                   */
+  const uint8_t* ext_mask[5];
+} xv_dropout_cfg;
+
+typedef struct xv_fcn_outputs {
+  /* T == 1 (or no dropout): per-image results; T > 1: per-sample results, batch = T*N        */
+  float* score;               /* [B,H,W,C] pre-softmax class scores ('score', simple_fcn.py:133) */
+  float* prob;                /* [B,H,W,C] softmax (basic_fusion_model.py:21)                 */
+  int64_t* label_i64;         /* [B,H,W]   argmax (basic_fusion_model.py:22)                  */
+  uint8_t* label_u8;          /* [B,H,W]   same, compact                                      */
+  /* T > 1 only: moments over the T samples (variance_mix.py:62-66), no sample tensor is ever
+   * written                                                                                 */
+  float* mean_prob;           /* [N,H,W,C]                                                    */
+  float* var_prob;            /* [N,H,W,C] population variance                                */
+  float* mean_var;            /* [N,H,W]   mean over classes of var_prob                      */
+} xv_fcn_outputs;
+
+int xv_fcn_create(xv_fcn** out, int cin, int num_units, int num_classes, int batchnorm,
+                  int precision);
+int xv_fcn_destroy(xv_fcn* net);
+/* `name` is the variable name below the expert prefix, e.g. "conv1_1/kernel", "score/bias",
+ * "upscore/kernel", "conv3_2/moving_variance" (layout: SURVEY.md Appendix B;
+ * base_model.py:395-451 import_weights assigns the same arrays to tf variables). */
+int xv_fcn_set_param_host(xv_fcn* net, const char* name, const float* data_host,
+                          const int64_t* shape_host, int ndim);
+/* Packs the weights for the device (folds test-time batch norm, converts to bf16, detects the
+ * channel-diagonal bilinear transposed convolutions).  Must be called after the last
+ * xv_fcn_set_param_host and before xv_fcn_forward. */
+int xv_fcn_finalize(xv_fcn* net);
+/* x: [N,H,W,cin] float32.  H and W must be multiples of 16 (xview/datasets/augmentation.py
+ * crop_multiple).  drop may be NULL (deterministic test-time network, simple_fcn.py:218-224). */
+int xv_fcn_forward(xv_fcn* net, const float* x, int n, int h, int w, const xv_dropout_cfg* drop,
+                   const xv_fcn_outputs* outputs, void* stream);
+/* Diagnostics: copies the activation of a named layer of the LAST forward call to the host as
+ * float32 NHWC (the reference returns every layer in the dict of simple_fcn.py:37-87).
+ * shape_out_host receives [B,H,W,C].  Synchronous. */
+int xv_fcn_get_layer_host(xv_fcn* net, const char* layer, float* out_host, size_t capacity_floats,
+                          int64_t* shape_out_host, void* stream);
+
+/* ---- single layers (xview/models/custom_layers.py:124-139 conv2d, :71-121 deconv2d) ---- */
+/* x [N,H,W,cin] -> out [N,H,W,cout]; k in {1,3}; stride 1 'same'.  precision BF16 needs
+ * cin % 64 == 0 (or k == 3 with cin <= 3, the conv1_1 operand-packing path). */
+int xv_conv2d(const float* x, const float* w_hwio_host, const float* bias_host, int n, int h,
+              int w, int cin, int cout, int k, int relu, int precision, float* out,
+              void* stream);
+/* conv2d_transpose 'same', no bias: x [N,h,w,cin] -> out [N,h*stride,w*stride,cout] */
+int xv_deconv2d(const float* x, const float* w_khkwoi_host, int n, int h, int w, int cin,
+                int cout, int k, int stride, int relu, float* out, void* stream);
+int xv_maxpool2x2(const float* x, int n, int h, int w, int c, float* out, void* stream);
+
+/* ---- per-pixel fusion stage ---------------------------------------------------------- */
+/* tf.nn.softmax + tf.argmax, basic_fusion_model.py:21-22.  prob / label may be NULL. */
+int xv_softmax_argmax(const float* score, int64_t npix, int num_classes, float* prob,
+                      void* label, int label_bytes, void* stream);
+/* Bayes fusion through the decision table of bayes_mix.py:61-112: out = lut[l_0][l_1]...;
+ * labels_host: host array of `num_experts` device pointers; lut: device int32 [C^M]. */
+int xv_bayes_fuse_lut(const void* const* labels_host, int num_experts, int label_bytes,
+                      const int32_t* lut, int num_classes, int64_t npix, void* out, void* stream);
+/* Literal Bayes fusion, bayes_mix.py:12-58: score = sum_m log_cond[m][l_m][:] + log_prior;
+ * log_cond: device [M,C,C] = log(1e-20 + conditional), log_prior: device [C].
+ * score (float32 [npix,C]) and label may be NULL. */
+int xv_bayes_fuse_score(const void* const* labels_host, int num_experts, int label_bytes,
+                        const float* log_cond, const float* log_prior, int num_classes,
+                        int64_t npix, float* score, void* label, void* stream);
+/* Dirichlet fusion, dirichlet_mix.py:14-36 + :100-113.  alpha_m1: device [M,C_out,C_gt] =
+ * sigma*alpha - 1, log_norm: device [M,C_gt] = lbeta(sigma*alpha[:,c]), log_prior: device [C]
+ * = log(1e-20 + prior). */
+int xv_dirichlet_fuse(const float* const* probs_host, int num_experts, const float* alpha_m1,
+                      const float* log_norm, const float* log_prior, int num_classes,
+                      int64_t npix, float* score, void* label, int label_bytes, void* stream);
+/* average_mix.py:18-21 */
+int xv_average_fuse(const float* const* probs_host, int num_experts, int num_classes,
+                    int64_t npix, float* score, void* label, int label_bytes, void* stream);
+/* variance_mix.py:7-15; vars_host[m]: device float32 [npix] */
+int xv_variance_fuse(const float* const* probs_host, const float* const* vars_host,
+                     int num_experts, int num_classes, int64_t npix, float* score, void* label,
+                     int label_bytes, void* stream);
+/* MC-dropout moments over materialised samples [T,npix,C] (variance_mix.py:62-66,
+ * bayesian_fcn.py:48-57).  Every output may be NULL. */
+int xv_mc_moments(const float* samples, int num_samples, int64_t npix, int num_classes,
+                  float* mean, float* var, float* mean_var, float* entropy, float* cond_entropy,
+                  float* sum_var, void* stream);
+/* Dirichlet sufficient statistics, dirichlet_mix.py:142-163: ACCUMULATES into
+ * stats (device float64 [C,C]) and counts (device int64 [C]). */
+int xv_dirichlet_suffstats(const float* prob, const int32_t* labels, int64_t npix,
+                           int num_classes, double* stats, int64_t* counts, void* stream);
+/* Confusion matrix, base_model.py:140-151: ACCUMULATES into cm (device int64 [C,C], rows =
+ * ground-truth label, cols = prediction); negative labels are ignored. */
+int xv_confusion_accumulate(const void* pred, int pred_bytes, const int32_t* labels, int64_t npix,
+                            int num_classes, int64_t* cm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XVIEW_B200_H_ */

@@ -1,0 +1,977 @@
+// C-ABI layer of libxview_b200: handle management, weight packing, the layer schedule of the
+// FCN expert and thin wrappers around the fusion kernels.  See include/xview_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/xview_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xv {
+
+// ------------------------------------------------------------------ error + device state
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(const std::string& msg) {
+  g_error = msg;
+  return -1;
+}
+
+static DeviceInfo g_dev;
+const DeviceInfo& device_info() { return g_dev; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int ensure_init() {
+  if (g_dev.device >= 0) return 0;
+  int dev = 0;
+  XV_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  XV_CUDA(cudaGetDeviceProperties(&prop, dev));
+  XV_CHECK(prop.major == 10, "xview_b200 needs an sm_100-class GPU (found sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  XV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  XV_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+           "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  g_dev.num_sms = prop.multiProcessorCount;
+  g_dev.smem_optin = prop.sharedMemPerBlockOptin;
+  g_dev.device = dev;
+  return 0;
+}
+
+// ------------------------------------------------------------------ TMA descriptors
+static int make_tmap_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int th,
+                         int tw) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
+                        static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string(r));
+  return 0;
+}
+
+static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(cout_pad)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kdim) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(block_n)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(r));
+  return 0;
+}
+
+// 128-pixel spatial tile minimising padded area, then preferring square-ish patches.
+static void choose_tile(int H, int W, int* th, int* tw) {
+  long best_area = -1;
+  int best_skew = 0;
+  for (int t = 1; t <= 128; t *= 2) {
+    const int a = t, b = 128 / t;   // th = a, tw = b
+    const long area = static_cast<long>(div_up(H, a)) * a * div_up(W, b) * b;
+    const int skew = a > b ? a / b : b / a;
+    if (best_area < 0 || area < best_area || (area == best_area && skew < best_skew)) {
+      best_area = area;
+      best_skew = skew;
+      *th = a;
+      *tw = b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ device buffers
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int ensure(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    XV_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return 0;
+  }
+  template <typename T>
+  int upload(const std::vector<T>& v) {
+    XV_TRY(ensure(v.size() * sizeof(T)));
+    XV_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+  }
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0;
+  void* alloc(size_t bytes) {
+    off = (off + 1023) & ~static_cast<size_t>(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct HostParam {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct ConvLayer {
+  std::string name;
+  int k = 3, cin = 0, cout = 0, relu = 1;
+  // bf16 path
+  int taps = 9, kdim = 0, cin_gemm = 0, cout_pad = 0, block_n = 0;
+  DevBuf w_packed, bias_pad;
+  // fp32 path
+  DevBuf w_f32, bias_f32, bn_scale, bn_shift;
+  bool has_bn = false;
+};
+
+enum class DType { F32, BF16, U8 };
+struct Act {
+  void* p = nullptr;
+  DType dt = DType::F32;
+  int B = 0, H = 0, W = 0, C = 0;
+  size_t elems() const { return static_cast<size_t>(B) * H * W * C; }
+};
+
+}  // namespace xv
+
+using namespace xv;
+
+struct xv_fcn {
+  int cin = 0, nu = 0, C = 0, batchnorm = 0, precision = 0;
+  bool finalized = false;
+  std::map<std::string, HostParam> params;
+  std::vector<std::unique_ptr<ConvLayer>> convs;   // conv1_1..conv5_3, score_conv4, score_conv5, score
+  // decoder
+  bool fast_up5 = false, fast_up = false;
+  DevBuf g4, g16, w_score_nuxc, b_score;           // fast paths
+  DevBuf w_up5, w_up, up5_scale, up5_shift, up_scale, up_shift;   // generic paths
+  DevBuf arena_buf;
+  std::map<std::string, Act> layers;
+  std::map<std::tuple<const void*, int, int, int, int, int, int>, CUtensorMap> tmaps;
+
+  ConvLayer* conv(const std::string& n) {
+    for (auto& c : convs)
+      if (c->name == n) return c.get();
+    return nullptr;
+  }
+};
+
+namespace xv {
+
+static const char* kConvNames[13] = {"conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1",
+                                     "conv3_2", "conv3_3", "conv4_1", "conv4_2", "conv4_3",
+                                     "conv5_1", "conv5_2", "conv5_3"};
+static const int kConvCout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+
+static int get_param(xv_fcn* net, const std::string& name, std::vector<int64_t> shape,
+                     const HostParam** out) {
+  auto it = net->params.find(name);
+  XV_CHECK(it != net->params.end(), "parameter '" + name + "' was never set");
+  XV_CHECK(it->second.shape == shape, "parameter '" + name + "' has the wrong shape");
+  *out = &it->second;
+  return 0;
+}
+
+// BN folding factors: y = scale * conv + shift (test-time tf.layers.batch_normalization,
+// epsilon 1e-3, custom_layers.py:116,132-134)
+static int bn_factors(xv_fcn* net, const std::string& layer, int cout, std::vector<float>* scale,
+                      std::vector<float>* shift) {
+  scale->assign(cout, 1.f);
+  shift->assign(cout, 0.f);
+  if (!net->batchnorm) return 0;
+  const HostParam *g, *b, *m, *v;
+  XV_TRY(get_param(net, layer + "/gamma", {cout}, &g));
+  XV_TRY(get_param(net, layer + "/beta", {cout}, &b));
+  XV_TRY(get_param(net, layer + "/moving_mean", {cout}, &m));
+  XV_TRY(get_param(net, layer + "/moving_variance", {cout}, &v));
+  for (int c = 0; c < cout; ++c) {
+    const float s = g->data[c] / std::sqrt(v->data[c] + 1e-3f);
+    (*scale)[c] = s;
+    (*shift)[c] = b->data[c] - m->data[c] * s;
+  }
+  return 0;
+}
+
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// Packs one conv layer for both precisions.  `special_c1`: conv1_1 operand layout
+// [hi taps | lo taps | 0] with K = 64 (see layers.cu im2col_c1_kernel).
+static int pack_conv(xv_fcn* net, ConvLayer* L, const float* w_hwio, const float* bias,
+                     const std::vector<float>& scale, const std::vector<float>& shift,
+                     bool bn) {
+  const int k = L->k, cin = L->cin, cout = L->cout, taps = k * k;
+  if (net->precision == XV_PRECISION_FP32) {
+    std::vector<float> w(w_hwio, w_hwio + static_cast<size_t>(taps) * cin * cout);
+    std::vector<float> b(cout, 0.f);
+    if (bias) b.assign(bias, bias + cout);
+    XV_TRY(L->w_f32.upload(w));
+    XV_TRY(L->bias_f32.upload(b));
+    L->has_bn = bn;
+    if (bn) {
+      XV_TRY(L->bn_scale.upload(scale));
+      XV_TRY(L->bn_shift.upload(shift));
+    }
+    return 0;
+  }
+  const bool special_c1 = (k == 3 && cin <= 3);
+  XV_CHECK(special_c1 || cin % 64 == 0,
+           "bf16 path: Cin of '" + L->name + "' must be a multiple of 64 (or <= 3 for a 3x3 layer)");
+  L->taps = special_c1 ? 1 : taps;
+  L->cin_gemm = special_c1 ? 64 : cin;
+  L->kdim = L->taps * L->cin_gemm;
+  L->block_n = conv_igemm_block_n(cout);
+  L->cout_pad = div_up(cout, L->block_n) * L->block_n;
+  std::vector<uint16_t> wp(static_cast<size_t>(L->cout_pad) * L->kdim, 0);
+  std::vector<float> bp(L->cout_pad, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    for (int t = 0; t < taps; ++t)
+      for (int ci = 0; ci < cin; ++ci) {
+        const float v = w_hwio[(static_cast<size_t>(t) * cin + ci) * cout + co] * scale[co];
+        const uint16_t q = f2bf(v);
+        if (special_c1) {
+          wp[static_cast<size_t>(co) * 64 + t * cin + ci] = q;             // hi part
+          wp[static_cast<size_t>(co) * 64 + 9 * cin + t * cin + ci] = q;   // lo part
+        } else {
+          wp[static_cast<size_t>(co) * L->kdim + t * cin + ci] = q;
+        }
+      }
+    bp[co] = (bias ? bias[co] : 0.f) * scale[co] + shift[co];
+  }
+  XV_TRY(L->w_packed.upload(wp));
+  XV_TRY(L->bias_pad.upload(bp));
+  return 0;
+}
+
+static int get_tmap(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W, int C,
+                    int th, int tw) {
+  auto key = std::make_tuple(ptr, N, H, W, C, th, tw);
+  if (net) {
+    auto it = net->tmaps.find(key);
+    if (it != net->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  XV_TRY(make_tmap_act(out, ptr, N, H, W, C, th, tw));
+  if (net) net->tmaps[key] = *out;
+  return 0;
+}
+
+// in: bf16 [B,H,W,cin_gemm]; out: bf16 [B,H,W,cout] (cout % 64 == 0) or fp32 [B,H,W,cout]
+static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
+                     void* out, bool out_f32, cudaStream_t s) {
+  ConvIgemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  choose_tile(H, W, &p.th, &p.tw);
+  XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, p.th, p.tw));
+  XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
+  if (!out_f32) {
+    XV_CHECK(L.cout % 64 == 0, "bf16 epilogue needs Cout % 64 == 0");
+    XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, p.th, p.tw));
+  } else {
+    p.tmap_out = p.tmap_in;
+    p.out_f32 = static_cast<float*>(out);
+  }
+  p.bias = static_cast<const float*>(L.bias_pad.p);
+  p.N = B;
+  p.H = H;
+  p.W = W;
+  p.cin = L.cin_gemm;
+  p.cout = L.cout;
+  p.tiles_x = div_up(W, p.tw);
+  p.tiles_y = div_up(H, p.th);
+  p.n_blocks = L.cout_pad / L.block_n;
+  p.relu = L.relu;
+  return launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+}
+
+// ------------------------------------------------------------------ forward schedule
+struct Forward {
+  xv_fcn* net;
+  Arena arena;
+  cudaStream_t s;
+  bool dry;
+  int T = 1;
+  const xv_dropout_cfg* drop = nullptr;
+
+  bool bf16() const { return net->precision == XV_PRECISION_BF16; }
+  size_t esize(DType d) const { return d == DType::F32 ? 4 : (d == DType::BF16 ? 2 : 1); }
+
+  Act make(const std::string& name, DType dt, int B, int H, int W, int C) {
+    Act a;
+    a.dt = dt;
+    a.B = B;
+    a.H = H;
+    a.W = W;
+    a.C = C;
+    a.p = arena.alloc(a.elems() * esize(dt));
+    if (!dry && !name.empty()) net->layers[name] = a;
+    return a;
+  }
+
+  int conv(const std::string& name, const Act& in, Act* out, bool force_f32_out = false) {
+    ConvLayer* L = net->conv(name);
+    XV_CHECK(L != nullptr, "unknown conv layer " + name);
+    if (bf16()) {
+      const bool f32o = force_f32_out;
+      *out = make(name, f32o ? DType::F32 : DType::BF16, in.B, in.H, in.W, L->cout);
+      if (dry) return 0;
+      return run_igemm(net, *L, in.p, in.B, in.H, in.W, out->p, f32o, s);
+    }
+    *out = make(name, DType::F32, in.B, in.H, in.W, L->cout);
+    if (dry) return 0;
+    const bool relu_in_conv = L->relu && !L->has_bn;
+    XV_TRY(launch_conv_f32(static_cast<const float*>(in.p), static_cast<const float*>(L->w_f32.p),
+                           static_cast<const float*>(L->bias_f32.p), static_cast<float*>(out->p),
+                           in.B, in.H, in.W, L->cin, L->cout, L->k, relu_in_conv, s));
+    if (L->has_bn)
+      XV_TRY(launch_affine_f32(static_cast<float*>(out->p),
+                               static_cast<const float*>(L->bn_scale.p),
+                               static_cast<const float*>(L->bn_shift.p),
+                               static_cast<size_t>(in.B) * in.H * in.W, L->cout, L->relu, s));
+    return 0;
+  }
+
+  int pool(const std::string& name, const Act& in, Act* out) {
+    *out = make(name, in.dt, in.B, in.H / 2, in.W / 2, in.C);
+    if (dry) return 0;
+    if (in.dt == DType::BF16)
+      return launch_maxpool_bf16(static_cast<const __nv_bfloat16*>(in.p),
+                                 static_cast<__nv_bfloat16*>(out->p), in.B, in.H, in.W, in.C, s);
+    return launch_maxpool_f32(static_cast<const float*>(in.p), static_cast<float*>(out->p), in.B,
+                              in.H, in.W, in.C, s);
+  }
+
+  // dropout site `idx` (0 pool3, 1 pool4, 2 conv4_3, 3 conv5_3, 4 features); `active` false
+  // with replicate > 1 degenerates to a plain T-fold copy.
+  int dropout(const std::string& name, int idx, bool active, const Act& in, int replicate,
+              Act* out) {
+    *out = make(name, in.dt, in.B * replicate, in.H, in.W, in.C);
+    if (dry) return 0;
+    DropoutSpec d;
+    d.rate = active ? drop->rate : 0.f;
+    d.ext_mask = active ? drop->ext_mask[idx] : nullptr;
+    d.seed = drop ? drop->seed : 0;
+    d.offset = static_cast<uint64_t>(idx + 1) << 40;
+    if (!active) {
+      static const uint8_t* none = nullptr;
+      d.ext_mask = none;
+    }
+    if (in.dt == DType::BF16)
+      return launch_dropout_bf16(static_cast<const __nv_bfloat16*>(in.p),
+                                 static_cast<__nv_bfloat16*>(out->p), in.elems(), replicate, d, s);
+    return launch_dropout_f32(static_cast<const float*>(in.p), static_cast<float*>(out->p),
+                              in.elems(), replicate, d, s);
+  }
+
+  int run(const float* x, int N, int H, int W, const xv_fcn_outputs* o);
+};
+
+int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
+  const uint32_t sites = drop ? drop->sites : 0u;
+  const bool mc = T > 1;
+  Act cur;
+  if (bf16()) {
+    Act a0 = make("conv1_1_operand", DType::BF16, N, H, W, 64);
+    if (!dry)
+      XV_TRY(launch_im2col_c1(x, static_cast<__nv_bfloat16*>(a0.p), N, H, W, net->cin, s));
+    cur = a0;
+  } else {
+    cur.p = const_cast<float*>(x);
+    cur.dt = DType::F32;
+    cur.B = N;
+    cur.H = H;
+    cur.W = W;
+    cur.C = net->cin;
+  }
+  Act t;
+  XV_TRY(conv("conv1_1", cur, &t));
+  XV_TRY(conv("conv1_2", t, &cur));
+  XV_TRY(pool("pool1", cur, &t));
+  XV_TRY(conv("conv2_1", t, &cur));
+  XV_TRY(conv("conv2_2", cur, &t));
+  XV_TRY(pool("pool2", t, &cur));
+  XV_TRY(conv("conv3_1", cur, &t));
+  XV_TRY(conv("conv3_2", t, &cur));
+  XV_TRY(conv("conv3_3", cur, &t));
+  XV_TRY(pool("pool3", t, &cur));
+  bool replicated = false;
+  if (sites & XV_DROP_POOL3) {
+    XV_TRY(dropout("pool3_drop", 0, true, cur, T, &t));
+    cur = t;
+    replicated = true;
+  }
+  XV_TRY(conv("conv4_1", cur, &t));
+  XV_TRY(conv("conv4_2", t, &cur));
+  Act c43;
+  XV_TRY(conv("conv4_3", cur, &c43));
+  XV_TRY(pool("pool4", c43, &cur));
+  if (sites & XV_DROP_POOL3) {   // sic: simple_fcn.py:61 gates pool4 dropout on 'pool3'
+    XV_TRY(dropout("pool4_drop", 1, true, cur, 1, &t));
+    cur = t;
+  }
+  XV_TRY(conv("conv5_1", cur, &t));
+  XV_TRY(conv("conv5_2", t, &cur));
+  Act c53;
+  XV_TRY(conv("conv5_3", cur, &c53));
+  Act s4in = c43, s5in = c53;
+  const bool branch_sites = (sites & (XV_DROP_CONV4_3 | XV_DROP_CONV5_3)) != 0;
+  if (branch_sites) {
+    const int rep = replicated ? 1 : T;
+    if ((sites & XV_DROP_CONV4_3) || rep > 1)
+      XV_TRY(dropout("conv4_3_drop", 2, (sites & XV_DROP_CONV4_3) != 0, c43, rep, &s4in));
+    if ((sites & XV_DROP_CONV5_3) || rep > 1)
+      XV_TRY(dropout("conv5_3_drop", 3, (sites & XV_DROP_CONV5_3) != 0, c53, rep, &s5in));
+    replicated = true;
+  }
+  Act s4, s5, fused;
+  XV_TRY(conv("score_conv4", s4in, &s4, /*force_f32_out=*/true));
+  XV_TRY(conv("score_conv5", s5in, &s5, /*force_f32_out=*/true));
+  const int nu = net->nu;
+  // upscore_conv5 + skip add (simple_fcn.py:82-85)
+  fused = make("fused", DType::F32, s4.B, s4.H, s4.W, nu);
+  if (net->fast_up5) {
+    if (!dry)
+      XV_TRY(launch_upscore2_add(static_cast<const float*>(s5.p), static_cast<const float*>(s4.p),
+                                 static_cast<const float*>(net->g4.p),
+                                 static_cast<float*>(fused.p), s5.B, s5.H, s5.W, nu, s));
+  } else if (!net->batchnorm) {
+    if (!dry)
+      XV_TRY(launch_deconv_f32(static_cast<const float*>(s5.p),
+                               static_cast<const float*>(net->w_up5.p),
+                               static_cast<float*>(fused.p), s5.B, s5.H, s5.W, nu, nu, 4, 2, 1,
+                               static_cast<const float*>(s4.p), s));
+  } else {
+    // deconv -> BN -> ReLU (custom_layers.py:112-119), then the skip add
+    Act up5 = make("upscore_conv5", DType::F32, s4.B, s4.H, s4.W, nu);
+    if (!dry) {
+      XV_TRY(launch_deconv_f32(static_cast<const float*>(s5.p),
+                               static_cast<const float*>(net->w_up5.p),
+                               static_cast<float*>(up5.p), s5.B, s5.H, s5.W, nu, nu, 4, 2, 0,
+                               nullptr, s));
+      XV_TRY(launch_affine_f32(static_cast<float*>(up5.p),
+                               static_cast<const float*>(net->up5_scale.p),
+                               static_cast<const float*>(net->up5_shift.p), up5.elems() / nu, nu,
+                               1, s));
+      XV_TRY(launch_add_f32(static_cast<const float*>(s4.p), static_cast<const float*>(up5.p),
+                            static_cast<float*>(fused.p), fused.elems(), s));
+    }
+  }
+  Act feat = fused;
+  if (sites & XV_DROP_FEATURES) {
+    XV_TRY(dropout("features_drop", 4, true, fused, replicated ? 1 : T, &feat));
+    replicated = true;
+  }
+  const int B = feat.B;
+  const int Hf = feat.H * 8, Wf = feat.W * 8;
+  const int C = net->C;
+  const size_t npix = static_cast<size_t>(B) * Hf * Wf;
+  const bool want_samples = o->score || o->prob || o->label_i64 || o->label_u8;
+  const bool want_moments = mc && (o->mean_prob || o->var_prob || o->mean_var);
+
+  if (net->fast_up) {
+    Act low = make("score_lowres", DType::F32, B, feat.H, feat.W, C);
+    if (!dry) {
+      XV_TRY(launch_score_lowres(static_cast<const float*>(feat.p),
+                                 static_cast<const float*>(net->w_score_nuxc.p),
+                                 static_cast<float*>(low.p),
+                                 static_cast<size_t>(B) * feat.H * feat.W, nu, C, s));
+      if (want_samples) {
+        DecodeOut d;
+        d.label_u8 = o->label_u8;
+        d.label_i64 = o->label_i64;
+        d.prob = o->prob;
+        d.score = o->score;
+        XV_TRY(launch_decode_upsample8(static_cast<const float*>(low.p),
+                                       static_cast<const float*>(net->g16.p),
+                                       static_cast<const float*>(net->b_score.p), B, feat.H,
+                                       feat.W, C, d, s));
+      }
+      if (want_moments)
+        XV_TRY(launch_decode_upsample8_mc(static_cast<const float*>(low.p),
+                                          static_cast<const float*>(net->g16.p),
+                                          static_cast<const float*>(net->b_score.p), T, B / T,
+                                          feat.H, feat.W, C, o->mean_prob, o->var_prob,
+                                          o->mean_var, s));
+    }
+    return 0;
+  }
+
+  // generic decoder, reference op order: upscore (dense transposed conv) -> [BN] -> ReLU ->
+  // 1x1 score -> softmax -> argmax (simple_fcn.py:129-133, basic_fusion_model.py:21-22)
+  Act up = make("upscore", DType::F32, B, Hf, Wf, nu);
+  Act sc;
+  const bool bn = net->batchnorm != 0;
+  if (!dry) {
+    XV_TRY(launch_deconv_f32(static_cast<const float*>(feat.p),
+                             static_cast<const float*>(net->w_up.p), static_cast<float*>(up.p), B,
+                             feat.H, feat.W, nu, nu, 16, 8, bn ? 0 : 1, nullptr, s));
+    if (bn)
+      XV_TRY(launch_affine_f32(static_cast<float*>(up.p),
+                               static_cast<const float*>(net->up_scale.p),
+                               static_cast<const float*>(net->up_shift.p), npix, nu, 1, s));
+  }
+  {
+    // the final 1x1 score conv always runs in fp32 on the CUDA cores in this path
+    ConvLayer* L = net->conv("score");
+    sc = make("score", DType::F32, B, Hf, Wf, C);
+    if (!dry) {
+      XV_TRY(launch_conv_f32(static_cast<const float*>(up.p),
+                             static_cast<const float*>(L->w_f32.p),
+                             static_cast<const float*>(L->bias_f32.p), static_cast<float*>(sc.p),
+                             B, Hf, Wf, nu, C, 1, 0, s));
+      if (L->has_bn)
+        XV_TRY(launch_affine_f32(static_cast<float*>(sc.p),
+                                 static_cast<const float*>(L->bn_scale.p),
+                                 static_cast<const float*>(L->bn_shift.p), npix, C, 0, s));
+    }
+  }
+  Act prob_tmp;
+  float* prob_ptr = o->prob;
+  if (want_moments && !prob_ptr) {
+    prob_tmp = make("prob_samples", DType::F32, B, Hf, Wf, C);
+    prob_ptr = static_cast<float*>(prob_tmp.p);
+  }
+  if (!dry) {
+    if (o->score)
+      XV_CUDA(cudaMemcpyAsync(o->score, sc.p, npix * C * sizeof(float), cudaMemcpyDeviceToDevice,
+                              s));
+    if (want_samples || want_moments)
+      XV_TRY(launch_softmax_argmax(static_cast<const float*>(sc.p), npix, C, prob_ptr,
+                                   o->label_i64, o->label_u8, s));
+    if (want_moments)
+      XV_TRY(launch_mc_moments(prob_ptr, T, npix / T, C, o->mean_prob, o->var_prob, o->mean_var,
+                               nullptr, nullptr, nullptr, s));
+  }
+  return 0;
+}
+
+}  // namespace xv
+
+// =================================================================== extern "C"
+#define XV_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int xv_abi_version(void) { return XV_ABI_VERSION; }
+const char* xv_last_error(void) { return g_error.c_str(); }
+
+int xv_init(int device) {
+  XV_CUDA(cudaSetDevice(device));
+  g_dev.device = -1;
+  return ensure_init();
+}
+int xv_device_sm_count(int* out) {
+  XV_TRY(ensure_init());
+  *out = g_dev.num_sms;
+  return 0;
+}
+
+int xv_malloc(void** out, size_t bytes) {
+  XV_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+}
+int xv_free(void* p) {
+  XV_CUDA(cudaFree(p));
+  return 0;
+}
+int xv_malloc_host(void** out, size_t bytes) {
+  XV_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return 0;
+}
+int xv_free_host(void* p) {
+  XV_CUDA(cudaFreeHost(p));
+  return 0;
+}
+int xv_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+  XV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, XV_STREAM(stream)));
+  return 0;
+}
+int xv_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+  XV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, XV_STREAM(stream)));
+  return 0;
+}
+int xv_memset(void* dst, int value, size_t bytes, void* stream) {
+  XV_CUDA(cudaMemsetAsync(dst, value, bytes, XV_STREAM(stream)));
+  return 0;
+}
+int xv_stream_sync(void* stream) {
+  XV_CUDA(cudaStreamSynchronize(XV_STREAM(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ FCN expert
+int xv_fcn_create(xv_fcn** out, int cin, int num_units, int num_classes, int batchnorm,
+                  int precision) {
+  XV_CHECK(out != nullptr, "xv_fcn_create: out is NULL");
+  XV_CHECK(cin >= 1 && num_units >= 1, "xv_fcn_create: bad channel counts");
+  XV_CHECK(num_classes >= 2 && num_classes <= kMaxClasses,
+           "xv_fcn_create: num_classes must be in [2, 24]");
+  XV_CHECK(precision == XV_PRECISION_BF16 || precision == XV_PRECISION_FP32,
+           "xv_fcn_create: unknown precision");
+  if (precision == XV_PRECISION_BF16)
+    XV_CHECK(cin <= 3, "xv_fcn_create: the bf16 path packs conv1_1 for Cin <= 3");
+  xv_fcn* net = new xv_fcn();
+  net->cin = cin;
+  net->nu = num_units;
+  net->C = num_classes;
+  net->batchnorm = batchnorm;
+  net->precision = precision;
+  *out = net;
+  return 0;
+}
+
+int xv_fcn_destroy(xv_fcn* net) {
+  delete net;
+  return 0;
+}
+
+int xv_fcn_set_param_host(xv_fcn* net, const char* name, const float* data,
+                          const int64_t* shape, int ndim) {
+  XV_CHECK(net && name && data && shape, "xv_fcn_set_param_host: NULL argument");
+  HostParam hp;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    hp.shape.push_back(shape[i]);
+    n *= static_cast<size_t>(shape[i]);
+  }
+  hp.data.assign(data, data + n);
+  net->params[name] = std::move(hp);
+  net->finalized = false;
+  return 0;
+}
+
+// A [k,k,Cout,Cin] transposed-conv kernel is "diagonal" when only [:,:,i,i] is non-zero.
+static bool deconv_is_diagonal(const HostParam& w, int k, int nu) {
+  for (int t = 0; t < k * k; ++t)
+    for (int co = 0; co < nu; ++co)
+      for (int ci = 0; ci < nu; ++ci)
+        if (co != ci && w.data[(static_cast<size_t>(t) * nu + co) * nu + ci] != 0.f) return false;
+  return true;
+}
+
+int xv_fcn_finalize(xv_fcn* net) {
+  XV_CHECK(net != nullptr, "xv_fcn_finalize: NULL handle");
+  XV_TRY(ensure_init());
+  net->convs.clear();
+  net->tmaps.clear();
+  const int nu = net->nu, C = net->C;
+  int cin = net->cin;
+  std::vector<float> scale, shift;
+  auto add_conv = [&](const std::string& name, int k, int ci, int co, int relu) -> int {
+    const HostParam *w, *b;
+    XV_TRY(get_param(net, name + "/kernel", {k, k, ci, co}, &w));
+    XV_TRY(get_param(net, name + "/bias", {co}, &b));
+    XV_TRY(bn_factors(net, name, co, &scale, &shift));
+    std::unique_ptr<ConvLayer> L(new ConvLayer());
+    L->name = name;
+    L->k = k;
+    L->cin = ci;
+    L->cout = co;
+    L->relu = relu;
+    XV_TRY(pack_conv(net, L.get(), w->data.data(), b->data.data(), scale, shift,
+                     net->batchnorm != 0));
+    net->convs.push_back(std::move(L));
+    return 0;
+  };
+  for (int i = 0; i < 13; ++i) {
+    XV_TRY(add_conv(kConvNames[i], 3, cin, kConvCout[i], 1));
+    cin = kConvCout[i];
+  }
+  XV_TRY(add_conv("score_conv4", 1, 512, nu, 1));
+  XV_TRY(add_conv("score_conv5", 1, 512, nu, 1));
+  {
+    // final 1x1 score conv: fp32 weights are always kept (generic decoder); the fast decoder
+    // uses the [nu,C] matrix directly
+    const HostParam *w, *b;
+    XV_TRY(get_param(net, "score/kernel", {1, 1, nu, C}, &w));
+    XV_TRY(get_param(net, "score/bias", {C}, &b));
+    XV_TRY(bn_factors(net, "score", C, &scale, &shift));
+    std::unique_ptr<ConvLayer> L(new ConvLayer());
+    L->name = "score";
+    L->k = 1;
+    L->cin = nu;
+    L->cout = C;
+    L->relu = 0;
+    XV_TRY(L->w_f32.upload(w->data));
+    XV_TRY(L->bias_f32.upload(b->data));
+    L->has_bn = net->batchnorm != 0;
+    if (L->has_bn) {
+      XV_TRY(L->bn_scale.upload(scale));
+      XV_TRY(L->bn_shift.upload(shift));
+    }
+    net->convs.push_back(std::move(L));
+    XV_TRY(net->w_score_nuxc.upload(w->data));
+    XV_TRY(net->b_score.upload(b->data));
+  }
+  const HostParam *w5, *w16;
+  XV_TRY(get_param(net, "upscore_conv5/kernel", {4, 4, nu, nu}, &w5));
+  XV_TRY(get_param(net, "upscore/kernel", {16, 16, nu, nu}, &w16));
+  XV_TRY(net->w_up5.upload(w5->data));
+  XV_TRY(net->w_up.upload(w16->data));
+  if (net->batchnorm) {
+    XV_TRY(bn_factors(net, "upscore_conv5", nu, &scale, &shift));
+    XV_TRY(net->up5_scale.upload(scale));
+    XV_TRY(net->up5_shift.upload(shift));
+    XV_TRY(bn_factors(net, "upscore", nu, &scale, &shift));
+    XV_TRY(net->up_scale.upload(scale));
+    XV_TRY(net->up_shift.upload(shift));
+  }
+  // Fast decoder paths exist in the bf16 production mode only; the fp32 validation mode keeps
+  // the reference op order (dense transposed convolutions).
+  net->fast_up5 = net->fast_up = false;
+  if (net->precision == XV_PRECISION_BF16 && !net->batchnorm) {
+    if (deconv_is_diagonal(*w5, 4, nu)) {
+      std::vector<float> g(16 * nu);
+      for (int t = 0; t < 16; ++t)
+        for (int u = 0; u < nu; ++u) g[t * nu + u] = w5->data[(static_cast<size_t>(t) * nu + u) * nu + u];
+      XV_TRY(net->g4.upload(g));
+      net->fast_up5 = true;
+    }
+    if (deconv_is_diagonal(*w16, 16, nu)) {
+      // the 1x1 score conv commutes with the upsampling only if every channel shares one
+      // non-negative 16x16 kernel (then ReLU after it is the identity on non-negative input)
+      bool shared = true;
+      std::vector<float> g(256);
+      for (int t = 0; t < 256 && shared; ++t) {
+        g[t] = w16->data[static_cast<size_t>(t) * nu * nu];
+        if (g[t] < 0.f) shared = false;
+        for (int u = 1; u < nu; ++u)
+          if (w16->data[(static_cast<size_t>(t) * nu + u) * nu + u] != g[t]) shared = false;
+      }
+      if (shared) {
+        XV_TRY(net->g16.upload(g));
+        net->fast_up = true;
+      }
+    }
+  }
+  net->finalized = true;
+  return 0;
+}
+
+int xv_fcn_forward(xv_fcn* net, const float* x, int n, int h, int w, const xv_dropout_cfg* drop,
+                   const xv_fcn_outputs* outputs, void* stream) {
+  XV_CHECK(net && x && outputs, "xv_fcn_forward: NULL argument");
+  XV_CHECK(net->finalized, "xv_fcn_forward: call xv_fcn_finalize first");
+  XV_CHECK(n >= 1 && h >= 16 && w >= 16 && h % 16 == 0 && w % 16 == 0,
+           "xv_fcn_forward: H and W must be positive multiples of 16");
+  xv_dropout_cfg cfg;
+  const xv_dropout_cfg* d = nullptr;
+  int T = 1;
+  if (drop && drop->sites != 0) {
+    cfg = *drop;
+    XV_CHECK(cfg.rate >= 0.f && cfg.rate < 1.f, "xv_fcn_forward: dropout rate must be in [0,1)");
+    XV_CHECK(cfg.num_samples >= 1, "xv_fcn_forward: num_samples must be >= 1");
+    T = cfg.num_samples;
+    d = &cfg;
+  }
+  Forward plan{net, Arena(), XV_STREAM(stream), true, T, d};
+  XV_TRY(plan.run(x, n, h, w, outputs));
+  XV_TRY(net->arena_buf.ensure(plan.arena.off + 1024));
+  Forward real{net, Arena(), XV_STREAM(stream), false, T, d};
+  real.arena.base = static_cast<char*>(net->arena_buf.p);
+  net->layers.clear();
+  return real.run(x, n, h, w, outputs);
+}
+
+int xv_fcn_get_layer_host(xv_fcn* net, const char* layer, float* out_host, size_t capacity,
+                          int64_t* shape_out, void* stream) {
+  XV_CHECK(net && layer && shape_out, "xv_fcn_get_layer_host: NULL argument");
+  auto it = net->layers.find(layer);
+  XV_CHECK(it != net->layers.end(), std::string("no activation named '") + layer + "'");
+  const Act& a = it->second;
+  shape_out[0] = a.B;
+  shape_out[1] = a.H;
+  shape_out[2] = a.W;
+  shape_out[3] = a.C;
+  if (!out_host) return 0;
+  XV_CHECK(capacity >= a.elems(), "xv_fcn_get_layer_host: buffer too small");
+  cudaStream_t s = XV_STREAM(stream);
+  if (a.dt == DType::F32) {
+    XV_CUDA(cudaMemcpyAsync(out_host, a.p, a.elems() * 4, cudaMemcpyDeviceToHost, s));
+  } else {
+    DevBuf tmp;
+    XV_TRY(tmp.ensure(a.elems() * 4));
+    XV_TRY(launch_bf16_to_f32(static_cast<const __nv_bfloat16*>(a.p), static_cast<float*>(tmp.p),
+                              a.elems(), s));
+    XV_CUDA(cudaMemcpyAsync(out_host, tmp.p, a.elems() * 4, cudaMemcpyDeviceToHost, s));
+    XV_CUDA(cudaStreamSynchronize(s));
+  }
+  XV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------ single layers
+int xv_conv2d(const float* x, const float* w_host, const float* bias_host, int n, int h, int w,
+              int cin, int cout, int k, int relu, int precision, float* out, void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(x && w_host && out, "xv_conv2d: NULL argument");
+  XV_CHECK(k == 1 || k == 3, "xv_conv2d: k must be 1 or 3");
+  cudaStream_t s = XV_STREAM(stream);
+  xv_fcn fake;
+  fake.precision = precision;
+  ConvLayer L;
+  L.name = "conv2d";
+  L.k = k;
+  L.cin = cin;
+  L.cout = cout;
+  L.relu = relu;
+  std::vector<float> scale(cout, 1.f), shift(cout, 0.f);
+  XV_TRY(pack_conv(&fake, &L, w_host, bias_host, scale, shift, false));
+  const size_t npix = static_cast<size_t>(n) * h * w;
+  if (precision == XV_PRECISION_FP32) {
+    XV_TRY(launch_conv_f32(x, static_cast<const float*>(L.w_f32.p),
+                           static_cast<const float*>(L.bias_f32.p), out, n, h, w, cin, cout, k,
+                           relu, s));
+    XV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
+  DevBuf in_bf16;
+  XV_TRY(in_bf16.ensure(npix * L.cin_gemm * 2));
+  if (L.taps == 1 && k == 3) {
+    XV_TRY(launch_im2col_c1(x, static_cast<__nv_bfloat16*>(in_bf16.p), n, h, w, cin, s));
+  } else {
+    XV_TRY(launch_f32_to_bf16(x, static_cast<__nv_bfloat16*>(in_bf16.p), npix * cin, s));
+  }
+  if (cout % 64 == 0) {
+    DevBuf out_bf16;
+    XV_TRY(out_bf16.ensure(npix * cout * 2));
+    XV_TRY(run_igemm(nullptr, L, in_bf16.p, n, h, w, out_bf16.p, false, s));
+    XV_TRY(launch_bf16_to_f32(static_cast<const __nv_bfloat16*>(out_bf16.p), out, npix * cout, s));
+    XV_CUDA(cudaStreamSynchronize(s));
+  } else {
+    XV_TRY(run_igemm(nullptr, L, in_bf16.p, n, h, w, out, true, s));
+    XV_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+int xv_deconv2d(const float* x, const float* w_host, int n, int h, int w, int cin, int cout, int k,
+                int stride, int relu, float* out, void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(x && w_host && out, "xv_deconv2d: NULL argument");
+  cudaStream_t s = XV_STREAM(stream);
+  DevBuf wd;
+  std::vector<float> wv(w_host, w_host + static_cast<size_t>(k) * k * cout * cin);
+  XV_TRY(wd.upload(wv));
+  XV_TRY(launch_deconv_f32(x, static_cast<const float*>(wd.p), out, n, h, w, cin, cout, k, stride,
+                           relu, nullptr, s));
+  XV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int xv_maxpool2x2(const float* x, int n, int h, int w, int c, float* out, void* stream) {
+  XV_TRY(ensure_init());
+  return launch_maxpool_f32(x, out, n, h, w, c, XV_STREAM(stream));
+}
+
+// ------------------------------------------------------------------ fusion stage
+static int check_label_bytes(int b) {
+  XV_CHECK(b == 8 || b == 1, "label_bytes must be 8 (int64) or 1 (uint8)");
+  return 0;
+}
+
+int xv_softmax_argmax(const float* score, int64_t npix, int C, float* prob, void* label,
+                      int label_bytes, void* stream) {
+  XV_TRY(ensure_init());
+  XV_TRY(check_label_bytes(label_bytes));
+  return launch_softmax_argmax(score, npix, C, prob,
+                               label_bytes == 8 ? static_cast<int64_t*>(label) : nullptr,
+                               label_bytes == 1 ? static_cast<uint8_t*>(label) : nullptr,
+                               XV_STREAM(stream));
+}
+
+int xv_bayes_fuse_lut(const void* const* labels, int M, int label_bytes, const int32_t* lut, int C,
+                      int64_t npix, void* out, void* stream) {
+  XV_TRY(ensure_init());
+  return launch_bayes_lut(labels, M, label_bytes, lut, C, npix, out, XV_STREAM(stream));
+}
+
+int xv_bayes_fuse_score(const void* const* labels, int M, int label_bytes, const float* log_cond,
+                        const float* log_prior, int C, int64_t npix, float* score, void* label,
+                        void* stream) {
+  XV_TRY(ensure_init());
+  XV_TRY(check_label_bytes(label_bytes));
+  return launch_bayes_score(labels, M, label_bytes, log_cond, log_prior, C, npix, score, label,
+                            XV_STREAM(stream));
+}
+
+int xv_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m1,
+                      const float* log_norm, const float* log_prior, int C, int64_t npix,
+                      float* score, void* label, int label_bytes, void* stream) {
+  XV_TRY(ensure_init());
+  XV_TRY(check_label_bytes(label_bytes));
+  return launch_dirichlet_fuse(probs, M, alpha_m1, log_norm, log_prior, C, npix, score, label,
+                               label_bytes, XV_STREAM(stream));
+}
+
+int xv_average_fuse(const float* const* probs, int M, int C, int64_t npix, float* score,
+                    void* label, int label_bytes, void* stream) {
+  XV_TRY(ensure_init());
+  XV_TRY(check_label_bytes(label_bytes));
+  return launch_average_fuse(probs, M, C, npix, score, label, label_bytes, XV_STREAM(stream));
+}
+
+int xv_variance_fuse(const float* const* probs, const float* const* vars, int M, int C,
+                     int64_t npix, float* score, void* label, int label_bytes, void* stream) {
+  XV_TRY(ensure_init());
+  XV_TRY(check_label_bytes(label_bytes));
+  return launch_variance_fuse(probs, vars, M, C, npix, score, label, label_bytes,
+                              XV_STREAM(stream));
+}
+
+int xv_mc_moments(const float* samples, int T, int64_t npix, int C, float* mean, float* var,
+                  float* mean_var, float* entropy, float* cond_entropy, float* sum_var,
+                  void* stream) {
+  XV_TRY(ensure_init());
+  return launch_mc_moments(samples, T, npix, C, mean, var, mean_var, entropy, cond_entropy,
+                           sum_var, XV_STREAM(stream));
+}
+
+int xv_dirichlet_suffstats(const float* prob, const int32_t* labels, int64_t npix, int C,
+                           double* stats, int64_t* counts, void* stream) {
+  XV_TRY(ensure_init());
+  return launch_suffstats(prob, labels, npix, C, stats, reinterpret_cast<long long*>(counts),
+                          XV_STREAM(stream));
+}
+
+int xv_confusion_accumulate(const void* pred, int pred_bytes, const int32_t* labels, int64_t npix,
+                            int C, int64_t* cm, void* stream) {
+  XV_TRY(ensure_init());
+  return launch_confusion(pred, pred_bytes, labels, npix, C, reinterpret_cast<long long*>(cm),
+                          XV_STREAM(stream));
+}
+
+}  // extern "C"

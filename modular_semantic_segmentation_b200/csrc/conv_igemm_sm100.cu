@@ -1,0 +1,296 @@
+// bf16 implicit-GEMM convolution for sm_100a: tcgen05.mma with TMEM accumulators, operands
+// staged by TMA, fused bias + ReLU epilogue.
+//
+// Replaces tf.layers.conv2d as wrapped by xview/models/custom_layers.py:124-139 (3x3 and
+// 1x1, stride 1, 'same', + bias, ReLU) for every convolution of the VGG16-FCN expert
+// (xview/models/simple_fcn.py:39-79).
+//
+// GEMM view:  D[pixels, Cout] = sum over (tap, cin) A[pixel shifted by tap, cin] * W[cout, tap, cin]
+//   M tile  = 128 output pixels = a TH x TW patch of one image (TH*TW == 128)
+//   N tile  = BLOCK_N output channels
+//   K block = 64 input channels of one filter tap (64 bf16 = 128 B = one swizzle row)
+// The A operand of a K block is ONE 4-D TMA box {64 ch, TW, TH, 1 image} whose start
+// coordinate is shifted by the tap offset; out-of-image coordinates are zero-filled by the
+// TMA unit, which is exactly the 'same' padding.  The box lands in shared memory as 128
+// rows of 128 B in the 128B-swizzled K-major layout tcgen05.mma consumes, so there is no
+// im2col buffer anywhere.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane)
+//   warps 2..5  epilogue: tcgen05.ld -> bias/ReLU -> bf16 -> swizzled smem -> TMA store
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xv {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kOutBufBytes = kBlockM * 128;      // one 64-channel bf16 output chunk
+constexpr int kThreads = 192;
+
+template <int BLOCK_N>
+struct IgemmCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 196608 / kStageBytes;   // 4 / 6 / 8 for N = 256 / 128 / 64
+  static constexpr int kTmemCols = 2 * BLOCK_N;          // two accumulator stages
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes =
+      1024 /*align slack*/ + kStages * kStageBytes + 2 * kOutBufBytes + kBarBytes;
+};
+
+struct TileCoord {
+  int img, y0, x0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvIgemmParams& p, int tile,
+                                                 int block_n) {
+  TileCoord c;
+  int nb = tile % p.n_blocks;
+  int mt = tile / p.n_blocks;
+  int tx = mt % p.tiles_x;
+  int rest = mt / p.tiles_x;
+  int ty = rest % p.tiles_y;
+  c.img = rest / p.tiles_y;
+  c.y0 = ty * p.th;
+  c.x0 = tx * p.tw;
+  c.n0 = nb * block_n;
+  return c;
+}
+
+template <int BLOCK_N, int TAPS, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint8_t* smem_out = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 2 * kOutBufBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_blocks;
+  const int cin_chunks = p.cin / kBlockK;
+  const int num_kb = TAPS * cin_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_in);
+    tma_prefetch_desc(&p.tmap_w);
+    if (!OUT_F32) tma_prefetch_desc(&p.tmap_out);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile, BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / cin_chunks;
+          const int cc = kb - tap * cin_chunks;
+          const int dy = (TAPS == 9) ? tap / 3 - 1 : 0;
+          const int dx = (TAPS == 9) ? tap % 3 - 1 : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(smem_a + stage * kABytes, &p.tmap_in, &full_bar[stage], cc * kBlockK,
+                      c.x0 + dx, c.y0 + dy, c.img);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmap_w, &full_bar[stage],
+                      tap * p.cin + cc * kBlockK, c.n0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 1024, 0),
+                      umma_desc_sw128(b_addr + k * 32, 1024, 0), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem stage when the MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue (128 threads)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;           // pixel index inside the tile
+    const int py = row / p.tw;
+    const int px = row - py * p.tw;
+    const bool issuer = (threadIdx.x == 64);
+    uint32_t acc = 0, acc_phase = 0, gchunk = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile(p, tile, BLOCK_N);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++gchunk) {
+        if constexpr (!OUT_F32) {
+          uint8_t* buf = smem_out + (gchunk & 1) * kOutBufBytes;
+          if (issuer) tma_store_wait_read<1>();   // the store that last used `buf` has drained
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + chunk * 64 + half * 32, r);
+            tmem_ld_wait();
+            const float* bias = p.bias + c.n0 + chunk * 64 + half * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t packed[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float v0 = __uint_as_float(r[j * 8 + e * 2]) + __ldg(bias + j * 8 + e * 2);
+                float v1 =
+                    __uint_as_float(r[j * 8 + e * 2 + 1]) + __ldg(bias + j * 8 + e * 2 + 1);
+                if (p.relu) {
+                  v0 = fmaxf(v0, 0.f);
+                  v1 = fmaxf(v1, 0.f);
+                }
+                packed[e] = pack_bf16x2(v0, v1);
+              }
+              const int piece = (half * 4 + j) ^ (row & 7);   // 128B swizzle
+              *reinterpret_cast<uint4*>(buf + row * 128 + piece * 16) =
+                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_4d(&p.tmap_out, buf, c.n0 + chunk * 64, c.x0, c.y0, c.img);
+            tma_store_commit();
+          }
+        } else {
+          const int y = c.y0 + py, x = c.x0 + px;
+          const bool valid = (y < p.H) && (x < p.W);
+          float* dst = p.out_f32 +
+                       ((static_cast<size_t>(c.img) * p.H + y) * p.W + x) * p.cout;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + chunk * 64 + half * 32, r);
+            tmem_ld_wait();
+            const int col0 = c.n0 + chunk * 64 + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (valid && col < p.cout) {
+                float v = __uint_as_float(r[j]) + __ldg(p.bias + col);
+                if (p.relu) v = fmaxf(v, 0.f);
+                dst[col] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);      // 128 arrivals hand the accumulator back
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (!OUT_F32 && issuer) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_N, int TAPS, bool OUT_F32>
+int launch_one(const ConvIgemmParams& p, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  auto kernel = conv_igemm_kernel<BLOCK_N, TAPS, OUT_F32>;
+  static bool configured = false;
+  if (!configured) {
+    XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_blocks;
+  const int grid = total_tiles < device_info().num_sms ? total_tiles : device_info().num_sms;
+  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int conv_igemm_block_n(int cout) { return cout > 128 ? 256 : (cout > 64 ? 128 : 64); }
+
+int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,
+                      cudaStream_t stream) {
+  XV_CHECK(p.th * p.tw == kBlockM, "conv_igemm: tile must hold 128 pixels");
+  XV_CHECK(p.cin % kBlockK == 0, "conv_igemm: Cin must be a multiple of 64");
+  XV_CHECK(taps == 1 || taps == 9, "conv_igemm: only 1x1 and 3x3 kernels");
+#define XV_IGEMM_CASE(BN)                                                              \
+  if (block_n == BN) {                                                                 \
+    if (taps == 9) {                                                                   \
+      return out_f32 ? launch_one<BN, 9, true>(p, stream)                              \
+                     : launch_one<BN, 9, false>(p, stream);                            \
+    }                                                                                  \
+    return out_f32 ? launch_one<BN, 1, true>(p, stream) : launch_one<BN, 1, false>(p, stream); \
+  }
+  XV_IGEMM_CASE(64)
+  XV_IGEMM_CASE(128)
+  XV_IGEMM_CASE(256)
+#undef XV_IGEMM_CASE
+  return fail("conv_igemm: unsupported BLOCK_N");
+}
+
+}  // namespace xv

@@ -1,0 +1,110 @@
+// Internal C++ interface between the C-ABI layer (abi.cu) and the kernel files.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xv {
+
+// ------------------------------------------------------------- conv_igemm_sm100.cu
+struct ConvIgemmParams {
+  CUtensorMap tmap_in;    // bf16 [N,H,W,Cin] viewed as (Cin, W, H, N), box {64, tw, th, 1}, SW128
+  CUtensorMap tmap_w;     // bf16 [CoutPad, taps*Cin], box {64, BLOCK_N}, SW128
+  CUtensorMap tmap_out;   // bf16 [N,H,W,Cout] box {64, tw, th, 1}, SW128 (bf16 epilogue only)
+  const float* bias;      // [CoutPad] fp32
+  float* out_f32;         // fp32 epilogue: [N,H,W,cout]
+  int N, H, W;
+  int cin;                // multiple of 64
+  int cout;               // real output channels (<= CoutPad)
+  int th, tw;             // spatial tile, th*tw == 128
+  int tiles_x, tiles_y;
+  int n_blocks;           // CoutPad / BLOCK_N
+  int relu;
+};
+int conv_igemm_block_n(int cout);
+int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,
+                      cudaStream_t stream);
+
+// ------------------------------------------------------------- layers.cu
+int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, int cin,
+                     cudaStream_t s);
+int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
+int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t s);
+int launch_maxpool_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int H, int W, int C,
+                        cudaStream_t s);
+int launch_maxpool_f32(const float* in, float* out, int N, int H, int W, int C, cudaStream_t s);
+
+struct DropoutSpec {
+  float rate = 0.f;               // drop probability; keep = 1 - rate
+  const uint8_t* ext_mask = nullptr;  // optional keep-mask, one byte per OUTPUT element
+  uint64_t seed = 0;              // Philox key
+  uint64_t offset = 0;            // Philox counter offset (distinct per site)
+};
+// out[r * n + i] = dropout(in[i]) for r in [0, replicate); n elements per copy.
+int launch_dropout_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, int replicate,
+                        const DropoutSpec& d, cudaStream_t s);
+int launch_dropout_f32(const float* in, float* out, size_t n, int replicate,
+                       const DropoutSpec& d, cudaStream_t s);
+
+// generic fp32 reference-order layers (validation mode, any shapes)
+int launch_conv_f32(const float* x, const float* w_hwio, const float* bias, float* out, int N,
+                    int H, int W, int cin, int cout, int k, int relu, cudaStream_t s);
+int launch_deconv_f32(const float* x, const float* w_khkwoi, float* out, int N, int hin, int win,
+                      int cin, int cout, int k, int stride, int relu, const float* addend,
+                      cudaStream_t s);
+int launch_add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t s);
+int launch_affine_f32(float* x, const float* scale, const float* shift, size_t npix, int C,
+                      int relu, cudaStream_t s);
+
+// fast decoder pieces (channel-diagonal transposed convolutions)
+// fused = s4 + relu(sum_taps g[ky,kx,u] * s5[tap,u]);  s4 [N,2h,2w,nu], s5 [N,h,w,nu]
+int launch_upscore2_add(const float* s5, const float* s4, const float* g_4x4xnu, float* fused,
+                        int N, int h, int w, int nu, cudaStream_t s);
+// low[n,y,x,c] = sum_u fused[n,y,x,u] * w[u,c]
+int launch_score_lowres(const float* fused, const float* w_nuxc, float* low, size_t npix, int nu,
+                        int C, cudaStream_t s);
+
+struct DecodeOut {
+  uint8_t* label_u8 = nullptr;    // [N,H,W]
+  int64_t* label_i64 = nullptr;   // [N,H,W]
+  float* prob = nullptr;          // [N,H,W,C]
+  float* score = nullptr;         // [N,H,W,C]
+};
+// score = x8 bilinear-like upsample (shared 16x16 kernel g) of `low` + bias; softmax; argmax
+int launch_decode_upsample8(const float* low, const float* g_16x16, const float* bias, int N,
+                            int h, int w, int C, const DecodeOut& out, cudaStream_t s);
+// MC variant: `low` holds T sample maps [T,N,h,w,C]; accumulates population mean / variance
+// of the per-sample softmax without materialising the samples.
+int launch_decode_upsample8_mc(const float* low, const float* g_16x16, const float* bias, int T,
+                               int N, int h, int w, int C, float* mean_prob, float* var_prob,
+                               float* mean_var, cudaStream_t s);
+
+// ------------------------------------------------------------- fusion.cu
+int launch_softmax_argmax(const float* score, int64_t npix, int C, float* prob, int64_t* label64,
+                          uint8_t* label8, cudaStream_t s);
+int launch_bayes_lut(const void* const* labels_dev, int M, int label_bytes, const int32_t* lut,
+                     int C, int64_t npix, void* out, cudaStream_t s);
+int launch_bayes_score(const void* const* labels_dev, int M, int label_bytes,
+                       const float* logcond /*[M,C,C]*/, const float* logprior /*[C]*/, int C,
+                       int64_t npix, float* score, void* label_out, cudaStream_t s);
+int launch_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m1 /*[M,C,C]*/,
+                          const float* lognorm /*[M,C]*/, const float* logprior /*[C]*/, int C,
+                          int64_t npix, float* score, void* label_out, int label_bytes,
+                          cudaStream_t s);
+int launch_average_fuse(const float* const* probs, int M, int C, int64_t npix, float* score,
+                        void* label_out, int label_bytes, cudaStream_t s);
+int launch_variance_fuse(const float* const* probs, const float* const* vars, int M, int C,
+                         int64_t npix, float* score, void* label_out, int label_bytes,
+                         cudaStream_t s);
+int launch_mc_moments(const float* samples /*[T,npix,C]*/, int T, int64_t npix, int C, float* mean,
+                      float* var, float* mean_var, float* entropy, float* cond_entropy,
+                      float* sum_var, cudaStream_t s);
+int launch_suffstats(const float* prob, const int32_t* labels, int64_t npix, int C,
+                     double* S /*[C,C] +=*/, long long* n /*[C] +=*/, cudaStream_t s);
+int launch_confusion(const void* pred, int pred_bytes, const int32_t* labels, int64_t npix, int C,
+                     long long* cm /*[C,C] +=*/, cudaStream_t s);
+
+constexpr int kMaxClasses = 24;
+
+}  // namespace xv

@@ -1,0 +1,590 @@
+// Non-GEMM layers of the FCN expert: conv1_1 operand packing, pooling, MC-dropout, the
+// channel-diagonal (bilinear) transposed convolutions and the fused decoder tail, plus the
+// generic fp32 "validation mode" layers that follow the reference op order literally.
+//
+// Reference: xview/models/simple_fcn.py:10-134, xview/models/custom_layers.py:8-25,71-139.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xv {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(size_t work, int threads = kThreads) {
+  size_t g = (work + threads - 1) / threads;
+  size_t cap = static_cast<size_t>(device_info().num_sms) * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------ conv1_1 operand
+// Packs the 3x3 neighbourhood of every pixel of the raw fp32 input (Cin <= 3) into one
+// 64-element bf16 row [hi(9*Cin) | lo(9*Cin) | 0...] so conv1_1 runs on the tensor cores as
+// a 1x1 GEMM with K = 64.  hi + lo carries 16 mantissa bits, enough for raw uint16 depth.
+__global__ void im2col_c1_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                 int N, int H, int W, int cin) {
+  const size_t total = static_cast<size_t>(N) * H * W * 8;
+  const int k9 = 9 * cin;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int piece = static_cast<int>(idx & 7);
+    const size_t pix = idx >> 3;
+    const int px = static_cast<int>(pix % W);
+    const int py = static_cast<int>((pix / W) % H);
+    const size_t img = pix / (static_cast<size_t>(W) * H);
+    uint32_t packed[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int k = piece * 8 + e2 * 2 + h;
+        float val = 0.f;
+        if (k < 2 * k9) {
+          const bool lo = k >= k9;
+          if (lo) k -= k9;
+          const int tap = k / cin, ci = k - tap * cin;
+          const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float raw = __ldg(x + ((img * H + yy) * W + xx) * cin + ci);
+            const float hi = __bfloat162float(__float2bfloat16_rn(raw));
+            val = lo ? (raw - hi) : hi;
+          }
+        }
+        v[h] = val;
+      }
+      packed[e2] = pack_bf16x2(v[0], v[1]);
+    }
+    reinterpret_cast<uint4*>(out)[idx] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                   size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                   size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+// ------------------------------------------------------------------ 2x2/2 max pooling
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a),
+                             *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z),
+                    bf16x2_max(a.w, b.w));
+}
+// one thread = one output pixel x 8 channels (16 B)
+__global__ void maxpool_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
+                                    int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    size_t t = idx / C8;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const size_t n = t / Ho;
+    const size_t base = ((n * H + 2 * yo) * W + 2 * xo) * C8 + c;
+    const size_t row = static_cast<size_t>(W) * C8;
+    uint4 a = __ldg(in + base), b = __ldg(in + base + C8);
+    uint4 cc = __ldg(in + base + row), d = __ldg(in + base + row + C8);
+    out[idx] = bf16x8_max(bf16x8_max(a, b), bf16x8_max(cc, d));
+  }
+}
+__global__ void maxpool_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int N,
+                                   int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    size_t t = idx / C;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const size_t n = t / Ho;
+    const size_t base = ((n * H + 2 * yo) * W + 2 * xo) * C + c;
+    const size_t row = static_cast<size_t>(W) * C;
+    out[idx] = fmaxf(fmaxf(in[base], in[base + C]), fmaxf(in[base + row], in[base + row + C]));
+  }
+}
+
+// ------------------------------------------------------------------ MC dropout
+// Philox4x32-10 (Salmon et al. 2011): counter = element-group index (+offset), key = seed.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (r >> 8) * (1.0f / 16777216.0f); }
+
+// tf.nn.dropout: y = (x / keep) * floor(keep + U[0,1)); element kept iff U >= rate.
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n,
+                               int replicate, float rate, const uint8_t* __restrict__ ext_mask,
+                               uint64_t seed, uint64_t offset) {
+  const float keep = 1.f - rate;
+  const size_t total = n * static_cast<size_t>(replicate);
+  const size_t groups = (total + 3) / 4;
+  for (size_t gidx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; gidx < groups;
+       gidx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (ext_mask == nullptr) {
+      const uint64_t c = gidx + offset;
+      rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32),
+                                     0x58564231u, 0u),
+                          make_uint2(static_cast<uint32_t>(seed),
+                                     static_cast<uint32_t>(seed >> 32)));
+    }
+    const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const size_t i = gidx * 4 + e;
+      if (i < total) {
+        const bool kept = ext_mask ? (ext_mask[i] != 0) : (u01(rr[e]) >= rate);
+        const float v = static_cast<float>(in[i % n]);
+        out[i] = static_cast<T>(kept ? v / keep : 0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ generic fp32 layers
+// one thread = one output pixel x 8 output channels; validation mode only.
+__global__ void conv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                const float* __restrict__ bias, float* __restrict__ out, int N,
+                                int H, int W, int cin, int cout, int k, int relu) {
+  const int cg = (cout + 7) / 8;
+  const size_t total = static_cast<size_t>(N) * H * W * cg;
+  const int pad = (k - 1) / 2;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % cg);
+    const size_t pix = idx / cg;
+    const int px = static_cast<int>(pix % W);
+    const int py = static_cast<int>((pix / W) % H);
+    const size_t img = pix / (static_cast<size_t>(W) * H);
+    const int co0 = g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int yy = py + ky - pad;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int xx = px + kx - pad;
+        if (xx < 0 || xx >= W) continue;
+        const float* xp = x + ((img * H + yy) * W + xx) * cin;
+        const float* wp = w + static_cast<size_t>(ky * k + kx) * cin * cout + co0;
+        for (int ci = 0; ci < cin; ++ci) {
+          const float xv = __ldg(xp + ci);
+          const float* wr = wp + static_cast<size_t>(ci) * cout;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (co0 + j < cout) acc[j] = fmaf(xv, __ldg(wr + j), acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (co0 + j < cout) {
+        float v = acc[j] + (bias ? bias[co0 + j] : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        out[pix * cout + co0 + j] = v;
+      }
+    }
+  }
+}
+
+// conv2d_transpose 'same': out = in*stride, pad = (k-stride)/2, w[ky,kx,co,ci];
+// out[oy,ox,co] = sum over (iy,ky): oy = iy*stride - pad + ky.  Optional ReLU, then + addend.
+__global__ void deconv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                  float* __restrict__ out, int N, int hin, int win, int cin,
+                                  int cout, int k, int stride, int relu,
+                                  const float* __restrict__ addend) {
+  const int ho = hin * stride, wo = win * stride, pad = (k - stride) / 2;
+  const size_t total = static_cast<size_t>(N) * ho * wo * cout;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(idx % cout);
+    size_t t = idx / cout;
+    const int ox = static_cast<int>(t % wo);
+    t /= wo;
+    const int oy = static_cast<int>(t % ho);
+    const size_t img = t / ho;
+    float acc = 0.f;
+    for (int ky = (oy + pad) % stride; ky < k; ky += stride) {
+      const int iy = (oy + pad - ky) / stride;
+      if (oy + pad - ky < 0 || iy >= hin) continue;
+      for (int kx = (ox + pad) % stride; kx < k; kx += stride) {
+        const int ix = (ox + pad - kx) / stride;
+        if (ox + pad - kx < 0 || ix >= win) continue;
+        const float* xp = x + ((img * hin + iy) * win + ix) * cin;
+        const float* wp = w + (static_cast<size_t>(ky * k + kx) * cout + co) * cin;
+        for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(xp + ci), __ldg(wp + ci), acc);
+      }
+    }
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (addend) acc += addend[idx];
+    out[idx] = acc;
+  }
+}
+
+// per-channel affine (+ReLU): test-time batch norm for layers where it cannot be folded.
+__global__ void affine_f32_kernel(float* __restrict__ x, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, size_t total, int C,
+                                  int relu) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    float v = x[i] * scale[c] + shift[c];
+    if (relu) v = fmaxf(v, 0.f);
+    x[i] = v;
+  }
+}
+
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                               float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = a[i] + b[i];
+}
+
+// ------------------------------------------------------------------ fast decoder pieces
+// fused[n,Y,X,u] = s4[n,Y,X,u] + relu( sum_{ky,kx} g[ky,kx,u] * s5[n,iy,ix,u] ),
+// 4x4 stride-2 channel-diagonal transposed conv (simple_fcn.py:82-85).
+__global__ void upscore2_add_kernel(const float* __restrict__ s5, const float* __restrict__ s4,
+                                    const float* __restrict__ g, float* __restrict__ fused,
+                                    int N, int h, int w, int nu) {
+  const int ho = 2 * h, wo = 2 * w;
+  const size_t total = static_cast<size_t>(N) * ho * wo * nu;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(idx % nu);
+    size_t t = idx / nu;
+    const int ox = static_cast<int>(t % wo);
+    t /= wo;
+    const int oy = static_cast<int>(t % ho);
+    const size_t img = t / ho;
+    float acc = 0.f;
+    // oy = 2*iy - 1 + ky  ->  ky in {(oy+1)%2, (oy+1)%2 + 2}
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ((oy + 1) & 1) + 2 * a;
+      const int iy = (oy + 1 - ky) / 2;
+      if (oy + 1 - ky < 0 || iy >= h) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int kx = ((ox + 1) & 1) + 2 * b;
+        const int ix = (ox + 1 - kx) / 2;
+        if (ox + 1 - kx < 0 || ix >= w) continue;
+        acc = fmaf(__ldg(g + (ky * 4 + kx) * nu + u),
+                   __ldg(s5 + ((img * h + iy) * w + ix) * nu + u), acc);
+      }
+    }
+    fused[idx] = s4[idx] + fmaxf(acc, 0.f);
+  }
+}
+
+// low[p,c] = sum_u fused[p,u] * w[u,c]   (the 1x1 `score` conv applied BEFORE the x8 upsampling;
+// valid because the upsampling kernel is shared by all channels and ReLU is the identity on
+// its non-negative output - see DESIGN.md "decoder reordering").
+__global__ void score_lowres_kernel(const float* __restrict__ fused, const float* __restrict__ w,
+                                    float* __restrict__ low, size_t npix, int nu, int C) {
+  const size_t total = npix * C;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const size_t p = idx / C;
+    const float* f = fused + p * nu;
+    float acc = 0.f;
+    for (int u = 0; u < nu; ++u) acc = fmaf(__ldg(f + u), __ldg(w + u * C + c), acc);
+    low[idx] = acc;
+  }
+}
+
+// Decoder tail: 16x16 stride-8 upsampling of the low-res class scores + bias + softmax +
+// argmax in one pass; block = 16x16 output pixels, the <= 4x4 contributing low-res pixels
+// are staged in shared memory.  T > 1: loop over MC samples and accumulate moments.
+template <int C, bool MC>
+__global__ void __launch_bounds__(256)
+decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__ g,
+                        const float* __restrict__ bias, int T, int N, int h, int w,
+                        DecodeOut out, float* __restrict__ mean_prob,
+                        float* __restrict__ var_prob, float* __restrict__ mean_var) {
+  __shared__ float s_low[16 * C];
+  __shared__ float s_g[256];
+  const int H = 8 * h, W = 8 * w;
+  const int bx = blockIdx.x * 16, by = blockIdx.y * 16;
+  const int img = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int ox = bx + tx, oy = by + ty;
+  const bool valid = ox < W && oy < H;
+  s_g[threadIdx.x] = g[threadIdx.x];
+  // 16 output rows/cols touch low-res rows/cols iy0..iy0+3 with iy0 = by/8 - 1
+  const int iy0 = (by + 4) / 8 - 1, ix0 = (bx + 4) / 8 - 1;
+  const int ay = (oy + 4) >> 3, ry = (oy + 4) & 7;   // taps: (iy=ay, ky=ry), (iy=ay-1, ky=ry+8)
+  const int ax = (ox + 4) >> 3, rx = (ox + 4) & 7;
+
+  float mean[C], m2[C];
+  if (MC) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) mean[c] = m2[c] = 0.f;
+  }
+  for (int t = 0; t < T; ++t) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * C; i += 256) {
+      const int c = i % C, cell = i / C;
+      const int iy = iy0 + cell / 4, ix = ix0 + cell % 4;
+      float v = 0.f;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+        v = __ldg(low + (((static_cast<size_t>(t) * N + img) * h + iy) * w + ix) * C + c);
+      s_low[i] = v;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    float s[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) s[c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int iy = ay - a, ky = ry + 8 * a;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ix = ax - b, kx = rx + 8 * b;
+        if (ix < 0 || ix >= w) continue;
+        const float wgt = s_g[ky * 16 + kx];
+        const float* lp = s_low + ((iy - iy0) * 4 + (ix - ix0)) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) s[c] = fmaf(wgt, lp[c], s[c]);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      s[c] += __ldg(bias + c);
+      mx = fmaxf(mx, s[c]);
+    }
+    const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox;
+    if (!MC && out.score) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) out.score[pix * C + c] = s[c];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      s[c] = expf(s[c] - mx);
+      sum += s[c];
+    }
+    if (MC) {
+      // Welford update of the per-class mean / sum of squared deviations
+      const float inv_n = 1.f / static_cast<float>(t + 1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float pr = s[c] / sum;
+        const float d = pr - mean[c];
+        mean[c] += d * inv_n;
+        m2[c] = fmaf(d, pr - mean[c], m2[c]);
+      }
+    } else {
+      int best = 0;
+      float bestv = -1.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float pr = s[c] / sum;
+        if (out.prob) out.prob[pix * C + c] = pr;
+        if (pr > bestv) {
+          bestv = pr;
+          best = c;
+        }
+      }
+      if (out.label_u8) out.label_u8[pix] = static_cast<uint8_t>(best);
+      if (out.label_i64) out.label_i64[pix] = best;
+    }
+  }
+  if (MC && valid) {
+    const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox;
+    float mv = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float v = m2[c] / static_cast<float>(T);
+      if (mean_prob) mean_prob[pix * C + c] = mean[c];
+      if (var_prob) var_prob[pix * C + c] = v;
+      mv += v;
+    }
+    if (mean_var) mean_var[pix] = mv / static_cast<float>(C);
+  }
+}
+
+template <int C>
+int decode_dispatch(bool mc, const float* low, const float* g, const float* bias, int T, int N,
+                    int h, int w, const DecodeOut& out, float* mean_prob, float* var_prob,
+                    float* mean_var, cudaStream_t s) {
+  dim3 grid(div_up(8 * w, 16), div_up(8 * h, 16), N);
+  if (mc)
+    decode_upsample8_kernel<C, true><<<grid, 256, 0, s>>>(low, g, bias, T, N, h, w, out,
+                                                           mean_prob, var_prob, mean_var);
+  else
+    decode_upsample8_kernel<C, false><<<grid, 256, 0, s>>>(low, g, bias, 1, N, h, w, out,
+                                                            nullptr, nullptr, nullptr);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define XV_DISPATCH_C(C, CALL)                                                          \
+  switch (C) {                                                                          \
+    case 2: { constexpr int kC = 2; return CALL; }                                      \
+    case 3: { constexpr int kC = 3; return CALL; }                                      \
+    case 4: { constexpr int kC = 4; return CALL; }                                      \
+    case 5: { constexpr int kC = 5; return CALL; }                                      \
+    case 6: { constexpr int kC = 6; return CALL; }                                      \
+    case 7: { constexpr int kC = 7; return CALL; }                                      \
+    case 8: { constexpr int kC = 8; return CALL; }                                      \
+    case 9: { constexpr int kC = 9; return CALL; }                                      \
+    case 10: { constexpr int kC = 10; return CALL; }                                    \
+    case 11: { constexpr int kC = 11; return CALL; }                                    \
+    case 12: { constexpr int kC = 12; return CALL; }                                    \
+    case 13: { constexpr int kC = 13; return CALL; }                                    \
+    case 14: { constexpr int kC = 14; return CALL; }                                    \
+    case 15: { constexpr int kC = 15; return CALL; }                                    \
+    case 16: { constexpr int kC = 16; return CALL; }                                    \
+    case 17: { constexpr int kC = 17; return CALL; }                                    \
+    case 18: { constexpr int kC = 18; return CALL; }                                    \
+    case 19: { constexpr int kC = 19; return CALL; }                                    \
+    case 20: { constexpr int kC = 20; return CALL; }                                    \
+    case 21: { constexpr int kC = 21; return CALL; }                                    \
+    case 22: { constexpr int kC = 22; return CALL; }                                    \
+    case 23: { constexpr int kC = 23; return CALL; }                                    \
+    case 24: { constexpr int kC = 24; return CALL; }                                    \
+    default: return fail("num_classes must be in [2, 24]");                             \
+  }
+
+}  // namespace
+
+int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, int cin,
+                     cudaStream_t s) {
+  XV_CHECK(cin >= 1 && 18 * cin <= 64, "conv1_1 packing supports Cin <= 3");
+  const size_t total = static_cast<size_t>(N) * H * W * 8;
+  im2col_c1_kernel<<<grid_for(total), kThreads, 0, s>>>(x, out, N, H, W, cin);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
+  f32_to_bf16_kernel<<<grid_for(n), kThreads, 0, s>>>(in, out, n);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t s) {
+  bf16_to_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(in, out, n);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_maxpool_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int H, int W, int C,
+                        cudaStream_t s) {
+  XV_CHECK(C % 8 == 0, "maxpool_bf16: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool_bf16_kernel<<<grid_for(total), kThreads, 0, s>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), N, H, W, C / 8);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_maxpool_f32(const float* in, float* out, int N, int H, int W, int C, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * C;
+  maxpool_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, N, H, W, C);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_dropout_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, int replicate,
+                        const DropoutSpec& d, cudaStream_t s) {
+  const size_t groups = (n * replicate + 3) / 4;
+  dropout_kernel<__nv_bfloat16><<<grid_for(groups), kThreads, 0, s>>>(
+      in, out, n, replicate, d.rate, d.ext_mask, d.seed, d.offset);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_dropout_f32(const float* in, float* out, size_t n, int replicate,
+                       const DropoutSpec& d, cudaStream_t s) {
+  const size_t groups = (n * replicate + 3) / 4;
+  dropout_kernel<float><<<grid_for(groups), kThreads, 0, s>>>(in, out, n, replicate, d.rate,
+                                                               d.ext_mask, d.seed, d.offset);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_conv_f32(const float* x, const float* w, const float* bias, float* out, int N, int H,
+                    int W, int cin, int cout, int k, int relu, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * H * W * ((cout + 7) / 8);
+  conv_f32_kernel<<<grid_for(total, 128), 128, 0, s>>>(x, w, bias, out, N, H, W, cin, cout, k,
+                                                       relu);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_deconv_f32(const float* x, const float* w, float* out, int N, int hin, int win, int cin,
+                      int cout, int k, int stride, int relu, const float* addend,
+                      cudaStream_t s) {
+  XV_CHECK((k - stride) % 2 == 0 && k >= stride, "deconv: (k - stride) must be even");
+  const size_t total = static_cast<size_t>(N) * hin * stride * win * stride * cout;
+  deconv_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(x, w, out, N, hin, win, cin, cout, k,
+                                                         stride, relu, addend);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t s) {
+  add_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(a, b, out, n);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_affine_f32(float* x, const float* scale, const float* shift, size_t npix, int C,
+                      int relu, cudaStream_t s) {
+  affine_f32_kernel<<<grid_for(npix * C), kThreads, 0, s>>>(x, scale, shift, npix * C, C, relu);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_upscore2_add(const float* s5, const float* s4, const float* g, float* fused, int N,
+                        int h, int w, int nu, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * 4 * h * w * nu;
+  upscore2_add_kernel<<<grid_for(total), kThreads, 0, s>>>(s5, s4, g, fused, N, h, w, nu);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_score_lowres(const float* fused, const float* w, float* low, size_t npix, int nu, int C,
+                        cudaStream_t s) {
+  score_lowres_kernel<<<grid_for(npix * C), kThreads, 0, s>>>(fused, w, low, npix, nu, C);
+  XV_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_decode_upsample8(const float* low, const float* g, const float* bias, int N, int h,
+                            int w, int C, const DecodeOut& out, cudaStream_t s) {
+  XV_DISPATCH_C(C, (decode_dispatch<kC>(false, low, g, bias, 1, N, h, w, out, nullptr, nullptr,
+                                        nullptr, s)));
+}
+int launch_decode_upsample8_mc(const float* low, const float* g, const float* bias, int T, int N,
+                               int h, int w, int C, float* mean_prob, float* var_prob,
+                               float* mean_var, cudaStream_t s) {
+  DecodeOut none;
+  XV_DISPATCH_C(C, (decode_dispatch<kC>(true, low, g, bias, T, N, h, w, none, mean_prob,
+                                        var_prob, mean_var, s)));
+}
+
+}  // namespace xv

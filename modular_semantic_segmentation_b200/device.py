@@ -1,0 +1,329 @@
+"""Tensor-level Python wrappers over the C ABI.
+
+torch is used for plumbing only: device memory (torch.empty on cuda), the current CUDA stream
+and (elsewhere) torch.distributed.  Every function below launches hand-written kernels from
+libxview_b200.so through ctypes; nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import call
+
+_inited = set()
+
+
+def init(device=None):
+    """Bind the library to a CUDA device (xv_init) once per device."""
+    if not torch.cuda.is_available():
+        raise _abi.XViewError('no CUDA device: xview_b200 has no CPU fallback')
+    if device is None:
+        device = torch.cuda.current_device()
+    device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    torch.cuda.set_device(idx)
+    if idx not in _inited:
+        torch.zeros(1, device=device)          # make sure the primary context exists
+        call('xv_init', idx)
+        _inited.add(idx)
+    return torch.device('cuda', idx)
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'device wrappers need contiguous CUDA tensors'
+    return C.c_void_p(t.data_ptr())
+
+
+def to_device(a, dtype=None):
+    """numpy / torch (any device) -> contiguous CUDA tensor on the current device."""
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        a = a.to(dtype)
+    return a.cuda(non_blocking=True).contiguous()
+
+
+def _label_bytes(t):
+    if t.dtype == torch.int64:
+        return 8
+    if t.dtype == torch.uint8:
+        return 1
+    raise TypeError('labels must be int64 or uint8, got %s' % t.dtype)
+
+
+def _new_label(shape, label_dtype, device):
+    return torch.empty(shape, dtype=label_dtype, device=device)
+
+
+# --------------------------------------------------------------------------- FCN expert
+class FcnExpert(object):
+    """One VGG16-FCN expert on the device (xv_fcn handle): the `fcn()` of
+    xview/models/simple_fcn.py:137-170 plus softmax/argmax of basic_fusion_model.py:21-22."""
+
+    def __init__(self, cin, num_units, num_classes, batchnorm=False, precision='bf16'):
+        init()
+        self.cin, self.num_units, self.num_classes = cin, num_units, num_classes
+        self.batchnorm = bool(batchnorm)
+        self.precision = precision
+        handle = C.c_void_p()
+        call('xv_fcn_create', C.byref(handle), cin, num_units, num_classes, int(self.batchnorm),
+             {'bf16': _abi.XV_PRECISION_BF16, 'fp32': _abi.XV_PRECISION_FP32}[precision])
+        self._h = handle
+        self._dirty = True
+
+    def set_param(self, name, array):
+        array = np.ascontiguousarray(array, dtype=np.float32)
+        shape = (C.c_int64 * array.ndim)(*array.shape)
+        call('xv_fcn_set_param_host', self._h, name.encode(), array.ctypes.data_as(C.c_void_p),
+             shape, array.ndim)
+        self._dirty = True
+
+    def set_params(self, params):
+        for name, array in params.items():
+            self.set_param(name, array)
+
+    def finalize(self):
+        call('xv_fcn_finalize', self._h)
+        self._dirty = False
+
+    def forward(self, x, want=('label',), dropout=None, label_dtype=torch.int64):
+        """x: float32 CUDA tensor [N,H,W,cin].  want: any of 'score','prob','label',
+        'mean_prob','var_prob','mean_var'.  dropout: None or dict(rate, layers, num_samples,
+        seed, masks={site: uint8 CUDA tensor}).  Returns a dict of CUDA tensors."""
+        if self._dirty:
+            self.finalize()
+        assert x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == self.cin
+        x = x.contiguous()
+        n, h, w, _ = x.shape
+        cfg = None
+        t_samples = 1
+        keep_alive = []
+        if dropout is not None and dropout.get('layers'):
+            cfg = _abi.DropoutCfg()
+            cfg.rate = float(dropout.get('rate', 0.0))
+            cfg.sites = 0
+            for site in dropout['layers']:
+                cfg.sites |= _abi.DROPOUT_SITES[site]
+            cfg.num_samples = int(dropout.get('num_samples', 1))
+            cfg.seed = int(dropout.get('seed', 0))
+            masks = dropout.get('masks') or {}
+            for i, site in enumerate(_abi.MASK_ORDER):
+                m = masks.get(site)
+                if m is not None:
+                    m = to_device(m, torch.uint8)
+                    keep_alive.append(m)
+                    cfg.ext_mask[i] = m.data_ptr()
+                else:
+                    cfg.ext_mask[i] = None
+            t_samples = cfg.num_samples
+        b = n * t_samples
+        c = self.num_classes
+        dev = x.device
+        out = {}
+        o = _abi.FcnOutputs()
+        if 'score' in want:
+            out['score'] = torch.empty((b, h, w, c), dtype=torch.float32, device=dev)
+            o.score = out['score'].data_ptr()
+        if 'prob' in want:
+            out['prob'] = torch.empty((b, h, w, c), dtype=torch.float32, device=dev)
+            o.prob = out['prob'].data_ptr()
+        if 'label' in want:
+            out['label'] = torch.empty((b, h, w), dtype=label_dtype, device=dev)
+            if label_dtype == torch.int64:
+                o.label_i64 = out['label'].data_ptr()
+            else:
+                o.label_u8 = out['label'].data_ptr()
+        if t_samples > 1:
+            if 'mean_prob' in want:
+                out['mean_prob'] = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+                o.mean_prob = out['mean_prob'].data_ptr()
+            if 'var_prob' in want:
+                out['var_prob'] = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+                o.var_prob = out['var_prob'].data_ptr()
+            if 'mean_var' in want:
+                out['mean_var'] = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+                o.mean_var = out['mean_var'].data_ptr()
+        call('xv_fcn_forward', self._h, ptr(x), n, h, w, C.byref(cfg) if cfg is not None else None,
+             C.byref(o), stream_ptr())
+        if keep_alive:
+            torch.cuda.current_stream().synchronize()
+        return out
+
+    def layer(self, name):
+        """Activation of a named layer of the last forward call as float32 numpy NHWC."""
+        shape = (C.c_int64 * 4)()
+        call('xv_fcn_get_layer_host', self._h, name.encode(), None, 0, shape, stream_ptr())
+        out = np.empty(tuple(shape), dtype=np.float32)
+        call('xv_fcn_get_layer_host', self._h, name.encode(), out.ctypes.data_as(C.c_void_p),
+             out.size, shape, stream_ptr())
+        return out
+
+    def close(self):
+        if getattr(self, '_h', None):
+            _abi.load().xv_fcn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------- single layers
+def conv2d(x, kernel, bias=None, relu=True, precision='bf16'):
+    """custom_layers.py:124-139 without batch norm; x CUDA float32 NHWC, kernel numpy HWIO."""
+    init()
+    kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+    k, _, cin, cout = kernel.shape
+    n, h, w, _ = x.shape
+    bias_p = None
+    if bias is not None:
+        bias = np.ascontiguousarray(bias, dtype=np.float32)
+        bias_p = bias.ctypes.data_as(C.c_void_p)
+    out = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
+    call('xv_conv2d', ptr(x.contiguous()), kernel.ctypes.data_as(C.c_void_p), bias_p, n, h, w, cin,
+         cout, k, int(relu), {'bf16': 0, 'fp32': 1}[precision], ptr(out), stream_ptr())
+    return out
+
+
+def deconv2d(x, kernel, stride, relu=True):
+    """custom_layers.py:71-121 without batch norm; kernel numpy [kh,kw,Cout,Cin]."""
+    init()
+    kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+    k, _, cout, cin = kernel.shape
+    n, h, w, _ = x.shape
+    out = torch.empty((n, h * stride, w * stride, cout), dtype=torch.float32, device=x.device)
+    call('xv_deconv2d', ptr(x.contiguous()), kernel.ctypes.data_as(C.c_void_p), n, h, w, cin, cout,
+         k, stride, int(relu), ptr(out), stream_ptr())
+    return out
+
+
+def maxpool2x2(x):
+    init()
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=x.device)
+    call('xv_maxpool2x2', ptr(x.contiguous()), n, h, w, c, ptr(out), stream_ptr())
+    return out
+
+
+# --------------------------------------------------------------------------- fusion stage
+def softmax_argmax(score, want_prob=True, label_dtype=torch.int64):
+    init()
+    c = score.shape[-1]
+    npix = score.numel() // c
+    prob = torch.empty_like(score) if want_prob else None
+    label = _new_label(score.shape[:-1], label_dtype, score.device)
+    call('xv_softmax_argmax', ptr(score), npix, c, ptr(prob), ptr(label), _label_bytes(label),
+         stream_ptr())
+    return prob, label
+
+
+def bayes_fuse_lut(labels, lut, num_classes):
+    """labels: list of int64/uint8 CUDA tensors of equal shape; lut: int32 CUDA tensor [C]*M."""
+    init()
+    arr, keep = _abi.ptr_array([t.data_ptr() for t in labels])
+    out = torch.empty_like(labels[0])
+    call('xv_bayes_fuse_lut', arr, len(labels), _label_bytes(labels[0]), ptr(lut), num_classes,
+         labels[0].numel(), ptr(out), stream_ptr())
+    del keep
+    return out
+
+
+def bayes_fuse_score(labels, log_cond, log_prior, want_score=True):
+    """log_cond float32 CUDA [M,C,C], log_prior float32 CUDA [C]."""
+    init()
+    c = log_prior.numel()
+    arr, keep = _abi.ptr_array([t.data_ptr() for t in labels])
+    score = (torch.empty(labels[0].shape + (c,), dtype=torch.float32, device=labels[0].device)
+             if want_score else None)
+    out = torch.empty_like(labels[0])
+    call('xv_bayes_fuse_score', arr, len(labels), _label_bytes(labels[0]), ptr(log_cond),
+         ptr(log_prior), c, labels[0].numel(), ptr(score), ptr(out), stream_ptr())
+    del keep
+    return score, out
+
+
+def dirichlet_fuse(probs, alpha_m1, log_norm, log_prior, want_score=False,
+                   label_dtype=torch.int64):
+    init()
+    c = probs[0].shape[-1]
+    npix = probs[0].numel() // c
+    arr, keep = _abi.ptr_array([t.data_ptr() for t in probs])
+    score = torch.empty_like(probs[0]) if want_score else None
+    label = _new_label(probs[0].shape[:-1], label_dtype, probs[0].device)
+    call('xv_dirichlet_fuse', arr, len(probs), ptr(alpha_m1), ptr(log_norm), ptr(log_prior), c,
+         npix, ptr(score), ptr(label), _label_bytes(label), stream_ptr())
+    del keep
+    return score, label
+
+
+def average_fuse(probs, want_score=False, label_dtype=torch.int64):
+    init()
+    c = probs[0].shape[-1]
+    npix = probs[0].numel() // c
+    arr, keep = _abi.ptr_array([t.data_ptr() for t in probs])
+    score = torch.empty_like(probs[0]) if want_score else None
+    label = _new_label(probs[0].shape[:-1], label_dtype, probs[0].device)
+    call('xv_average_fuse', arr, len(probs), c, npix, ptr(score), ptr(label), _label_bytes(label),
+         stream_ptr())
+    del keep
+    return score, label
+
+
+def variance_fuse(probs, variances, want_score=False, label_dtype=torch.int64):
+    init()
+    c = probs[0].shape[-1]
+    npix = probs[0].numel() // c
+    arr, keep = _abi.ptr_array([t.data_ptr() for t in probs])
+    varr, vkeep = _abi.ptr_array([t.data_ptr() for t in variances])
+    score = torch.empty_like(probs[0]) if want_score else None
+    label = _new_label(probs[0].shape[:-1], label_dtype, probs[0].device)
+    call('xv_variance_fuse', arr, varr, len(probs), c, npix, ptr(score), ptr(label),
+         _label_bytes(label), stream_ptr())
+    del keep, vkeep
+    return score, label
+
+
+def mc_moments(samples, want=('mean', 'var', 'mean_var')):
+    """samples: float32 CUDA [T, ..., C] -> dict of requested statistics."""
+    init()
+    t = samples.shape[0]
+    c = samples.shape[-1]
+    npix = samples[0].numel() // c
+    dev = samples.device
+    out = {}
+    shape_c, shape_1 = samples.shape[1:], samples.shape[1:-1]
+    for key in ('mean', 'var'):
+        out[key] = torch.empty(shape_c, dtype=torch.float32, device=dev) if key in want else None
+    for key in ('mean_var', 'entropy', 'cond_entropy', 'sum_var'):
+        out[key] = torch.empty(shape_1, dtype=torch.float32, device=dev) if key in want else None
+    call('xv_mc_moments', ptr(samples), t, npix, c, ptr(out['mean']), ptr(out['var']),
+         ptr(out['mean_var']), ptr(out['entropy']), ptr(out['cond_entropy']),
+         ptr(out['sum_var']), stream_ptr())
+    return {k: v for k, v in out.items() if v is not None}
+
+
+def dirichlet_suffstats(prob, labels, stats, counts):
+    """Accumulates into stats (float64 CUDA [C,C]) and counts (int64 CUDA [C])."""
+    init()
+    c = prob.shape[-1]
+    assert labels.dtype == torch.int32 and stats.dtype == torch.float64
+    call('xv_dirichlet_suffstats', ptr(prob), ptr(labels), prob.numel() // c, c, ptr(stats),
+         ptr(counts), stream_ptr())
+
+
+def confusion_accumulate(pred, labels, cm):
+    """Accumulates into cm (int64 CUDA [C,C]); rows = ground truth, cols = prediction."""
+    init()
+    assert labels.dtype == torch.int32 and cm.dtype == torch.int64
+    call('xv_confusion_accumulate', ptr(pred), _label_bytes(pred), ptr(labels), pred.numel(),
+         cm.shape[0], ptr(cm), stream_ptr())

@@ -1,0 +1,320 @@
+"""Host-side mirror of xview/models/base_model.py (the sklearn-style model surface).
+
+Same constructor, same methods and return types as the reference `BaseModel`
+(base_model.py:51-451): `with Model(data_description, **config) as net`, `fit`, `predict`,
+`score`, `import_weights`, `export_weights`, `load_weights`, `close`.  The TensorFlow graph +
+session are replaced by device-resident experts driven through the C ABI
+(`modular_semantic_segmentation_b200.device`); variables are kept as host numpy arrays under
+their TensorFlow names so the npz layout of the reference round-trips.
+
+Multi-GPU: if `torch.distributed` is initialised (one process per GPU), `score()` and
+`predict()` shard the images over the ranks; `score()` all-reduces the int64 confusion matrix
+once at the end (the only collective on the path), `predict()` all-gathers the label maps.
+"""
+from collections import OrderedDict
+from copy import deepcopy
+from os import path
+
+import numpy as np
+import torch
+
+from .. import device as dev
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def measures_from_confusion_matrix(confusion_matrix):
+    """The float64 measures of base_model.py:315-329 (class 0 = void is excluded from
+    total_accuracy and mean_IoU)."""
+    confusion_matrix = np.asarray(confusion_matrix, dtype=np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        measures = {}
+        measures['confusion_matrix'] = confusion_matrix
+        diag = np.diag(confusion_matrix)
+        measures['recall'] = diag / confusion_matrix.sum(1)
+        measures['precision'] = diag / confusion_matrix.sum(0)
+        measures['F1'] = 2 * measures['precision'] * measures['recall'] / \
+            (measures['precision'] + measures['recall'])
+        measures['mean_F1'] = np.nanmean(measures['F1'])
+        measures['total_accuracy'] = diag[1:].sum() / confusion_matrix[1:, :].sum()
+        measures['IoU'] = diag / (confusion_matrix.sum(1) + confusion_matrix.sum(0) - diag)
+        measures['mean_IoU'] = np.nanmean(measures['IoU'][1:])
+    return measures
+
+
+class BaseModel(object):
+    """Structure for network models.  Subclasses implement `_build_graph()` (create the
+    experts and register their variables) and `_run_batch(batch, fetch)`."""
+
+    required_attributes = [["loss"], ["prediction"]]
+
+    def __init__(self, data_description, name=None, output_dir=None, custom_training=False,
+                 batchsize=1, **config):
+        self.name = type(self).__name__ if name is None else name
+        self.output_dir = output_dir
+        self.custom_training = custom_training
+        self.config = config
+        self.config['batchsize'] = batchsize
+        self.config['num_classes'] = data_description[2]
+        # same bookkeeping as base_model.py:84-94
+        self.testdata_description = [data_description[0], {
+            key: [None, *description] for key, description in data_description[1].items()}]
+        train_description = deepcopy(self.testdata_description[1])
+        if 'labels' in train_description:
+            train_description['labels'] = list(train_description['labels'])
+            train_description['labels'].append(self.config['num_classes'])
+        self.data_description = [self.testdata_description[0], train_description]
+        self.variables = OrderedDict()     # TF variable name -> float32 numpy array
+        self.global_step = 0
+        self._experts = OrderedDict()      # variable prefix -> device.FcnExpert
+        self._closed = False
+        self._initialize_graph()
+
+    # ------------------------------------------------------------------ graph lifecycle
+    def _initialize_graph(self):
+        """Counterpart of base_model.py:98-172: (re)build the experts."""
+        dev.init()
+        self._build_graph()
+        if not self.custom_training and not hasattr(self, 'prediction'):
+            self.prediction = 'prediction'
+        self._cm_device = torch.zeros(
+            (self.config['num_classes'], self.config['num_classes']), dtype=torch.int64,
+            device='cuda')
+
+    def _build_graph(self):
+        raise NotImplementedError
+
+    def _run_batch(self, batch, fetch='prediction'):
+        """Runs one batch (dict of CUDA tensors) and returns the CUDA tensor named `fetch`."""
+        raise NotImplementedError
+
+    def _register_expert(self, prefix, expert, params):
+        """Adds an expert and its variables (named `<prefix>/<layer>/<var>`)."""
+        self._experts[prefix] = expert
+        for name, value in params.items():
+            self.variables[name] = np.asarray(value, dtype=np.float32)
+        self._push_variables(prefix)
+
+    def _push_variables(self, prefix=None):
+        for pre, expert in self._experts.items():
+            if prefix is not None and pre != prefix:
+                continue
+            head = pre + '/'
+            expert.set_params({n[len(head):]: v for n, v in self.variables.items()
+                               if n.startswith(head)})
+
+    # ------------------------------------------------------------------ data plumbing
+    def _my_rows(self, first_index, count):
+        """Rows of a batch this rank evaluates (images sharded round-robin over ranks)."""
+        dist = _dist()
+        if dist is None:
+            return slice(None)
+        world, rank = dist.get_world_size(), dist.get_rank()
+        rows = [i for i in range(count) if (first_index + i) % world == rank]
+        return rows
+
+    def _batches(self, data):
+        """Replaces transform_inputdata (base_model.py:10-38): `data` is a dict of arrays
+        batched on axis 0 (numpy or torch), or any iterable of such dicts.  Yields dicts of
+        host/device arrays holding this rank's share of every batch."""
+        if isinstance(data, dict):
+            total = len(next(iter(data.values())))
+            bs = self.config['batchsize']
+            dist = _dist()
+            step = bs * (dist.get_world_size() if dist else 1)
+
+            def gen():
+                for start in range(0, total, step):
+                    stop = min(start + step, total)
+                    rows = self._my_rows(start, stop - start)
+                    if isinstance(rows, slice):
+                        yield {k: v[start:stop] for k, v in data.items()}
+                    elif rows:
+                        yield {k: v[start + rows[0]:stop:len(range(stop - start)) and
+                                    (dist.get_world_size())] for k, v in data.items()}
+            return gen()
+
+        def gen_iter():
+            seen = 0
+            for blob in data:
+                count = len(next(iter(blob.values())))
+                rows = self._my_rows(seen, count)
+                seen += count
+                if isinstance(rows, slice):
+                    yield blob
+                elif rows:
+                    yield {k: v[rows] for k, v in blob.items()}
+        return gen_iter()
+
+    @staticmethod
+    def _to_device(batch):
+        out = {}
+        for key, value in batch.items():
+            if isinstance(value, np.ndarray):
+                value = torch.from_numpy(np.ascontiguousarray(value))
+            if key == 'labels':
+                if value.dim() == 4:        # one-hot labels of the training pipeline
+                    value = value.argmax(-1)
+                out[key] = value.to(device='cuda', dtype=torch.int32, non_blocking=True)
+            else:
+                out[key] = value.to(device='cuda', dtype=torch.float32, non_blocking=True)
+        return out
+
+    # ------------------------------------------------------------------ public API
+    def fit(self, dataset, iterations, output=True, validation_dataset=None,
+            validation_interval=100, additional_eval_datasets={}):
+        """base_model.py:179-261.  Gradient training of the expert is outside the round-1
+        scope of the B200 path."""
+        raise UserWarning("ERROR: Model %s does not support training" % self.name)
+
+    def predict(self, data, output_attr=None):
+        """base_model.py:263-292: returns the concatenation over all batches of
+        `self.prediction` ([num_images,H,W] int64) or of the attribute named `output_attr`."""
+        fetch = 'prediction'
+        if output_attr is not None and self._has_output(output_attr):
+            fetch = output_attr
+        ret = []
+        for batch in self._batches(data):
+            out = self._run_batch(self._to_device(batch), fetch)
+            ret.append(out)
+        dist = _dist()
+        if not ret:
+            local = None
+        else:
+            local = torch.cat(ret)
+        if dist is not None:
+            return self._gather_predictions(local, dist)
+        return local.cpu().numpy()
+
+    def _gather_predictions(self, local, dist):
+        """all_gather of the per-rank label maps; restores the original image order."""
+        world = dist.get_world_size()
+        count = torch.tensor([0 if local is None else local.shape[0]], device='cuda')
+        counts = [torch.zeros_like(count) for _ in range(world)]
+        dist.all_gather(counts, count)
+        counts = [int(c.item()) for c in counts]
+        shape_src = int(np.argmax(counts))
+        meta = torch.zeros(8, dtype=torch.int64, device='cuda')
+        if dist.get_rank() == shape_src:
+            meta[0] = local.dim()
+            for i, s in enumerate(local.shape[1:]):
+                meta[1 + i] = s
+            meta[7] = {torch.int64: 0, torch.float32: 1, torch.uint8: 2}[local.dtype]
+        dist.broadcast(meta, shape_src)
+        rest = tuple(int(v) for v in meta[1:int(meta[0])])
+        dtype = [torch.int64, torch.float32, torch.uint8][int(meta[7])]
+        pad = max(counts)
+        buf = torch.zeros((pad,) + rest, dtype=dtype, device='cuda')
+        if local is not None:
+            buf[:local.shape[0]] = local
+        bufs = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(bufs, buf)
+        total = sum(counts)
+        out = torch.zeros((total,) + rest, dtype=dtype, device='cuda')
+        for r in range(world):
+            out[r:total:world][:counts[r]] = bufs[r][:counts[r]]
+        return out.cpu().numpy()
+
+    def _has_output(self, attr):
+        return attr in getattr(self, 'output_attrs', ('prediction',))
+
+    def score(self, data, max_iterations=None):
+        """base_model.py:294-331: returns (measures dict, confusion matrix float64 [C,C]).
+        The confusion matrix is accumulated on the device in int64 and read back once."""
+        cm = self._cm_device
+        cm.zero_()
+        for batch in self._batches(data):
+            batch = self._to_device(batch)
+            prediction = self._run_batch(batch, 'prediction_compact')
+            dev.confusion_accumulate(prediction, batch['labels'].contiguous(), cm)
+        dist = _dist()
+        if dist is not None:
+            dist.all_reduce(cm, op=dist.ReduceOp.SUM)
+        confusion_matrix = cm.cpu().numpy().astype(np.float64)
+        measures = measures_from_confusion_matrix(confusion_matrix)
+        return measures, confusion_matrix
+
+    def load_weights(self, filepath):
+        """base_model.py:333-339 restores a TensorFlow checkpoint; only the npz route exists
+        here."""
+        raise UserWarning('ERROR: TensorFlow checkpoints are not supported, use import_weights')
+
+    def close(self):
+        for expert in self._experts.values():
+            expert.close()
+        self._experts = OrderedDict()
+        self._closed = True
+
+    def __exit__(self, *args):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def export_weights(self, save_dir=None):
+        """base_model.py:361-393: every variable under its TensorFlow name, plus global_step,
+        into `<name>_weights_<step>.npz`."""
+        if save_dir is None and self.output_dir is None:
+            print('ERROR: No path specified to save weights to.')
+            return
+        save_dict = {name: value for name, value in self.variables.items()}
+        save_dict['global_step'] = np.asarray(self.global_step)
+        output_path = save_dir if save_dir is not None else self.output_dir
+        output_path = path.join(output_path, '{}_weights_{}.npz'.format(self.name,
+                                                                        int(self.global_step)))
+        np.savez_compressed(output_path, **save_dict)
+        print('INFO: Weights saved to {}'.format(output_path))
+        return output_path
+
+    def import_weights(self, filepath, translate_prefix=False, chill_mode=False, warnings=True):
+        """base_model.py:395-451: assign arrays of an npz file to the variables of equal name
+        (or equal name with the first '/' replaced by '_', the legacy `rgb_conv1_1/kernel`
+        style).  Optimizer slots are skipped, unknown names and shape mismatches only warn."""
+        if warnings:
+            print(filepath)
+        weights = np.load(filepath)
+        keys = list(weights.keys())
+        import_prefix = keys[0].split('/')[0].split('_')[0] if keys else ''
+
+        def translate_name(name):
+            if not translate_prefix:
+                return name
+            if not name.startswith(translate_prefix):
+                return name
+            splitted = name.split('/')
+            further_splitted = splitted[0].split('_')
+            if further_splitted[0] == 'forest':
+                return name
+            further_splitted[0] = import_prefix
+            splitted[0] = '_'.join(further_splitted)
+            return '/'.join(splitted)
+
+        for var_name in list(self.variables.keys()):
+            name = translate_name(var_name)
+            if 'grad' in name or 'Adam' in name or 'RMS' in name:
+                continue
+            legacy = name.replace('/', '_', 1)
+            if name in weights or legacy in weights:
+                if legacy in weights:
+                    name = legacy
+                value = weights[name]
+                if tuple(self.variables[var_name].shape) != tuple(value.shape):
+                    if warnings:
+                        print('WARNING: wrong shape found for {}, but ignored in '
+                              'chill mode'.format(name))
+                        print('stored shape: ', value.shape,
+                              'expected shape: ', self.variables[var_name].shape)
+                    # the reference docstring: mismatching variables are left unassigned
+                    continue
+                self.variables[var_name] = np.asarray(value, dtype=np.float32)
+            else:
+                if warnings:
+                    print('WARNING: {} not found in saved weights'.format(name))
+        if 'global_step' in weights:
+            self.global_step = int(weights['global_step'])
+        self._push_variables()

@@ -1,0 +1,155 @@
+"""GPU parity: the whole FCN expert (xv_fcn_forward) against the oracle, layer by layer."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import cuda
+
+pytestmark = pytest.mark.gpu
+
+NU, C = 8, 5
+LAYERS = ['conv1_1', 'conv1_2', 'pool1', 'conv2_2', 'pool2', 'conv3_3', 'pool3', 'conv4_3',
+          'pool4', 'conv5_3', 'score_conv4', 'score_conv5', 'fused']
+
+
+def _net(dev, precision, cin, rng, batchnorm=False, gain=1.45):
+    params = oracle.glorot_fcn_params('m', cin, NU, C, rng, gain=gain, bias_scale=0.05,
+                                      batchnorm=batchnorm)
+    net = dev.FcnExpert(cin, NU, C, batchnorm=batchnorm, precision=precision)
+    net.set_params({k.split('/', 1)[1]: v for k, v in params.items()})
+    return net, params
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from modular_semantic_segmentation_b200 import device
+    device.init()
+    return device
+
+
+@pytest.mark.parametrize('cin,h,w', [(3, 32, 48), (1, 48, 32)])
+def test_fcn_fp32_validation_mode_matches_oracle(dev, cin, h, w):
+    """Probabilities within 1e-4 abs of the oracle (north_star fp32 validation tolerance)."""
+    rng = np.random.default_rng(cin)
+    net, params = _net(dev, 'fp32', cin, rng)
+    x = rng.uniform(0, 1, size=(2, h, w, cin)).astype(np.float32)
+    ref = oracle.test_pipeline(x, params, 'm', NU, C)
+    out = net.forward(cuda(x), want=('score', 'prob', 'label'))
+    for name in LAYERS + ['upscore', 'score']:
+        got = net.layer(name)
+        scale = max(np.abs(ref[name]).max(), 1e-6)
+        np.testing.assert_allclose(got, ref[name], rtol=0, atol=1e-4 * scale, err_msg=name)
+    np.testing.assert_allclose(out['prob'].cpu().numpy(), ref['prob'], rtol=0, atol=1e-4)
+    agree = (out['label'].cpu().numpy() == ref['classification']).mean()
+    assert agree > 0.999
+
+
+@pytest.mark.parametrize('cin,h,w', [(3, 64, 96), (1, 96, 64)])
+def test_fcn_bf16_tcgen05_matches_oracle(dev, cin, h, w):
+    """Probabilities within 2e-2 abs of the fp32 oracle (north_star bf16 tolerance)."""
+    rng = np.random.default_rng(10 + cin)
+    net, params = _net(dev, 'bf16', cin, rng)
+    hi = 255.0 if cin == 3 else 65535.0
+    x = rng.integers(0, int(hi) + 1, size=(2, h, w, cin)).astype(np.float32)
+    # fold the input range into conv1_1 so activations are O(1) ("trained-like" variant)
+    params['m/conv1_1/kernel'] = params['m/conv1_1/kernel'] / np.float32(hi)
+    net.set_param('conv1_1/kernel', params['m/conv1_1/kernel'])
+    ref = oracle.test_pipeline(x, params, 'm', NU, C)
+    out = net.forward(cuda(x), want=('score', 'prob', 'label'))
+    report = []
+    for name in LAYERS:
+        got = net.layer(name)
+        assert got.shape == ref[name].shape, name
+        err = np.abs(got - ref[name]).max() / max(np.abs(ref[name]).max(), 1e-6)
+        report.append('%s %.4f' % (name, err))
+        assert err < 0.05, (name, report)
+    print('relative max-abs error per layer:', ', '.join(report))
+    np.testing.assert_allclose(out['prob'].cpu().numpy(), ref['prob'], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(out['prob'].cpu().numpy().sum(-1), 1.0, atol=1e-5)
+    agree = (out['label'].cpu().numpy() == ref['classification']).mean()
+    assert agree > 0.97
+    # uint8 labels carry the same decisions
+    out8 = net.forward(cuda(x), want=('label',), label_dtype=torch.uint8)
+    np.testing.assert_array_equal(out8['label'].cpu().numpy(), out['label'].cpu().numpy())
+
+
+def test_fcn_batchnorm_fp32(dev):
+    rng = np.random.default_rng(5)
+    net, params = _net(dev, 'fp32', 3, rng, batchnorm=True)
+    x = rng.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)
+    ref = oracle.fcn(x, params, 'm', NU, C, batchnorm=True)
+    out = net.forward(cuda(x), want=('score',))
+    np.testing.assert_allclose(out['score'].cpu().numpy(), ref['score'], rtol=0,
+                               atol=1e-4 * np.abs(ref['score']).max())
+
+
+def test_fcn_batchnorm_bf16_folds_into_tensor_core_convs(dev):
+    rng = np.random.default_rng(6)
+    net, params = _net(dev, 'bf16', 3, rng, batchnorm=True)
+    x = rng.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)
+    ref = oracle.fcn(x, params, 'm', NU, C, batchnorm=True)
+    out = net.forward(cuda(x), want=('prob',))
+    np.testing.assert_allclose(out['prob'].cpu().numpy(), oracle.softmax(ref['score']), rtol=0,
+                               atol=2e-2)
+
+
+def _masks(rng, t, n, h, w, rate, sites):
+    shapes = {'pool3': (h // 8, w // 8, 256), 'pool4': (h // 16, w // 16, 512),
+              'conv4_3': (h // 8, w // 8, 512), 'conv5_3': (h // 16, w // 16, 512),
+              'features': (h // 8, w // 8, NU)}
+    need = set(sites)
+    if 'pool3' in need:
+        need.add('pool4')
+    return {s: (rng.random((t * n,) + shapes[s]) >= rate).astype(np.uint8) for s in need}
+
+
+@pytest.mark.parametrize('precision,sites', [('fp32', ['pool3']), ('fp32', ['conv4_3', 'features']),
+                                             ('bf16', ['pool3']), ('bf16', ['conv5_3'])])
+def test_mc_dropout_with_shared_masks(dev, precision, sites):
+    """Identical external keep-masks -> every MC sample equals the oracle's dropout pass, and
+    the fused moments equal the moments of those samples."""
+    rng = np.random.default_rng(len(sites) * 7 + (precision == 'bf16'))
+    t, n, h, w, rate = 3, 2, 32, 48, 0.3
+    net, params = _net(dev, precision, 3, rng)
+    x = rng.uniform(0, 1, size=(n, h, w, 3)).astype(np.float32)
+    masks = _masks(rng, t, n, h, w, rate, sites)
+    out = net.forward(cuda(x), want=('prob', 'mean_prob', 'var_prob', 'mean_var'),
+                      dropout={'rate': rate, 'layers': sites, 'num_samples': t, 'masks': masks})
+    got = out['prob'].cpu().numpy().reshape(t, n, h, w, C)
+    ref = []
+    for i in range(t):
+        m = {s: v[i * n:(i + 1) * n] for s, v in masks.items()}
+        ref.append(oracle.test_pipeline(x, params, 'm', NU, C, dropout_rate=rate,
+                                        dropout_layers=sites, masks=m)['prob'])
+    ref = np.stack(ref)
+    tol = 1e-4 if precision == 'fp32' else 2e-2
+    np.testing.assert_allclose(got, ref, rtol=0, atol=tol)
+    mean_ref, var_ref = oracle.mc_moments(got.astype(np.float64), 0)
+    np.testing.assert_allclose(out['mean_prob'].cpu().numpy(), mean_ref, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out['var_prob'].cpu().numpy(), var_ref, rtol=1e-3, atol=1e-7)
+    np.testing.assert_allclose(out['mean_var'].cpu().numpy(), var_ref.mean(-1), rtol=1e-3,
+                               atol=1e-7)
+
+
+def test_fused_philox_dropout_statistics(dev):
+    """Without external masks the fused Philox generator must drop ~rate of the units,
+    independently per sample, and be reproducible for a fixed seed."""
+    rng = np.random.default_rng(2)
+    t, n, h, w, rate = 8, 1, 32, 32, 0.4
+    net, _ = _net(dev, 'bf16', 3, rng)
+    x = rng.uniform(0, 1, size=(n, h, w, 3)).astype(np.float32)
+    cfg = {'rate': rate, 'layers': ['pool3'], 'num_samples': t, 'seed': 1234}
+    a = net.forward(cuda(x), want=('prob',), dropout=cfg)['prob'].cpu().numpy()
+    drop = net.layer('pool3_drop')
+    src = net.layer('pool3')
+    alive = src > 0
+    kept = (drop.reshape((t,) + src.shape)[:, alive] > 0).mean()
+    assert abs(kept - (1 - rate)) < 0.02, kept
+    per_sample = drop.reshape(t, -1)
+    assert not np.array_equal(per_sample[0], per_sample[1])
+    b = net.forward(cuda(x), want=('prob',), dropout=cfg)['prob'].cpu().numpy()
+    np.testing.assert_array_equal(a, b)
+    cfg['seed'] = 99
+    c = net.forward(cuda(x), want=('prob',), dropout=cfg)['prob'].cpu().numpy()
+    assert not np.array_equal(a, c)

@@ -1,0 +1,186 @@
+"""GPU parity: per-pixel fusion + score kernels (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import assert_labels_match, cuda, softmax_probs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from modular_semantic_segmentation_b200 import device
+    device.init()
+    return device
+
+
+@pytest.mark.parametrize('c,npix', [(12, 5000), (10, 256), (13, 777), (2, 33), (24, 1025)])
+def test_softmax_argmax(dev, c, npix):
+    rng = np.random.default_rng(c * 1000 + npix)
+    score = rng.normal(0, 3, size=(npix, c)).astype(np.float32)
+    prob, label = dev.softmax_argmax(cuda(score))
+    ref = oracle.softmax(score)
+    np.testing.assert_allclose(prob.cpu().numpy(), ref, rtol=2e-6, atol=1e-7)
+    assert label.dtype == torch.int64
+    assert_labels_match(label.cpu().numpy(), ref, 1e-6)
+    # ties resolve to the first maximal index (tf.argmax)
+    tie = np.zeros((64, c), np.float32)
+    tie[:, [1, c - 1]] = 5.0
+    _, lt = dev.softmax_argmax(cuda(tie), label_dtype=torch.uint8)
+    assert (lt.cpu().numpy() == 1).all()
+
+
+@pytest.mark.parametrize('prior', ['data', 'uniform', 0.3])
+@pytest.mark.parametrize('label_dtype', [torch.int64, torch.uint8])
+def test_bayes_fusion_bit_exact(dev, exp868, prior, label_dtype):
+    """Integer work: the device lookups must reproduce the oracle argmax exactly, both through
+    the decision table and through the literal log-likelihood sum."""
+    c = 12
+    rng = np.random.default_rng(5)
+    cms = [exp868['cm_measure_rgb'].astype('float32').T,
+           exp868['cm_measure_depth'].astype('float32').T]
+    labels = [rng.integers(0, c, size=(2, 37, 53)) for _ in range(2)]
+    score_ref, lls, _ = oracle.bayes_fusion(labels, cms, prior)
+    ref = oracle.argmax_first(score_ref)
+    # (a) decision table built with the oracle's float32 arithmetic, integer lookups on device
+    a, b = np.meshgrid(np.arange(c), np.arange(c), indexing='ij')
+    lut = oracle.argmax_first(oracle.bayes_fusion([a, b], cms, prior)[0]).astype(np.int32)
+    dl = [cuda(l, label_dtype) for l in labels]
+    out = dev.bayes_fuse_lut(dl, cuda(lut), c)
+    assert out.dtype == label_dtype
+    np.testing.assert_array_equal(out.cpu().numpy().astype(np.int64), ref)
+    # (b) literal form: device adds the same float32 table rows in the same order
+    with np.errstate(divide='ignore'):
+        log_cond = np.stack([np.log(np.float32(1e-20) + oracle.bayes_conditionals(m)) for m in cms])
+        log_prior = np.log(np.asarray(oracle.bayes_prior(cms[-1], prior), np.float32))
+    log_prior = np.broadcast_to(log_prior, (c,)).astype(np.float32)
+    score, out2 = dev.bayes_fuse_score(dl, cuda(log_cond), cuda(log_prior))
+    np.testing.assert_array_equal(score.cpu().numpy(), score_ref.astype(np.float32))
+    np.testing.assert_array_equal(out2.cpu().numpy().astype(np.int64), ref)
+
+
+def _dirichlet_tables(params, sigma, prior):
+    alpha = [(np.float32(sigma) * p.astype('float32')) for p in params]
+    am1 = np.stack([a - np.float32(1) for a in alpha]).astype(np.float32)
+    lognorm = np.stack([oracle.dirichlet_log_norm(a).astype(np.float32) for a in alpha])
+    logprior = np.log(np.float32(1e-20) + np.asarray(prior, np.float32)).astype(np.float32)
+    return am1, lognorm, logprior
+
+
+@pytest.mark.parametrize('c', [12, 14, 5])
+def test_dirichlet_fusion(dev, c):
+    rng = np.random.default_rng(c)
+    shape = (2, 40, 31, c)
+    probs = [softmax_probs(rng, shape), softmax_probs(rng, shape)]
+    params = [1 + rng.gamma(2, 2, size=(c, c)) for _ in range(2)]
+    counts = rng.integers(1, 1000, size=c)
+    prior = oracle.dirichlet_prior(counts)
+    ref64 = oracle.dirichlet_fusion(probs, params, prior, sigma=1.0, dtype=np.float64)
+    am1, lognorm, logprior = _dirichlet_tables(params, 1.0, prior)
+    score, label = dev.dirichlet_fuse([cuda(p) for p in probs], cuda(am1), cuda(lognorm),
+                                      cuda(logprior), want_score=True)
+    got = score.cpu().numpy()
+    scale = np.abs(ref64).max()
+    np.testing.assert_allclose(got, ref64, rtol=0, atol=2e-5 * scale)
+    assert_labels_match(label.cpu().numpy(), ref64, 4e-5 * scale)
+
+
+def test_dirichlet_fusion_exact_on_decisive_inputs(dev):
+    """Identical probabilities, decisive margins -> labels identical to the float32 oracle."""
+    c = 12
+    rng = np.random.default_rng(3)
+    shape = (1, 64, 64, c)
+    probs = [softmax_probs(rng, shape, 3.0), softmax_probs(rng, shape, 3.0)]
+    params = [1 + 8 * np.eye(c) + rng.random((c, c)) for _ in range(2)]
+    prior = oracle.dirichlet_prior(np.ones(c))
+    ref32 = oracle.dirichlet_fusion(probs, params, prior, dtype=np.float32)
+    am1, lognorm, logprior = _dirichlet_tables(params, 1.0, prior)
+    _, label = dev.dirichlet_fuse([cuda(p) for p in probs], cuda(am1), cuda(lognorm),
+                                  cuda(logprior))
+    from util import top2_margin
+    decisive = top2_margin(ref32.astype(np.float64)) > 1e-3
+    assert decisive.mean() > 0.99
+    np.testing.assert_array_equal(label.cpu().numpy()[decisive], np.argmax(ref32, -1)[decisive])
+
+
+def test_average_and_variance_fusion(dev):
+    c = 12
+    rng = np.random.default_rng(11)
+    shape = (2, 33, 47, c)
+    probs = [softmax_probs(rng, shape), softmax_probs(rng, shape)]
+    ref = oracle.average_fusion(probs)
+    score, label = dev.average_fuse([cuda(p) for p in probs], want_score=True)
+    np.testing.assert_allclose(score.cpu().numpy(), ref, rtol=1e-6, atol=1e-8)
+    assert_labels_match(label.cpu().numpy(), ref, 1e-6)
+    variances = [rng.random(shape[:-1] + (1,)).astype(np.float32) * 1e-2 for _ in range(2)]
+    variances[0][0, 0, :5] = 0.0           # exercises the 1e-20 guard
+    refv = oracle.variance_fusion(probs, variances)
+    score, label = dev.variance_fuse([cuda(p) for p in probs],
+                                     [cuda(v[..., 0]) for v in variances], want_score=True)
+    np.testing.assert_allclose(score.cpu().numpy(), refv, rtol=2e-6, atol=1e-8)
+    assert_labels_match(label.cpu().numpy(), refv, 1e-6)
+
+
+def test_mc_moments(dev):
+    c, t = 12, 20
+    rng = np.random.default_rng(7)
+    samples = softmax_probs(rng, (t, 2, 21, 35, c))
+    mean_ref, unc = oracle.sampling_uncertainty(samples.astype(np.float64))
+    _, var_ref = oracle.mc_moments(samples.astype(np.float64), 0)
+    out = dev.mc_moments(cuda(samples), want=('mean', 'var', 'mean_var', 'entropy',
+                                               'cond_entropy', 'sum_var'))
+    np.testing.assert_allclose(out['mean'].cpu().numpy(), mean_ref, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(out['var'].cpu().numpy(), var_ref, rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(out['mean_var'].cpu().numpy(), var_ref.mean(-1), rtol=1e-4,
+                               atol=1e-8)
+    np.testing.assert_allclose(out['sum_var'].cpu().numpy(), unc['variance'], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(out['entropy'].cpu().numpy(), unc['entropy'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out['cond_entropy'].cpu().numpy(), unc['cond_entropy'], rtol=1e-4,
+                               atol=1e-6)
+
+
+def test_sufficient_statistics(dev):
+    c = 12
+    rng = np.random.default_rng(13)
+    prob = softmax_probs(rng, (3, 40, 56, c))
+    labels = rng.integers(-1, c, size=(3, 40, 56)).astype(np.int32)
+    s_ref, n_ref = oracle.sufficient_statistics(prob, labels, c)
+    stats = torch.zeros((c, c), dtype=torch.float64, device='cuda')
+    counts = torch.zeros(c, dtype=torch.int64, device='cuda')
+    dev.dirichlet_suffstats(cuda(prob), cuda(labels), stats, counts)
+    dev.dirichlet_suffstats(cuda(prob), cuda(labels), stats, counts)   # accumulates
+    np.testing.assert_array_equal(counts.cpu().numpy(), 2 * n_ref)
+    np.testing.assert_allclose(stats.cpu().numpy(), 2 * s_ref, rtol=2e-6)
+
+
+@pytest.mark.parametrize('pred_dtype', [torch.int64, torch.uint8])
+def test_confusion_matrix_bit_exact(dev, pred_dtype):
+    c = 12
+    rng = np.random.default_rng(17)
+    labels = rng.integers(-1, c, size=(4, 96, 128)).astype(np.int32)
+    labels[0, :10] = 3                      # long same-class runs (warp aggregation path)
+    pred = rng.integers(0, c, size=labels.shape)
+    pred[0, :10] = 3
+    ref = oracle.confusion_matrix(labels, pred, c)
+    cm = torch.zeros((c, c), dtype=torch.int64, device='cuda')
+    dev.confusion_accumulate(cuda(pred, pred_dtype), cuda(labels), cm)
+    np.testing.assert_array_equal(cm.cpu().numpy(), ref)
+    dev.confusion_accumulate(cuda(pred, pred_dtype), cuda(labels), cm)
+    np.testing.assert_array_equal(cm.cpu().numpy(), 2 * ref)
+    assert cm.sum().item() == 2 * int((labels >= 0).sum())
+
+
+def test_empty_and_ragged_inputs(dev):
+    c = 12
+    cm = torch.zeros((c, c), dtype=torch.int64, device='cuda')
+    empty_pred = torch.zeros((0,), dtype=torch.int64, device='cuda')
+    empty_lab = torch.zeros((0,), dtype=torch.int32, device='cuda')
+    dev.confusion_accumulate(empty_pred, empty_lab, cm)
+    assert cm.sum().item() == 0
+    rng = np.random.default_rng(1)
+    for npix in (1, 255, 257):              # around the 256-pixel tile size
+        score = rng.normal(size=(npix, c)).astype(np.float32)
+        prob, label = dev.softmax_argmax(cuda(score))
+        np.testing.assert_allclose(prob.cpu().numpy(), oracle.softmax(score), rtol=2e-6, atol=1e-7)
