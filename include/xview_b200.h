@@ -40,6 +40,15 @@ const char* xv_last_error(void);
 int xv_init(int device);
 int xv_device_sm_count(int* out);
 
+/* ---- measurement hooks (no reference counterpart; used by bench.py) ------------------ */
+/* Number of kernels this library has launched since it was loaded. */
+int xv_launch_count(int64_t* out);
+/* on != 0: bracket every tensor-core convolution launch with CUDA events on its stream;
+ * on == 0: stop.  Either call discards the samples collected so far. */
+int xv_profile_enable(int on);
+/* Sum over the collected samples: device milliseconds, algorithmic FLOPs (2*MACs), launches. */
+int xv_profile_read(double* ms_out, double* flops_out, int64_t* launches_out);
+
 /* ---- plain memory / stream helpers (session feed/fetch, base_model.py:263-313) ----- */
 int xv_malloc(void** out, size_t bytes);
 int xv_free(void* p);

@@ -49,6 +49,9 @@ PROTOTYPES = {
     'xv_last_error': [],
     'xv_init': [_I],
     'xv_device_sm_count': [C.POINTER(_I)],
+    'xv_launch_count': [C.POINTER(_L)],
+    'xv_profile_enable': [_I],
+    'xv_profile_read': [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L)],
     'xv_malloc': [_PP, _Z],
     'xv_free': [_P],
     'xv_malloc_host': [_PP, _Z],

@@ -23,6 +23,18 @@ int fail(const std::string& msg) {
   return -1;
 }
 
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+
+// optional per-launch timing of the tensor-core convolutions (bench.py roofline)
+struct IgemmSample {
+  cudaEvent_t e0, e1;
+  double flops;
+  int block_n;
+};
+static bool g_profile = false;
+static std::vector<IgemmSample> g_samples;
+
 static DeviceInfo g_dev;
 const DeviceInfo& device_info() { return g_dev; }
 
@@ -314,7 +326,18 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   p.tiles_y = div_up(H, p.th);
   p.n_blocks = L.cout_pad / L.block_n;
   p.relu = L.relu;
-  return launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+  if (!g_profile) return launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+  IgemmSample smp;
+  XV_CUDA(cudaEventCreate(&smp.e0));
+  XV_CUDA(cudaEventCreate(&smp.e1));
+  // algorithmic FLOPs of the layer (2 * MACs, real channels only)
+  smp.flops = 2.0 * B * H * W * static_cast<double>(L.cout) * L.k * L.k * L.cin;
+  smp.block_n = L.block_n;
+  XV_CUDA(cudaEventRecord(smp.e0, s));
+  const int rc = launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+  XV_CUDA(cudaEventRecord(smp.e1, s));
+  g_samples.push_back(smp);
+  return rc;
 }
 
 // ------------------------------------------------------------------ forward schedule
@@ -596,6 +619,34 @@ int xv_init(int device) {
 int xv_device_sm_count(int* out) {
   XV_TRY(ensure_init());
   *out = g_dev.num_sms;
+  return 0;
+}
+
+int xv_launch_count(int64_t* out) {
+  *out = g_launches;
+  return 0;
+}
+int xv_profile_enable(int on) {
+  for (auto& smp : g_samples) {
+    cudaEventDestroy(smp.e0);
+    cudaEventDestroy(smp.e1);
+  }
+  g_samples.clear();
+  g_profile = on != 0;
+  return 0;
+}
+int xv_profile_read(double* ms_out, double* flops_out, int64_t* launches_out) {
+  double ms = 0, flops = 0;
+  for (auto& smp : g_samples) {
+    XV_CUDA(cudaEventSynchronize(smp.e1));
+    float t = 0.f;
+    XV_CUDA(cudaEventElapsedTime(&t, smp.e0, smp.e1));
+    ms += t;
+    flops += smp.flops;
+  }
+  if (ms_out) *ms_out = ms;
+  if (flops_out) *flops_out = flops;
+  if (launches_out) *launches_out = static_cast<int64_t>(g_samples.size());
   return 0;
 }
 

@@ -40,6 +40,7 @@ struct DeviceInfo {
   size_t smem_optin = 0;
 };
 const DeviceInfo& device_info();
+void count_launch(int n = 1);   // bumps the library-wide kernel-launch counter
 
 // ---------------------------------------------------------------- device PTX wrappers
 #ifdef __CUDACC__

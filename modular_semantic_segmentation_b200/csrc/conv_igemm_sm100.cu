@@ -266,6 +266,7 @@ int launch_one(const ConvIgemmParams& p, cudaStream_t stream) {
   const int grid = total_tiles < device_info().num_sms ? total_tiles : device_info().num_sms;
   kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

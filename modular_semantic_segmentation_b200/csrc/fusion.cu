@@ -538,6 +538,7 @@ int launch_softmax_argmax(const float* score, int64_t npix, int C, float* prob, 
   XV_DISPATCH_C(C, (softmax_argmax_kernel<kC><<<tiles_grid(npix), kPix, 0, s>>>(
                        score, npix, prob, label64, label8)));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -552,6 +553,7 @@ int launch_bayes_lut(const void* const* labels, int M, int label_bytes, const in
   bayes_lut_kernel<<<tiles_grid(npix), kPix, lut_size * sizeof(int32_t), s>>>(
       pk, M, label_bytes, lut, C, lut_size, npix, out);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -563,6 +565,7 @@ int launch_bayes_score(const void* const* labels, int M, int label_bytes, const 
   XV_DISPATCH_C(C, (bayes_score_kernel<kC><<<tiles_grid(npix), kPix, 0, s>>>(
                        pk, M, label_bytes, logcond, logprior, npix, score, label_out)));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -574,6 +577,7 @@ int launch_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m
   XV_DISPATCH_C(C, (dirichlet_fuse_kernel<kC><<<tiles_grid(npix), kPix, 0, s>>>(
                        pk, M, alpha_m1, lognorm, logprior, npix, score, label_out, label_bytes)));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -585,6 +589,7 @@ int launch_average_fuse(const float* const* probs, int M, int C, int64_t npix, f
   XV_DISPATCH_C(C, (mean_fuse_kernel<kC, false><<<tiles_grid(npix), kPix, 0, s>>>(
                        pk, none, M, npix, score, label_out, label_bytes)));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -597,6 +602,7 @@ int launch_variance_fuse(const float* const* probs, const float* const* vars, in
   XV_DISPATCH_C(C, (mean_fuse_kernel<kC, true><<<tiles_grid(npix), kPix, 0, s>>>(
                        pk, vk, M, npix, score, label_out, label_bytes)));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -607,6 +613,7 @@ int launch_mc_moments(const float* samples, int T, int64_t npix, int C, float* m
   XV_DISPATCH_C(C, (mc_moments_kernel<kC><<<tiles_grid(npix), kPix, 0, s>>>(
                        samples, T, npix, mean, var, mean_var, entropy, cond_entropy, sum_var)));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -615,6 +622,7 @@ int launch_suffstats(const float* prob, const int32_t* labels, int64_t npix, int
   XV_DISPATCH_C(C, (suffstats_kernel<kC><<<tiles_grid(npix), kPix, 0, s>>>(
                        prob, labels, npix, S, reinterpret_cast<unsigned long long*>(n))));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -625,6 +633,7 @@ int launch_confusion(const void* pred, int pred_bytes, const int32_t* labels, in
   confusion_kernel<<<tiles_grid(npix), kPix, C * C * sizeof(unsigned int), s>>>(
       pred, pred_bytes, labels, npix, C, reinterpret_cast<unsigned long long*>(cm));
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

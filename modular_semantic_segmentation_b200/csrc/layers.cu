@@ -24,41 +24,48 @@ inline int grid_for(size_t work, int threads = kThreads) {
 // Packs the 3x3 neighbourhood of every pixel of the raw fp32 input (Cin <= 3) into one
 // 64-element bf16 row [hi(9*Cin) | lo(9*Cin) | 0...] so conv1_1 runs on the tensor cores as
 // a 1x1 GEMM with K = 64.  hi + lo carries 16 mantissa bits, enough for raw uint16 depth.
-__global__ void im2col_c1_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                 int N, int H, int W, int cin) {
-  const size_t total = static_cast<size_t>(N) * H * W * 8;
-  const int k9 = 9 * cin;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int piece = static_cast<int>(idx & 7);
-    const size_t pix = idx >> 3;
+template <int CIN>
+__global__ void __launch_bounds__(256)
+im2col_c1_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
+                 int W) {
+  // one thread = one pixel: gathers its 3x3xCIN neighbourhood once, emits the 128-byte row
+  constexpr int K9 = 9 * CIN;
+  const size_t total = static_cast<size_t>(N) * H * W;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int px = static_cast<int>(pix % W);
     const int py = static_cast<int>((pix / W) % H);
     const size_t img = pix / (static_cast<size_t>(W) * H);
-    uint32_t packed[4];
+    float hi[K9], lo[K9];
 #pragma unroll
-    for (int e2 = 0; e2 < 4; ++e2) {
-      float v[2];
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const float* src = x + ((img * H + (in ? yy : py)) * W + (in ? xx : px)) * CIN;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int k = piece * 8 + e2 * 2 + h;
-        float val = 0.f;
-        if (k < 2 * k9) {
-          const bool lo = k >= k9;
-          if (lo) k -= k9;
-          const int tap = k / cin, ci = k - tap * cin;
-          const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const float raw = __ldg(x + ((img * H + yy) * W + xx) * cin + ci);
-            const float hi = __bfloat162float(__float2bfloat16_rn(raw));
-            val = lo ? (raw - hi) : hi;
-          }
-        }
-        v[h] = val;
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float raw = in ? __ldg(src + ci) : 0.f;
+        const float h = __bfloat162float(__float2bfloat16_rn(raw));
+        hi[tap * CIN + ci] = h;
+        lo[tap * CIN + ci] = raw - h;
       }
-      packed[e2] = pack_bf16x2(v[0], v[1]);
     }
-    reinterpret_cast<uint4*>(out)[idx] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    uint4* dst = reinterpret_cast<uint4*>(out) + pix * 8;
+#pragma unroll
+    for (int piece = 0; piece < 8; ++piece) {
+      uint32_t packed[4];
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = piece * 8 + e2 * 2 + h;   // compile-time after unrolling
+          v[h] = k < K9 ? hi[k < K9 ? k : 0] : (k < 2 * K9 ? lo[k < 2 * K9 ? k - K9 : 0] : 0.f);
+        }
+        packed[e2] = pack_bf16x2(v[0], v[1]);
+      }
+      dst[piece] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
   }
 }
 
@@ -450,6 +457,7 @@ int decode_dispatch(bool mc, const float* low, const float* g, const float* bias
     decode_upsample8_kernel<C, false><<<grid, 256, 0, s>>>(low, g, bias, 1, N, h, w, out,
                                                             nullptr, nullptr, nullptr);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -485,20 +493,26 @@ int decode_dispatch(bool mc, const float* low, const float* g, const float* bias
 
 int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, int cin,
                      cudaStream_t s) {
-  XV_CHECK(cin >= 1 && 18 * cin <= 64, "conv1_1 packing supports Cin <= 3");
-  const size_t total = static_cast<size_t>(N) * H * W * 8;
-  im2col_c1_kernel<<<grid_for(total), kThreads, 0, s>>>(x, out, N, H, W, cin);
+  XV_CHECK(cin >= 1 && cin <= 3, "conv1_1 packing supports Cin <= 3");
+  const size_t total = static_cast<size_t>(N) * H * W;
+  const int grid = grid_for(total);
+  if (cin == 1) im2col_c1_kernel<1><<<grid, kThreads, 0, s>>>(x, out, N, H, W);
+  if (cin == 2) im2col_c1_kernel<2><<<grid, kThreads, 0, s>>>(x, out, N, H, W);
+  if (cin == 3) im2col_c1_kernel<3><<<grid, kThreads, 0, s>>>(x, out, N, H, W);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
   f32_to_bf16_kernel<<<grid_for(n), kThreads, 0, s>>>(in, out, n);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t s) {
   bf16_to_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(in, out, n);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_maxpool_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int H, int W, int C,
@@ -508,12 +522,14 @@ int launch_maxpool_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int 
   maxpool_bf16_kernel<<<grid_for(total), kThreads, 0, s>>>(
       reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), N, H, W, C / 8);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_maxpool_f32(const float* in, float* out, int N, int H, int W, int C, cudaStream_t s) {
   const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * C;
   maxpool_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, N, H, W, C);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_dropout_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, int replicate,
@@ -522,6 +538,7 @@ int launch_dropout_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, i
   dropout_kernel<__nv_bfloat16><<<grid_for(groups), kThreads, 0, s>>>(
       in, out, n, replicate, d.rate, d.ext_mask, d.seed, d.offset);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_dropout_f32(const float* in, float* out, size_t n, int replicate,
@@ -530,6 +547,7 @@ int launch_dropout_f32(const float* in, float* out, size_t n, int replicate,
   dropout_kernel<float><<<grid_for(groups), kThreads, 0, s>>>(in, out, n, replicate, d.rate,
                                                                d.ext_mask, d.seed, d.offset);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_conv_f32(const float* x, const float* w, const float* bias, float* out, int N, int H,
@@ -538,6 +556,7 @@ int launch_conv_f32(const float* x, const float* w, const float* bias, float* ou
   conv_f32_kernel<<<grid_for(total, 128), 128, 0, s>>>(x, w, bias, out, N, H, W, cin, cout, k,
                                                        relu);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_deconv_f32(const float* x, const float* w, float* out, int N, int hin, int win, int cin,
@@ -548,17 +567,20 @@ int launch_deconv_f32(const float* x, const float* w, float* out, int N, int hin
   deconv_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(x, w, out, N, hin, win, cin, cout, k,
                                                          stride, relu, addend);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t s) {
   add_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(a, b, out, n);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_affine_f32(float* x, const float* scale, const float* shift, size_t npix, int C,
                       int relu, cudaStream_t s) {
   affine_f32_kernel<<<grid_for(npix * C), kThreads, 0, s>>>(x, scale, shift, npix * C, C, relu);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_upscore2_add(const float* s5, const float* s4, const float* g, float* fused, int N,
@@ -566,12 +588,14 @@ int launch_upscore2_add(const float* s5, const float* s4, const float* g, float*
   const size_t total = static_cast<size_t>(N) * 4 * h * w * nu;
   upscore2_add_kernel<<<grid_for(total), kThreads, 0, s>>>(s5, s4, g, fused, N, h, w, nu);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_score_lowres(const float* fused, const float* w, float* low, size_t npix, int nu, int C,
                         cudaStream_t s) {
   score_lowres_kernel<<<grid_for(npix * C), kThreads, 0, s>>>(fused, w, low, npix, nu, C);
   XV_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int launch_decode_upsample8(const float* low, const float* g, const float* bias, int N, int h,

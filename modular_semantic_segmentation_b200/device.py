@@ -327,3 +327,22 @@ def confusion_accumulate(pred, labels, cm):
     assert labels.dtype == torch.int32 and cm.dtype == torch.int64
     call('xv_confusion_accumulate', ptr(pred), _label_bytes(pred), ptr(labels), pred.numel(),
          cm.shape[0], ptr(cm), stream_ptr())
+
+
+# --------------------------------------------------------------------------- measurement
+def launch_count():
+    n = C.c_int64()
+    call('xv_launch_count', C.byref(n))
+    return n.value
+
+
+def profile_enable(on=True):
+    call('xv_profile_enable', int(on))
+
+
+def profile_read():
+    """(device ms, algorithmic FLOPs, launches) summed over the tensor-core conv launches
+    recorded since profile_enable(True)."""
+    ms, flops, n = C.c_double(), C.c_double(), C.c_int64()
+    call('xv_profile_read', C.byref(ms), C.byref(flops), C.byref(n))
+    return ms.value, flops.value, n.value

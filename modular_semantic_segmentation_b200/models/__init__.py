@@ -1,0 +1,23 @@
+"""B200-native counterparts of the `xview.models` classes (same names, same factory)."""
+from .simple_fcn import SimpleFCN
+from .bayes_mix import BayesFusion
+from .dirichlet_mix import DirichletFusion
+from .average_mix import AverageFusion
+from .variance_mix import VarianceFusion
+
+
+def get_model(name):
+    """xview/models/__init__.py:10-26.  'fusion_fcn' and 'adapnet' are outside the hot path
+    built so far and are reported exactly like an unknown model."""
+    if name == 'fcn':
+        return SimpleFCN
+    elif name in ['bayes_mix', 'bayes_fusion']:
+        return BayesFusion
+    elif name in ['dirichlet_mix', 'dirichlet_fusion']:
+        return DirichletFusion
+    elif name in ['average_fusion', 'average_mix']:
+        return AverageFusion
+    elif name in ['variance_mix', 'variance_fusion']:
+        return VarianceFusion
+    else:
+        raise UserWarning('ERROR: Model %s not found' % name)

@@ -19,13 +19,8 @@ import numpy as np
 import torch
 
 from .. import device as dev
-
-
-def _dist():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return dist
-    return None
+from .. import sharding
+from ..sharding import dist_or_none as _dist
 
 
 def measures_from_confusion_matrix(confusion_matrix):
@@ -111,12 +106,10 @@ class BaseModel(object):
     # ------------------------------------------------------------------ data plumbing
     def _my_rows(self, first_index, count):
         """Rows of a batch this rank evaluates (images sharded round-robin over ranks)."""
-        dist = _dist()
-        if dist is None:
+        rank, world = sharding.rank_world()
+        if world == 1 or not self.config.get('shard_images', True):
             return slice(None)
-        world, rank = dist.get_world_size(), dist.get_rank()
-        rows = [i for i in range(count) if (first_index + i) % world == rank]
-        return rows
+        return sharding.rows_for_rank(first_index, count, rank, world)
 
     def _batches(self, data):
         """Replaces transform_inputdata (base_model.py:10-38): `data` is a dict of arrays
@@ -125,8 +118,8 @@ class BaseModel(object):
         if isinstance(data, dict):
             total = len(next(iter(data.values())))
             bs = self.config['batchsize']
-            dist = _dist()
-            step = bs * (dist.get_world_size() if dist else 1)
+            shard = self.config.get('shard_images', True)
+            step = bs * (sharding.rank_world()[1] if shard else 1)
 
             def gen():
                 for start in range(0, total, step):
@@ -135,8 +128,8 @@ class BaseModel(object):
                     if isinstance(rows, slice):
                         yield {k: v[start:stop] for k, v in data.items()}
                     elif rows:
-                        yield {k: v[start + rows[0]:stop:len(range(stop - start)) and
-                                    (dist.get_world_size())] for k, v in data.items()}
+                        idx = [start + r for r in rows]
+                        yield {k: v[idx] for k, v in data.items()}
             return gen()
 
         def gen_iter():
@@ -182,43 +175,10 @@ class BaseModel(object):
         for batch in self._batches(data):
             out = self._run_batch(self._to_device(batch), fetch)
             ret.append(out)
-        dist = _dist()
-        if not ret:
-            local = None
-        else:
-            local = torch.cat(ret)
-        if dist is not None:
-            return self._gather_predictions(local, dist)
+        local = torch.cat(ret) if ret else None
+        if _dist() is not None:
+            local = sharding.gather_interleaved(local, 'cuda')
         return local.cpu().numpy()
-
-    def _gather_predictions(self, local, dist):
-        """all_gather of the per-rank label maps; restores the original image order."""
-        world = dist.get_world_size()
-        count = torch.tensor([0 if local is None else local.shape[0]], device='cuda')
-        counts = [torch.zeros_like(count) for _ in range(world)]
-        dist.all_gather(counts, count)
-        counts = [int(c.item()) for c in counts]
-        shape_src = int(np.argmax(counts))
-        meta = torch.zeros(8, dtype=torch.int64, device='cuda')
-        if dist.get_rank() == shape_src:
-            meta[0] = local.dim()
-            for i, s in enumerate(local.shape[1:]):
-                meta[1 + i] = s
-            meta[7] = {torch.int64: 0, torch.float32: 1, torch.uint8: 2}[local.dtype]
-        dist.broadcast(meta, shape_src)
-        rest = tuple(int(v) for v in meta[1:int(meta[0])])
-        dtype = [torch.int64, torch.float32, torch.uint8][int(meta[7])]
-        pad = max(counts)
-        buf = torch.zeros((pad,) + rest, dtype=dtype, device='cuda')
-        if local is not None:
-            buf[:local.shape[0]] = local
-        bufs = [torch.zeros_like(buf) for _ in range(world)]
-        dist.all_gather(bufs, buf)
-        total = sum(counts)
-        out = torch.zeros((total,) + rest, dtype=dtype, device='cuda')
-        for r in range(world):
-            out[r:total:world][:counts[r]] = bufs[r][:counts[r]]
-        return out.cpu().numpy()
 
     def _has_output(self, attr):
         return attr in getattr(self, 'output_attrs', ('prediction',))
@@ -232,12 +192,19 @@ class BaseModel(object):
             batch = self._to_device(batch)
             prediction = self._run_batch(batch, 'prediction_compact')
             dev.confusion_accumulate(prediction, batch['labels'].contiguous(), cm)
-        dist = _dist()
-        if dist is not None:
-            dist.all_reduce(cm, op=dist.ReduceOp.SUM)
+        sharding.allreduce_sum_(cm)
         confusion_matrix = cm.cpu().numpy().astype(np.float64)
         measures = measures_from_confusion_matrix(confusion_matrix)
         return measures, confusion_matrix
+
+    def score_batch_on_device(self, batch, confusion_matrix=None):
+        """One step of the score() loop for a batch that already lives in HBM (dict of CUDA
+        tensors): experts -> fusion -> confusion-matrix accumulation, no host transfer and no
+        synchronisation.  Returns the int64 device matrix being accumulated."""
+        cm = self._cm_device if confusion_matrix is None else confusion_matrix
+        prediction = self._run_batch(batch, 'prediction_compact')
+        dev.confusion_accumulate(prediction, batch['labels'], cm)
+        return cm
 
     def load_weights(self, filepath):
         """base_model.py:333-339 restores a TensorFlow checkpoint; only the npz route exists
@@ -278,43 +245,57 @@ class BaseModel(object):
         if warnings:
             print(filepath)
         weights = np.load(filepath)
-        keys = list(weights.keys())
-        import_prefix = keys[0].split('/')[0].split('_')[0] if keys else ''
-
-        def translate_name(name):
-            if not translate_prefix:
-                return name
-            if not name.startswith(translate_prefix):
-                return name
-            splitted = name.split('/')
-            further_splitted = splitted[0].split('_')
-            if further_splitted[0] == 'forest':
-                return name
-            further_splitted[0] = import_prefix
-            splitted[0] = '_'.join(further_splitted)
-            return '/'.join(splitted)
-
-        for var_name in list(self.variables.keys()):
-            name = translate_name(var_name)
-            if 'grad' in name or 'Adam' in name or 'RMS' in name:
-                continue
-            legacy = name.replace('/', '_', 1)
-            if name in weights or legacy in weights:
-                if legacy in weights:
-                    name = legacy
-                value = weights[name]
-                if tuple(self.variables[var_name].shape) != tuple(value.shape):
-                    if warnings:
-                        print('WARNING: wrong shape found for {}, but ignored in '
-                              'chill mode'.format(name))
-                        print('stored shape: ', value.shape,
-                              'expected shape: ', self.variables[var_name].shape)
-                    # the reference docstring: mismatching variables are left unassigned
-                    continue
-                self.variables[var_name] = np.asarray(value, dtype=np.float32)
-            else:
-                if warnings:
-                    print('WARNING: {} not found in saved weights'.format(name))
+        assigned, messages = match_weights(self.variables, weights, translate_prefix, chill_mode)
+        if warnings:
+            for line in messages:
+                print(line)
+        for var_name, value in assigned.items():
+            self.variables[var_name] = value
         if 'global_step' in weights:
             self.global_step = int(weights['global_step'])
         self._push_variables()
+
+
+def match_weights(variables, weights, translate_prefix=False, chill_mode=False):
+    """The name-matching rules of base_model.py:409-450 as a pure function.
+
+    variables: mapping TF variable name -> current array; weights: mapping stored name -> array
+    (an opened npz).  Returns ({variable name: float32 array to assign}, [warning lines])."""
+    keys = list(weights.keys())
+    import_prefix = keys[0].split('/')[0].split('_')[0] if keys else ''
+
+    def translate_name(name):
+        if not translate_prefix:
+            return name
+        if not name.startswith(translate_prefix):
+            return name
+        splitted = name.split('/')
+        further_splitted = splitted[0].split('_')
+        if further_splitted[0] == 'forest':
+            return name
+        further_splitted[0] = import_prefix
+        splitted[0] = '_'.join(further_splitted)
+        return '/'.join(splitted)
+
+    assigned, messages = {}, []
+    for var_name in variables.keys():
+        name = translate_name(var_name)
+        # optimizers have their own variables, do not load these (base_model.py:433)
+        if 'grad' in name or 'Adam' in name or 'RMS' in name:
+            continue
+        legacy = name.replace('/', '_', 1)
+        if name in weights or legacy in weights:
+            if legacy in weights:
+                name = legacy
+            value = weights[name]
+            if tuple(variables[var_name].shape) != tuple(value.shape):
+                messages.append('WARNING: wrong shape found for {}, but ignored in '
+                                'chill mode'.format(name))
+                messages.append('stored shape:  {} expected shape:  {}'.format(
+                    tuple(value.shape), tuple(variables[var_name].shape)))
+                # reference docstring: mismatching variables are left unassigned
+                continue
+            assigned[var_name] = np.asarray(value, dtype=np.float32)
+        else:
+            messages.append('WARNING: {} not found in saved weights'.format(name))
+    return assigned, messages

@@ -1,0 +1,126 @@
+"""Mirror of xview/models/bayes_mix.py: confusion-matrix Bayes fusion."""
+from itertools import product
+
+import numpy as np
+import torch
+
+from .. import device as dev
+from .basic_fusion_model import FusionModel
+
+
+def _conditional(confusion_matrix):
+    """bayes_mix.py:35: p(expert output | ground-truth class), nan -> 0."""
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return np.nan_to_num(confusion_matrix / confusion_matrix.sum(0))
+
+
+def _prior(confusion_matrix, class_prior):
+    """bayes_mix.py:42-54, including the constant 1/14 uniform prior and the use of the LAST
+    expert's matrix for the data prior."""
+    uniform_prior = 1.0 / 14
+    with np.errstate(divide='ignore', invalid='ignore'):
+        data_prior = confusion_matrix.sum(0) / confusion_matrix.sum()
+    if class_prior == 'uniform':
+        return uniform_prior
+    if class_prior == 'data':
+        return data_prior
+    weight = float(class_prior)
+    prior = weight * uniform_prior + (1 - weight) * data_prior
+    return prior / prior.sum()
+
+
+def bayes_tables(confusion_matrices, class_prior='data'):
+    """Host-side constants of bayes_fusion (bayes_mix.py:32-54) in the dtype of the matrices:
+    log(1e-20 + conditional) per expert [M,C,C] and log(prior) [C]."""
+    dtype = np.asarray(confusion_matrices[0]).dtype
+    with np.errstate(divide='ignore'):
+        log_cond = np.stack([np.log(np.asarray(1e-20, dtype) + _conditional(np.asarray(m)))
+                             for m in confusion_matrices])
+        log_prior = np.log(np.asarray(_prior(np.asarray(confusion_matrices[-1]), class_prior),
+                                      dtype))
+    num_classes = log_cond.shape[-1]
+    return log_cond, np.broadcast_to(log_prior, (num_classes,)).astype(dtype)
+
+
+def bayes_fusion(classifications, confusion_matrices, class_prior='data'):
+    """bayes_mix.py:12-58 on the device.  classifications: list of int64/uint8 CUDA label maps;
+    confusion_matrices: list of numpy arrays (rows = expert output, cols = ground truth).
+    Returns (fused score [.., C] float32 CUDA, log-likelihood tables, conditionals)."""
+    log_cond, log_prior = bayes_tables([np.asarray(m, np.float32) for m in confusion_matrices],
+                                       class_prior)
+    score, _ = dev.bayes_fuse_score(classifications, dev.to_device(log_cond),
+                                    dev.to_device(log_prior))
+    conditionals = [_conditional(np.asarray(m, np.float32)) for m in confusion_matrices]
+    return score, list(log_cond), conditionals
+
+
+def bayes_decision_table(confusion_matrices, class_prior='data'):
+    """All C^M label combinations evaluated with EXACTLY the arithmetic of `bayes_fusion`
+    (same dtype, same summation order: experts in order, then + log prior), so that integer
+    lookups on the device reproduce the argmax of the literal per-pixel rule bit for bit."""
+    log_cond, log_prior = bayes_tables(confusion_matrices, class_prior)
+    num_experts, num_classes = log_cond.shape[0], log_cond.shape[-1]
+    combos = np.array(list(product(*(range(num_classes) for _ in range(num_experts)))))
+    total = log_cond[0][combos[:, 0]]
+    for i in range(1, num_experts):
+        total = total + log_cond[i][combos[:, i]]
+    total = total + log_prior
+    return np.argmax(total, axis=1).reshape([num_classes] * num_experts).astype(np.int32)
+
+
+def bayes_decision_matrix(confusion_matrices, class_prior='data'):
+    """bayes_mix.py:61-112 verbatim semantics (float64 log-likelihood buffer)."""
+    num_classes = confusion_matrices[0].shape[0]
+    num_experts = len(confusion_matrices)
+    combos = np.array(list(product(*(range(num_classes) for _ in range(num_experts)))))
+    log_likelihoods = np.zeros((combos.shape[0], num_experts, num_classes))
+    for i_expert in range(num_experts):
+        conditional = _conditional(np.asarray(confusion_matrices[i_expert]))
+        with np.errstate(divide='ignore'):
+            log_likelihoods[:, i_expert, :] = np.log(1e-20 + conditional[combos[:, i_expert]])
+    prior = _prior(np.asarray(confusion_matrices[-1]), class_prior)
+    with np.errstate(divide='ignore'):
+        fused = np.argmax(log_likelihoods.sum(1) + np.log(prior), axis=1)
+    return fused.reshape([num_classes for _ in range(num_experts)])
+
+
+class BayesFusion(FusionModel):
+    """bayes_mix.py:115-161."""
+
+    output_attrs = ('prediction', 'fused_score')
+    expert_wants = ('label',)
+
+    def __init__(self, output_dir=None, confusion_matrices=False, **config):
+        standard_config = {'learning_rate': 0.0, 'class_prior': 'data'}
+        standard_config.update(config)
+        self.modalities = []
+        self.confusion_matrices = {}
+        if confusion_matrices:
+            for key, matrix in confusion_matrices.items():
+                self.modalities.append(key)
+                self.confusion_matrices[key] = np.asarray(matrix).astype('float32').T
+        else:
+            # bayes_mix.py:143-147 reads the matrices from stored sacred runs
+            from experiments.utils import ExperimentData
+            for key, exp_id in config['eval_experiments'].items():
+                self.confusion_matrices[key] = np.array(
+                    ExperimentData(exp_id).get_record()['info']['confusion_matrix']
+                    ['values']).astype('float32').T
+        FusionModel.__init__(self, 'BayesFusion', output_dir=output_dir, **standard_config)
+
+    def _build_graph(self):
+        FusionModel._build_graph(self)
+        matrices = [self.confusion_matrices[m] for m in self.modalities]
+        self.decision_table = bayes_decision_table(matrices, self.config['class_prior'])
+        self._lut = dev.to_device(self.decision_table)
+        log_cond, log_prior = bayes_tables(matrices, self.config['class_prior'])
+        self.likelihoods = list(log_cond)
+        self.conditionals = [_conditional(m) for m in matrices]
+        self._log_cond = dev.to_device(log_cond)
+        self._log_prior = dev.to_device(log_prior)
+
+    def _fusion(self, expert_outputs, fetch, label_dtype):
+        labels = [expert_outputs[m]['classification'] for m in self.modalities]
+        if fetch == 'fused_score':
+            return dev.bayes_fuse_score(labels, self._log_cond, self._log_prior)[0]
+        return dev.bayes_fuse_lut(labels, self._lut, self.config['num_classes'])

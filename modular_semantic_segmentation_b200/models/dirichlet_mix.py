@@ -1,0 +1,161 @@
+"""Mirror of xview/models/dirichlet_mix.py: Dirichlet fusion of the experts' softmax outputs."""
+from copy import deepcopy
+
+import numpy as np
+import torch
+from scipy.special import gammaln
+
+from .. import device as dev
+from .. import sharding
+from .base_model import BaseModel
+from .basic_fusion_model import build_test_pipeline
+from .dirichletDifferentiation import findDirichletPriors
+
+
+def dirichlet_tables(dirichlet_params, sigma, prior):
+    """Constants of dirichlet_fusion (dirichlet_mix.py:107-113,34-36) for the device kernel:
+    alpha-1 [M,C_out,C_gt], lbeta(alpha[:,c]) [M,C_gt] and log(1e-20+prior) [C], float32.
+    Column c of a parameter matrix is the concentration for ground-truth class c."""
+    alpha = [np.float32(sigma) * np.asarray(p).astype('float32') for p in dirichlet_params]
+    alpha_m1 = np.stack([a - np.float32(1) for a in alpha]).astype(np.float32)
+    log_norm = np.stack([(gammaln(a.astype(np.float64)).sum(0) -
+                          gammaln(a.astype(np.float64).sum(0))) for a in alpha]).astype(np.float32)
+    num_classes = alpha_m1.shape[-1]
+    prior = np.broadcast_to(np.asarray(prior, np.float32), (num_classes,))
+    with np.errstate(divide='ignore'):
+        log_prior = np.log(np.float32(1e-20) + prior).astype(np.float32)
+    return alpha_m1, log_norm, log_prior
+
+
+def class_prior_from_counts(class_counts, class_prior):
+    """dirichlet_mix.py:116-129 (uniform prior is the constant 1/14)."""
+    class_counts = np.asarray(class_counts).astype('float32')
+    uniform_prior = 1.0 / 14
+    data_prior = (class_counts / (1e-20 + class_counts.sum())).astype('float32')
+    if class_prior == 'uniform':
+        return uniform_prior
+    if class_prior == 'data':
+        return data_prior
+    weight = float(class_prior)
+    prior = weight * uniform_prior + (1 - weight) * data_prior
+    return prior / prior.sum()
+
+
+def dirichlet_fusion(probs, dirichlet_params, prior, sigma=1.0, want_score=True):
+    """dirichlet_mix.py:14-36 on the device.  probs: list of CUDA float32 [N,H,W,C] softmax
+    outputs; dirichlet_params: list of [C,C] numpy arrays; prior: [C] or scalar.  Returns the
+    fused score [N,H,W,C] (argmax over the last axis is the fused classification)."""
+    alpha_m1, log_norm, log_prior = dirichlet_tables(dirichlet_params, sigma, prior)
+    score, label = dev.dirichlet_fuse(probs, dev.to_device(alpha_m1), dev.to_device(log_norm),
+                                      dev.to_device(log_prior), want_score=want_score)
+    return score if want_score else label
+
+
+class DirichletFusion(BaseModel):
+    """dirichlet_mix.py:39-273.  The modality name doubles as the variable prefix (:98)."""
+
+    output_attrs = ('prediction', 'fused_score')
+
+    def __init__(self, output_dir=None, **config):
+        standard_config = {'learning_rate': 0.0, 'sigma': 1.0, 'class_prior': 'data',
+                           'delta': 1e-2, 'beta': 1e-2}
+        standard_config.update(config)
+        self.modalities = config['modalities']
+        if 'measurement_exp' in config or 'dirichlet_params' in config:
+            if 'measurement_exp' in config:
+                from experiments.utils import ExperimentData
+                measurements = np.load(ExperimentData(config["measurement_exp"])
+                                       .get_artifact("counts.npz"))
+            else:
+                measurements = config['dirichlet_params']
+            self.dirichlet_params = {m: np.asarray(measurements[m]).astype('float32')
+                                     for m in self.modalities}
+            self.class_counts = np.asarray(measurements['class_counts']).astype('float32')
+        else:
+            print('WARNING: Could not yet import measurements, you need to fit this '
+                  'model first.')
+        BaseModel.__init__(self, name='DirichletFusion', output_dir=output_dir,
+                           custom_training=True, **standard_config)
+
+    def _build_graph(self):
+        if not self._experts:       # re-entered by fit(): keep the experts and their weights
+            for m in self.modalities:
+                expert, variables = build_test_pipeline(m, self.config['num_channels'][m],
+                                                        **self.config)
+                self._register_expert(m, expert, variables)
+        if hasattr(self, 'dirichlet_params'):
+            prior = class_prior_from_counts(self.class_counts, self.config['class_prior'])
+            tables = dirichlet_tables([self.dirichlet_params[m] for m in self.modalities],
+                                      self.config['sigma'], prior)
+            self._tables = [dev.to_device(t) for t in tables]
+            self.prediction = 'prediction'
+        else:
+            self._tables = None
+            self.prediction = 0     # dirichlet_mix.py:166-167: nothing to fuse before fit()
+
+    def _probs(self, batch):
+        return [self._experts[m].forward(batch[m], want=('prob',))['prob']
+                for m in self.modalities]
+
+    def _run_batch(self, batch, fetch='prediction'):
+        if self._tables is None:
+            raise UserWarning('ERROR: DirichletFusion has to be fitted before inference')
+        label_dtype = torch.uint8 if fetch == 'prediction_compact' else torch.int64
+        self.probs = dict(zip(self.modalities, self._probs(batch)))
+        score, label = dev.dirichlet_fuse([self.probs[m] for m in self.modalities],
+                                          *self._tables, want_score=(fetch == 'fused_score'),
+                                          label_dtype=label_dtype)
+        return score if fetch == 'fused_score' else label
+
+    def _get_sufficient_statistic(self, data):
+        """dirichlet_mix.py:173-205: per modality S[c,k] = sum_{label==c} log(1e-10+prob[k])
+        and the class counts, accumulated on the device (float64 / int64) over all batches and
+        summed over ranks."""
+        c = self.config['num_classes']
+        stats = {m: torch.zeros((c, c), dtype=torch.float64, device='cuda')
+                 for m in self.modalities}
+        counts = torch.zeros(c, dtype=torch.int64, device='cuda')
+        scratch = torch.zeros(c, dtype=torch.int64, device='cuda')
+        for batch in self._batches(data):
+            batch = self._to_device(batch)
+            labels = batch['labels'].contiguous()
+            for i, (m, prob) in enumerate(zip(self.modalities, self._probs(batch))):
+                dev.dirichlet_suffstats(prob, labels, stats[m], counts if i == 0 else scratch)
+        for m in self.modalities:
+            sharding.allreduce_sum_(stats[m])
+        sharding.allreduce_sum_(counts)
+        return {m: s.cpu().numpy() for m, s in stats.items()}, counts.cpu().numpy()
+
+    def _fit_sufficient_statistic(self, counts, class_counts):
+        """dirichlet_mix.py:207-257 (host, float64)."""
+        num_classes = self.config['num_classes']
+
+        def dirichlet_em(measurements):
+            params = np.ones((num_classes, num_classes)).astype('float64')
+            for c in range(num_classes):
+                if class_counts[c] == 0:
+                    params[:, c] = np.ones(num_classes)
+                    continue
+                ss = (measurements[c, :] / class_counts[c]).astype('float64')
+                neg_ss = (measurements.sum(0) - measurements[c, :]) / \
+                    (class_counts.sum() - class_counts[c])
+                prior = np.ones((num_classes)).astype('float64')
+                params[:, c] = findDirichletPriors(ss, neg_ss, prior, max_iter=10000,
+                                                   delta=self.config['delta'],
+                                                   beta=self.config['beta'])
+            return params
+
+        self.dirichlet_params = {m: dirichlet_em(counts[m]) for m in self.modalities}
+        self.class_counts = class_counts
+        self._build_graph()
+
+    def fit(self, data, *args, **kwargs):
+        """dirichlet_mix.py:259-273: measure the experts on `data`, fit the class-conditional
+        Dirichlets, return {modality: params [C,C], 'class_counts': [C]}."""
+        modality_counts, class_counts = self._get_sufficient_statistic(data)
+        print('INFO: Measurements of classifiers finished, now EM')
+        self._fit_sufficient_statistic(modality_counts, class_counts)
+        print("INFO: MixFCN fitted to data")
+        return_dict = deepcopy(self.dirichlet_params)
+        return_dict['class_counts'] = self.class_counts
+        return return_dict

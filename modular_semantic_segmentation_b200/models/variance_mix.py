@@ -1,0 +1,42 @@
+"""Mirror of xview/models/variance_mix.py.  The reference class cannot be constructed as
+shipped (pre-refactor BaseModel signature); the working statement is
+experiments/timing.py:180-233, which this class follows."""
+from .. import device as dev
+from .basic_fusion_model import FusionModel
+
+
+def variance_fusion(probs, variances, want_score=True):
+    """variance_mix.py:7-15 on the device: inverse-variance weighted mean of the experts'
+    probabilities.  variances: per-pixel float32 CUDA maps [N,H,W]."""
+    return dev.variance_fuse(probs, variances, want_score=want_score)[0 if want_score else 1]
+
+
+class VarianceFusion(FusionModel):
+    """variance_mix.py:18-83: MC-dropout (dropout after pool3, `num_samples` samples sharing
+    one weight load) gives the per-pixel variance, a dropout-free pass gives the
+    probabilities."""
+
+    output_attrs = ('prediction', 'fused_score')
+
+    def __init__(self, output_dir=None, **config):
+        standard_config = {'learning_rate': 0.0}
+        standard_config.update(config)
+        if 'prefixes' not in standard_config:
+            standard_config['prefixes'] = {m: m for m in standard_config['modalities']}
+        FusionModel.__init__(self, 'VarianceMixture', output_dir=output_dir, **standard_config)
+
+    def _run_batch(self, batch, fetch='prediction'):
+        import torch
+        label_dtype = torch.uint8 if fetch == 'prediction_compact' else torch.int64
+        probs, variances = [], []
+        for i, m in enumerate(self.modalities):
+            expert = self._experts[self._expert_prefix(m)]
+            probs.append(expert.forward(batch[m], want=('prob',))['prob'])
+            mc = expert.forward(batch[m], want=('mean_var',), dropout={
+                'rate': self.config['dropout_rate'], 'layers': ['pool3'],
+                'num_samples': self.config['num_samples'],
+                'seed': self.config.get('seed', 0) + i})
+            variances.append(mc['mean_var'])
+        score, label = dev.variance_fuse(probs, variances, want_score=(fetch == 'fused_score'),
+                                         label_dtype=label_dtype)
+        return score if fetch == 'fused_score' else label

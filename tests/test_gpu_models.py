@@ -1,0 +1,199 @@
+"""GPU parity: the model classes (the reference-facing API) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import assert_labels_match, top2_margin
+
+pytestmark = pytest.mark.gpu
+
+NU = 8
+
+
+def _description(c):
+    return ({'rgb': np.float32, 'depth': np.float32, 'labels': np.int32},
+            {'rgb': (None, None, 3), 'depth': (None, None, 1), 'labels': (None, None)}, c)
+
+
+def _data(rng, n, h, w, c):
+    return {'rgb': rng.integers(0, 256, size=(n, h, w, 3)).astype(np.float32),
+            'depth': rng.integers(0, 65536, size=(n, h, w, 1)).astype(np.float32),
+            'labels': rng.integers(-1, c, size=(n, h, w)).astype(np.int32)}
+
+
+def _trained_like(rng, c, nu=NU):
+    params = {}
+    for m, cin, hi in (('rgb', 3, 255.0), ('depth', 1, 65535.0)):
+        p = oracle.glorot_fcn_params(m, cin, nu, c, rng, gain=1.45, bias_scale=0.05)
+        p[m + '/conv1_1/kernel'] /= np.float32(hi)
+        params.update(p)
+    return params
+
+
+def _load(net, params):
+    for name, value in params.items():
+        if name in net.variables:
+            net.variables[name] = value
+    net._push_variables()
+
+
+def test_simple_fcn_predict_and_score_config0(tmp_path):
+    """BASELINE configs[0]: SimpleFCN rgb-only (README example: num_classes=10,
+    dropout_probability=0.2 - a key the model ignores) predict + score on a Synthia-shaped
+    batch, against the CPU oracle."""
+    from xview.models import get_model
+    c, n, h, w = 10, 2, 368, 640
+    rng = np.random.default_rng(0)
+    data = _data(rng, n, h, w, c)
+    params = {k: v for k, v in _trained_like(rng, c, 16).items() if k.startswith('rgb/')}
+    with get_model('fcn')('rgb', _description(c), 'rgb', num_units=16, batch_normalization=False,
+                          dropout_probability=0.2, batchsize=1, output_dir=str(tmp_path)) as net:
+        _load(net, params)
+        pred = net.predict({'rgb': data['rgb']})          # labels may be omitted (README:79)
+        measures, cm = net.score(data)
+        prob = net.predict(data, output_attr='prob')
+        path = net.export_weights()
+    ref = oracle.test_pipeline(data['rgb'], params, 'rgb', 16, c)
+    assert pred.dtype == np.int64 and pred.shape == (n, h, w)
+    np.testing.assert_allclose(prob, ref['prob'], rtol=0, atol=2e-2)
+    assert (pred == ref['classification']).mean() > 0.97
+    # score() on the device's own predictions is exact integer work
+    np.testing.assert_array_equal(cm, oracle.confusion_matrix(data['labels'], pred, c))
+    ref_m = oracle.score_measures(cm)
+    for key in ('mean_IoU', 'total_accuracy', 'mean_F1'):
+        assert measures[key] == ref_m[key]
+    # mIoU within 0.1 point of the oracle's end-to-end value
+    ref_cm = oracle.confusion_matrix(data['labels'], ref['classification'], c)
+    assert abs(measures['mean_IoU'] - oracle.score_measures(ref_cm)['mean_IoU']) < 1e-3
+    assert os.path.basename(path) == 'SimpleFCN_weights_0.npz'
+    stored = np.load(path)
+    assert set(stored.keys()) == set(params) | {'global_step'}
+
+
+def test_import_weights_roundtrip_and_legacy_names(tmp_path, capsys):
+    from xview.models import get_model
+    c = 5
+    rng = np.random.default_rng(1)
+    params = {k: v for k, v in _trained_like(rng, c).items() if k.startswith('depth/')}
+    legacy = {k.replace('/', '_', 1): v for k, v in params.items()}     # depth_conv1_1/kernel
+    legacy['depth_conv1_1/kernel/Adam'] = np.zeros((3, 3, 1, 64), np.float32)
+    legacy.pop('depth_score/bias')
+    np.savez_compressed(tmp_path / 'w.npz', **legacy)
+    x = rng.integers(0, 65536, size=(1, 32, 32, 1)).astype(np.float32)
+    with get_model('fcn')('depth', _description(c), 'depth', num_units=NU,
+                          batch_normalization=False) as net:
+        before = net.predict({'depth': x}, output_attr='score')
+        net.import_weights(str(tmp_path / 'w.npz'))
+        after = net.predict({'depth': x}, output_attr='score')
+        np.testing.assert_array_equal(net.variables['depth/conv3_2/kernel'],
+                                      params['depth/conv3_2/kernel'])
+        assert not net.variables['depth/score/bias'].any()     # missing -> left at its init
+    out = capsys.readouterr().out
+    assert 'WARNING: depth/score/bias not found in saved weights' in out
+    assert not np.allclose(before, after)
+    p2 = dict(params)
+    p2['depth/score/bias'] = np.zeros(c, np.float32)
+    ref = oracle.fcn(x, p2, 'depth', NU, c)['score']
+    np.testing.assert_allclose(after, ref, rtol=0, atol=0.05 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize('prior', ['data', 'uniform'])
+def test_bayes_fusion_model(prior):
+    from xview.models import get_model
+    c, n, h, w = 6, 5, 32, 48
+    rng = np.random.default_rng(2)
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    cms = {m: rng.integers(0, 60, size=(c, c)).astype(np.float64) + 150 * np.eye(c)
+           for m in ('rgb', 'depth')}
+    with get_model('bayes_fusion')(
+            confusion_matrices=cms, data_description=_description(c),
+            prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn', num_units=NU,
+            num_channels={'rgb': 3, 'depth': 1}, batchsize=2, class_prior=prior) as net:
+        _load(net, params)
+        fused = net.predict({'rgb': data['rgb'], 'depth': data['depth']})
+        measures, cm = net.score(data)                      # 5 images in batches of 2: ragged
+        score = net.predict(data, output_attr='fused_score')
+        # one-image expert classifications of the last batch for the integer-parity check
+        last = {m: net.expert_outputs[m]['classification'].cpu().numpy() for m in net.modalities}
+    assert fused.shape == (n, h, w) and fused.dtype == np.int64
+    tables = [cms[m].astype('float32').T for m in ('rgb', 'depth')]
+    # fusion of the device's own expert labels: bit-exact vs the oracle's float32 rule
+    ref_score, _, _ = oracle.bayes_fusion([last['rgb'].astype(np.int64),
+                                           last['depth'].astype(np.int64)], tables, prior)
+    np.testing.assert_array_equal(score[-1:], ref_score.astype(np.float32))
+    np.testing.assert_array_equal(fused[-1:], oracle.argmax_first(ref_score))
+    np.testing.assert_array_equal(cm, oracle.confusion_matrix(data['labels'], fused, c))
+    # end to end vs the fp32 oracle experts: high agreement, mIoU close
+    cls = [oracle.test_pipeline(data[m], params, m, NU, c)['classification']
+           for m in ('rgb', 'depth')]
+    ref_fused = oracle.argmax_first(oracle.bayes_fusion(cls, tables, prior)[0])
+    assert (fused == ref_fused).mean() > 0.95
+    ref_m = oracle.score_measures(oracle.confusion_matrix(data['labels'], ref_fused, c))
+    assert abs(measures['mean_IoU'] - ref_m['mean_IoU']) < 1e-2
+
+
+def test_dirichlet_fusion_fit_and_predict():
+    from xview.models import get_model
+    c, n, h, w = 5, 4, 32, 48
+    rng = np.random.default_rng(3)
+    data = _data(rng, n, h, w, c)
+    data['labels'][data['labels'] == 3] = 1          # class 3 never occurs -> alpha column of ones
+    params = _trained_like(rng, c)
+    config = dict(data_description=_description(c), modalities=['rgb', 'depth'],
+                  expert_model='fcn', num_units=NU, num_channels={'rgb': 3, 'depth': 1},
+                  batchsize=2, sigma=0.8, delta=1e-2, beta=1e-2, class_prior='data')
+    with get_model('dirichlet_fusion')(**config) as net:
+        _load(net, params)
+        with pytest.raises(UserWarning):
+            net.predict(data)
+        fit = net.fit(data)
+        probs = {m: net._experts[m].forward(torch.from_numpy(data[m]).cuda(),
+                                            want=('prob',))['prob'].cpu().numpy()
+                 for m in ('rgb', 'depth')}
+        fused = net.predict(data)
+        score = net.predict(data, output_attr='fused_score')
+    # sufficient statistics + host fit reproduce the oracle given the device's probabilities
+    for m in ('rgb', 'depth'):
+        s_ref, n_ref = oracle.sufficient_statistics(probs[m], data['labels'], c)
+        alpha_ref = oracle.fit_sufficient_statistic(s_ref, n_ref, delta=1e-2, beta=1e-2)
+        np.testing.assert_array_equal(fit['class_counts'], n_ref)
+        np.testing.assert_allclose(fit[m], alpha_ref, rtol=2e-4)
+        np.testing.assert_array_equal(fit[m][:, 3], np.ones(c))
+    prior = oracle.dirichlet_prior(fit['class_counts'])
+    ref = oracle.dirichlet_fusion([probs['rgb'], probs['depth']], [fit['rgb'], fit['depth']],
+                                  prior, sigma=0.8, dtype=np.float64)
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(score, ref, rtol=0, atol=3e-5 * scale)
+    assert_labels_match(fused, ref, 6e-5 * scale)
+    # a second model constructed from the fitted parameters gives the same prediction
+    with get_model('dirichlet_mix')(dirichlet_params=fit, **config) as net2:
+        _load(net2, params)
+        np.testing.assert_array_equal(net2.predict(data), fused)
+
+
+def test_average_and_variance_fusion_models():
+    from xview.models import get_model
+    c, n, h, w = 5, 2, 32, 32
+    rng = np.random.default_rng(4)
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    common = dict(data_description=_description(c), prefixes={'rgb': 'rgb', 'depth': 'depth'},
+                  expert_model='fcn', num_units=NU, num_channels={'rgb': 3, 'depth': 1},
+                  batchsize=2)
+    with get_model('average_fusion')(**common) as net:
+        _load(net, params)
+        fused = net.predict(data)
+        probs = [net.expert_outputs[m]['prob'].cpu().numpy() for m in net.modalities]
+    assert_labels_match(fused, oracle.average_fusion(probs), 1e-6)
+    with get_model('variance_fusion')(modalities=['rgb', 'depth'], dropout_rate=0.3,
+                                      num_samples=6, **common) as net:
+        _load(net, params)
+        fused = net.predict(data)
+        score = net.predict(data, output_attr='fused_score')
+    assert fused.shape == (n, h, w)
+    np.testing.assert_allclose(score.sum(-1), 1.0, atol=1e-4)   # convex mix of probabilities
+    np.testing.assert_array_equal(fused, np.argmax(score, -1))

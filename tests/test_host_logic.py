@@ -1,0 +1,169 @@
+"""CPU tests of the host-side logic of the B200 package: C-ABI export list, variable layout,
+npz name matching, Bayes/Dirichlet table construction, the float64 Dirichlet fit, measures."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, ROOT
+
+
+@pytest.fixture(scope='module')
+def built_lib():
+    import __graft_entry__
+    __graft_entry__.build()
+    from modular_semantic_segmentation_b200 import _abi
+    return _abi.load()
+
+
+def test_library_exports_every_symbol_of_the_header(built_lib):
+    header = open(os.path.join(ROOT, 'include', 'xview_b200.h')).read()
+    declared = set(re.findall(r'^(?:int|const char\*)\s+(xv_[a-z0-9_]+)\s*\(', header, re.M))
+    assert len(declared) >= 28
+    from modular_semantic_segmentation_b200 import _abi
+    assert declared == set(_abi.PROTOTYPES), declared ^ set(_abi.PROTOTYPES)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert built_lib.xv_abi_version() == 1
+
+
+def test_product_fails_loudly_without_a_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from modular_semantic_segmentation_b200 import _abi, device
+    with pytest.raises(_abi.XViewError):
+        device.init()
+    n = ctypes.c_int()
+    assert built_lib.xv_device_sm_count(ctypes.byref(n)) != 0
+    assert built_lib.xv_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'modular_semantic_segmentation_b200')
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(base, f)).read()
+                assert not re.search(r'^\s*(import|from)\s+oracle', src, re.M), f
+
+
+def test_variable_layout_matches_reference_key_list():
+    from modular_semantic_segmentation_b200.models.simple_fcn import init_fcn_variables
+    keys = json.load(open(os.path.join(GOLDEN, 'fcn_weight_keys.json')))
+    for prefix, cin in (('rgb', 3), ('depth', 1)):
+        v = init_fcn_variables(prefix, cin, 64, 12, rng=np.random.default_rng(0))
+        assert list(v) == keys[prefix]
+        shapes = oracle.fcn_param_shapes(prefix, cin, 64, 12)
+        assert {k: a.shape for k, a in v.items()} == shapes
+        np.testing.assert_array_equal(v[prefix + '/upscore/kernel'],
+                                      oracle.bilinear_filter((16, 16, 64, 64)))
+        assert not v[prefix + '/conv3_2/bias'].any()
+    bn = init_fcn_variables('rgb', 3, 8, 5, batchnorm=True, rng=np.random.default_rng(0))
+    assert 'rgb/conv1_1/moving_variance' in bn and 'rgb/upscore/gamma' in bn
+
+
+def test_match_weights_follows_reference_rules():
+    from modular_semantic_segmentation_b200.models.base_model import match_weights
+    variables = {'rgb/conv1_1/kernel': np.zeros((3, 3, 3, 64), np.float32),
+                 'rgb/conv1_1/bias': np.zeros(64, np.float32),
+                 'rgb/conv1_2/kernel': np.zeros((3, 3, 64, 64), np.float32),
+                 'rgb/score/kernel': np.zeros((1, 1, 64, 12), np.float32),
+                 'rgb/conv1_1/kernel/Adam': np.zeros((3, 3, 3, 64), np.float32)}
+    stored = {'rgb/conv1_1/kernel': np.ones((3, 3, 3, 64)),            # exact name
+              'rgb_conv1_1/bias': np.full(64, 2.0),                     # legacy first '/' -> '_'
+              'rgb/conv1_2/kernel': np.ones((3, 3, 32, 64)),            # wrong shape -> skipped
+              'rgb/conv1_1/kernel/Adam': np.full((3, 3, 3, 64), 9.0),   # optimizer slot
+              'global_step': np.asarray(7)}
+    assigned, messages = match_weights(variables, stored)
+    assert set(assigned) == {'rgb/conv1_1/kernel', 'rgb/conv1_1/bias'}
+    assert assigned['rgb/conv1_1/bias'].dtype == np.float32 and assigned['rgb/conv1_1/bias'][0] == 2
+    text = '\n'.join(messages)
+    assert 'WARNING: wrong shape found for rgb/conv1_2/kernel' in text
+    assert 'WARNING: rgb/score/kernel not found in saved weights' in text
+    assert 'Adam' not in text
+    # translate_prefix: variables of prefix 'depth' are filled from an 'rgb' file
+    variables_d = {'depth/conv1_1/bias': np.zeros(64, np.float32)}
+    assigned, _ = match_weights(variables_d, {'rgb/conv1_1/bias': np.full(64, 3.0)},
+                                translate_prefix='depth')
+    assert assigned['depth/conv1_1/bias'][0] == 3
+
+
+def test_bayes_decision_table_reproduces_literal_rule(exp868):
+    from modular_semantic_segmentation_b200.models.bayes_mix import (bayes_decision_matrix,
+                                                                     bayes_decision_table,
+                                                                     bayes_tables)
+    cms = [exp868['cm_measure_rgb'].astype('float32').T,
+           exp868['cm_measure_depth'].astype('float32').T]
+    c = 12
+    a, b = np.meshgrid(np.arange(c), np.arange(c), indexing='ij')
+    for prior in ('data', 'uniform', 0.5):
+        table = bayes_decision_table(cms, prior)
+        ref = oracle.argmax_first(oracle.bayes_fusion([a, b], cms, prior)[0])
+        np.testing.assert_array_equal(table, ref)
+        log_cond, log_prior = bayes_tables(cms, prior)
+        assert log_cond.dtype == np.float32 and log_cond.shape == (2, c, c)
+    cms64 = [exp868['cm_measure_rgb'].T, exp868['cm_measure_depth'].T]
+    np.testing.assert_array_equal(bayes_decision_matrix(cms64),
+                                  oracle.bayes_decision_matrix(cms64))
+
+
+def test_dirichlet_tables_match_oracle_terms():
+    from modular_semantic_segmentation_b200.models.dirichlet_mix import (class_prior_from_counts,
+                                                                         dirichlet_tables)
+    rng = np.random.default_rng(0)
+    c = 12
+    params = [1 + rng.gamma(2, 2, size=(c, c)) for _ in range(2)]
+    counts = rng.integers(0, 100, size=c)
+    prior = class_prior_from_counts(counts, 'data')
+    np.testing.assert_array_equal(prior, oracle.dirichlet_prior(counts))
+    am1, lognorm, logprior = dirichlet_tables(params, 0.5, prior)
+    assert am1.shape == (2, c, c) and lognorm.shape == (2, c) and logprior.shape == (c,)
+    alpha = 0.5 * params[1].astype(np.float32).astype(np.float64)
+    np.testing.assert_allclose(lognorm[1], oracle.dirichlet_log_norm(alpha), rtol=1e-6)
+    # a pixel evaluated by hand equals the oracle score
+    p = rng.dirichlet(np.ones(c), size=2).astype(np.float32)
+    ref = oracle.dirichlet_fusion([p[0][None, None, None], p[1][None, None, None]], params, prior,
+                                  sigma=0.5, dtype=np.float64)[0, 0, 0]
+    mine = sum(np.log(1e-20 + (p[m] / p[m].sum()).astype(np.float64)) @ am1[m].astype(np.float64)
+               - lognorm[m] for m in range(2)) + logprior
+    np.testing.assert_allclose(mine, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_host_dirichlet_fit_matches_reference_outputs(dirichlet_golden):
+    from modular_semantic_segmentation_b200.models.dirichletDifferentiation import \
+        findDirichletPriors
+    g = dirichlet_golden
+    for i in g['fit_cases']:
+        delta, beta = g['fit%d_delta_beta' % i]
+        c = len(g['fit%d_ss' % i])
+        alpha = findDirichletPriors(g['fit%d_ss' % i], g['fit%d_neg_ss' % i], np.ones(c),
+                                    max_iter=10000, delta=delta, beta=beta)
+        np.testing.assert_allclose(np.asarray(alpha, np.float64), g['fit%d_alpha' % i],
+                                   rtol=1e-9)
+
+
+def test_measures_match_stored_run(exp868):
+    from modular_semantic_segmentation_b200.models.base_model import \
+        measures_from_confusion_matrix
+    m = measures_from_confusion_matrix(exp868['cm_test_fusion'])
+    assert m['mean_IoU'] == 0.6877204624612501
+    assert m['total_accuracy'] == 0.920302592013555
+    assert set(m) == {'confusion_matrix', 'recall', 'precision', 'F1', 'mean_F1',
+                      'total_accuracy', 'IoU', 'mean_IoU'}
+
+
+def test_get_model_names():
+    from xview.models import get_model
+    import xview.models.bayes_mix as bm
+    assert get_model('fcn').__name__ == 'SimpleFCN'
+    assert get_model('bayes_fusion') is get_model('bayes_mix') is bm.BayesFusion
+    assert get_model('dirichlet_mix').__name__ == 'DirichletFusion'
+    assert get_model('average_fusion').__name__ == 'AverageFusion'
+    assert get_model('variance_mix').__name__ == 'VarianceFusion'
+    with pytest.raises(UserWarning):
+        get_model('nope')

@@ -1,0 +1,55 @@
+"""world_size-2 gloo test (CPU) of the image sharding + confusion-matrix all-reduce +
+prediction gather used by score()/predict() when one process drives each GPU."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+import oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from modular_semantic_segmentation_b200 import sharding
+    rng = np.random.default_rng(0)                 # same data on every rank
+    c, n_img = 5, 7                                 # uneven split: 4 + 3 images
+    labels = rng.integers(-1, c, size=(n_img, 6, 8))
+    pred = rng.integers(0, c, size=(n_img, 6, 8))
+    r, w = sharding.rank_world()
+    assert (r, w) == (rank, world)
+    mine = []
+    for start in range(0, n_img, 3):                # batches of 3 images
+        count = min(3, n_img - start)
+        mine += [start + i for i in sharding.rows_for_rank(start, count, rank, world)]
+    assert mine == list(range(rank, n_img, world))
+    cm = torch.from_numpy(oracle.confusion_matrix(labels[mine], pred[mine], c))
+    sharding.allreduce_sum_(cm)
+    gathered = sharding.gather_interleaved(torch.from_numpy(pred[mine]), 'cpu')
+    np.save(os.path.join(out_dir, 'cm%d.npy' % rank), cm.numpy())
+    np.save(os.path.join(out_dir, 'pred%d.npy' % rank), gathered.numpy())
+    np.save(os.path.join(out_dir, 'ref_cm.npy'), oracle.confusion_matrix(labels, pred, c))
+    np.save(os.path.join(out_dir, 'ref_pred.npy'), pred)
+    dist.destroy_process_group()
+
+
+def test_two_rank_score_and_predict_plumbing(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ref_cm = np.load(tmp_path / 'ref_cm.npy')
+    ref_pred = np.load(tmp_path / 'ref_pred.npy')
+    for rank in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / ('cm%d.npy' % rank)), ref_cm)
+        np.testing.assert_array_equal(np.load(tmp_path / ('pred%d.npy' % rank)), ref_pred)
