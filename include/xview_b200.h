@@ -41,6 +41,10 @@ int xv_init(int device);
 int xv_device_sm_count(int* out);
 
 /* ---- measurement hooks (no reference counterpart; used by bench.py) ------------------ */
+/* Debug switches for parity tests: bit0 = never fuse max pooling into the conv epilogue,
+ * bit1 = never use the transposed-role conv kernel, bit2 = conv1_1 through a materialised
+ * operand buffer instead of in-kernel packing.  0 = production behaviour. */
+int xv_set_debug_flags(int flags);
 /* Number of kernels this library has launched since it was loaded. */
 int xv_launch_count(int64_t* out);
 /* on != 0: bracket every tensor-core convolution launch with CUDA events on its stream;
@@ -48,6 +52,11 @@ int xv_launch_count(int64_t* out);
 int xv_profile_enable(int on);
 /* Sum over the collected samples: device milliseconds, algorithmic FLOPs (2*MACs), launches. */
 int xv_profile_read(double* ms_out, double* flops_out, int64_t* launches_out);
+
+/* Times `iters` launches of one tensor-core convolution layer on synthetic bf16 data
+ * (kernel study only; `flags` selects timing experiments, 0 = the production kernel). */
+int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters, int flags,
+                        float* ms_out);
 
 /* ---- plain memory / stream helpers (session feed/fetch, base_model.py:263-313) ----- */
 int xv_malloc(void** out, size_t bytes);

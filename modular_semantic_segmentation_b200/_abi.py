@@ -49,9 +49,11 @@ PROTOTYPES = {
     'xv_last_error': [],
     'xv_init': [_I],
     'xv_device_sm_count': [C.POINTER(_I)],
+    'xv_set_debug_flags': [_I],
     'xv_launch_count': [C.POINTER(_L)],
     'xv_profile_enable': [_I],
     'xv_profile_read': [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L)],
+    'xv_bench_conv_igemm': [_I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_float)],
     'xv_malloc': [_PP, _Z],
     'xv_free': [_P],
     'xv_malloc_host': [_PP, _Z],

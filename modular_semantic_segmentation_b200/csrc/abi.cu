@@ -35,6 +35,8 @@ struct IgemmSample {
 static bool g_profile = false;
 static std::vector<IgemmSample> g_samples;
 
+static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer
+
 static DeviceInfo g_dev;
 const DeviceInfo& device_info() { return g_dev; }
 
@@ -80,6 +82,12 @@ static int make_tmap_act(CUtensorMap* m, const void* ptr, int N, int H, int W, i
   XV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string(r));
   return 0;
 }
+
+static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n);
+
+// in: bf16 [B,H,W,cin]; out: bf16 [B,H,W,cout] or, with pool, [B,H/2,W/2,cout]
+static int run_igemm_t(const struct ConvLayer& L, const void* in, int B, int H, int W, void* out,
+                       bool pool, cudaStream_t s);
 
 static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n) {
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(cout_pad)};
@@ -156,6 +164,7 @@ struct ConvLayer {
   int k = 3, cin = 0, cout = 0, relu = 1;
   // bf16 path
   int taps = 9, kdim = 0, cin_gemm = 0, cout_pad = 0, block_n = 0;
+  bool use_t = false;   // few output channels: transposed-role kernel (conv_igemm_t_sm100.cu)
   DevBuf w_packed, bias_pad;
   // fp32 path
   DevBuf w_f32, bias_f32, bn_scale, bn_shift;
@@ -265,6 +274,8 @@ static int pack_conv(xv_fcn* net, ConvLayer* L, const float* w_hwio, const float
   L->kdim = L->taps * L->cin_gemm;
   L->block_n = conv_igemm_block_n(cout);
   L->cout_pad = div_up(cout, L->block_n) * L->block_n;
+  L->use_t = (k == 3 && !special_c1 && cout <= 128 && cout % 64 == 0);
+  if (L->use_t) L->cout_pad = div_up(cout, 128) * 128;   // weight rows padded to the M block
   std::vector<uint16_t> wp(static_cast<size_t>(L->cout_pad) * L->kdim, 0);
   std::vector<float> bp(L->cout_pad, 0.f);
   for (int co = 0; co < cout; ++co) {
@@ -304,6 +315,7 @@ static int get_tmap(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H
 // in: bf16 [B,H,W,cin_gemm]; out: bf16 [B,H,W,cout] (cout % 64 == 0) or fp32 [B,H,W,cout]
 static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
                      void* out, bool out_f32, cudaStream_t s) {
+  if (L.use_t && !out_f32 && !(g_debug_flags & 2)) return run_igemm_t(L, in, B, H, W, out, false, s);
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
@@ -335,6 +347,74 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   smp.block_n = L.block_n;
   XV_CUDA(cudaEventRecord(smp.e0, s));
   const int rc = launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+  XV_CUDA(cudaEventRecord(smp.e1, s));
+  g_samples.push_back(smp);
+  return rc;
+}
+
+static int run_igemm_t(const ConvLayer& L, const void* in, int B, int H, int W, void* out,
+                       bool pool, cudaStream_t s) {
+  ConvIgemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.th = p.tw = 16;
+  XV_TRY(make_tmap_act(&p.tmap_in, in, B, H, W, L.cin_gemm, 16, 16));
+  XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
+  if (pool) {
+    XV_TRY(make_tmap_act(&p.tmap_out, out, B, H / 2, W / 2, L.cout, 8, 8));
+  } else {
+    XV_TRY(make_tmap_act(&p.tmap_out, out, B, H, W, L.cout, 8, 16));
+  }
+  p.bias = static_cast<const float*>(L.bias_pad.p);
+  p.N = B;
+  p.H = H;
+  p.W = W;
+  p.cin = L.cin_gemm;
+  p.cout = L.cout;
+  p.tiles_x = div_up(W, 16);
+  p.tiles_y = div_up(H, 16);
+  p.n_blocks = L.cout_pad / 128;
+  p.relu = L.relu;
+  if (!g_profile) return launch_conv_igemm_t(p, pool, s);
+  IgemmSample smp;
+  XV_CUDA(cudaEventCreate(&smp.e0));
+  XV_CUDA(cudaEventCreate(&smp.e1));
+  smp.flops = 2.0 * B * H * W * static_cast<double>(L.cout) * L.k * L.k * L.cin;
+  smp.block_n = 0;
+  XV_CUDA(cudaEventRecord(smp.e0, s));
+  const int rc = launch_conv_igemm_t(p, pool, s);
+  XV_CUDA(cudaEventRecord(smp.e1, s));
+  g_samples.push_back(smp);
+  return rc;
+}
+
+// conv1_1 on the raw fp32 input: operand rows are packed inside the kernel
+static int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, int H, int W,
+                        void* out, cudaStream_t s) {
+  ConvIgemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  choose_tile(H, W, &p.th, &p.tw);
+  XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
+  XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, p.th, p.tw));
+  p.tmap_in = p.tmap_out;            // unused in this mode, kept valid for the descriptor prefetch
+  p.bias = static_cast<const float*>(L.bias_pad.p);
+  p.x_raw = x;
+  p.N = B;
+  p.H = H;
+  p.W = W;
+  p.cin = 64;
+  p.cout = L.cout;
+  p.tiles_x = div_up(W, p.tw);
+  p.tiles_y = div_up(H, p.th);
+  p.n_blocks = 1;
+  p.relu = L.relu;
+  if (!g_profile) return launch_conv_igemm_c1(p, L.cin, s);
+  IgemmSample smp;
+  XV_CUDA(cudaEventCreate(&smp.e0));
+  XV_CUDA(cudaEventCreate(&smp.e1));
+  smp.flops = 2.0 * B * H * W * static_cast<double>(L.cout) * L.k * L.k * L.cin;
+  smp.block_n = 64;
+  XV_CUDA(cudaEventRecord(smp.e0, s));
+  const int rc = launch_conv_igemm_c1(p, L.cin, s);
   XV_CUDA(cudaEventRecord(smp.e1, s));
   g_samples.push_back(smp);
   return rc;
@@ -387,6 +467,21 @@ struct Forward {
     return 0;
   }
 
+  // conv followed by the 2x2 max pool of simple_fcn.py:41,44,48 - fused into the conv epilogue
+  // where the transposed kernel applies (the unpooled activation is then never materialised)
+  int conv_pool(const std::string& name, const std::string& pool_name, const Act& in, Act* out) {
+    ConvLayer* L = net->conv(name);
+    XV_CHECK(L != nullptr, "unknown conv layer " + name);
+    if (bf16() && L->use_t && !(g_debug_flags & 3)) {
+      *out = make(pool_name, DType::BF16, in.B, in.H / 2, in.W / 2, L->cout);
+      if (dry) return 0;
+      return run_igemm_t(*L, in.p, in.B, in.H, in.W, out->p, true, s);
+    }
+    Act full;
+    XV_TRY(conv(name, in, &full));
+    return pool(pool_name, full, out);
+  }
+
   int pool(const std::string& name, const Act& in, Act* out) {
     *out = make(name, in.dt, in.B, in.H / 2, in.W / 2, in.C);
     if (dry) return 0;
@@ -425,12 +520,17 @@ struct Forward {
 int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
   const uint32_t sites = drop ? drop->sites : 0u;
   const bool mc = T > 1;
-  Act cur;
-  if (bf16()) {
+  Act cur, t;
+  if (bf16() && !(g_debug_flags & 4)) {
+    // conv1_1 straight from the raw fp32 input (operand packing fused into the GEMM producer)
+    ConvLayer* L = net->conv("conv1_1");
+    t = make("conv1_1", DType::BF16, N, H, W, L->cout);
+    if (!dry) XV_TRY(run_igemm_c1(net, *L, x, N, H, W, t.p, s));
+  } else if (bf16()) {
     Act a0 = make("conv1_1_operand", DType::BF16, N, H, W, 64);
     if (!dry)
       XV_TRY(launch_im2col_c1(x, static_cast<__nv_bfloat16*>(a0.p), N, H, W, net->cin, s));
-    cur = a0;
+    XV_TRY(conv("conv1_1", a0, &t));
   } else {
     cur.p = const_cast<float*>(x);
     cur.dt = DType::F32;
@@ -438,14 +538,13 @@ int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
     cur.H = H;
     cur.W = W;
     cur.C = net->cin;
+    XV_TRY(conv("conv1_1", cur, &t));
   }
-  Act t;
-  XV_TRY(conv("conv1_1", cur, &t));
-  XV_TRY(conv("conv1_2", t, &cur));
-  XV_TRY(pool("pool1", cur, &t));
+  XV_TRY(conv_pool("conv1_2", "pool1", t, &cur));
+  t = cur;
   XV_TRY(conv("conv2_1", t, &cur));
-  XV_TRY(conv("conv2_2", cur, &t));
-  XV_TRY(pool("pool2", t, &cur));
+  XV_TRY(conv_pool("conv2_2", "pool2", cur, &t));
+  cur = t;
   XV_TRY(conv("conv3_1", cur, &t));
   XV_TRY(conv("conv3_2", t, &cur));
   XV_TRY(conv("conv3_3", cur, &t));
@@ -622,6 +721,10 @@ int xv_device_sm_count(int* out) {
   return 0;
 }
 
+int xv_set_debug_flags(int flags) {
+  g_debug_flags = flags;
+  return 0;
+}
 int xv_launch_count(int64_t* out) {
   *out = g_launches;
   return 0;
@@ -911,6 +1014,14 @@ int xv_conv2d(const float* x, const float* w_host, const float* bias_host, int n
   }
   DevBuf in_bf16;
   XV_TRY(in_bf16.ensure(npix * L.cin_gemm * 2));
+  if (L.taps == 1 && k == 3 && cout == 64 && !(g_debug_flags & 4)) {
+    DevBuf out_bf16;
+    XV_TRY(out_bf16.ensure(npix * cout * 2));
+    XV_TRY(run_igemm_c1(nullptr, L, x, n, h, w, out_bf16.p, s));
+    XV_TRY(launch_bf16_to_f32(static_cast<const __nv_bfloat16*>(out_bf16.p), out, npix * cout, s));
+    XV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
   if (L.taps == 1 && k == 3) {
     XV_TRY(launch_im2col_c1(x, static_cast<__nv_bfloat16*>(in_bf16.p), n, h, w, cin, s));
   } else {
@@ -946,6 +1057,60 @@ int xv_deconv2d(const float* x, const float* w_host, int n, int h, int w, int ci
 int xv_maxpool2x2(const float* x, int n, int h, int w, int c, float* out, void* stream) {
   XV_TRY(ensure_init());
   return launch_maxpool_f32(x, out, n, h, w, c, XV_STREAM(stream));
+}
+
+// Timing harness for one tensor-core conv layer on synthetic bf16 data (not a reference
+// entry point; used by tools/conv_bench.py to study the kernel in isolation).
+int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters, int flags,
+                        float* ms_out) {
+  XV_TRY(ensure_init());
+  xv_fcn fake;
+  fake.precision = XV_PRECISION_BF16;
+  ConvLayer L;
+  L.name = "bench";
+  L.k = k;
+  L.cin = cin;
+  L.cout = cout;
+  L.relu = 1;
+  std::vector<float> wv(static_cast<size_t>(k) * k * cin * cout), bv(cout, 0.1f);
+  for (size_t i = 0; i < wv.size(); ++i) wv[i] = 0.01f * static_cast<float>((i * 2654435761u) % 17) - 0.08f;
+  std::vector<float> scale(cout, 1.f), shift(cout, 0.f);
+  XV_TRY(pack_conv(&fake, &L, wv.data(), bv.data(), scale, shift, false));
+  const size_t npix = static_cast<size_t>(n) * h * w;
+  DevBuf in, out;
+  XV_TRY(in.ensure(npix * cin * 2));
+  XV_TRY(out.ensure(npix * cout * 2));
+  XV_CUDA(cudaMemset(in.p, 0x3c, npix * cin * 2));
+  ConvIgemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  choose_tile(h, w, &p.th, &p.tw);
+  XV_TRY(make_tmap_act(&p.tmap_in, in.p, n, h, w, cin, p.th, p.tw));
+  XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
+  XV_TRY(make_tmap_act(&p.tmap_out, out.p, n, h, w, cout, p.th, p.tw));
+  p.bias = static_cast<const float*>(L.bias_pad.p);
+  p.N = n; p.H = h; p.W = w; p.cin = cin; p.cout = cout;
+  p.tiles_x = div_up(w, p.tw); p.tiles_y = div_up(h, p.th);
+  p.n_blocks = L.cout_pad / L.block_n; p.relu = 1; p.debug_flags = flags;
+  cudaEvent_t e0, e1;
+  XV_CUDA(cudaEventCreate(&e0));
+  XV_CUDA(cudaEventCreate(&e1));
+  const bool use_t = (flags & 512) != 0 && L.use_t;
+  const bool t_pool = (flags & 1024) != 0;
+  auto once = [&]() -> int {
+    if (use_t) return run_igemm_t(L, in.p, n, h, w, out.p, t_pool, 0);
+    return launch_conv_igemm(p, L.block_n, L.taps, false, 0);
+  };
+  XV_TRY(once());
+  XV_CUDA(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) XV_TRY(once());
+  XV_CUDA(cudaEventRecord(e1, 0));
+  XV_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  XV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
 }
 
 // ------------------------------------------------------------------ fusion stage

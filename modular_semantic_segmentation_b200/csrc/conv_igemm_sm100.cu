@@ -32,6 +32,7 @@ constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kOutBufBytes = kBlockM * 128;      // one 64-channel bf16 output chunk
 constexpr int kThreads = 192;
+constexpr int kPrefetchTiles = 2;               // L2 prefetch distance in tiles per CTA
 
 template <int BLOCK_N>
 struct IgemmCfg {
@@ -63,8 +64,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvIgemmParams& p, int t
   return c;
 }
 
-template <int BLOCK_N, int TAPS, bool OUT_F32>
-__global__ void __launch_bounds__(kThreads, 1)
+// C1 > 0: conv1_1 mode with C1 raw input channels - warps 6..9 build the A operand rows from the
+// fp32 input (3x3 neighbourhood split into hi + lo bf16 halves, see layers.cu), TMA loads only
+// the 8 KB weight tile.
+template <int BLOCK_N, int TAPS, bool OUT_F32, int C1 = 0>
+__global__ void __launch_bounds__(C1 > 0 ? kThreads + 128 : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
@@ -93,7 +97,7 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
     tma_prefetch_desc(&p.tmap_w);
     if (!OUT_F32) tma_prefetch_desc(&p.tmap_out);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], C1 > 0 ? 129 : 1);   // + 128 operand-packing threads
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -108,42 +112,76 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run their loops warp-uniformly and elect one lane only around the
+  // issue instructions: TMA / tcgen05 operands live in uniform registers, and a loop nested
+  // inside a divergent `lane == 0` branch makes the compiler wrap every UTMALDG / UTCHMMA in
+  // a waterfall loop (measured: ~145 cycles per MMA instead of the 32..128 cycle floor).
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile(p, tile, BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / cin_chunks;
-          const int cc = kb - tap * cin_chunks;
-          const int dy = (TAPS == 9) ? tap / 3 - 1 : 0;
-          const int dx = (TAPS == 9) ? tap % 3 - 1 : 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(smem_a + stage * kABytes, &p.tmap_in, &full_bar[stage], cc * kBlockK,
-                      c.x0 + dx, c.y0 + dy, c.img);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmap_w, &full_bar[stage],
-                      tap * p.cin + cc * kBlockK, c.n0);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (p.debug_flags & 256) break;       // experiment: MMA warp free-runs, no smem pipeline
+      const TileCoord c = decode_tile(p, tile, BLOCK_N);
+      if (p.debug_flags & 128) {            // experiment: L2 prefetch of a later tile
+        const int ahead = tile + kPrefetchTiles * static_cast<int>(gridDim.x);
+        if (ahead < total_tiles && elect_one_sync()) {
+          const TileCoord f = decode_tile(p, ahead, BLOCK_N);
+          for (int cc = 0; cc < cin_chunks; ++cc)
+            tma_prefetch_l2_4d(&p.tmap_in, cc * kBlockK, f.x0, f.y0, f.img);
+        }
+        __syncwarp();
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / cin_chunks;
+        const int cc = kb - tap * cin_chunks;
+        const int dy = (TAPS == 9) ? tap / 3 - 1 : 0;
+        const int dx = (TAPS == 9) ? tap % 3 - 1 : 0;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (C1 > 0) {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmap_w, &full_bar[stage], 0, c.n0);
           }
+        } else if (elect_one_sync()) {
+          if (p.debug_flags & 64) {         // experiment: no TMA traffic at all
+            mbar_arrive(&full_bar[stage]);
+          } else if (p.debug_flags & 1) {          // experiment: no weight traffic
+            mbar_arrive_expect_tx(&full_bar[stage], kABytes);
+            tma_load_4d(smem_a + stage * kABytes, &p.tmap_in, &full_bar[stage], cc * kBlockK,
+                        c.x0 + dx, c.y0 + dy, c.img);
+          } else if (p.debug_flags & 2) {   // experiment: no activation traffic
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmap_w, &full_bar[stage],
+                        tap * p.cin + cc * kBlockK, c.n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(smem_a + stage * kABytes, &p.tmap_in, &full_bar[stage], cc * kBlockK,
+                        c.x0 + dx, c.y0 + dy, c.img);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmap_w, &full_bar[stage],
+                        tap * p.cin + cc * kBlockK, c.n0);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (!(p.debug_flags & 256)) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+        }
+        if (elect_one_sync()) {
           const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
@@ -152,15 +190,67 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
                       umma_desc_sw128(b_addr + k * 32, 1024, 0), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem stage when the MMAs retire
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (!(p.debug_flags & 256)) umma_commit(&empty_bar[stage]);   // frees the smem stage
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);   // accumulator complete
         }
-        umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (C1 > 0 && warp >= 6) {
+    // ------------------------------------------------------------- conv1_1 operand packing
+    constexpr int CIN = C1 > 0 ? C1 : 1;
+    constexpr int K9 = 9 * CIN;
+    const int row = threadIdx.x - kThreads;     // pixel index inside the tile
+    const int py = row / p.tw;
+    const int px = row - py * p.tw;
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile(p, tile, BLOCK_N);
+      const int y = c.y0 + py, x = c.x0 + px;
+      float hi[K9], lo[K9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        const bool in = y < p.H && x < p.W && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        const float* src =
+            p.x_raw + ((static_cast<size_t>(c.img) * p.H + (in ? yy : 0)) * p.W + (in ? xx : 0)) * CIN;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float raw = in ? __ldg(src + ci) : 0.f;
+          const float h = __bfloat162float(__float2bfloat16_rn(raw));
+          hi[tap * CIN + ci] = h;
+          lo[tap * CIN + ci] = raw - h;
+        }
+      }
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* dst = smem_a + stage * kABytes + row * 128;
+#pragma unroll
+      for (int piece = 0; piece < 8; ++piece) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = piece * 8 + e2 * 2 + h;   // compile-time after unrolling
+            v[h] = k < K9 ? hi[k < K9 ? k : 0] : (k < 2 * K9 ? lo[k < 2 * K9 ? k - K9 : 0] : 0.f);
+          }
+          packed[e2] = pack_bf16x2(v[0], v[1]);
+        }
+        *reinterpret_cast<uint4*>(dst + ((piece ^ (row & 7)) << 4)) =
+            make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
+      fence_proxy_async_smem();                 // generic-proxy writes -> visible to the MMA
+      mbar_arrive(&full_bar[stage]);
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else {
@@ -178,6 +268,7 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++gchunk) {
+        if (p.debug_flags & 8) continue;   // experiment: no epilogue work at all
         if constexpr (!OUT_F32) {
           uint8_t* buf = smem_out + (gchunk & 1) * kOutBufBytes;
           if (issuer) tma_store_wait_read<1>();   // the store that last used `buf` has drained
@@ -209,7 +300,7 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
           }
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
-          if (issuer) {
+          if (issuer && !(p.debug_flags & 4)) {
             tma_store_4d(&p.tmap_out, buf, c.n0 + chunk * 64, c.x0, c.y0, c.img);
             tma_store_commit();
           }
@@ -270,6 +361,36 @@ int launch_one(const ConvIgemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
+template <int C1>
+int launch_c1(const ConvIgemmParams& p, cudaStream_t stream) {
+  using Cfg = IgemmCfg<64>;
+  auto kernel = conv_igemm_kernel<64, 1, false, C1>;
+  static bool configured = false;
+  if (!configured) {
+    XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_blocks;
+  const int grid = total_tiles < device_info().num_sms ? total_tiles : device_info().num_sms;
+  kernel<<<grid, kThreads + 128, Cfg::kSmemBytes, stream>>>(p);
+  XV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+int launch_conv_igemm_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t stream) {
+  XV_CHECK(p.th * p.tw == kBlockM, "conv_igemm_c1: tile must hold 128 pixels");
+  XV_CHECK(p.cout == 64 && p.n_blocks == 1, "conv_igemm_c1: conv1_1 has 64 output channels");
+  if (cin_raw == 1) return launch_c1<1>(p, stream);
+  if (cin_raw == 2) return launch_c1<2>(p, stream);
+  if (cin_raw == 3) return launch_c1<3>(p, stream);
+  return fail("conv_igemm_c1: Cin must be 1, 2 or 3");
+}
+
+namespace {
 }  // namespace
 
 int conv_igemm_block_n(int cout) { return cout > 128 ? 256 : (cout > 64 ? 128 : 64); }

@@ -21,10 +21,19 @@ struct ConvIgemmParams {
   int tiles_x, tiles_y;
   int n_blocks;           // CoutPad / BLOCK_N
   int relu;
+  int debug_flags;        // timing experiments only (xv_bench_conv_igemm); 0 in production
+  const float* x_raw;     // conv1_1 mode: raw fp32 input [N,H,W,cin_raw] (operand packed on the fly)
 };
 int conv_igemm_block_n(int cout);
 int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,
                       cudaStream_t stream);
+// conv1_1: 3x3 conv of the raw fp32 input (cin_raw <= 3) as a K=64 GEMM whose A rows
+// [hi taps | lo taps | 0] are built in shared memory by producer warps (no im2col buffer).
+int launch_conv_igemm_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t stream);
+
+// conv_igemm_t_sm100.cu: 3x3, Cout <= 128 per block of 128, 16x16 pixel tiles, optional fused
+// 2x2 max pool (then tmap_out describes the pooled tensor, box {64,8,8,1}; else {64,16,8,1}).
+int launch_conv_igemm_t(const ConvIgemmParams& p, bool pool, cudaStream_t stream);
 
 // ------------------------------------------------------------- layers.cu
 int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, int cin,

@@ -330,6 +330,11 @@ def confusion_accumulate(pred, labels, cm):
 
 
 # --------------------------------------------------------------------------- measurement
+def set_debug_flags(flags):
+    """bit0: never fuse pooling, bit1: never use the transposed conv kernel (tests only)."""
+    call('xv_set_debug_flags', int(flags))
+
+
 def launch_count():
     n = C.c_int64()
     call('xv_launch_count', C.byref(n))

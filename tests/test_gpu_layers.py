@@ -26,6 +26,8 @@ def _conv_case(rng, n, h, w, cin, cout, k, in_scale=1.0):
 BF16_CASES = [
     # n, h, w, cin, cout, k
     (1, 16, 8, 64, 64, 3),        # exactly one 128-pixel tile
+    (1, 16, 16, 64, 64, 3),       # exactly one 256-pixel tile of the transposed-role kernel
+    (2, 40, 24, 128, 128, 3),     # transposed-role kernel, ragged 16x16 tiles, 2 K chunks
     (2, 32, 48, 64, 64, 3),       # conv1_2-like
     (1, 24, 40, 64, 128, 3),      # ragged tiles in both directions
     (1, 16, 24, 128, 256, 3),     # BLOCK_N = 256
@@ -48,6 +50,12 @@ def test_conv2d_tcgen05_matches_oracle(dev, n, h, w, cin, cout, k, relu):
     # identical bf16 operands, fp32 accumulation; the bf16 epilogue rounds the result once
     tol = (2.0 ** -8 if cout % 64 == 0 else 1e-5) * scale
     np.testing.assert_allclose(got, ref, rtol=0, atol=tol)
+    if cout <= 128 and cout % 64 == 0 and k == 3:
+        # same layer through the pixel-major kernel (debug bit1) must agree to bf16 rounding
+        dev.set_debug_flags(2)
+        alt = dev.conv2d(cuda(xb), kb, bias, relu=relu, precision='bf16').cpu().numpy()
+        dev.set_debug_flags(0)
+        np.testing.assert_allclose(alt, ref, rtol=0, atol=tol)
 
 
 @pytest.mark.parametrize('cin', [3, 1])
@@ -63,6 +71,10 @@ def test_conv1_1_operand_packing_keeps_16_bits(dev, cin):
                                                'l/bias': bias.astype(np.float64)}, 'l')
     got = dev.conv2d(cuda(x), kb, bias, relu=True, precision='bf16').cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=0, atol=2.0 ** -8 * np.abs(ref).max())
+    dev.set_debug_flags(4)          # materialised operand buffer: same numbers
+    alt = dev.conv2d(cuda(x), kb, bias, relu=True, precision='bf16').cpu().numpy()
+    dev.set_debug_flags(0)
+    np.testing.assert_array_equal(alt, got)
 
 
 @pytest.mark.parametrize('n,h,w,cin,cout,k', [(1, 16, 24, 3, 64, 3), (2, 8, 8, 64, 20, 3),

@@ -1,7 +1,8 @@
 #!/bin/bash
-mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_layers.py tests/test_gpu_fcn.py -q -m gpu -x 2>&1 | tail -15
 python tools/perf_probe.py 16 5 3 2>&1 | tail -1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 47 -c 23 --csv --log-file gpurun_out/launches_probe.csv python tools/perf_probe.py 16 1 3 > gpurun_out/probe_ncu.log 2>&1
+python tools/perf_probe.py 16 5 1 2>&1 | tail -1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 41 -c 20 --csv --log-file gpurun_out/launches_probe.csv python tools/perf_probe.py 16 1 3 > gpurun_out/probe_ncu.log 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/launches_probe.csv')) if len(r)>5]
