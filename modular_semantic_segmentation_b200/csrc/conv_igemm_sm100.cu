@@ -32,6 +32,7 @@ constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kOutBufBytes = kBlockM * 128;      // one 64-channel bf16 output chunk
 constexpr int kThreads = 192;
+constexpr int kPackThreads = 256;                // conv1_1 mode: two groups of 128 operand packers
 constexpr int kPrefetchTiles = 2;               // L2 prefetch distance in tiles per CTA
 
 template <int BLOCK_N>
@@ -68,7 +69,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvIgemmParams& p, int t
 // fp32 input (3x3 neighbourhood split into hi + lo bf16 halves, see layers.cu), TMA loads only
 // the 8 KB weight tile.
 template <int BLOCK_N, int TAPS, bool OUT_F32, int C1 = 0>
-__global__ void __launch_bounds__(C1 > 0 ? kThreads + 128 : kThreads, 1)
+__global__ void __launch_bounds__(C1 > 0 ? kThreads + kPackThreads : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
@@ -206,11 +207,17 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
     // ------------------------------------------------------------- conv1_1 operand packing
     constexpr int CIN = C1 > 0 ? C1 : 1;
     constexpr int K9 = 9 * CIN;
-    const int row = threadIdx.x - kThreads;     // pixel index inside the tile
+    // two groups of 128 threads alternate tiles so the global loads of one tile overlap the
+    // packing / barrier wait of the previous one
+    const int group = (threadIdx.x - kThreads) >> 7;
+    const int row = (threadIdx.x - kThreads) & 127;     // pixel index inside the tile
     const int py = row / p.tw;
     const int px = row - py * p.tw;
-    uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      if ((local & 1) != group) continue;
+      const uint32_t stage = static_cast<uint32_t>(local) % kStages;
+      const uint32_t phase = (static_cast<uint32_t>(local) / kStages) & 1u;
       const TileCoord c = decode_tile(p, tile, BLOCK_N);
       const int y = c.y0 + py, x = c.x0 + px;
       float hi[K9], lo[K9];
@@ -248,10 +255,6 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
       }
       fence_proxy_async_smem();                 // generic-proxy writes -> visible to the MMA
       mbar_arrive(&full_bar[stage]);
-      if (++stage == kStages) {
-        stage = 0;
-        phase ^= 1;
-      }
     }
   } else {
     // ------------------------------------------------------------- epilogue (128 threads)
@@ -373,7 +376,7 @@ int launch_c1(const ConvIgemmParams& p, cudaStream_t stream) {
   }
   const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_blocks;
   const int grid = total_tiles < device_info().num_sms ? total_tiles : device_info().num_sms;
-  kernel<<<grid, kThreads + 128, Cfg::kSmemBytes, stream>>>(p);
+  kernel<<<grid, kThreads + kPackThreads, Cfg::kSmemBytes, stream>>>(p);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

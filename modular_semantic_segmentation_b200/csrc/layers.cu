@@ -314,6 +314,45 @@ __global__ void upscore2_add_kernel(const float* __restrict__ s5, const float* _
   }
 }
 
+// nu % 4 == 0: one thread = one output pixel x 4 channels, 16-byte accesses
+__global__ void upscore2_add_v4_kernel(const float4* __restrict__ s5, const float4* __restrict__ s4,
+                                       const float4* __restrict__ g, float4* __restrict__ fused,
+                                       int N, int h, int w, int nu4) {
+  const int ho = 2 * h, wo = 2 * w;
+  const size_t total = static_cast<size_t>(N) * ho * wo * nu4;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(idx % nu4);
+    size_t t = idx / nu4;
+    const int ox = static_cast<int>(t % wo);
+    t /= wo;
+    const int oy = static_cast<int>(t % ho);
+    const size_t img = t / ho;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ((oy + 1) & 1) + 2 * a;
+      const int iy = (oy + 1 - ky) / 2;
+      if (oy + 1 - ky < 0 || iy >= h) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int kx = ((ox + 1) & 1) + 2 * b;
+        const int ix = (ox + 1 - kx) / 2;
+        if (ox + 1 - kx < 0 || ix >= w) continue;
+        const float4 gv = __ldg(g + (ky * 4 + kx) * nu4 + u);
+        const float4 sv = __ldg(s5 + ((img * h + iy) * w + ix) * nu4 + u);
+        acc.x = fmaf(gv.x, sv.x, acc.x);
+        acc.y = fmaf(gv.y, sv.y, acc.y);
+        acc.z = fmaf(gv.z, sv.z, acc.z);
+        acc.w = fmaf(gv.w, sv.w, acc.w);
+      }
+    }
+    const float4 base = __ldg(s4 + idx);
+    fused[idx] = make_float4(base.x + fmaxf(acc.x, 0.f), base.y + fmaxf(acc.y, 0.f),
+                             base.z + fmaxf(acc.z, 0.f), base.w + fmaxf(acc.w, 0.f));
+  }
+}
+
 // low[p,c] = sum_u fused[p,u] * w[u,c]   (the 1x1 `score` conv applied BEFORE the x8 upsampling;
 // valid because the upsampling kernel is shared by all channels and ReLU is the identity on
 // its non-negative output - see DESIGN.md "decoder reordering").
@@ -331,10 +370,57 @@ __global__ void score_lowres_kernel(const float* __restrict__ fused, const float
   }
 }
 
+// nu % 4 == 0: 4 threads per pixel, each reduces a quarter of the units with float4 loads and
+// the [nu,C] matrix in shared memory, quad shuffle-reduction at the end.
+template <int C>
+__global__ void __launch_bounds__(256)
+score_lowres_v4_kernel(const float4* __restrict__ fused, const float* __restrict__ w,
+                       float* __restrict__ low, size_t npix, int nu) {
+  extern __shared__ float s_w[];
+  for (int i = threadIdx.x; i < nu * C; i += 256) s_w[i] = w[i];
+  __syncthreads();
+  const int nu4 = nu >> 2;
+  const int part = threadIdx.x & 3;
+  const size_t quads = static_cast<size_t>(gridDim.x) * 64;
+  // uniform trip count per warp so the full-mask shuffles below are legal
+  const size_t iters = (npix + quads - 1) / quads;
+  for (size_t it = 0; it < iters; ++it) {
+    const size_t p = it * quads + blockIdx.x * 64 + (threadIdx.x >> 2);
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    if (p < npix) {
+      const float4* f = fused + p * nu4;
+      for (int u4 = part; u4 < nu4; u4 += 4) {
+        const float4 v = __ldg(f + u4);
+        const float* wr = s_w + u4 * 4 * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          acc[c] = fmaf(v.x, wr[c], acc[c]);
+          acc[c] = fmaf(v.y, wr[C + c], acc[c]);
+          acc[c] = fmaf(v.z, wr[2 * C + c], acc[c]);
+          acc[c] = fmaf(v.w, wr[3 * C + c], acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+    }
+    if (p < npix && part == 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) low[p * C + c] = acc[c];
+    }
+  }
+}
+
 // Decoder tail: 16x16 stride-8 upsampling of the low-res class scores + bias + softmax +
 // argmax in one pass; block = 16x16 output pixels, the <= 4x4 contributing low-res pixels
 // are staged in shared memory.  T > 1: loop over MC samples and accumulate moments.
-template <int C, bool MC>
+// SOFTMAX == false: labels (and raw scores) only - the argmax is taken on the scores, the
+// exponentials are skipped.
+template <int C, bool MC, bool SOFTMAX = true>
 __global__ void __launch_bounds__(256)
 decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__ g,
                         const float* __restrict__ bias, int T, int N, int h, int w,
@@ -399,6 +485,20 @@ decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__
 #pragma unroll
       for (int c = 0; c < C; ++c) out.score[pix * C + c] = s[c];
     }
+    if (!MC && !SOFTMAX) {
+      int best = 0;
+      float bestv = s[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) {
+        if (s[c] > bestv) {
+          bestv = s[c];
+          best = c;
+        }
+      }
+      if (out.label_u8) out.label_u8[pix] = static_cast<uint8_t>(best);
+      if (out.label_i64) out.label_i64[pix] = best;
+      continue;
+    }
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -453,9 +553,12 @@ int decode_dispatch(bool mc, const float* low, const float* g, const float* bias
   if (mc)
     decode_upsample8_kernel<C, true><<<grid, 256, 0, s>>>(low, g, bias, T, N, h, w, out,
                                                            mean_prob, var_prob, mean_var);
-  else
+  else if (out.prob)
     decode_upsample8_kernel<C, false><<<grid, 256, 0, s>>>(low, g, bias, 1, N, h, w, out,
                                                             nullptr, nullptr, nullptr);
+  else
+    decode_upsample8_kernel<C, false, false><<<grid, 256, 0, s>>>(low, g, bias, 1, N, h, w, out,
+                                                                   nullptr, nullptr, nullptr);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -586,13 +689,34 @@ int launch_affine_f32(float* x, const float* scale, const float* shift, size_t n
 int launch_upscore2_add(const float* s5, const float* s4, const float* g, float* fused, int N,
                         int h, int w, int nu, cudaStream_t s) {
   const size_t total = static_cast<size_t>(N) * 4 * h * w * nu;
-  upscore2_add_kernel<<<grid_for(total), kThreads, 0, s>>>(s5, s4, g, fused, N, h, w, nu);
+  if (nu % 4 == 0)
+    upscore2_add_v4_kernel<<<grid_for(total / 4), kThreads, 0, s>>>(
+        reinterpret_cast<const float4*>(s5), reinterpret_cast<const float4*>(s4),
+        reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(fused), N, h, w, nu / 4);
+  else
+    upscore2_add_kernel<<<grid_for(total), kThreads, 0, s>>>(s5, s4, g, fused, N, h, w, nu);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
+template <int C>
+int score_lowres_v4_dispatch(const float* fused, const float* w, float* low, size_t npix, int nu,
+                             cudaStream_t s) {
+  const size_t blocks = (npix + 63) / 64;
+  const size_t cap = static_cast<size_t>(device_info().num_sms) * 8;
+  score_lowres_v4_kernel<C><<<static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap), 256,
+                              nu * C * sizeof(float), s>>>(
+      reinterpret_cast<const float4*>(fused), w, low, npix, nu);
+  XV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int launch_score_lowres(const float* fused, const float* w, float* low, size_t npix, int nu, int C,
                         cudaStream_t s) {
+  if (nu % 16 == 0 && nu * C * 4 <= 40 * 1024) {
+    XV_DISPATCH_C(C, (score_lowres_v4_dispatch<kC>(fused, w, low, npix, nu, s)));
+  }
   score_lowres_kernel<<<grid_for(npix * C), kThreads, 0, s>>>(fused, w, low, npix, nu, C);
   XV_CUDA(cudaGetLastError());
   count_launch();

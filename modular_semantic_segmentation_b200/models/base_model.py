@@ -144,6 +144,59 @@ class BaseModel(object):
                     yield {k: v[rows] for k, v in blob.items()}
         return gen_iter()
 
+    def _device_batches(self, data):
+        """Yields this rank's batches as dicts of CUDA tensors.  Host batches are uploaded on
+        a side stream one batch ahead, so the H2D copy of batch i+1 overlaps the kernels of
+        batch i (the reference feeds every sess.run synchronously, base_model.py:308-313)."""
+        compute = torch.cuda.current_stream()
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream()
+        copy = self._copy_stream
+
+        def upload(host_batch):
+            if all(isinstance(v, torch.Tensor) and v.is_cuda for v in host_batch.values()):
+                return self._to_device(host_batch), None
+            copy.wait_stream(compute)          # never overwrite buffers the kernels still read
+            with torch.cuda.stream(copy):
+                dev_batch = self._to_device(host_batch)
+                event = torch.cuda.Event()
+                event.record(copy)
+            for t in dev_batch.values():
+                t.record_stream(compute)
+            return dev_batch, event
+
+        def pieces():
+            # a large host batch is uploaded in `upload_split` pieces so that its own copy
+            # overlaps its own kernels (matters when score() is called one batch at a time)
+            split = int(self.config.get('upload_split', 2))
+            for blob in self._batches(data):
+                count = len(next(iter(blob.values())))
+                on_host = not all(isinstance(v, torch.Tensor) and v.is_cuda
+                                  for v in blob.values())
+                if on_host and split > 1 and count >= 8 * split:
+                    step = (count + split - 1) // split
+                    for start in range(0, count, step):
+                        yield {k: v[start:start + step] for k, v in blob.items()}
+                else:
+                    yield blob
+
+        it = iter(pieces())
+        try:
+            pending = upload(next(it))
+        except StopIteration:
+            return
+        while pending is not None:
+            dev_batch, event = pending
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if event is not None:
+                compute.wait_event(event)
+            # issue the next upload before the caller launches this batch's kernels
+            pending = upload(nxt) if nxt is not None else None
+            yield dev_batch
+
     @staticmethod
     def _to_device(batch):
         out = {}
@@ -172,8 +225,8 @@ class BaseModel(object):
         if output_attr is not None and self._has_output(output_attr):
             fetch = output_attr
         ret = []
-        for batch in self._batches(data):
-            out = self._run_batch(self._to_device(batch), fetch)
+        for batch in self._device_batches(data):
+            out = self._run_batch(batch, fetch)
             ret.append(out)
         local = torch.cat(ret) if ret else None
         if _dist() is not None:
@@ -188,8 +241,7 @@ class BaseModel(object):
         The confusion matrix is accumulated on the device in int64 and read back once."""
         cm = self._cm_device
         cm.zero_()
-        for batch in self._batches(data):
-            batch = self._to_device(batch)
+        for batch in self._device_batches(data):
             prediction = self._run_batch(batch, 'prediction_compact')
             dev.confusion_accumulate(prediction, batch['labels'].contiguous(), cm)
         sharding.allreduce_sum_(cm)

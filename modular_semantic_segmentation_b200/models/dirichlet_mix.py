@@ -116,8 +116,7 @@ class DirichletFusion(BaseModel):
                  for m in self.modalities}
         counts = torch.zeros(c, dtype=torch.int64, device='cuda')
         scratch = torch.zeros(c, dtype=torch.int64, device='cuda')
-        for batch in self._batches(data):
-            batch = self._to_device(batch)
+        for batch in self._device_batches(data):
             labels = batch['labels'].contiguous()
             for i, (m, prob) in enumerate(zip(self.modalities, self._probs(batch))):
                 dev.dirichlet_suffstats(prob, labels, stats[m], counts if i == 0 else scratch)
