@@ -168,6 +168,21 @@ int xv_variance_fuse(const float* const* probs_host, const float* const* vars_ho
 int xv_mc_moments(const float* samples, int num_samples, int64_t npix, int num_classes,
                   float* mean, float* var, float* mean_var, float* entropy, float* cond_entropy,
                   float* sum_var, void* stream);
+/* Per-pixel maximum-likelihood Dirichlet fit over MC-dropout samples [T,npix,C]: moment
+ * initialisation + Minka fixed point (dirichlet_fastfit.py:188-204,376-395, the batched form of
+ * what dirichlet_mix.py:237-242 calls per class).  alpha: float32 [npix,C]; iterations
+ * (int32 [npix], fixed-point steps taken) may be NULL. */
+int xv_dirichlet_fit_samples(const float* samples, int num_samples, int64_t npix, int num_classes,
+                             float tol, int maxiter, float* alpha, int32_t* iterations,
+                             void* stream);
+/* Uncertainty-mixed Dirichlet fusion, uncertainty_dirichlet_mix.py:18-52: per pixel and expert the
+ * parameters are cond*(1-mix) + mix*(I+1) with mix = mean_c var / max(var); vars_host[m]: device
+ * float32 [npix,C] MC-dropout variances, cond_params: device [M,C_out,C_gt], log_prior: device
+ * [C] = log(1e-20 + prior). */
+int xv_dirichlet_uncertainty_fuse(const float* const* probs_host, const float* const* vars_host,
+                                  int num_experts, const float* cond_params,
+                                  const float* log_prior, int num_classes, int64_t npix,
+                                  float* score, void* label, int label_bytes, void* stream);
 /* Dirichlet sufficient statistics, dirichlet_mix.py:142-163: ACCUMULATES into
  * stats (device float64 [C,C]) and counts (device int64 [C]). */
 int xv_dirichlet_suffstats(const float* prob, const int32_t* labels, int64_t npix,

@@ -79,6 +79,8 @@ PROTOTYPES = {
     'xv_variance_fuse': [_PP, _PP, _I, _I, _L, _P, _P, _I, _P],
     'xv_mc_moments': [_P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P],
     'xv_dirichlet_suffstats': [_P, _P, _L, _I, _P, _P, _P],
+    'xv_dirichlet_fit_samples': [_P, _I, _L, _I, C.c_float, _I, _P, _P, _P],
+    'xv_dirichlet_uncertainty_fuse': [_PP, _PP, _I, _P, _P, _I, _L, _P, _P, _I, _P],
     'xv_confusion_accumulate': [_P, _I, _P, _L, _I, _P, _P],
 }
 

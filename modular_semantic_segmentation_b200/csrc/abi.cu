@@ -1176,6 +1176,33 @@ int xv_mc_moments(const float* samples, int T, int64_t npix, int C, float* mean,
                            sum_var, XV_STREAM(stream));
 }
 
+int xv_dirichlet_fit_samples(const float* samples, int T, int64_t npix, int C, float tol,
+                             int maxiter, float* alpha, int32_t* iterations, void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(samples && alpha, "xv_dirichlet_fit_samples: NULL argument");
+  return launch_dirichlet_fit_samples(samples, T, npix, C, tol, maxiter, alpha, iterations,
+                                      XV_STREAM(stream));
+}
+
+int xv_dirichlet_uncertainty_fuse(const float* const* probs, const float* const* vars, int M,
+                                  const float* cond_params, const float* log_prior, int C,
+                                  int64_t npix, float* score, void* label, int label_bytes,
+                                  void* stream) {
+  XV_TRY(ensure_init());
+  XV_TRY(check_label_bytes(label_bytes));
+  XV_CHECK(M >= 1 && M <= 4, "number of experts must be in [1, 4]");
+  static DevBuf maxbuf;
+  XV_TRY(maxbuf.ensure(4 * sizeof(float)));
+  const float* maxp[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int m = 0; m < M; ++m) {
+    float* slot = static_cast<float*>(maxbuf.p) + m;
+    XV_TRY(launch_reduce_max(vars[m], npix * C, slot, XV_STREAM(stream)));
+    maxp[m] = slot;
+  }
+  return launch_dirichlet_uncertainty_fuse(probs, vars, maxp, M, cond_params, log_prior, C, npix,
+                                           score, label, label_bytes, XV_STREAM(stream));
+}
+
 int xv_dirichlet_suffstats(const float* prob, const int32_t* labels, int64_t npix, int C,
                            double* stats, int64_t* counts, void* stream) {
   XV_TRY(ensure_init());

@@ -17,7 +17,7 @@ namespace xv {
 
 namespace {
 
-constexpr int kPix = 256;   // pixels per block-tile == threads per block
+constexpr int kPix = 256;   // threads per block, one pixel per thread and iteration
 constexpr int kMaxM = 4;    // experts per fusion call
 
 struct PtrPack {
@@ -25,72 +25,114 @@ struct PtrPack {
 };
 
 inline int tiles_grid(int64_t npix) {
-  int64_t tiles = div_up64(npix, kPix);
-  int64_t cap = static_cast<int64_t>(device_info().num_sms) * 8;
-  return static_cast<int>(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+  int64_t blocks = div_up64(npix, kPix);
+  int64_t cap = static_cast<int64_t>(device_info().num_sms) * 16;
+  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// One pixel's C class values straight into registers with the widest aligned vector access
+// (C % 4 == 0: 16 B, C % 2 == 0: 8 B).  A warp touches a contiguous 32*C*4-byte span; the
+// partially used sectors of one instruction are completed by the next ones out of L1.
+template <int C>
+__device__ __forceinline__ void load_px(const float* __restrict__ g, int64_t pix, float (&v)[C]) {
+  const float* p = g + pix * C;
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      v[4 * i] = t.x;
+      v[4 * i + 1] = t.y;
+      v[4 * i + 2] = t.z;
+      v[4 * i + 3] = t.w;
+    }
+  } else if constexpr (C % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 2; ++i) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(p) + i);
+      v[2 * i] = t.x;
+      v[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) v[i] = __ldg(p + i);
+  }
 }
 
 template <int C>
-struct Tile {
-  static constexpr int CP = C | 1;   // odd row pitch -> conflict-free thread-per-pixel access
-  static constexpr int kFloats = kPix * CP;
+__device__ __forceinline__ void store_px(float* __restrict__ g, int64_t pix, const float (&v)[C]) {
+  float* p = g + pix * C;
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i)
+      reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if constexpr (C % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) p[i] = v[i];
+  }
+}
+
+// Odd C: rows are only 4-byte aligned, so a warp stages its 32 consecutive pixels through a
+// private shared-memory slice with fully coalesced accesses; reading row `lane` back has
+// stride C (odd, hence conflict-free).  `base` = first pixel of the warp, `cnt` = valid pixels.
+template <int C>
+struct WarpStage {
+  static constexpr bool kUse = (C % 2) != 0;
+  static constexpr int kFloats = kUse ? (kPix / 32) * 32 * C : 1;
 };
-
-// global [pix0 .. pix0+cnt) x C  ->  smem rows of pitch CP (coalesced float4 reads)
 template <int C>
-__device__ __forceinline__ void tile_load(const float* __restrict__ g, int64_t pix0, int cnt,
-                                          float* __restrict__ s) {
-  constexpr int CP = Tile<C>::CP;
-  const float* base = g + pix0 * C;          // pix0 % 256 == 0 -> 16-byte aligned
-  const int n = cnt * C;
-  const int n4 = n >> 2;
-  const float4* b4 = reinterpret_cast<const float4*>(base);
-  for (int i = threadIdx.x; i < n4; i += kPix) {
-    const float4 v = __ldg(b4 + i);
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-    int e = i * 4;
-    int p = e / C, k = e - p * C;
+__device__ __forceinline__ void warp_load(const float* __restrict__ g, int64_t base, int cnt,
+                                          float* __restrict__ slice, float (&v)[C]) {
+  const int lane = threadIdx.x & 31;
+  const float* p = g + base * C;
+  __syncwarp();
+  for (int i = lane; i < cnt * C; i += 32) slice[i] = __ldg(p + i);
+  __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      s[p * CP + k] = vv[j];
-      if (++k == C) {
-        k = 0;
-        ++p;
-      }
-    }
-  }
-  for (int e = n4 * 4 + threadIdx.x; e < n; e += kPix) {
-    const int p = e / C, k = e - p * C;
-    s[p * CP + k] = __ldg(base + e);
-  }
+  for (int k = 0; k < C; ++k) v[k] = lane < cnt ? slice[lane * C + k] : 0.f;
+}
+template <int C>
+__device__ __forceinline__ void warp_store(float* __restrict__ g, int64_t base, int cnt,
+                                           float* __restrict__ slice, const float (&v)[C]) {
+  const int lane = threadIdx.x & 31;
+  float* p = g + base * C;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < C; ++k) slice[lane * C + k] = v[k];
+  __syncwarp();
+  for (int i = lane; i < cnt * C; i += 32) p[i] = slice[i];
 }
 
-// smem rows of pitch CP -> global [pix0 .. pix0+cnt) x C (coalesced float4 writes)
+// Pixel access used by every kernel below: direct vector access for even C, warp staging for
+// odd C.  The loops are written over warp-sized groups so both variants share one structure.
+#define XV_WARP_LOOP(base, cnt, npix)                                                          \
+  const int64_t _groups = ((npix) + 31) / 32;                                                  \
+  const int64_t _gstride = static_cast<int64_t>(gridDim.x) * (kPix / 32);                      \
+  for (int64_t _g = blockIdx.x * static_cast<int64_t>(kPix / 32) + (threadIdx.x >> 5),         \
+               base = _g * 32;                                                                  \
+       _g < _groups; _g += _gstride, base = _g * 32)                                           \
+    if (const int cnt = static_cast<int>(((npix) - base) < 32 ? ((npix) - base) : 32); true)
+
 template <int C>
-__device__ __forceinline__ void tile_store(float* __restrict__ g, int64_t pix0, int cnt,
-                                           const float* __restrict__ s) {
-  constexpr int CP = Tile<C>::CP;
-  float* base = g + pix0 * C;
-  const int n = cnt * C;
-  const int n4 = n >> 2;
-  float4* b4 = reinterpret_cast<float4*>(base);
-  for (int i = threadIdx.x; i < n4; i += kPix) {
-    float vv[4];
-    int e = i * 4;
-    int p = e / C, k = e - p * C;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      vv[j] = s[p * CP + k];
-      if (++k == C) {
-        k = 0;
-        ++p;
-      }
-    }
-    b4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+__device__ __forceinline__ void px_load(const float* __restrict__ g, int64_t base, int cnt,
+                                        float* slice, float (&v)[C]) {
+  if constexpr (WarpStage<C>::kUse) {
+    warp_load<C>(g, base, cnt, slice, v);
+  } else {
+    const int lane = threadIdx.x & 31;
+    if (lane < cnt) load_px<C>(g, base + lane, v);
   }
-  for (int e = n4 * 4 + threadIdx.x; e < n; e += kPix) {
-    const int p = e / C, k = e - p * C;
-    base[e] = s[p * CP + k];
+}
+template <int C>
+__device__ __forceinline__ void px_store(float* __restrict__ g, int64_t base, int cnt, float* slice,
+                                         const float (&v)[C]) {
+  if constexpr (WarpStage<C>::kUse) {
+    warp_store<C>(g, base, cnt, slice, v);
+  } else {
+    const int lane = threadIdx.x & 31;
+    if (lane < cnt) store_px<C>(g, base + lane, v);
   }
 }
 
@@ -119,28 +161,27 @@ __device__ __forceinline__ int load_label(const void* in, int label_bytes, int64
                           : static_cast<int>(reinterpret_cast<const uint8_t*>(in)[pix]);
 }
 
+#define XV_PIXEL_LOOP(pix, npix)                                                        \
+  for (int64_t pix = blockIdx.x * static_cast<int64_t>(kPix) + threadIdx.x; pix < (npix); \
+       pix += static_cast<int64_t>(gridDim.x) * kPix)
+
 // ------------------------------------------------------------------ softmax + argmax
 template <int C>
 __global__ void __launch_bounds__(kPix)
 softmax_argmax_kernel(const float* __restrict__ score, int64_t npix, float* __restrict__ prob,
                       int64_t* __restrict__ label64, uint8_t* __restrict__ label8) {
-  __shared__ float s[Tile<C>::kFloats];
-  constexpr int CP = Tile<C>::CP;
-  const int64_t tiles = (npix + kPix - 1) / kPix;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t pix0 = tile * kPix;
-    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPix), npix - pix0));
-    __syncthreads();
-    tile_load<C>(score, pix0, cnt, s);
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-      float v[C];
-      float mx = -INFINITY;
+  __shared__ float s_stage[WarpStage<C>::kFloats];
+  float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
+  const int lane = threadIdx.x & 31;
+  XV_WARP_LOOP(base, cnt, npix) {
+    float v[C];
+    px_load<C>(score, base, cnt, slice, v);
+    const bool live = lane < cnt;
+    int best = 0;
+    if (live) {
+      float mx = v[0];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        v[c] = s[threadIdx.x * CP + c];
-        mx = fmaxf(mx, v[c]);
-      }
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, v[c]);
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -148,18 +189,12 @@ softmax_argmax_kernel(const float* __restrict__ score, int64_t npix, float* __re
         sum += v[c];
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        v[c] = v[c] / sum;
-        s[threadIdx.x * CP + c] = v[c];
-      }
-      const int best = argmax_first<C>(v);
-      if (label64) label64[pix0 + threadIdx.x] = best;
-      if (label8) label8[pix0 + threadIdx.x] = static_cast<uint8_t>(best);
+      for (int c = 0; c < C; ++c) v[c] = v[c] / sum;
+      best = argmax_first<C>(v);
+      if (label64) label64[base + lane] = best;
+      if (label8) label8[base + lane] = static_cast<uint8_t>(best);
     }
-    if (prob) {
-      __syncthreads();
-      tile_store<C>(prob, pix0, cnt, s);
-    }
+    if (prob) px_store<C>(prob, base, cnt, slice, v);
   }
 }
 
@@ -171,8 +206,7 @@ bayes_lut_kernel(PtrPack labels, int M, int label_bytes, const int32_t* __restri
   extern __shared__ int32_t s_lut[];
   for (int i = threadIdx.x; i < lut_size; i += blockDim.x) s_lut[i] = lut[i];
   __syncthreads();
-  for (int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; pix < npix;
-       pix += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  XV_PIXEL_LOOP(pix, npix) {
     int idx = 0;
     bool ok = true;
     for (int m = 0; m < M; ++m) {
@@ -184,6 +218,41 @@ bayes_lut_kernel(PtrPack labels, int M, int label_bytes, const int32_t* __restri
   }
 }
 
+// uint8 labels, 16 pixels (one 16-byte vector per expert) per thread and iteration
+__global__ void __launch_bounds__(kPix)
+bayes_lut_u8x16_kernel(PtrPack labels, int M, const int32_t* __restrict__ lut, int C, int lut_size,
+                       int64_t nvec, uint4* __restrict__ out) {
+  extern __shared__ int32_t s_lut[];
+  for (int i = threadIdx.x; i < lut_size; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  XV_PIXEL_LOOP(vec, nvec) {
+    uint32_t idx[16];
+    bool ok[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      idx[j] = 0;
+      ok[j] = true;
+    }
+    for (int m = 0; m < M; ++m) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(labels.p[m]) + vec);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t l = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        ok[j] = ok[j] && (l < static_cast<uint32_t>(C));
+        idx[j] = idx[j] * C + l;
+      }
+    }
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t f = ok[j] ? static_cast<uint32_t>(s_lut[idx[j]]) & 0xffu : 0u;
+      o[j >> 2] |= f << (8 * (j & 3));
+    }
+    out[vec] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // Literal form (bayes_mix.py:12-58): score[c] = sum_m logcond[m][l_m][c] + logprior[c].
 template <int C>
 __global__ void __launch_bounds__(kPix)
@@ -191,105 +260,93 @@ bayes_score_kernel(PtrPack labels, int M, int label_bytes, const float* __restri
                    const float* __restrict__ logprior, int64_t npix, float* __restrict__ score,
                    void* __restrict__ label_out) {
   __shared__ float s_tab[kMaxM * C * C + C];
-  __shared__ float s[Tile<C>::kFloats];
-  constexpr int CP = Tile<C>::CP;
   for (int i = threadIdx.x; i < M * C * C; i += kPix) s_tab[i] = logcond[i];
   for (int i = threadIdx.x; i < C; i += kPix) s_tab[kMaxM * C * C + i] = logprior[i];
-  const int64_t tiles = (npix + kPix - 1) / kPix;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t pix0 = tile * kPix;
-    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPix), npix - pix0));
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-      float v[C];
-      for (int m = 0; m < M; ++m) {
-        int l = load_label(labels.p[m], label_bytes, pix0 + threadIdx.x);
-        l = min(max(l, 0), C - 1);
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float t = s_tab[(m * C + l) * C + c];
-          v[c] = (m == 0) ? t : v[c] + t;   // stack + reduce_sum in expert order
-        }
-      }
+  __syncthreads();
+  XV_PIXEL_LOOP(pix, npix) {
+    float v[C];
+    for (int m = 0; m < M; ++m) {
+      int l = load_label(labels.p[m], label_bytes, pix);
+      l = min(max(l, 0), C - 1);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        v[c] += s_tab[kMaxM * C * C + c];
-        s[threadIdx.x * CP + c] = v[c];
+        const float t = s_tab[(m * C + l) * C + c];
+        v[c] = (m == 0) ? t : v[c] + t;   // stack + reduce_sum in expert order
       }
-      if (label_out) store_label(label_out, label_bytes, pix0 + threadIdx.x, argmax_first<C>(v));
     }
-    if (score) {
-      __syncthreads();
-      tile_store<C>(score, pix0, cnt, s);
-    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] += s_tab[kMaxM * C * C + c];
+    if (label_out) store_label(label_out, label_bytes, pix, argmax_first<C>(v));
+    if (score) store_px<C>(score, pix, v);
   }
 }
 
 // ------------------------------------------------------------------ Dirichlet fusion
 // score[c] = sum_m ( sum_k am1[m][k][c] * log(1e-20 + p_m[k]/sum p_m) - lognorm[m][c] ) + logprior[c]
+// The (alpha-1) tables sit in shared memory with rows padded to a multiple of 4 floats so one
+// broadcast LDS.128 feeds four FMAs.
 template <int C>
 __global__ void __launch_bounds__(kPix)
 dirichlet_fuse_kernel(PtrPack probs, int M, const float* __restrict__ alpha_m1,
                       const float* __restrict__ lognorm, const float* __restrict__ logprior,
                       int64_t npix, float* __restrict__ score, void* __restrict__ label_out,
                       int label_bytes) {
-  __shared__ float s_am1[kMaxM * C * C];
+  constexpr int CP = (C + 3) & ~3;
+  __shared__ __align__(16) float s_am1[kMaxM * C * CP];
   __shared__ float s_norm[kMaxM * C];
   __shared__ float s_prior[C];
-  __shared__ float s[Tile<C>::kFloats];
-  constexpr int CP = Tile<C>::CP;
-  for (int i = threadIdx.x; i < M * C * C; i += kPix) s_am1[i] = alpha_m1[i];
+  for (int i = threadIdx.x; i < M * C * CP; i += kPix) {
+    const int c = i % CP, mk = i / CP;
+    s_am1[i] = c < C ? alpha_m1[mk * C + c] : 0.f;
+  }
   for (int i = threadIdx.x; i < M * C; i += kPix) s_norm[i] = lognorm[i];
   for (int i = threadIdx.x; i < C; i += kPix) s_prior[i] = logprior[i];
-  const int64_t tiles = (npix + kPix - 1) / kPix;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t pix0 = tile * kPix;
-    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPix), npix - pix0));
+  __shared__ float s_stage[WarpStage<C>::kFloats];
+  float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
+  const int lane = threadIdx.x & 31;
+  __syncthreads();
+  XV_WARP_LOOP(base, cnt, npix) {
+    const int64_t pix = base + lane;
+    const bool live = lane < cnt;
     float total[C];
     for (int m = 0; m < M; ++m) {
-      __syncthreads();
-      tile_load<C>(reinterpret_cast<const float*>(probs.p[m]), pix0, cnt, s);
-      __syncthreads();
-      if (threadIdx.x < cnt) {
-        float lx[C];
-        float sum = 0.f;
+      float lx[C];
 #pragma unroll
-        for (int k = 0; k < C; ++k) {
-          lx[k] = s[threadIdx.x * CP + k];
-          sum += lx[k];
-        }
+      for (int k = 0; k < C; ++k) lx[k] = 1.f;
+      px_load<C>(reinterpret_cast<const float*>(probs.p[m]), base, cnt, slice, lx);
+      float sum = 0.f;
 #pragma unroll
-        for (int k = 0; k < C; ++k) lx[k] = logf(1e-20f + lx[k] / sum);
-        float ll[C];
+      for (int k = 0; k < C; ++k) sum += lx[k];
+      // one reciprocal per expert, MUFU lg2 for the logarithm (|error| ~1e-6 relative to the
+      // score scale; the parity tests bound it)
+      const float inv = 1.f / sum;
 #pragma unroll
-        for (int c = 0; c < C; ++c) ll[c] = 0.f;
+      for (int k = 0; k < C; ++k) lx[k] = __logf(1e-20f + lx[k] * inv);
+      float ll[CP];
 #pragma unroll
-        for (int k = 0; k < C; ++k) {
-          const float* row = s_am1 + (m * C + k) * C;
+      for (int c = 0; c < CP; ++c) ll[c] = 0.f;
 #pragma unroll
-          for (int c = 0; c < C; ++c) ll[c] = fmaf(lx[k], row[c], ll[c]);
-        }
+      for (int k = 0; k < C; ++k) {
+        const float4* row = reinterpret_cast<const float4*>(s_am1 + (m * C + k) * CP);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float t = ll[c] - s_norm[m * C + c];
-          total[c] = (m == 0) ? t : total[c] + t;
+        for (int c4 = 0; c4 < CP / 4; ++c4) {
+          const float4 a = row[c4];
+          ll[4 * c4] = fmaf(lx[k], a.x, ll[4 * c4]);
+          ll[4 * c4 + 1] = fmaf(lx[k], a.y, ll[4 * c4 + 1]);
+          ll[4 * c4 + 2] = fmaf(lx[k], a.z, ll[4 * c4 + 2]);
+          ll[4 * c4 + 3] = fmaf(lx[k], a.w, ll[4 * c4 + 3]);
         }
       }
-    }
-    __syncthreads();
-    if (threadIdx.x < cnt) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        total[c] += s_prior[c];
-        s[threadIdx.x * CP + c] = total[c];
+        const float t = ll[c] - s_norm[m * C + c];
+        total[c] = (m == 0) ? t : total[c] + t;
       }
-      if (label_out)
-        store_label(label_out, label_bytes, pix0 + threadIdx.x, argmax_first<C>(total));
     }
-    if (score) {
-      __syncthreads();
-      tile_store<C>(score, pix0, cnt, s);
-    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) total[c] += s_prior[c];
+    if (label_out && live) store_label(label_out, label_bytes, pix, argmax_first<C>(total));
+    if (score) px_store<C>(score, base, cnt, slice, total);
   }
 }
 
@@ -298,45 +355,34 @@ template <int C, bool VAR>
 __global__ void __launch_bounds__(kPix)
 mean_fuse_kernel(PtrPack probs, PtrPack vars, int M, int64_t npix, float* __restrict__ score,
                  void* __restrict__ label_out, int label_bytes) {
-  __shared__ float s[Tile<C>::kFloats];
-  constexpr int CP = Tile<C>::CP;
-  const int64_t tiles = (npix + kPix - 1) / kPix;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t pix0 = tile * kPix;
-    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPix), npix - pix0));
+  __shared__ float s_stage[WarpStage<C>::kFloats];
+  float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
+  const int lane = threadIdx.x & 31;
+  XV_WARP_LOOP(base, cnt, npix) {
+    const int64_t pix = base + lane;
+    const bool live = lane < cnt;
     float acc[C];
     float csum = 0.f;
     for (int m = 0; m < M; ++m) {
-      __syncthreads();
-      tile_load<C>(reinterpret_cast<const float*>(probs.p[m]), pix0, cnt, s);
-      __syncthreads();
-      if (threadIdx.x < cnt) {
-        float wgt = 1.f;
-        if (VAR) {   // certainty = 1 / (1e-20 + variance), variance_mix.py:11
-          wgt = 1.f / (1e-20f + __ldg(reinterpret_cast<const float*>(vars.p[m]) + pix0 +
-                                      threadIdx.x));
-          csum = (m == 0) ? wgt : csum + wgt;
-        }
+      float v[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float t = wgt * s[threadIdx.x * CP + c];
-          acc[c] = (m == 0) ? t : acc[c] + t;
-        }
+      for (int c = 0; c < C; ++c) v[c] = 0.f;
+      px_load<C>(reinterpret_cast<const float*>(probs.p[m]), base, cnt, slice, v);
+      float wgt = 1.f;
+      if (VAR) {   // certainty = 1 / (1e-20 + variance), variance_mix.py:11
+        wgt = 1.f / (1e-20f + (live ? __ldg(reinterpret_cast<const float*>(vars.p[m]) + pix) : 1.f));
+        csum = (m == 0) ? wgt : csum + wgt;
       }
-    }
-    __syncthreads();
-    if (threadIdx.x < cnt) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        acc[c] = VAR ? acc[c] / csum : acc[c] / static_cast<float>(M);
-        s[threadIdx.x * CP + c] = acc[c];
+        const float t = wgt * v[c];
+        acc[c] = (m == 0) ? t : acc[c] + t;
       }
-      if (label_out) store_label(label_out, label_bytes, pix0 + threadIdx.x, argmax_first<C>(acc));
     }
-    if (score) {
-      __syncthreads();
-      tile_store<C>(score, pix0, cnt, s);
-    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = VAR ? acc[c] / csum : acc[c] / static_cast<float>(M);
+    if (label_out && live) store_label(label_out, label_bytes, pix, argmax_first<C>(acc));
+    if (score) px_store<C>(score, base, cnt, slice, acc);
   }
 }
 
@@ -349,67 +395,50 @@ mc_moments_kernel(const float* __restrict__ samples, int T, int64_t npix, float*
                   float* __restrict__ var, float* __restrict__ mean_var,
                   float* __restrict__ entropy, float* __restrict__ cond_entropy,
                   float* __restrict__ sum_var) {
-  __shared__ float s[Tile<C>::kFloats];
-  constexpr int CP = Tile<C>::CP;
   const float inv_logc = 1.f / logf(static_cast<float>(C));
-  const int64_t tiles = (npix + kPix - 1) / kPix;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t pix0 = tile * kPix;
-    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPix), npix - pix0));
+  const bool want_ce = cond_entropy != nullptr;
+  __shared__ float s_stage[WarpStage<C>::kFloats];
+  float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
+  const int lane = threadIdx.x & 31;
+  XV_WARP_LOOP(base, cnt, npix) {
+    const int64_t pix = base + lane;
+    const bool live = lane < cnt;
     float mu[C], m2[C];
     float ce = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) mu[c] = m2[c] = 0.f;
+#pragma unroll 4
     for (int t = 0; t < T; ++t) {
-      __syncthreads();
-      tile_load<C>(samples + static_cast<int64_t>(t) * npix * C, pix0, cnt, s);
-      __syncthreads();
-      if (threadIdx.x < cnt) {
-        const float inv_n = 1.f / static_cast<float>(t + 1);
-        float h = 0.f;
+      float x[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float x = s[threadIdx.x * CP + c];
-          const float d = x - mu[c];
-          mu[c] += d * inv_n;
-          m2[c] = fmaf(d, x - mu[c], m2[c]);
-          h -= x * logf(fminf(fmaxf(x, 1e-10f), 1.f));
-        }
-        ce += h * inv_logc;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-      float sv = 0.f, h = 0.f;
+      for (int c = 0; c < C; ++c) x[c] = 0.f;
+      px_load<C>(samples + static_cast<int64_t>(t) * npix * C, base, cnt, slice, x);
+      const float inv_n = 1.f / static_cast<float>(t + 1);
+      float h = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        m2[c] = m2[c] / static_cast<float>(T);
-        sv += m2[c];
-        h -= mu[c] * logf(fminf(fmaxf(mu[c], 1e-10f), 1.f));
+        const float d = x[c] - mu[c];
+        mu[c] += d * inv_n;
+        m2[c] = fmaf(d, x[c] - mu[c], m2[c]);
+        if (want_ce) h -= x[c] * logf(fminf(fmaxf(x[c], 1e-10f), 1.f));
       }
-      const int64_t pix = pix0 + threadIdx.x;
+      ce += h * inv_logc;
+    }
+    float sv = 0.f, h = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      m2[c] = m2[c] / static_cast<float>(T);
+      sv += m2[c];
+      if (entropy) h -= mu[c] * logf(fminf(fmaxf(mu[c], 1e-10f), 1.f));
+    }
+    if (live) {
       if (mean_var) mean_var[pix] = sv / static_cast<float>(C);
       if (sum_var) sum_var[pix] = sv;
       if (entropy) entropy[pix] = h * inv_logc;
       if (cond_entropy) cond_entropy[pix] = ce / static_cast<float>(T);
     }
-    if (mean) {
-      if (threadIdx.x < cnt) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) s[threadIdx.x * CP + c] = mu[c];
-      }
-      __syncthreads();
-      tile_store<C>(mean, pix0, cnt, s);
-    }
-    if (var) {
-      __syncthreads();
-      if (threadIdx.x < cnt) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) s[threadIdx.x * CP + c] = m2[c];
-      }
-      __syncthreads();
-      tile_store<C>(var, pix0, cnt, s);
-    }
+    if (mean) px_store<C>(mean, base, cnt, slice, mu);
+    if (var) px_store<C>(var, base, cnt, slice, m2);
   }
 }
 
@@ -419,30 +448,25 @@ template <int C>
 __global__ void __launch_bounds__(kPix)
 suffstats_kernel(const float* __restrict__ prob, const int32_t* __restrict__ labels, int64_t npix,
                  double* __restrict__ S, unsigned long long* __restrict__ n) {
-  __shared__ float s[Tile<C>::kFloats];
   __shared__ double s_S[C * C];
   __shared__ unsigned int s_n[C];
-  constexpr int CP = Tile<C>::CP;
   for (int i = threadIdx.x; i < C * C; i += kPix) s_S[i] = 0.0;
   for (int i = threadIdx.x; i < C; i += kPix) s_n[i] = 0u;
+  __syncthreads();
+  __shared__ float s_stage[WarpStage<C>::kFloats];
+  float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
   const int lane = threadIdx.x & 31;
-  const int64_t tiles = (npix + kPix - 1) / kPix;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t pix0 = tile * kPix;
-    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPix), npix - pix0));
-    __syncthreads();
-    tile_load<C>(prob, pix0, cnt, s);
-    __syncthreads();
+  XV_WARP_LOOP(base, cnt, npix) {
     int label = -1;
     float lp[C];
-    if (threadIdx.x < cnt) {
-      label = __ldg(labels + pix0 + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < C; ++k) lp[k] = 1.f;
+    px_load<C>(prob, base, cnt, slice, lp);
+    if (lane < cnt) {
+      label = __ldg(labels + base + lane);
       if (label < 0 || label >= C) label = -1;
 #pragma unroll
-      for (int k = 0; k < C; ++k) lp[k] = logf(1e-10f + s[threadIdx.x * CP + k]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < C; ++k) lp[k] = 0.f;
+      for (int k = 0; k < C; ++k) lp[k] = logf(1e-10f + lp[k]);
     }
     // one pass per distinct class present in the warp: shuffle-reduce, one smem add per (c,k)
     unsigned remaining = __ballot_sync(0xffffffffu, label >= 0);
@@ -459,7 +483,6 @@ suffstats_kernel(const float* __restrict__ prob, const int32_t* __restrict__ lab
       }
       if (lane == 0) atomicAdd(&s_n[c], __popc(same));
       remaining &= ~same;
-      __syncwarp();
     }
   }
   __syncthreads();
@@ -469,28 +492,62 @@ suffstats_kernel(const float* __restrict__ prob, const int32_t* __restrict__ lab
 }
 
 // ------------------------------------------------------------------ confusion matrix
-// cm[label][pred] += 1 for 0 <= label < C (negative labels = ignore, base_model.py:140-143)
-__global__ void __launch_bounds__(kPix)
+// cm[label][pred] += 1 for 0 <= label < C (negative labels = ignore, base_model.py:140-143).
+// Label maps are spatially coherent: a warp whose 32 pixels share one (label, pred) pair adds
+// 32 with a single shared-memory atomic; mixed warps aggregate equal keys with match_any.
+__global__ void __launch_bounds__(1024)
 confusion_kernel(const void* __restrict__ pred, int pred_bytes, const int32_t* __restrict__ labels,
                  int64_t npix, int C, unsigned long long* __restrict__ cm) {
   extern __shared__ unsigned int s_cm[];
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cm[i] = 0u;
   __syncthreads();
+  const int lane = threadIdx.x & 31;
+  // each thread owns 4 consecutive pixels (16-byte label load); uniform trip count per warp
+  const int64_t nquad = (npix + 3) / 4;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t start = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  // uniform trip count so the full-mask match below is legal
-  const int64_t iters = (npix + stride - 1) / stride;
+  const int64_t iters = (nquad + stride - 1) / stride;
+  const bool vec = (npix % 4 == 0);
   for (int64_t it = 0; it < iters; ++it) {
-    const int64_t pix = start + it * stride;
-    int key = -1;
-    if (pix < npix) {
-      const int l = __ldg(labels + pix);
-      const int pr = load_label(pred, pred_bytes, pix);
-      if (l >= 0 && l < C && pr >= 0 && pr < C) key = l * C + pr;
+    const int64_t quad = start + it * stride;
+    int key[4] = {-1, -1, -1, -1};
+    if (quad < nquad) {
+      int l[4], pr[4];
+      const int64_t p0 = quad * 4;
+      if (vec) {
+        const int4 lv = __ldg(reinterpret_cast<const int4*>(labels) + quad);
+        l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+        if (pred_bytes == 1) {
+          const uchar4 pv = __ldg(reinterpret_cast<const uchar4*>(pred) + quad);
+          pr[0] = pv.x; pr[1] = pv.y; pr[2] = pv.z; pr[3] = pv.w;
+        } else {
+          const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(pred) + 2 * quad);
+          const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(pred) + 2 * quad + 1);
+          pr[0] = static_cast<int>(a.x); pr[1] = static_cast<int>(a.y);
+          pr[2] = static_cast<int>(b.x); pr[3] = static_cast<int>(b.y);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool in = p0 + j < npix;
+          l[j] = in ? __ldg(labels + p0 + j) : -1;
+          pr[j] = in ? load_label(pred, pred_bytes, p0 + j) : 0;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (l[j] >= 0 && l[j] < C && pr[j] >= 0 && pr[j] < C) key[j] = l[j] * C + pr[j];
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (key >= 0 && (__ffs(peers) - 1) == (threadIdx.x & 31))
-      atomicAdd(&s_cm[key], __popc(peers));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int key0 = __shfl_sync(0xffffffffu, key[j], 0);
+      if (__all_sync(0xffffffffu, key[j] == key0)) {
+        if (lane == 0 && key0 >= 0) atomicAdd(&s_cm[key0], 32u);
+      } else {
+        const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
+        if (key[j] >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&s_cm[key[j]], __popc(peers));
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * C; i += blockDim.x)
@@ -550,8 +607,14 @@ int launch_bayes_lut(const void* const* labels, int M, int label_bytes, const in
   int lut_size = 1;
   for (int m = 0; m < M; ++m) lut_size *= C;
   XV_CHECK(lut_size * 4 <= 48 * 1024, "decision table too large for shared memory");
-  bayes_lut_kernel<<<tiles_grid(npix), kPix, lut_size * sizeof(int32_t), s>>>(
-      pk, M, label_bytes, lut, C, lut_size, npix, out);
+  bool vec_ok = label_bytes == 1 && npix % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int m = 0; m < M; ++m) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(labels[m]) & 15) == 0;
+  if (vec_ok)
+    bayes_lut_u8x16_kernel<<<tiles_grid(npix / 16), kPix, lut_size * sizeof(int32_t), s>>>(
+        pk, M, lut, C, lut_size, npix / 16, reinterpret_cast<uint4*>(out));
+  else
+    bayes_lut_kernel<<<tiles_grid(npix), kPix, lut_size * sizeof(int32_t), s>>>(
+        pk, M, label_bytes, lut, C, lut_size, npix, out);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -619,7 +682,11 @@ int launch_mc_moments(const float* samples, int T, int64_t npix, int C, float* m
 
 int launch_suffstats(const float* prob, const int32_t* labels, int64_t npix, int C, double* S,
                      long long* n, cudaStream_t s) {
-  XV_DISPATCH_C(C, (suffstats_kernel<kC><<<tiles_grid(npix), kPix, 0, s>>>(
+  // few blocks: every block ends with C*C float64 global atomics on the same addresses
+  int64_t sblocks = div_up64(npix, kPix);
+  const int64_t scap = static_cast<int64_t>(device_info().num_sms) * 8;
+  sblocks = sblocks < scap ? (sblocks > 0 ? sblocks : 1) : scap;
+  XV_DISPATCH_C(C, (suffstats_kernel<kC><<<static_cast<int>(sblocks), kPix, 0, s>>>(
                        prob, labels, npix, S, reinterpret_cast<unsigned long long*>(n))));
   XV_CUDA(cudaGetLastError());
   count_launch();
@@ -630,7 +697,12 @@ int launch_confusion(const void* pred, int pred_bytes, const int32_t* labels, in
                      long long* cm, cudaStream_t s) {
   XV_CHECK(pred_bytes == 8 || pred_bytes == 1, "pred_bytes must be 8 (int64) or 1 (uint8)");
   XV_CHECK(C >= 1 && C * C * 4 <= 48 * 1024, "confusion: too many classes");
-  confusion_kernel<<<tiles_grid(npix), kPix, C * C * sizeof(unsigned int), s>>>(
+  // few, fat blocks: every block ends with C*C global atomics on the same addresses
+  const int64_t quads = (npix + 3) / 4;
+  int64_t blocks = div_up64(quads, 1024);
+  const int64_t cap = static_cast<int64_t>(device_info().num_sms) * 2;
+  blocks = blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
+  confusion_kernel<<<static_cast<int>(blocks), 1024, C * C * sizeof(unsigned int), s>>>(
       pred, pred_bytes, labels, npix, C, reinterpret_cast<unsigned long long*>(cm));
   XV_CUDA(cudaGetLastError());
   count_launch();

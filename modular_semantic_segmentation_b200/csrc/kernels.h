@@ -114,6 +114,15 @@ int launch_suffstats(const float* prob, const int32_t* labels, int64_t npix, int
 int launch_confusion(const void* pred, int pred_bytes, const int32_t* labels, int64_t npix, int C,
                      long long* cm /*[C,C] +=*/, cudaStream_t s);
 
+// ------------------------------------------------------------- mc_dirichlet.cu
+int launch_dirichlet_fit_samples(const float* samples, int T, int64_t npix, int C, float tol,
+                                 int maxiter, float* alpha, int* iters, cudaStream_t s);
+int launch_dirichlet_uncertainty_fuse(const float* const* probs, const float* const* vars,
+                                      const float* const* max_var, int M, const float* cond,
+                                      const float* logprior, int C, int64_t npix, float* score,
+                                      void* label_out, int label_bytes, cudaStream_t s);
+int launch_reduce_max(const float* x, int64_t n, float* out, cudaStream_t s);
+
 constexpr int kMaxClasses = 24;
 
 }  // namespace xv

@@ -312,6 +312,35 @@ def mc_moments(samples, want=('mean', 'var', 'mean_var')):
     return {k: v for k, v in out.items() if v is not None}
 
 
+def dirichlet_fit_samples(samples, tol=1e-7, maxiter=100, want_iterations=False):
+    """samples: float32 CUDA [T, ..., C] softmax samples -> per-pixel Dirichlet alpha [..., C]."""
+    init()
+    t, c = samples.shape[0], samples.shape[-1]
+    npix = samples[0].numel() // c
+    alpha = torch.empty(samples.shape[1:], dtype=torch.float32, device=samples.device)
+    iters = (torch.empty(samples.shape[1:-1], dtype=torch.int32, device=samples.device)
+             if want_iterations else None)
+    call('xv_dirichlet_fit_samples', ptr(samples), t, npix, c, C.c_float(tol), maxiter, ptr(alpha),
+         ptr(iters), stream_ptr())
+    return (alpha, iters) if want_iterations else alpha
+
+
+def dirichlet_uncertainty_fuse(probs, variances, cond_params, log_prior, want_score=False,
+                               label_dtype=torch.int64):
+    """uncertainty_dirichlet_mix.py:18-52; variances: list of float32 CUDA [..., C]."""
+    init()
+    c = probs[0].shape[-1]
+    npix = probs[0].numel() // c
+    arr, keep = _abi.ptr_array([t.data_ptr() for t in probs])
+    varr, vkeep = _abi.ptr_array([t.data_ptr() for t in variances])
+    score = torch.empty_like(probs[0]) if want_score else None
+    label = _new_label(probs[0].shape[:-1], label_dtype, probs[0].device)
+    call('xv_dirichlet_uncertainty_fuse', arr, varr, len(probs), ptr(cond_params), ptr(log_prior),
+         c, npix, ptr(score), ptr(label), _label_bytes(label), stream_ptr())
+    del keep, vkeep
+    return score, label
+
+
 def dirichlet_suffstats(prob, labels, stats, counts):
     """Accumulates into stats (float64 CUDA [C,C]) and counts (int64 CUDA [C])."""
     init()

@@ -32,6 +32,7 @@ from .fcn import (bilinear_kernel_1d, bilinear_filter, glorot_fcn_params, fcn_pa
                   softmax, argmax_first, test_pipeline, cross_entropy)
 from .fusion import (bayes_conditionals, bayes_prior, bayes_fusion, bayes_decision_matrix,
                      dirichlet_log_norm, dirichlet_fusion, dirichlet_prior,
+                     dirichlet_uncertainty_fusion,
                      average_fusion, variance_fusion, mc_moments, normed_entropy,
                      sampling_uncertainty, sufficient_statistics)
 from .score import confusion_matrix, score_measures

@@ -118,6 +118,24 @@ def dirichlet_fusion(probs, dirichlet_params, prior, sigma=1.0, dtype=np.float32
     return total + np.log(np.asarray(1e-20, dtype) + np.asarray(prior, dtype))
 
 
+def dirichlet_uncertainty_fusion(probs, conditional_params, uncertainties, prior,
+                                 dtype=np.float64):
+    """uncertainty_dirichlet_mix.py:18-52: per pixel alpha = cond*(1-mix) + mix*(I+1) with
+    mix = mean_c(var) / max(var over the whole tensor); score[c] = sum_m Dirichlet(alpha[:,c])
+    .log_prob(1e-20 + p_m) + log(1e-20 + prior[c])."""
+    num_classes = probs[0].shape[-1]
+    standard = (np.eye(num_classes) + np.ones((num_classes, num_classes))).astype(dtype)
+    total = None
+    for p, cond, unc in zip(probs, conditional_params, uncertainties):
+        unc = unc.astype(dtype)
+        mix = (unc.mean(axis=-1) / unc.max())[..., None, None]
+        alpha = cond.astype(dtype) * (1 - mix) + mix * standard          # [..., C_out, C_gt]
+        logx = np.log(np.asarray(1e-20, dtype) + p.astype(dtype))[..., None]
+        ll = ((alpha - 1) * logx).sum(-2) - (gammaln(alpha).sum(-2) - gammaln(alpha.sum(-2)))
+        total = ll if total is None else total + ll
+    return total + np.log(np.asarray(1e-20, dtype) + np.asarray(prior, dtype))
+
+
 # ------------------------------------------------------------ average / variance / MC
 def average_fusion(probs):
     """average_mix.py:18-21: argmax(mean_m prob_m)."""

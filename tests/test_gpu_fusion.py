@@ -184,3 +184,46 @@ def test_empty_and_ragged_inputs(dev):
         score = rng.normal(size=(npix, c)).astype(np.float32)
         prob, label = dev.softmax_argmax(cuda(score))
         np.testing.assert_allclose(prob.cpu().numpy(), oracle.softmax(score), rtol=2e-6, atol=1e-7)
+
+
+def test_per_pixel_dirichlet_fit_over_mc_samples(dev):
+    """a15: batched moment-init + fixed-point Dirichlet MLE; every pixel against the float64
+    oracle (dirichlet_fastfit restatement, itself pinned to the reference's outputs)."""
+    c, t = 5, 20
+    rng = np.random.default_rng(23)
+    true_alpha = rng.gamma(2.0, 2.0, size=(6, 7, c)) + 0.5
+    samples = np.stack([np.stack([rng.dirichlet(true_alpha[i, j], size=t) for j in range(7)])
+                        for i in range(6)])                        # [6,7,T,C]
+    samples = np.ascontiguousarray(np.moveaxis(samples, 2, 0)).astype(np.float32)   # [T,6,7,C]
+    alpha, iters = dev.dirichlet_fit_samples(cuda(samples), tol=1e-6, maxiter=200,
+                                             want_iterations=True)
+    alpha = alpha.cpu().numpy()
+    assert alpha.shape == (6, 7, c) and (iters.cpu().numpy() >= 1).all()
+    for i in range(6):
+        for j in range(7):
+            ref = oracle.fixedpoint_fit(samples[:, i, j].astype(np.float64), tol=1e-9,
+                                        maxiter=5000)
+            np.testing.assert_allclose(alpha[i, j], ref, rtol=2e-2)
+    # the moment initialisation alone (maxiter=0) equals dirichlet_fastfit._init_a
+    a0 = dev.dirichlet_fit_samples(cuda(samples), maxiter=0).cpu().numpy()
+    np.testing.assert_allclose(a0[2, 3], oracle.init_a_moments(samples[:, 2, 3].astype(np.float64)),
+                               rtol=2e-3)
+
+
+def test_dirichlet_uncertainty_fusion(dev):
+    c = 6
+    rng = np.random.default_rng(29)
+    shape = (2, 17, 23, c)
+    probs = [softmax_probs(rng, shape), softmax_probs(rng, shape)]
+    variances = [(rng.random(shape) * 1e-2).astype(np.float32) for _ in range(2)]
+    cond = [1 + rng.gamma(2, 2, size=(c, c)).astype(np.float32) for _ in range(2)]
+    prior = oracle.dirichlet_prior(rng.integers(1, 100, size=c))
+    ref = oracle.dirichlet_uncertainty_fusion(probs, cond, variances, prior)
+    logprior = np.log(np.float32(1e-20) + prior).astype(np.float32)
+    score, label = dev.dirichlet_uncertainty_fuse([cuda(p) for p in probs],
+                                                  [cuda(v) for v in variances],
+                                                  cuda(np.stack(cond)), cuda(logprior),
+                                                  want_score=True)
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(score.cpu().numpy(), ref, rtol=0, atol=1e-4 * scale)
+    assert_labels_match(label.cpu().numpy(), ref, 2e-4 * scale)

@@ -1,0 +1,73 @@
+"""Multi-GPU parity (needs >= 2 GPUs): images sharded over ranks, NCCL all-reduce of the int64
+confusion matrix, all-gather of the label maps - results must equal the single-GPU run exactly."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ['XV_ROOT'])
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+from xview.models import get_model
+data = dict(np.load(os.environ['XV_DATA']))
+c = int(data.pop('c'))
+desc = ({'rgb': np.float32, 'depth': np.float32, 'labels': np.int32},
+        {'rgb': (None, None, 3), 'depth': (None, None, 1), 'labels': (None, None)}, c)
+cms = {'rgb': data.pop('cm_rgb'), 'depth': data.pop('cm_depth')}
+with get_model('bayes_fusion')(confusion_matrices=cms, data_description=desc,
+                               prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn',
+                               num_units=8, num_channels={'rgb': 3, 'depth': 1}, batchsize=2,
+                               seed=3) as net:
+    measures, cm = net.score(data)
+    pred = net.predict({'rgb': data['rgb'], 'depth': data['depth']})
+if rank == 0:
+    np.savez(os.environ['XV_OUT'], cm=cm, pred=pred, miou=measures['mean_IoU'])
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_gpu_score_and_predict_equal_single_gpu(tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.default_rng(0)
+    c, n, h, w = 6, 7, 32, 48                       # 7 images: uneven split over 2 ranks
+    np.savez(tmp_path / 'data.npz', c=c,
+             rgb=rng.integers(0, 256, size=(n, h, w, 3)).astype(np.float32),
+             depth=rng.integers(0, 65536, size=(n, h, w, 1)).astype(np.float32),
+             labels=rng.integers(-1, c, size=(n, h, w)).astype(np.int32),
+             cm_rgb=rng.integers(1, 50, size=(c, c)).astype(np.float64) + 100 * np.eye(c),
+             cm_depth=rng.integers(1, 50, size=(c, c)).astype(np.float64) + 100 * np.eye(c))
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    results = {}
+    for world in (1, 2):
+        env = dict(os.environ, XV_ROOT=root, XV_DATA=str(tmp_path / 'data.npz'),
+                   XV_OUT=str(tmp_path / ('out%d.npz' % world)))
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+               '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
+               '--master-port', str(_free_port()), str(script)]
+        proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+        results[world] = dict(np.load(tmp_path / ('out%d.npz' % world)))
+    np.testing.assert_array_equal(results[2]['cm'], results[1]['cm'])
+    np.testing.assert_array_equal(results[2]['pred'], results[1]['pred'])
+    assert results[2]['miou'] == results[1]['miou']
+    assert results[1]['pred'].shape == (n, h, w)
