@@ -84,10 +84,14 @@ static int make_tmap_act(CUtensorMap* m, const void* ptr, int N, int H, int W, i
 }
 
 static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n);
+static int get_tmap(struct xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W,
+                    int C, int th, int tw);
+static int get_tmap_w(struct xv_fcn* net, CUtensorMap* out, const void* ptr, int kdim, int cout_pad,
+                      int block_n);
 
 // in: bf16 [B,H,W,cin]; out: bf16 [B,H,W,cout] or, with pool, [B,H/2,W/2,cout]
-static int run_igemm_t(const struct ConvLayer& L, const void* in, int B, int H, int W, void* out,
-                       bool pool, cudaStream_t s);
+static int run_igemm_t(struct xv_fcn* net, const struct ConvLayer& L, const void* in, int B, int H,
+                       int W, void* out, bool pool, cudaStream_t s);
 
 static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n) {
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(cout_pad)};
@@ -312,15 +316,31 @@ static int get_tmap(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H
   return 0;
 }
 
+static int get_tmap_w(xv_fcn* net, CUtensorMap* out, const void* ptr, int kdim, int cout_pad,
+                      int block_n) {
+  auto key = std::make_tuple(ptr, kdim, cout_pad, block_n, -1, -1, -1);
+  if (net) {
+    auto it = net->tmaps.find(key);
+    if (it != net->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  XV_TRY(make_tmap_w(out, ptr, kdim, cout_pad, block_n));
+  if (net) net->tmaps[key] = *out;
+  return 0;
+}
+
 // in: bf16 [B,H,W,cin_gemm]; out: bf16 [B,H,W,cout] (cout % 64 == 0) or fp32 [B,H,W,cout]
 static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
                      void* out, bool out_f32, cudaStream_t s) {
-  if (L.use_t && !out_f32 && !(g_debug_flags & 2)) return run_igemm_t(L, in, B, H, W, out, false, s);
+  if (L.use_t && !out_f32 && !(g_debug_flags & 2))
+    return run_igemm_t(net, L, in, B, H, W, out, false, s);
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
   XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, p.th, p.tw));
-  XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
+  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
   if (!out_f32) {
     XV_CHECK(L.cout % 64 == 0, "bf16 epilogue needs Cout % 64 == 0");
     XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, p.th, p.tw));
@@ -352,17 +372,17 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   return rc;
 }
 
-static int run_igemm_t(const ConvLayer& L, const void* in, int B, int H, int W, void* out,
-                       bool pool, cudaStream_t s) {
+static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
+                       void* out, bool pool, cudaStream_t s) {
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   p.th = p.tw = 16;
-  XV_TRY(make_tmap_act(&p.tmap_in, in, B, H, W, L.cin_gemm, 16, 16));
-  XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
+  XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, 16, 16));
+  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
   if (pool) {
-    XV_TRY(make_tmap_act(&p.tmap_out, out, B, H / 2, W / 2, L.cout, 8, 8));
+    XV_TRY(get_tmap(net, &p.tmap_out, out, B, H / 2, W / 2, L.cout, 8, 8));
   } else {
-    XV_TRY(make_tmap_act(&p.tmap_out, out, B, H, W, L.cout, 8, 16));
+    XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, 8, 16));
   }
   p.bias = static_cast<const float*>(L.bias_pad.p);
   p.N = B;
@@ -393,7 +413,7 @@ static int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, 
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
-  XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
+  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
   XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, p.th, p.tw));
   p.tmap_in = p.tmap_out;            // unused in this mode, kept valid for the descriptor prefetch
   p.bias = static_cast<const float*>(L.bias_pad.p);
@@ -475,7 +495,7 @@ struct Forward {
     if (bf16() && L->use_t && !(g_debug_flags & 3)) {
       *out = make(pool_name, DType::BF16, in.B, in.H / 2, in.W / 2, L->cout);
       if (dry) return 0;
-      return run_igemm_t(*L, in.p, in.B, in.H, in.W, out->p, true, s);
+      return run_igemm_t(net, *L, in.p, in.B, in.H, in.W, out->p, true, s);
     }
     Act full;
     XV_TRY(conv(name, in, &full));
@@ -1097,7 +1117,7 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
   const bool use_t = (flags & 512) != 0 && L.use_t;
   const bool t_pool = (flags & 1024) != 0;
   auto once = [&]() -> int {
-    if (use_t) return run_igemm_t(L, in.p, n, h, w, out.p, t_pool, 0);
+    if (use_t) return run_igemm_t(nullptr, L, in.p, n, h, w, out.p, t_pool, 0);
     return launch_conv_igemm(p, L.block_n, L.taps, false, 0);
   };
   XV_TRY(once());

@@ -322,21 +322,26 @@ dirichlet_fuse_kernel(PtrPack probs, int M, const float* __restrict__ alpha_m1,
       const float inv = 1.f / sum;
 #pragma unroll
       for (int k = 0; k < C; ++k) lx[k] = __logf(1e-20f + lx[k] * inv);
-      float ll[CP];
+      // packed fp32 FMAs (fma.rn.f32x2, sm_100): one broadcast LDS.128 feeds two 2-wide FMAs
+      unsigned long long ll2[CP / 2];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) ll[c] = 0.f;
+      for (int c = 0; c < CP / 2; ++c) ll2[c] = 0ull;
 #pragma unroll
       for (int k = 0; k < C; ++k) {
-        const float4* row = reinterpret_cast<const float4*>(s_am1 + (m * C + k) * CP);
+        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(s_am1 + (m * C + k) * CP);
+        unsigned long long xx;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(lx[k]));
 #pragma unroll
         for (int c4 = 0; c4 < CP / 4; ++c4) {
-          const float4 a = row[c4];
-          ll[4 * c4] = fmaf(lx[k], a.x, ll[4 * c4]);
-          ll[4 * c4 + 1] = fmaf(lx[k], a.y, ll[4 * c4 + 1]);
-          ll[4 * c4 + 2] = fmaf(lx[k], a.z, ll[4 * c4 + 2]);
-          ll[4 * c4 + 3] = fmaf(lx[k], a.w, ll[4 * c4 + 3]);
+          const ulonglong2 a = row[c4];
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ll2[2 * c4]) : "l"(xx), "l"(a.x));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ll2[2 * c4 + 1]) : "l"(xx), "l"(a.y));
         }
       }
+      float ll[CP];
+#pragma unroll
+      for (int c = 0; c < CP / 2; ++c)
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(ll[2 * c]), "=f"(ll[2 * c + 1]) : "l"(ll2[c]));
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float t = ll[c] - s_norm[m * C + c];

@@ -29,6 +29,9 @@ def _prior(confusion_matrix, class_prior):
     return prior / prior.sum()
 
 
+_TABLE_CACHE = {}
+
+
 def bayes_tables(confusion_matrices, class_prior='data'):
     """Host-side constants of bayes_fusion (bayes_mix.py:32-54) in the dtype of the matrices:
     log(1e-20 + conditional) per expert [M,C,C] and log(prior) [C]."""
@@ -46,12 +49,17 @@ def bayes_fusion(classifications, confusion_matrices, class_prior='data'):
     """bayes_mix.py:12-58 on the device.  classifications: list of int64/uint8 CUDA label maps;
     confusion_matrices: list of numpy arrays (rows = expert output, cols = ground truth).
     Returns (fused score [.., C] float32 CUDA, log-likelihood tables, conditionals)."""
-    log_cond, log_prior = bayes_tables([np.asarray(m, np.float32) for m in confusion_matrices],
-                                       class_prior)
-    score, _ = dev.bayes_fuse_score(classifications, dev.to_device(log_cond),
-                                    dev.to_device(log_prior))
-    conditionals = [_conditional(np.asarray(m, np.float32)) for m in confusion_matrices]
-    return score, list(log_cond), conditionals
+    # the tables are graph constants in the reference; build + upload them once per set of matrices
+    key = (tuple(np.asarray(m, np.float32).tobytes() for m in confusion_matrices), str(class_prior))
+    if key not in _TABLE_CACHE:
+        log_cond, log_prior = bayes_tables([np.asarray(m, np.float32)
+                                            for m in confusion_matrices], class_prior)
+        conditionals = [_conditional(np.asarray(m, np.float32)) for m in confusion_matrices]
+        _TABLE_CACHE[key] = (dev.to_device(log_cond), dev.to_device(log_prior), list(log_cond),
+                             conditionals)
+    d_cond, d_prior, log_cond, conditionals = _TABLE_CACHE[key]
+    score, _ = dev.bayes_fuse_score(classifications, d_cond, d_prior)
+    return score, log_cond, conditionals
 
 
 def bayes_decision_table(confusion_matrices, class_prior='data'):

@@ -157,22 +157,27 @@ def main():
             name, row['mean_s'], row['std_s'], row['median_warm_s']))
         if args.graph:
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                fn()
+            try:
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fn()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(graph, stream=side):
+                        captured = fn()
                 torch.cuda.synchronize()
-                with torch.cuda.graph(graph, stream=side):
-                    captured = fn()
-            torch.cuda.synchronize()
 
-            def replay():
-                graph.replay()
-                return captured
-            gt = time_command(replay, args.repetitions, lambda t: t.cpu().numpy())
-            row['graph_median_warm_s'] = float(np.median(gt[3:]))
-            print('time_%-18s CUDA graph replay: warm median %.5fs' % (name, row['graph_median_warm_s']))
+                def replay():
+                    graph.replay()
+                    return captured
+                gt = time_command(replay, args.repetitions, lambda t: t.cpu().numpy())
+                row['graph_median_warm_s'] = float(np.median(gt[3:]))
+                print('time_%-18s CUDA graph replay: warm median %.5fs' % (
+                    name, row['graph_median_warm_s']))
+            except RuntimeError as err:
+                torch.cuda.synchronize()
+                print('time_%-18s CUDA graph capture not possible: %s' % (name, str(err)[:80]))
         out['rows'].append(row)
     if args.cpu:
         for name, fn in cpu_commands().items():
