@@ -125,6 +125,31 @@ int xv_fcn_forward(xv_fcn* net, const float* x, int n, int h, int w, const xv_dr
 int xv_fcn_get_layer_host(xv_fcn* net, const char* layer, float* out_host, size_t capacity_floats,
                           int64_t* shape_out_host, void* stream);
 
+/* ---- training of the expert (SimpleFCN.fit: base_model.py:179-261, loss simple_fcn.py:205-215 +
+ * utils.py:43-53, tf.train.AdamOptimizer base_model.py:153-162).  bf16 path, no batch norm. ---- */
+/* Moves fp32 master copies of the trainable variables (conv kernels/biases, score_conv4/5, score;
+ * the bilinear transposed convs are not trainable, simple_fcn.py:81,119-121) plus Adam moments
+ * to the device.  num_params_out = length of the flat parameter / gradient vectors. */
+int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out);
+/* Position of a variable ("conv3_2/kernel", "score/bias", ...) in the flat vectors. */
+int xv_fcn_param_span(xv_fcn* net, const char* name, int64_t* offset_out, int64_t* size_out);
+/* Forward + backward of one batch: x [N,H,W,cin] float32, labels [N,H,W] int32 (labels outside
+ * [0,C) are ignored).  grads (device float32 [num_params]) is OVERWRITTEN with the gradient of
+ * the summed cross-entropy, divided by the number of valid pixels if normalize != 0; loss_out
+ * (device float64[2], may be NULL) receives {sum of -log p[label], number of valid pixels}. */
+int xv_fcn_train_gradients(xv_fcn* net, const float* x, const int32_t* labels, int n, int h, int w,
+                           int train_encoder, int normalize, float* grads, double* loss_out,
+                           void* stream);
+/* grads *= 1 / (1e-20 + loss[1]) (after summing un-normalised gradients and counts over ranks). */
+int xv_scale_by_count(float* grads, int64_t n, const double* loss, void* stream);
+/* One Adam step (lr_t = lr sqrt(1-beta2^t)/(1-beta1^t)) on the master parameters followed by a
+ * refresh of the bf16 operand copies used by the forward and data-gradient kernels. */
+int xv_fcn_adam_step(xv_fcn* net, const float* grads, float learning_rate, float beta1,
+                     float beta2, float epsilon, void* stream);
+/* Current master parameters (flat) to the host; synchronous. */
+int xv_fcn_get_params_host(xv_fcn* net, float* out_host, int64_t capacity, void* stream);
+int xv_fcn_train_end(xv_fcn* net);
+
 /* ---- single layers (xview/models/custom_layers.py:124-139 conv2d, :71-121 deconv2d) ---- */
 /* x [N,H,W,cin] -> out [N,H,W,cout]; k in {1,3}; stride 1 'same'.  precision BF16 needs
  * cin % 64 == 0 (or k == 3 with cin <= 3, the conv1_1 operand-packing path). */

@@ -68,6 +68,13 @@ PROTOTYPES = {
     'xv_fcn_finalize': [_P],
     'xv_fcn_forward': [_P, _P, _I, _I, _I, C.POINTER(DropoutCfg), C.POINTER(FcnOutputs), _P],
     'xv_fcn_get_layer_host': [_P, C.c_char_p, _P, _Z, C.POINTER(_L), _P],
+    'xv_fcn_train_begin': [_P, C.POINTER(_L)],
+    'xv_fcn_param_span': [_P, C.c_char_p, C.POINTER(_L), C.POINTER(_L)],
+    'xv_fcn_train_gradients': [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    'xv_scale_by_count': [_P, _L, _P, _P],
+    'xv_fcn_adam_step': [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P],
+    'xv_fcn_get_params_host': [_P, _P, _L, _P],
+    'xv_fcn_train_end': [_P],
     'xv_conv2d': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'xv_deconv2d': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'xv_maxpool2x2': [_P, _I, _I, _I, _I, _P, _P],

@@ -448,6 +448,7 @@ struct Forward {
   bool dry;
   int T = 1;
   const xv_dropout_cfg* drop = nullptr;
+  bool training = false;     // keep every activation (no pool fusion), materialise score + up5
 
   bool bf16() const { return net->precision == XV_PRECISION_BF16; }
   size_t esize(DType d) const { return d == DType::F32 ? 4 : (d == DType::BF16 ? 2 : 1); }
@@ -460,7 +461,7 @@ struct Forward {
     a.W = W;
     a.C = C;
     a.p = arena.alloc(a.elems() * esize(dt));
-    if (!dry && !name.empty()) net->layers[name] = a;
+    if (!name.empty()) net->layers[name] = a;   // the dry pass records shapes (null pointers)
     return a;
   }
 
@@ -492,7 +493,7 @@ struct Forward {
   int conv_pool(const std::string& name, const std::string& pool_name, const Act& in, Act* out) {
     ConvLayer* L = net->conv(name);
     XV_CHECK(L != nullptr, "unknown conv layer " + name);
-    if (bf16() && L->use_t && !(g_debug_flags & 3)) {
+    if (bf16() && L->use_t && !(g_debug_flags & 3) && !training) {
       *out = make(pool_name, DType::BF16, in.B, in.H / 2, in.W / 2, L->cout);
       if (dry) return 0;
       return run_igemm_t(net, *L, in.p, in.B, in.H, in.W, out->p, true, s);
@@ -605,10 +606,13 @@ int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
   // upscore_conv5 + skip add (simple_fcn.py:82-85)
   fused = make("fused", DType::F32, s4.B, s4.H, s4.W, nu);
   if (net->fast_up5) {
+    Act up5;
+    if (training) up5 = make("upscore_conv5", DType::F32, s4.B, s4.H, s4.W, nu);
     if (!dry)
       XV_TRY(launch_upscore2_add(static_cast<const float*>(s5.p), static_cast<const float*>(s4.p),
                                  static_cast<const float*>(net->g4.p),
-                                 static_cast<float*>(fused.p), s5.B, s5.H, s5.W, nu, s));
+                                 static_cast<float*>(fused.p), s5.B, s5.H, s5.W, nu, s,
+                                 training ? static_cast<float*>(up5.p) : nullptr));
   } else if (!net->batchnorm) {
     if (!dry)
       XV_TRY(launch_deconv_f32(static_cast<const float*>(s5.p),
@@ -645,6 +649,14 @@ int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
 
   if (net->fast_up) {
     Act low = make("score_lowres", DType::F32, B, feat.H, feat.W, C);
+    xv_fcn_outputs train_out;
+    if (training) {
+      Act sc = make("train_score", DType::F32, B, Hf, Wf, C);
+      std::memset(&train_out, 0, sizeof(train_out));
+      train_out.score = static_cast<float*>(sc.p);
+      o = &train_out;
+    }
+    const bool want_samples = o->score || o->prob || o->label_i64 || o->label_u8;
     if (!dry) {
       XV_TRY(launch_score_lowres(static_cast<const float*>(feat.p),
                                  static_cast<const float*>(net->w_score_nuxc.p),
@@ -724,6 +736,7 @@ int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
 
 // =================================================================== extern "C"
 #define XV_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+extern "C" int xv_fcn_train_end(xv_fcn* net);
 
 extern "C" {
 
@@ -828,6 +841,7 @@ int xv_fcn_create(xv_fcn** out, int cin, int num_units, int num_classes, int bat
 }
 
 int xv_fcn_destroy(xv_fcn* net) {
+  xv_fcn_train_end(net);
   delete net;
   return 0;
 }
@@ -1235,6 +1249,370 @@ int xv_confusion_accumulate(const void* pred, int pred_bytes, const int32_t* lab
   XV_TRY(ensure_init());
   return launch_confusion(pred, pred_bytes, labels, npix, C, reinterpret_cast<long long*>(cm),
                           XV_STREAM(stream));
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ training (fit)
+namespace xv {
+
+struct TrainLayer {
+  std::string name;
+  int k, cin, cout;
+  size_t w_off, b_off;               // offsets into the flat parameter / gradient buffers
+  std::unique_ptr<ConvLayer> bwd;    // data-gradient conv (flipped + transposed weights)
+};
+
+struct TrainState {
+  std::vector<TrainLayer> layers;    // conv1_1..conv5_3, score_conv4, score_conv5, score
+  size_t total = 0;
+  DevBuf master, m, v;               // fp32 flat
+  DevBuf loss;                       // double[2]: sum of -log p, #valid pixels
+  int64_t step = 0;
+};
+
+static std::map<xv_fcn*, std::unique_ptr<TrainState>> g_train;
+
+static TrainLayer* find_layer(TrainState* ts, const std::string& n) {
+  for (auto& l : ts->layers)
+    if (l.name == n) return &l;
+  return nullptr;
+}
+
+// master fp32 -> bf16 operand copies (forward + data-gradient) and padded biases of one layer
+static int repack_layer(xv_fcn* net, TrainState* ts, TrainLayer& tl, cudaStream_t s) {
+  ConvLayer* L = net->conv(tl.name);
+  const float* w = static_cast<const float*>(ts->master.p) + tl.w_off;
+  const float* b = static_cast<const float*>(ts->master.p) + tl.b_off;
+  if (tl.name == "score") {
+    XV_CUDA(cudaMemcpyAsync(L->w_f32.p, w, sizeof(float) * tl.cin * tl.cout,
+                            cudaMemcpyDeviceToDevice, s));
+    XV_CUDA(cudaMemcpyAsync(L->bias_f32.p, b, sizeof(float) * tl.cout, cudaMemcpyDeviceToDevice, s));
+    XV_CUDA(cudaMemcpyAsync(net->w_score_nuxc.p, w, sizeof(float) * tl.cin * tl.cout,
+                            cudaMemcpyDeviceToDevice, s));
+    XV_CUDA(cudaMemcpyAsync(net->b_score.p, b, sizeof(float) * tl.cout, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  const bool c1 = (L->taps == 1 && L->k == 3);
+  __nv_bfloat16* bwd = tl.bwd ? static_cast<__nv_bfloat16*>(tl.bwd->w_packed.p) : nullptr;
+  const int bwd_kdim = tl.bwd ? tl.bwd->kdim : 0;
+  XV_TRY(launch_pack_weights(w, static_cast<__nv_bfloat16*>(L->w_packed.p), bwd, tl.k * tl.k, tl.cin,
+                             tl.cout, L->kdim, bwd_kdim, c1 ? 1 : 0, s));
+  XV_CUDA(cudaMemcpyAsync(L->bias_pad.p, b, sizeof(float) * tl.cout, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+struct Backward {
+  xv_fcn* net;
+  TrainState* ts;
+  Arena* arena;
+  cudaStream_t s;
+  bool dry;
+  float* grads;
+
+  Act make(DType dt, int B, int H, int W, int C) {
+    Act a;
+    a.dt = dt;
+    a.B = B;
+    a.H = H;
+    a.W = W;
+    a.C = C;
+    a.p = arena->alloc(a.elems() * (dt == DType::F32 ? 4 : 2));
+    return a;
+  }
+  Act layer(const std::string& n) { return net->layers.at(n); }
+  // dY (already masked by the layer's ReLU) -> weight/bias gradients, optional data gradient
+  int conv_bwd(const std::string& name, const Act& x, const Act& dy, bool need_dx, Act* dx) {
+    TrainLayer* tl = find_layer(ts, name);
+    XV_CHECK(tl != nullptr, "no train layer " + name);
+    if (need_dx) *dx = make(DType::BF16, dy.B, dy.H, dy.W, tl->cin);
+    if (dry) return 0;
+    const size_t npix = static_cast<size_t>(dy.B) * dy.H * dy.W;
+    XV_TRY(launch_bias_grad_bf16(static_cast<const __nv_bfloat16*>(dy.p), grads + tl->b_off, npix,
+                                 tl->cout, s));
+    XV_TRY(launch_conv_wgrad(static_cast<const __nv_bfloat16*>(x.p),
+                             static_cast<const __nv_bfloat16*>(dy.p), grads + tl->w_off, dy.B, dy.H,
+                             dy.W, tl->cin, tl->cout, s));
+    if (need_dx) XV_TRY(run_igemm(net, *tl->bwd, dy.p, dy.B, dy.H, dy.W, dx->p, false, s));
+    return 0;
+  }
+  int relu_bwd(const Act& da, const Act* db, const Act& y, Act* out) {
+    *out = make(DType::BF16, y.B, y.H, y.W, y.C);
+    if (dry) return 0;
+    return launch_relu_bwd_bf16(static_cast<const __nv_bfloat16*>(da.p),
+                                db ? static_cast<const __nv_bfloat16*>(db->p) : nullptr,
+                                static_cast<const __nv_bfloat16*>(y.p),
+                                static_cast<__nv_bfloat16*>(out->p), y.elems(), s);
+  }
+  int pool_bwd(const Act& dp, const Act& y, const Act& p, Act* out) {
+    *out = make(DType::BF16, y.B, y.H, y.W, y.C);
+    if (dry) return 0;
+    return launch_maxpool_bwd_bf16(static_cast<const __nv_bfloat16*>(dp.p),
+                                   static_cast<const __nv_bfloat16*>(y.p),
+                                   static_cast<const __nv_bfloat16*>(p.p),
+                                   static_cast<__nv_bfloat16*>(out->p), y.B, y.H, y.W, y.C, s);
+  }
+  // 1x1 head conv with fp32 ReLU output y: returns the un-masked gradient wrt its bf16 input
+  int head_bwd(const std::string& name, const Act& x, const Act& y, const Act& dy, Act* dx) {
+    TrainLayer* tl = find_layer(ts, name);
+    const int nu = tl->cout, nu_pad = tl->bwd->cin_gemm;
+    Act dpre = make(DType::F32, y.B, y.H, y.W, nu);
+    Act dpre16 = make(DType::BF16, y.B, y.H, y.W, nu_pad);
+    *dx = make(DType::BF16, y.B, y.H, y.W, tl->cin);
+    if (dry) return 0;
+    const size_t npix = static_cast<size_t>(y.B) * y.H * y.W;
+    XV_TRY(launch_relu_mask_f32(static_cast<const float*>(dy.p), static_cast<const float*>(y.p),
+                                static_cast<float*>(dpre.p),
+                                static_cast<__nv_bfloat16*>(dpre16.p), npix, nu, nu_pad, s));
+    XV_TRY(launch_bias_grad_f32(static_cast<const float*>(dpre.p), grads + tl->b_off, npix, nu, s));
+    XV_TRY(launch_outer_sum_bf16(static_cast<const __nv_bfloat16*>(x.p),
+                                 static_cast<const float*>(dpre.p), grads + tl->w_off, npix, tl->cin,
+                                 nu, s));
+    return run_igemm(net, *tl->bwd, dpre16.p, y.B, y.H, y.W, dx->p, false, s);
+  }
+
+  int run(const float* x, const int32_t* labels, int N, int H, int W, int train_encoder);
+};
+
+int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, int train_encoder) {
+  const int nu = net->nu, C = net->C;
+  const int h8 = H / 8, w8 = W / 8, h16 = H / 16, w16 = W / 16;
+  TrainLayer* tscore = find_layer(ts, "score");
+  Act score = layer("train_score"), low = layer("score_lowres"), fused = layer("fused");
+  Act up5 = layer("upscore_conv5"), s4 = layer("score_conv4"), s5 = layer("score_conv5");
+  const size_t npix = static_cast<size_t>(N) * H * W;
+  const size_t nlow = static_cast<size_t>(N) * h8 * w8;
+  // loss + d(score); transposes of the two fixed bilinear layers; score 1x1
+  Act dlow = make(DType::F32, N, h8, w8, C);
+  Act dfused = make(DType::F32, N, h8, w8, nu);
+  Act ds5 = make(DType::F32, N, h16, w16, nu);
+  if (!dry) {
+    XV_TRY(launch_ce_grad(static_cast<float*>(score.p), labels, static_cast<int64_t>(npix), C,
+                          static_cast<double*>(ts->loss.p), grads + tscore->b_off, s));
+    XV_TRY(launch_upsample8_transpose(static_cast<const float*>(score.p),
+                                      static_cast<const float*>(net->g16.p),
+                                      static_cast<float*>(dlow.p), N, h8, w8, C, s));
+    XV_TRY(launch_score_bwd(static_cast<const float*>(dlow.p), static_cast<const float*>(fused.p),
+                            static_cast<const float*>(net->w_score_nuxc.p),
+                            static_cast<float*>(dfused.p), grads + tscore->w_off, nlow, nu, C, s));
+    XV_TRY(launch_upscore2_bwd(static_cast<const float*>(dfused.p),
+                               static_cast<const float*>(up5.p),
+                               static_cast<const float*>(net->g4.p), static_cast<float*>(ds5.p), N,
+                               h16, w16, nu, s));
+  }
+  (void)low;
+  // heads: d(fused) is also d(score_conv4 output)
+  Act c43 = layer("conv4_3"), c53 = layer("conv5_3");
+  Act d43a, d53;
+  XV_TRY(head_bwd("score_conv4", c43, s4, dfused, &d43a));
+  XV_TRY(head_bwd("score_conv5", c53, s5, ds5, &d53));
+  if (!train_encoder) return 0;
+  // encoder, last layer first
+  Act g, dx, dp;
+  XV_TRY(relu_bwd(d53, nullptr, c53, &g));
+  XV_TRY(conv_bwd("conv5_3", layer("conv5_2"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv5_2"), &g));
+  XV_TRY(conv_bwd("conv5_2", layer("conv5_1"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv5_1"), &g));
+  XV_TRY(conv_bwd("conv5_1", layer("pool4"), g, true, &dp));
+  XV_TRY(pool_bwd(dp, c43, layer("pool4"), &dx));
+  XV_TRY(relu_bwd(dx, &d43a, c43, &g));
+  XV_TRY(conv_bwd("conv4_3", layer("conv4_2"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv4_2"), &g));
+  XV_TRY(conv_bwd("conv4_2", layer("conv4_1"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv4_1"), &g));
+  XV_TRY(conv_bwd("conv4_1", layer("pool3"), g, true, &dp));
+  XV_TRY(pool_bwd(dp, layer("conv3_3"), layer("pool3"), &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv3_3"), &g));
+  XV_TRY(conv_bwd("conv3_3", layer("conv3_2"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv3_2"), &g));
+  XV_TRY(conv_bwd("conv3_2", layer("conv3_1"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv3_1"), &g));
+  XV_TRY(conv_bwd("conv3_1", layer("pool2"), g, true, &dp));
+  XV_TRY(pool_bwd(dp, layer("conv2_2"), layer("pool2"), &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv2_2"), &g));
+  XV_TRY(conv_bwd("conv2_2", layer("conv2_1"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv2_1"), &g));
+  XV_TRY(conv_bwd("conv2_1", layer("pool1"), g, true, &dp));
+  XV_TRY(pool_bwd(dp, layer("conv1_2"), layer("pool1"), &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv1_2"), &g));
+  XV_TRY(conv_bwd("conv1_2", layer("conv1_1"), g, true, &dx));
+  XV_TRY(relu_bwd(dx, nullptr, layer("conv1_1"), &g));
+  // conv1_1: weight + bias gradients only (its input is the image)
+  TrainLayer* t11 = find_layer(ts, "conv1_1");
+  if (!dry) {
+    XV_TRY(launch_bias_grad_bf16(static_cast<const __nv_bfloat16*>(g.p), grads + t11->b_off, npix,
+                                 t11->cout, s));
+    XV_TRY(launch_conv_wgrad_c1(x, static_cast<const __nv_bfloat16*>(g.p), grads + t11->w_off, N, H,
+                                W, t11->cin, t11->cout, s));
+  }
+  return 0;
+}
+
+}  // namespace xv
+
+extern "C" {
+
+int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out) {
+  XV_CHECK(net && net->finalized, "xv_fcn_train_begin: finalize the expert first");
+  XV_CHECK(net->precision == XV_PRECISION_BF16 && !net->batchnorm,
+           "fit() runs on the bf16 path without batch normalisation");
+  XV_CHECK(net->fast_up5 && net->fast_up,
+           "fit() needs the (non-trainable) bilinear transposed-conv kernels");
+  std::unique_ptr<TrainState> ts(new TrainState());
+  auto add = [&](const std::string& name, int k, int cin, int cout, bool need_bwd) -> int {
+    TrainLayer tl;
+    tl.name = name;
+    tl.k = k;
+    tl.cin = cin;
+    tl.cout = cout;
+    tl.w_off = ts->total;
+    ts->total += static_cast<size_t>(k) * k * cin * cout;
+    tl.b_off = ts->total;
+    ts->total += cout;
+    if (need_bwd) {
+      // data-gradient conv: Cin' = Cout (padded to 64 for the 1x1 heads), Cout' = Cin, no bias/ReLU
+      tl.bwd.reset(new ConvLayer());
+      ConvLayer* B = tl.bwd.get();
+      B->name = name + "_bwd";
+      B->k = k;
+      B->cin = div_up(cout, 64) * 64;
+      B->cout = cin;
+      B->relu = 0;
+      B->taps = k * k;
+      B->cin_gemm = B->cin;
+      B->kdim = B->taps * B->cin;
+      B->block_n = conv_igemm_block_n(cin);
+      B->cout_pad = div_up(cin, B->block_n) * B->block_n;
+      B->use_t = (k == 3 && cin <= 128 && cin % 64 == 0);
+      if (B->use_t) B->cout_pad = div_up(cin, 128) * 128;
+      std::vector<uint16_t> zw(static_cast<size_t>(B->cout_pad) * B->kdim, 0);
+      std::vector<float> zb(B->cout_pad, 0.f);
+      XV_TRY(B->w_packed.upload(zw));
+      XV_TRY(B->bias_pad.upload(zb));
+    }
+    ts->layers.push_back(std::move(tl));
+    return 0;
+  };
+  int cin = net->cin;
+  for (int i = 0; i < 13; ++i) {
+    XV_TRY(add(kConvNames[i], 3, cin, kConvCout[i], i > 0));
+    cin = kConvCout[i];
+  }
+  XV_TRY(add("score_conv4", 1, 512, net->nu, true));
+  XV_TRY(add("score_conv5", 1, 512, net->nu, true));
+  XV_TRY(add("score", 1, net->nu, net->C, false));
+  // the 1x1 heads' data-gradient operand has K = padded nu: kdim of bwd = cin (padded)
+  std::vector<float> flat(ts->total, 0.f);
+  for (auto& tl : ts->layers) {
+    const HostParam *w, *b;
+    XV_TRY(get_param(net, tl.name + "/kernel", {tl.k, tl.k, tl.cin, tl.cout}, &w));
+    XV_TRY(get_param(net, tl.name + "/bias", {tl.cout}, &b));
+    std::copy(w->data.begin(), w->data.end(), flat.begin() + tl.w_off);
+    std::copy(b->data.begin(), b->data.end(), flat.begin() + tl.b_off);
+  }
+  XV_TRY(ts->master.upload(flat));
+  std::vector<float> zeros(ts->total, 0.f);
+  XV_TRY(ts->m.upload(zeros));
+  XV_TRY(ts->v.upload(zeros));
+  std::vector<double> lz(2, 0.0);
+  XV_TRY(ts->loss.upload(lz));
+  for (auto& tl : ts->layers) XV_TRY(repack_layer(net, ts.get(), tl, 0));
+  XV_CUDA(cudaStreamSynchronize(0));
+  if (num_params_out) *num_params_out = static_cast<int64_t>(ts->total);
+  g_train[net] = std::move(ts);
+  return 0;
+}
+
+int xv_fcn_param_span(xv_fcn* net, const char* name, int64_t* offset, int64_t* size) {
+  auto it = g_train.find(net);
+  XV_CHECK(it != g_train.end(), "xv_fcn_param_span: call xv_fcn_train_begin first");
+  std::string n(name);
+  const size_t slash = n.rfind('/');
+  XV_CHECK(slash != std::string::npos, "parameter name must look like 'conv1_1/kernel'");
+  TrainLayer* tl = find_layer(it->second.get(), n.substr(0, slash));
+  XV_CHECK(tl != nullptr, "not a trainable parameter: " + n);
+  const bool is_w = n.substr(slash + 1) == "kernel";
+  *offset = static_cast<int64_t>(is_w ? tl->w_off : tl->b_off);
+  *size = is_w ? static_cast<int64_t>(tl->k) * tl->k * tl->cin * tl->cout : tl->cout;
+  return 0;
+}
+
+// Forward + backward of one batch.  grads: device float32 [num_params], OVERWRITTEN with the
+// gradient of the cross-entropy (mean over valid pixels if normalize != 0, else the plain sum); loss_out: device double[2], OVERWRITTEN with
+// {sum of -log p over valid pixels, number of valid pixels}.
+int xv_fcn_train_gradients(xv_fcn* net, const float* x, const int32_t* labels, int n, int h, int w,
+                           int train_encoder, int normalize, float* grads, double* loss_out,
+                           void* stream) {
+  auto it = g_train.find(net);
+  XV_CHECK(it != g_train.end(), "xv_fcn_train_gradients: call xv_fcn_train_begin first");
+  XV_CHECK(x && labels && grads, "xv_fcn_train_gradients: NULL argument");
+  XV_CHECK(n >= 1 && h % 16 == 0 && w % 16 == 0, "H and W must be multiples of 16");
+  TrainState* ts = it->second.get();
+  cudaStream_t s = XV_STREAM(stream);
+  xv_fcn_outputs none;
+  std::memset(&none, 0, sizeof(none));
+  Forward plan{net, Arena(), s, true, 1, nullptr};
+  plan.training = true;
+  XV_TRY(plan.run(x, n, h, w, &none));
+  Backward bplan{net, ts, &plan.arena, s, true, grads};
+  XV_TRY(bplan.run(x, labels, n, h, w, train_encoder));
+  XV_TRY(net->arena_buf.ensure(plan.arena.off + 1024));
+  Forward real{net, Arena(), s, false, 1, nullptr};
+  real.training = true;
+  real.arena.base = static_cast<char*>(net->arena_buf.p);
+  net->layers.clear();
+  XV_TRY(real.run(x, n, h, w, &none));
+  XV_CUDA(cudaMemsetAsync(grads, 0, ts->total * sizeof(float), s));
+  XV_CUDA(cudaMemsetAsync(ts->loss.p, 0, 2 * sizeof(double), s));
+  Backward breal{net, ts, &real.arena, s, false, grads};
+  XV_TRY(breal.run(x, labels, n, h, w, train_encoder));
+  if (normalize)
+    XV_TRY(launch_scale_by_count(grads, ts->total, static_cast<const double*>(ts->loss.p), s));
+  if (loss_out)
+    XV_CUDA(cudaMemcpyAsync(loss_out, ts->loss.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+// grads *= 1 / (1e-20 + loss[1]) - the mean over the valid pixels counted in loss[1] (device
+// double[2] as written by xv_fcn_train_gradients, possibly summed over ranks)
+int xv_scale_by_count(float* grads, int64_t n, const double* loss, void* stream) {
+  XV_TRY(ensure_init());
+  return launch_scale_by_count(grads, static_cast<size_t>(n), loss, XV_STREAM(stream));
+}
+
+// tf.train.AdamOptimizer step on the flat parameters, then refresh of the bf16 operand copies.
+int xv_fcn_adam_step(xv_fcn* net, const float* grads, float learning_rate, float beta1, float beta2,
+                     float epsilon, void* stream) {
+  auto it = g_train.find(net);
+  XV_CHECK(it != g_train.end(), "xv_fcn_adam_step: call xv_fcn_train_begin first");
+  TrainState* ts = it->second.get();
+  cudaStream_t s = XV_STREAM(stream);
+  ts->step += 1;
+  const double t = static_cast<double>(ts->step);
+  const float lr_t = static_cast<float>(learning_rate * std::sqrt(1.0 - std::pow(beta2, t)) /
+                                        (1.0 - std::pow(beta1, t)));
+  XV_TRY(launch_adam(static_cast<float*>(ts->master.p), grads, static_cast<float*>(ts->m.p),
+                     static_cast<float*>(ts->v.p), ts->total, lr_t, beta1, beta2, epsilon, s));
+  for (auto& tl : ts->layers) XV_TRY(repack_layer(net, ts, tl, s));
+  return 0;
+}
+
+// Copies the current fp32 master parameters (flat, layout of xv_fcn_param_span) to the host.
+int xv_fcn_get_params_host(xv_fcn* net, float* out_host, int64_t capacity, void* stream) {
+  auto it = g_train.find(net);
+  XV_CHECK(it != g_train.end(), "xv_fcn_get_params_host: call xv_fcn_train_begin first");
+  TrainState* ts = it->second.get();
+  XV_CHECK(capacity >= static_cast<int64_t>(ts->total), "xv_fcn_get_params_host: buffer too small");
+  XV_CUDA(cudaMemcpyAsync(out_host, ts->master.p, ts->total * sizeof(float), cudaMemcpyDeviceToHost,
+                          XV_STREAM(stream)));
+  XV_CUDA(cudaStreamSynchronize(XV_STREAM(stream)));
+  return 0;
+}
+
+int xv_fcn_train_end(xv_fcn* net) {
+  g_train.erase(net);
+  return 0;
 }
 
 }  // extern "C"

@@ -69,7 +69,7 @@ int launch_affine_f32(float* x, const float* scale, const float* shift, size_t n
 // fast decoder pieces (channel-diagonal transposed convolutions)
 // fused = s4 + relu(sum_taps g[ky,kx,u] * s5[tap,u]);  s4 [N,2h,2w,nu], s5 [N,h,w,nu]
 int launch_upscore2_add(const float* s5, const float* s4, const float* g_4x4xnu, float* fused,
-                        int N, int h, int w, int nu, cudaStream_t s);
+                        int N, int h, int w, int nu, cudaStream_t s, float* up5 = nullptr);
 // low[n,y,x,c] = sum_u fused[n,y,x,u] * w[u,c]
 int launch_score_lowres(const float* fused, const float* w_nuxc, float* low, size_t npix, int nu,
                         int C, cudaStream_t s);
@@ -122,6 +122,36 @@ int launch_dirichlet_uncertainty_fuse(const float* const* probs, const float* co
                                       const float* logprior, int C, int64_t npix, float* score,
                                       void* label_out, int label_bytes, cudaStream_t s);
 int launch_reduce_max(const float* x, int64_t n, float* out, cudaStream_t s);
+
+// ------------------------------------------------------------- train.cu
+int launch_ce_grad(float* score, const int32_t* labels, int64_t npix, int C, double* loss,
+                   float* dbias, cudaStream_t s);
+int launch_upsample8_transpose(const float* dscore, const float* g, float* dlow, int N, int h,
+                               int w, int C, cudaStream_t s);
+int launch_score_bwd(const float* dlow, const float* fused, const float* w, float* dfused,
+                     float* dw, size_t npix, int nu, int C, cudaStream_t s);
+int launch_outer_sum_bf16(const __nv_bfloat16* a, const float* b, float* dw, size_t npix, int I,
+                          int J, cudaStream_t s);
+int launch_upscore2_bwd(const float* dfused, const float* up5, const float* g, float* ds5, int N,
+                        int h, int w, int nu, cudaStream_t s);
+int launch_relu_mask_f32(const float* dy, const float* y, float* dpre, __nv_bfloat16* dpre_bf16,
+                         size_t npix, int c, int c_pad, cudaStream_t s);
+int launch_relu_bwd_bf16(const __nv_bfloat16* da, const __nv_bfloat16* db, const __nv_bfloat16* y,
+                         __nv_bfloat16* dy, size_t n, cudaStream_t s);
+int launch_maxpool_bwd_bf16(const __nv_bfloat16* dp, const __nv_bfloat16* y, const __nv_bfloat16* p,
+                            __nv_bfloat16* dy, int N, int H, int W, int C, cudaStream_t s);
+int launch_bias_grad_bf16(const __nv_bfloat16* dy, float* db, size_t npix, int cout,
+                          cudaStream_t s);
+int launch_bias_grad_f32(const float* dy, float* db, size_t npix, int cout, cudaStream_t s);
+int launch_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H,
+                      int W, int cin, int cout, cudaStream_t s);
+int launch_conv_wgrad_c1(const float* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W,
+                         int cin, int cout, cudaStream_t s);
+int launch_scale_by_count(float* g, size_t n, const double* loss, cudaStream_t s);
+int launch_adam(float* w, const float* g, float* m, float* v, size_t n, float lr_t, float b1,
+                float b2, float eps, cudaStream_t s);
+int launch_pack_weights(const float* w, __nv_bfloat16* fwd, __nv_bfloat16* bwd, int taps, int cin,
+                        int cout, int fwd_kdim, int bwd_kdim, int c1_layout, cudaStream_t s);
 
 constexpr int kMaxClasses = 24;
 

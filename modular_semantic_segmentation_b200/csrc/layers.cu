@@ -283,7 +283,7 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
 // 4x4 stride-2 channel-diagonal transposed conv (simple_fcn.py:82-85).
 __global__ void upscore2_add_kernel(const float* __restrict__ s5, const float* __restrict__ s4,
                                     const float* __restrict__ g, float* __restrict__ fused,
-                                    int N, int h, int w, int nu) {
+                                    float* __restrict__ up5, int N, int h, int w, int nu) {
   const int ho = 2 * h, wo = 2 * w;
   const size_t total = static_cast<size_t>(N) * ho * wo * nu;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -311,6 +311,7 @@ __global__ void upscore2_add_kernel(const float* __restrict__ s5, const float* _
       }
     }
     fused[idx] = s4[idx] + fmaxf(acc, 0.f);
+    if (up5) up5[idx] = fmaxf(acc, 0.f);     // kept for the backward pass (ReLU mask)
   }
 }
 
@@ -687,14 +688,14 @@ int launch_affine_f32(float* x, const float* scale, const float* shift, size_t n
   return 0;
 }
 int launch_upscore2_add(const float* s5, const float* s4, const float* g, float* fused, int N,
-                        int h, int w, int nu, cudaStream_t s) {
+                        int h, int w, int nu, cudaStream_t s, float* up5) {
   const size_t total = static_cast<size_t>(N) * 4 * h * w * nu;
-  if (nu % 4 == 0)
+  if (nu % 4 == 0 && up5 == nullptr)
     upscore2_add_v4_kernel<<<grid_for(total / 4), kThreads, 0, s>>>(
         reinterpret_cast<const float4*>(s5), reinterpret_cast<const float4*>(s4),
         reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(fused), N, h, w, nu / 4);
   else
-    upscore2_add_kernel<<<grid_for(total), kThreads, 0, s>>>(s5, s4, g, fused, N, h, w, nu);
+    upscore2_add_kernel<<<grid_for(total), kThreads, 0, s>>>(s5, s4, g, fused, up5, N, h, w, nu);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -1,0 +1,579 @@
+// Backward / optimizer kernels for SimpleFCN.fit() (xview/models/base_model.py:179-261 with the
+// loss of simple_fcn.py:205-215 + utils.py:43-53 and tf.train.AdamOptimizer, base_model.py:153-162).
+//
+// The data gradients of the 3x3 / 1x1 convolutions reuse the forward tcgen05 implicit-GEMM
+// kernels with flipped + transposed weights (conv_igemm*_sm100.cu); this file holds the rest:
+// softmax-cross-entropy gradient, transposes of the two bilinear transposed convolutions,
+// ReLU / max-pool backward, weight + bias gradients (fp32 accumulation on the CUDA cores, round 1)
+// and the Adam update with re-packing of the bf16 operand copies.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xv {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(size_t work, int threads = kThreads, int per_sm = 16) {
+  size_t g = (work + threads - 1) / threads;
+  size_t cap = static_cast<size_t>(device_info().num_sms) * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------ loss
+// score [npix,C] -> dscore in place = softmax(score) - onehot(label) for valid labels, 0 else.
+// loss[0] += sum -log_softmax(score)[label], loss[1] += #valid, dbias[c] += sum dscore[.,c].
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+ce_grad_kernel(float* __restrict__ score, const int32_t* __restrict__ labels, int64_t npix,
+               double* __restrict__ loss, float* __restrict__ dbias) {
+  __shared__ float s_db[C];
+  __shared__ float s_loss[2];
+  if (threadIdx.x < C) s_db[threadIdx.x] = 0.f;
+  if (threadIdx.x < 2) s_loss[threadIdx.x] = 0.f;
+  __syncthreads();
+  float my_loss = 0.f, my_cnt = 0.f;
+  float db[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) db[c] = 0.f;
+  for (int64_t pix = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; pix < npix;
+       pix += static_cast<int64_t>(gridDim.x) * kThreads) {
+    float* s = score + pix * C;
+    const int label = __ldg(labels + pix);
+    const bool valid = label >= 0 && label < C;
+    float v[C];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      v[c] = s[c];
+      mx = fmaxf(mx, v[c]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      v[c] = expf(v[c] - mx);
+      sum += v[c];
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float g = 0.f;
+      if (valid) {
+        g = v[c] * inv - (c == label ? 1.f : 0.f);
+        if (c == label) my_loss -= logf(fmaxf(v[c] * inv, 1e-38f));
+      }
+      s[c] = g;
+      db[c] += g;
+    }
+    if (valid) my_cnt += 1.f;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float t = db[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_db[c], t);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    my_loss += __shfl_xor_sync(0xffffffffu, my_loss, off);
+    my_cnt += __shfl_xor_sync(0xffffffffu, my_cnt, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_loss[0], my_loss);
+    atomicAdd(&s_loss[1], my_cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) atomicAdd(dbias + threadIdx.x, s_db[threadIdx.x]);
+  if (threadIdx.x < 2) atomicAdd(loss + threadIdx.x, static_cast<double>(s_loss[threadIdx.x]));
+}
+
+// Transpose of the x8 upsampling (16x16 stride-8 shared kernel g): one warp per low-res pixel.
+// dlow[n,iy,ix,c] = sum_{ky,kx} g[ky][kx] * dscore[n, 8iy-4+ky, 8ix-4+kx, c]
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+upsample8_transpose_kernel(const float* __restrict__ dscore, const float* __restrict__ g,
+                           float* __restrict__ dlow, int N, int h, int w) {
+  const int H = 8 * h, W = 8 * w;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = static_cast<int64_t>(N) * h * w;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (kThreads / 32);
+  for (int64_t cell = blockIdx.x * static_cast<int64_t>(kThreads / 32) + (threadIdx.x >> 5);
+       cell < total; cell += warps) {
+    const int ix = static_cast<int>(cell % w);
+    const int iy = static_cast<int>((cell / w) % h);
+    const int64_t img = cell / (static_cast<int64_t>(w) * h);
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int t = lane; t < 256; t += 32) {
+      const int ky = t >> 4, kx = t & 15;
+      const int oy = 8 * iy - 4 + ky, ox = 8 * ix - 4 + kx;
+      if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
+      const float wgt = __ldg(g + t);
+      const float* src = dscore + ((img * H + oy) * W + ox) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, __ldg(src + c), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float t = acc[c];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (lane == 0) dlow[cell * C + c] = t;
+    }
+  }
+}
+
+// 1x1 score conv at low resolution: low = fused . W  ->  dfused = dlow . W^T, dW += fused^T . dlow
+__global__ void score_bwd_data_kernel(const float* __restrict__ dlow, const float* __restrict__ w,
+                                      float* __restrict__ dfused, size_t npix, int nu, int C) {
+  const size_t total = npix * nu;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(idx % nu);
+    const size_t p = idx / nu;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(__ldg(dlow + p * C + c), __ldg(w + u * C + c), acc);
+    dfused[idx] = acc;
+  }
+}
+// generic small "A^T . B" over pixels: dW[i][j] += sum_p a[p][i] * b[p][j]  (a: [P,I], b: [P,J])
+template <typename TA>
+__global__ void __launch_bounds__(kThreads)
+outer_sum_kernel(const TA* __restrict__ a, const float* __restrict__ b, float* __restrict__ dw,
+                 size_t npix, int I, int J) {
+  // each block owns a contiguous pixel range; thread t owns entries t, t+256, ... of [I,J]
+  const size_t per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const size_t p0 = blockIdx.x * per_block;
+  const size_t p1 = p0 + per_block < npix ? p0 + per_block : npix;
+  for (int e = threadIdx.x; e < I * J; e += kThreads) {
+    const int i = e / J, j = e - i * J;
+    float acc = 0.f;
+    for (size_t p = p0; p < p1; ++p)
+      acc = fmaf(static_cast<float>(a[p * I + i]), __ldg(b + p * J + j), acc);
+    atomicAdd(dw + e, acc);
+  }
+}
+
+// Transpose of upscore_conv5 (4x4 stride-2 channel-diagonal kernel g[ky,kx,u]) incl. its ReLU:
+// ds5[n,iy,ix,u] = sum_{ky,kx} g * dfused[n,2iy-1+ky,2ix-1+kx,u] * [up5 > 0]
+__global__ void upscore2_bwd_kernel(const float* __restrict__ dfused, const float* __restrict__ up5,
+                                    const float* __restrict__ g, float* __restrict__ ds5, int N,
+                                    int h, int w, int nu) {
+  const int ho = 2 * h, wo = 2 * w;
+  const size_t total = static_cast<size_t>(N) * h * w * nu;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(idx % nu);
+    size_t t = idx / nu;
+    const int ix = static_cast<int>(t % w);
+    t /= w;
+    const int iy = static_cast<int>(t % h);
+    const size_t img = t / h;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int oy = 2 * iy - 1 + ky;
+      if (oy < 0 || oy >= ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ox = 2 * ix - 1 + kx;
+        if (ox < 0 || ox >= wo) continue;
+        const size_t o = ((img * ho + oy) * wo + ox) * nu + u;
+        if (up5[o] > 0.f) acc = fmaf(__ldg(g + (ky * 4 + kx) * nu + u), dfused[o], acc);
+      }
+    }
+    ds5[idx] = acc;
+  }
+}
+
+// head convs (1x1, ReLU, fp32 output y): dpre = dy * [y > 0], also as bf16 for the data-gradient GEMM
+__global__ void relu_mask_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                     float* __restrict__ dpre, __nv_bfloat16* __restrict__ dpre_bf16,
+                                     size_t npix, int c, int c_pad) {
+  const size_t total = npix * c_pad;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c_pad);
+    const size_t p = i / c_pad;
+    float v = 0.f;
+    if (ch < c) {
+      v = y[p * c + ch] > 0.f ? dy[p * c + ch] : 0.f;
+      dpre[p * c + ch] = v;
+    }
+    dpre_bf16[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// dy <- (y > 0) ? (da [+ db]) : 0   (bf16, 8 elements per thread)
+__global__ void relu_bwd_bf16_kernel(const uint4* __restrict__ da, const uint4* __restrict__ db,
+                                     const uint4* __restrict__ y, uint4* __restrict__ dy, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 a = da[i], yy = y[i];
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (db) b = db[i];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w},
+                   yw[4] = {yy.x, yy.y, yy.z, yy.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+      const __nv_bfloat162 bv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
+      const __nv_bfloat162 yv = *reinterpret_cast<const __nv_bfloat162*>(&yw[j]);
+      const float lo = __bfloat162float(yv.x) > 0.f
+                           ? __bfloat162float(av.x) + __bfloat162float(bv.x) : 0.f;
+      const float hi = __bfloat162float(yv.y) > 0.f
+                           ? __bfloat162float(av.y) + __bfloat162float(bv.y) : 0.f;
+      o[j] = pack_bf16x2(lo, hi);
+    }
+    dy[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// 2x2/2 max pool backward: the gradient of a pooled element goes to the FIRST window position
+// holding the maximum (row-major), everything else gets 0.  One thread = one pooled element.
+__global__ void maxpool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dp,
+                                        const __nv_bfloat16* __restrict__ y,
+                                        const __nv_bfloat16* __restrict__ p,
+                                        __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    size_t t = idx / C;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const size_t n = t / Ho;
+    const size_t base = ((n * H + 2 * yo) * W + 2 * xo) * C + c;
+    const size_t offs[4] = {base, base + C, base + static_cast<size_t>(W) * C,
+                            base + static_cast<size_t>(W) * C + C};
+    const float pv = __bfloat162float(p[idx]);
+    const __nv_bfloat16 g = dp[idx];
+    bool given = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool hit = !given && __bfloat162float(y[offs[j]]) == pv;
+      dy[offs[j]] = hit ? g : __float2bfloat16_rn(0.f);
+      given = given || hit;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weight / bias gradients
+// db[co] += sum_p dy[p][co]
+__global__ void __launch_bounds__(kThreads)
+bias_grad_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, size_t npix,
+                      int cout) {
+  // block = 256 threads = (256 / cout_tile) pixel lanes x cout_tile channels, cout_tile = min(cout,256)
+  const int ct = cout < 256 ? cout : 256;
+  const int lanes = kThreads / ct;
+  const int ch = threadIdx.x % ct, lane = threadIdx.x / ct;
+  for (int c0 = 0; c0 < cout; c0 += ct) {
+    float acc = 0.f;
+    for (size_t p = blockIdx.x * static_cast<size_t>(lanes) + lane; p < npix;
+         p += static_cast<size_t>(gridDim.x) * lanes)
+      acc += __bfloat162float(dy[p * cout + c0 + ch]);
+    atomicAdd(db + c0 + ch, acc);
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+bias_grad_f32_kernel(const float* __restrict__ dy, float* __restrict__ db, size_t npix, int cout) {
+  const int lanes = kThreads / cout;            // cout <= 256
+  const int ch = threadIdx.x % cout, lane = threadIdx.x / cout;
+  if (lane >= lanes) return;
+  float acc = 0.f;
+  for (size_t p = blockIdx.x * static_cast<size_t>(lanes) + lane; p < npix;
+       p += static_cast<size_t>(gridDim.x) * lanes)
+    acc += dy[p * cout + ch];
+  atomicAdd(db + ch, acc);
+}
+
+// 3x3 weight gradient, fp32 accumulation on the CUDA cores:
+//   dW[tap][ci][co] += sum_p x[p + tap][ci] * dy[p][co]        (x, dy bf16 NHWC)
+// Block = one (32 ci, 64 co) chunk pair x one slice of 8x8-pixel tiles.  Thread (ci, co-octet)
+// keeps 9 taps x 8 channels = 72 accumulators in registers for its whole slice, the halo'd
+// input tile and the dy tile are staged in shared memory.
+constexpr int kWgCi = 32, kWgCo = 64, kWgTile = 8;
+__global__ void __launch_bounds__(kThreads)
+conv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                  float* __restrict__ dw, int N, int H, int W, int cin, int cout, int tiles_x,
+                  int tiles_y, int num_slices) {
+  __shared__ __nv_bfloat16 s_x[(kWgTile + 2) * (kWgTile + 2) * kWgCi];   // 100 px x 32 ci
+  __shared__ __nv_bfloat16 s_dy[kWgTile * kWgTile * kWgCo];              // 64 px x 64 co
+  const int ci_chunks = cin / kWgCi, co_chunks = cout / kWgCo;
+  const int pair = blockIdx.x % (ci_chunks * co_chunks);
+  const int slice = blockIdx.x / (ci_chunks * co_chunks);
+  const int ci0 = (pair % ci_chunks) * kWgCi, co0 = (pair / ci_chunks) * kWgCo;
+  const int ci = threadIdx.x & 31;             // 0..31
+  const int cog = threadIdx.x >> 5;            // 0..7 -> co octet
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const int total_tiles = N * tiles_y * tiles_x;
+  for (int tile = slice; tile < total_tiles; tile += num_slices) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int img = tile / (tiles_x * tiles_y);
+    const int y0 = ty * kWgTile, x0 = tx * kWgTile;
+    __syncthreads();
+    // halo'd input tile: 100 pixels x 32 channels (64 B per pixel = 4 x 16 B)
+    for (int i = threadIdx.x; i < (kWgTile + 2) * (kWgTile + 2) * 4; i += kThreads) {
+      const int piece = i & 3, pix = i >> 2;
+      const int yy = y0 + pix / (kWgTile + 2) - 1, xx = x0 + pix % (kWgTile + 2) - 1;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = __ldg(reinterpret_cast<const uint4*>(
+            x + ((static_cast<size_t>(img) * H + yy) * W + xx) * cin + ci0 + piece * 8));
+      reinterpret_cast<uint4*>(s_x)[i] = v;
+    }
+    // dy tile: 64 pixels x 64 channels (128 B per pixel = 8 x 16 B)
+    for (int i = threadIdx.x; i < kWgTile * kWgTile * 8; i += kThreads) {
+      const int piece = i & 7, pix = i >> 3;
+      const int yy = y0 + pix / kWgTile, xx = x0 + pix % kWgTile;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (yy < H && xx < W)
+        v = __ldg(reinterpret_cast<const uint4*>(
+            dy + ((static_cast<size_t>(img) * H + yy) * W + xx) * cout + co0 + piece * 8));
+      reinterpret_cast<uint4*>(s_dy)[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int pix = 0; pix < kWgTile * kWgTile; ++pix) {
+      const int py = pix / kWgTile, px = pix % kWgTile;
+      const uint4 dv = reinterpret_cast<const uint4*>(s_dy)[pix * 8 + cog];   // warp broadcast
+      const uint32_t dwv[4] = {dv.x, dv.y, dv.z, dv.w};
+      float d[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 t2 = *reinterpret_cast<const __nv_bfloat162*>(&dwv[j]);
+        d[2 * j] = __bfloat162float(t2.x);
+        d[2 * j + 1] = __bfloat162float(t2.y);
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float xv = __bfloat162float(
+            s_x[((py + t / 3) * (kWgTile + 2) + px + t % 3) * kWgCi + ci]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv, d[j], acc[t][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      atomicAdd(dw + (static_cast<size_t>(t) * cin + ci0 + ci) * cout + co0 + cog * 8 + j, acc[t][j]);
+}
+
+// conv1_1 weight gradient: raw fp32 input with cin <= 3 channels; thread = (k = tap*cin+ci, co)
+__global__ void __launch_bounds__(kThreads)
+conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                     float* __restrict__ dw, int N, int H, int W, int cin, int cout) {
+  const int entries = 9 * cin * cout;
+  const size_t npix = static_cast<size_t>(N) * H * W;
+  const size_t per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const size_t p0 = blockIdx.x * per_block;
+  const size_t p1 = p0 + per_block < npix ? p0 + per_block : npix;
+  for (int e = threadIdx.x; e < entries; e += kThreads) {
+    const int co = e % cout, k = e / cout;
+    const int ci = k % cin, tap = k / cin;
+    const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
+    float acc = 0.f;
+    for (size_t p = p0; p < p1; ++p) {
+      const int px = static_cast<int>(p % W);
+      const int py = static_cast<int>((p / W) % H);
+      const int yy = py + dyy, xx = px + dxx;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const size_t img = p / (static_cast<size_t>(W) * H);
+      acc = fmaf(__ldg(x + ((img * H + yy) * W + xx) * cin + ci),
+                 __bfloat162float(dy[p * cout + co]), acc);
+    }
+    atomicAdd(dw + e, acc);
+  }
+}
+
+// ------------------------------------------------------------------ optimizer + re-packing
+__global__ void scale_kernel(float* __restrict__ g, size_t n, const double* __restrict__ loss) {
+  const float s = static_cast<float>(1.0 / (1e-20 + loss[1]));
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    g[i] *= s;
+}
+// tf.train.AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t); m, v moments; w -= lr_t m/(sqrt(v)+eps)
+__global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr_t, float b1, float b2,
+                            float eps) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+// fp32 HWIO master -> bf16 operand rows.  forward: [co][tap][ci]; backward (flipped + transposed,
+// for the data gradient): [ci][8-tap][co].  conv1_1 layout: [co][hi taps | lo taps | 0] (K = 64).
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                                    __nv_bfloat16* __restrict__ bwd, int taps, int cin, int cout,
+                                    int fwd_kdim, int bwd_kdim, int c1_layout) {
+  const size_t total = static_cast<size_t>(taps) * cin * cout;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % cout);
+    const int ci = static_cast<int>((i / cout) % cin);
+    const int t = static_cast<int>(i / (static_cast<size_t>(cout) * cin));
+    const __nv_bfloat16 q = __float2bfloat16_rn(w[i]);
+    if (c1_layout) {
+      fwd[static_cast<size_t>(co) * 64 + t * cin + ci] = q;
+      fwd[static_cast<size_t>(co) * 64 + 9 * cin + t * cin + ci] = q;
+    } else {
+      fwd[static_cast<size_t>(co) * fwd_kdim + t * cin + ci] = q;
+    }
+    if (bwd) bwd[static_cast<size_t>(ci) * bwd_kdim + (taps - 1 - t) * cout + co] = q;
+  }
+}
+
+#define XV_DISPATCH_C(C, CALL)                                                          \
+  switch (C) {                                                                          \
+    case 2: { constexpr int kC = 2; CALL; break; }                                      \
+    case 3: { constexpr int kC = 3; CALL; break; }                                      \
+    case 4: { constexpr int kC = 4; CALL; break; }                                      \
+    case 5: { constexpr int kC = 5; CALL; break; }                                      \
+    case 6: { constexpr int kC = 6; CALL; break; }                                      \
+    case 7: { constexpr int kC = 7; CALL; break; }                                      \
+    case 8: { constexpr int kC = 8; CALL; break; }                                      \
+    case 9: { constexpr int kC = 9; CALL; break; }                                      \
+    case 10: { constexpr int kC = 10; CALL; break; }                                    \
+    case 11: { constexpr int kC = 11; CALL; break; }                                    \
+    case 12: { constexpr int kC = 12; CALL; break; }                                    \
+    case 13: { constexpr int kC = 13; CALL; break; }                                    \
+    case 14: { constexpr int kC = 14; CALL; break; }                                    \
+    case 15: { constexpr int kC = 15; CALL; break; }                                    \
+    case 16: { constexpr int kC = 16; CALL; break; }                                    \
+    case 17: { constexpr int kC = 17; CALL; break; }                                    \
+    case 18: { constexpr int kC = 18; CALL; break; }                                    \
+    case 19: { constexpr int kC = 19; CALL; break; }                                    \
+    case 20: { constexpr int kC = 20; CALL; break; }                                    \
+    case 21: { constexpr int kC = 21; CALL; break; }                                    \
+    case 22: { constexpr int kC = 22; CALL; break; }                                    \
+    case 23: { constexpr int kC = 23; CALL; break; }                                    \
+    case 24: { constexpr int kC = 24; CALL; break; }                                    \
+    default: return fail("num_classes must be in [2, 24]");                             \
+  }
+
+#define XV_LAUNCHED()                 \
+  XV_CUDA(cudaGetLastError());        \
+  count_launch();                     \
+  return 0
+
+}  // namespace
+
+int launch_ce_grad(float* score, const int32_t* labels, int64_t npix, int C, double* loss,
+                   float* dbias, cudaStream_t s) {
+  XV_DISPATCH_C(C, (ce_grad_kernel<kC><<<grid_for(npix, kThreads, 4), kThreads, 0, s>>>(
+                       score, labels, npix, loss, dbias)));
+  XV_LAUNCHED();
+}
+int launch_upsample8_transpose(const float* dscore, const float* g, float* dlow, int N, int h,
+                               int w, int C, cudaStream_t s) {
+  const int64_t cells = static_cast<int64_t>(N) * h * w;
+  XV_DISPATCH_C(C, (upsample8_transpose_kernel<kC><<<grid_for(cells * 32), kThreads, 0, s>>>(
+                       dscore, g, dlow, N, h, w)));
+  XV_LAUNCHED();
+}
+int launch_score_bwd(const float* dlow, const float* fused, const float* w, float* dfused,
+                     float* dw, size_t npix, int nu, int C, cudaStream_t s) {
+  score_bwd_data_kernel<<<grid_for(npix * nu), kThreads, 0, s>>>(dlow, w, dfused, npix, nu, C);
+  XV_CUDA(cudaGetLastError());
+  outer_sum_kernel<float><<<device_info().num_sms * 2, kThreads, 0, s>>>(fused, dlow, dw, npix, nu, C);
+  count_launch();
+  XV_LAUNCHED();
+}
+int launch_outer_sum_bf16(const __nv_bfloat16* a, const float* b, float* dw, size_t npix, int I,
+                          int J, cudaStream_t s) {
+  outer_sum_kernel<__nv_bfloat16><<<device_info().num_sms * 2, kThreads, 0, s>>>(a, b, dw, npix, I, J);
+  XV_LAUNCHED();
+}
+int launch_upscore2_bwd(const float* dfused, const float* up5, const float* g, float* ds5, int N,
+                        int h, int w, int nu, cudaStream_t s) {
+  upscore2_bwd_kernel<<<grid_for(static_cast<size_t>(N) * h * w * nu), kThreads, 0, s>>>(
+      dfused, up5, g, ds5, N, h, w, nu);
+  XV_LAUNCHED();
+}
+int launch_relu_mask_f32(const float* dy, const float* y, float* dpre, __nv_bfloat16* dpre_bf16,
+                         size_t npix, int c, int c_pad, cudaStream_t s) {
+  relu_mask_f32_kernel<<<grid_for(npix * c_pad), kThreads, 0, s>>>(dy, y, dpre, dpre_bf16, npix, c,
+                                                                  c_pad);
+  XV_LAUNCHED();
+}
+int launch_relu_bwd_bf16(const __nv_bfloat16* da, const __nv_bfloat16* db, const __nv_bfloat16* y,
+                         __nv_bfloat16* dy, size_t n, cudaStream_t s) {
+  XV_CHECK(n % 8 == 0, "relu_bwd: element count must be a multiple of 8");
+  relu_bwd_bf16_kernel<<<grid_for(n / 8), kThreads, 0, s>>>(
+      reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(db),
+      reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(dy), n / 8);
+  XV_LAUNCHED();
+}
+int launch_maxpool_bwd_bf16(const __nv_bfloat16* dp, const __nv_bfloat16* y, const __nv_bfloat16* p,
+                            __nv_bfloat16* dy, int N, int H, int W, int C, cudaStream_t s) {
+  maxpool_bwd_bf16_kernel<<<grid_for(static_cast<size_t>(N) * (H / 2) * (W / 2) * C), kThreads, 0,
+                            s>>>(dp, y, p, dy, N, H, W, C);
+  XV_LAUNCHED();
+}
+int launch_bias_grad_bf16(const __nv_bfloat16* dy, float* db, size_t npix, int cout,
+                          cudaStream_t s) {
+  XV_CHECK(cout <= 256 ? 256 % cout == 0 : cout % 256 == 0, "bias_grad: unsupported Cout");
+  bias_grad_bf16_kernel<<<device_info().num_sms * 2, kThreads, 0, s>>>(dy, db, npix, cout);
+  XV_LAUNCHED();
+}
+int launch_bias_grad_f32(const float* dy, float* db, size_t npix, int cout, cudaStream_t s) {
+  XV_CHECK(cout <= 256, "bias_grad_f32: Cout too large");
+  bias_grad_f32_kernel<<<device_info().num_sms * 2, kThreads, 0, s>>>(dy, db, npix, cout);
+  XV_LAUNCHED();
+}
+int launch_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H,
+                      int W, int cin, int cout, cudaStream_t s) {
+  XV_CHECK(cin % kWgCi == 0 && cout % kWgCo == 0, "conv_wgrad: Cin % 32 and Cout % 64 required");
+  const int tiles_x = div_up(W, kWgTile), tiles_y = div_up(H, kWgTile);
+  const int pairs = (cin / kWgCi) * (cout / kWgCo);
+  const int total_tiles = N * tiles_x * tiles_y;
+  int slices = div_up(device_info().num_sms * 2, pairs);
+  if (slices > total_tiles) slices = total_tiles;
+  if (slices < 1) slices = 1;
+  conv_wgrad_kernel<<<pairs * slices, kThreads, 0, s>>>(x, dy, dw, N, H, W, cin, cout, tiles_x,
+                                                        tiles_y, slices);
+  XV_LAUNCHED();
+}
+int launch_conv_wgrad_c1(const float* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W,
+                         int cin, int cout, cudaStream_t s) {
+  conv_wgrad_c1_kernel<<<device_info().num_sms * 4, kThreads, 0, s>>>(x, dy, dw, N, H, W, cin, cout);
+  XV_LAUNCHED();
+}
+int launch_scale_by_count(float* g, size_t n, const double* loss, cudaStream_t s) {
+  scale_kernel<<<grid_for(n), kThreads, 0, s>>>(g, n, loss);
+  XV_LAUNCHED();
+}
+int launch_adam(float* w, const float* g, float* m, float* v, size_t n, float lr_t, float b1,
+                float b2, float eps, cudaStream_t s) {
+  adam_kernel<<<grid_for(n), kThreads, 0, s>>>(w, g, m, v, n, lr_t, b1, b2, eps);
+  XV_LAUNCHED();
+}
+int launch_pack_weights(const float* w, __nv_bfloat16* fwd, __nv_bfloat16* bwd, int taps, int cin,
+                        int cout, int fwd_kdim, int bwd_kdim, int c1_layout, cudaStream_t s) {
+  pack_weights_kernel<<<grid_for(static_cast<size_t>(taps) * cin * cout), kThreads, 0, s>>>(
+      w, fwd, bwd, taps, cin, cout, fwd_kdim, bwd_kdim, c1_layout);
+  XV_LAUNCHED();
+}
+
+}  // namespace xv

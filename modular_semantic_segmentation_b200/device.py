@@ -157,6 +157,45 @@ class FcnExpert(object):
             torch.cuda.current_stream().synchronize()
         return out
 
+    # ------------------------------------------------------------------ training
+    def train_begin(self):
+        """Creates the device-side fp32 master parameters + Adam state; returns their length."""
+        if self._dirty:
+            self.finalize()
+        n = C.c_int64()
+        call('xv_fcn_train_begin', self._h, C.byref(n))
+        self.num_params = n.value
+        return n.value
+
+    def param_span(self, name):
+        off, size = C.c_int64(), C.c_int64()
+        call('xv_fcn_param_span', self._h, name.encode(), C.byref(off), C.byref(size))
+        return off.value, size.value
+
+    def train_gradients(self, x, labels, train_encoder=True, normalize=True, grads=None,
+                        loss=None):
+        """One forward + backward pass.  Returns (grads float32 CUDA [num_params],
+        loss float64 CUDA [2] = {sum of -log p, number of valid pixels})."""
+        n, h, w, _ = x.shape
+        if grads is None:
+            grads = torch.empty(self.num_params, dtype=torch.float32, device=x.device)
+        if loss is None:
+            loss = torch.empty(2, dtype=torch.float64, device=x.device)
+        call('xv_fcn_train_gradients', self._h, ptr(x.contiguous()), ptr(labels.contiguous()), n, h,
+             w, int(train_encoder), int(normalize), ptr(grads), ptr(loss), stream_ptr())
+        return grads, loss
+
+    def adam_step(self, grads, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        call('xv_fcn_adam_step', self._h, ptr(grads), C.c_float(learning_rate), C.c_float(beta1),
+             C.c_float(beta2), C.c_float(epsilon), stream_ptr())
+
+    def get_params(self):
+        """Current master parameters as one flat float32 numpy vector."""
+        out = np.empty(self.num_params, dtype=np.float32)
+        call('xv_fcn_get_params_host', self._h, out.ctypes.data_as(C.c_void_p), out.size,
+             stream_ptr())
+        return out
+
     def layer(self, name):
         """Activation of a named layer of the last forward call as float32 numpy NHWC."""
         shape = (C.c_int64 * 4)()
@@ -362,6 +401,11 @@ def confusion_accumulate(pred, labels, cm):
 def set_debug_flags(flags):
     """bit0: never fuse pooling, bit1: never use the transposed conv kernel (tests only)."""
     call('xv_set_debug_flags', int(flags))
+
+
+def scale_by_count(grads, loss):
+    """grads *= 1 / (1e-20 + loss[1]) on the device."""
+    call('xv_scale_by_count', ptr(grads), grads.numel(), ptr(loss), stream_ptr())
 
 
 def launch_count():

@@ -123,6 +123,78 @@ class SimpleFCN(BaseModel):
         self._register_expert(self.prefix, expert, variables)
         self.prediction = 'prediction'
 
+    # ------------------------------------------------------------------ training
+    def _training_batches(self, dataset):
+        """Endless stream of training batches (the `.repeat().batch()` of base_model.py:203-206):
+        a dict of arrays is cycled in order, any other iterable of batch dicts is restarted when
+        it is exhausted (pass a list or a re-iterable object)."""
+        while True:
+            empty = True
+            for batch in self._batches(dataset):
+                empty = False
+                yield batch
+            if empty:
+                raise UserWarning('ERROR: empty training dataset')
+
+    def fit(self, dataset, iterations, output=True, validation_dataset=None,
+            validation_interval=100, additional_eval_datasets={}):
+        """base_model.py:179-261: `iterations` Adam steps (trainer / learning_rate from the
+        config, tf defaults beta1=0.9, beta2=0.999, eps=1e-8) on the cross-entropy of
+        simple_fcn.py:205-215.  With torch.distributed initialised every rank trains on its
+        share of each batch and the gradients are summed over ranks (one bucketed all-reduce
+        of the flat gradient vector) before the shared Adam step."""
+        from .. import sharding
+        if self.config.get('trainer', 'adam') != 'adam':
+            raise UserWarning('ERROR: only the adam trainer is available on the B200 path')
+        if self.config['batch_normalization']:
+            raise UserWarning('ERROR: fit() with batch normalisation is not built yet')
+        expert = self._experts[self.prefix]
+        expert.train_begin()
+        lr = float(self.config.get('learning_rate', 0.0001))
+        train_encoder = bool(self.config.get('train_encoder', True))
+        batches = self._training_batches(dataset)
+        grads = loss = None
+        print('INFO: Start training')
+        self.loss_history = []
+        for i in range(iterations):
+            batch = self._to_device(next(batches))
+            grads, loss = expert.train_gradients(batch[self.modality], batch['labels'],
+                                                 train_encoder=train_encoder, normalize=False,
+                                                 grads=grads, loss=loss)
+            sharding.allreduce_sum_(grads)           # bucketed: one flat tensor
+            sharding.allreduce_sum_(loss)
+            dev.scale_by_count(grads, loss)
+            expert.adam_step(grads, learning_rate=lr)
+            self.global_step += 1
+            if validation_dataset is not None and i % validation_interval == 0:
+                l = loss.cpu().numpy()
+                self.loss_history.append(float(l[0] / (1e-20 + l[1])))
+                self._pull_trained_variables()
+                score, _ = self.score(validation_dataset)
+                if output:
+                    print("{:4d}: accuracy {:.2f}, IoU {:.2f}".format(
+                        i, score['total_accuracy'], score['mean_IoU']))
+                if 'abort_at_iou' in self.config and \
+                        score['mean_IoU'] > self.config['abort_at_iou']:
+                    break
+        if loss is not None:
+            l = loss.cpu().numpy()
+            self.loss = float(l[0] / (1e-20 + l[1]))
+        self._pull_trained_variables()
+        print('INFO: Training finished.')
+
+    def _pull_trained_variables(self):
+        """Device master parameters -> self.variables (what export_weights writes)."""
+        expert = self._experts[self.prefix]
+        flat = expert.get_params()
+        for name in list(self.variables.keys()):
+            below = name.split('/', 1)[1]
+            try:
+                off, size = expert.param_span(below)
+            except Exception:
+                continue                               # non-trainable (bilinear kernels)
+            self.variables[name] = flat[off:off + size].reshape(self.variables[name].shape).copy()
+
     def _run_batch(self, batch, fetch='prediction'):
         expert = self._experts[self.prefix]
         x = batch[self.modality]

@@ -1,0 +1,117 @@
+"""GPU parity: SimpleFCN.fit() - gradients and Adam steps against the oracle (torch autograd)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.training import adam_update, loss_and_grads
+from util import cuda
+
+pytestmark = pytest.mark.gpu
+NU, C = 8, 5
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from modular_semantic_segmentation_b200 import device
+    device.init()
+    return device
+
+
+def _setup(dev, rng, cin=3, n=2, h=32, w=48):
+    params = oracle.glorot_fcn_params('m', cin, NU, C, rng, gain=1.45, bias_scale=0.05)
+    net = dev.FcnExpert(cin, NU, C, precision='bf16')
+    net.set_params({k.split('/', 1)[1]: v for k, v in params.items()})
+    x = rng.uniform(0, 1, size=(n, h, w, cin)).astype(np.float32)
+    labels = rng.integers(-1, C, size=(n, h, w)).astype(np.int32)
+    return net, params, x, labels
+
+
+@pytest.mark.parametrize('cin', [3, 1])
+def test_gradients_match_autograd(dev, cin):
+    rng = np.random.default_rng(40 + cin)
+    net, params, x, labels = _setup(dev, rng, cin)
+    total = net.train_begin()
+    grads, loss = net.train_gradients(cuda(x), cuda(labels))
+    grads = grads.cpu().numpy()
+    loss = loss.cpu().numpy()
+    ref_loss, ref = loss_and_grads(params, 'm', x, labels, C)
+    assert loss[1] == (labels >= 0).sum()
+    assert abs(loss[0] / loss[1] - ref_loss) < 2e-2 * abs(ref_loss)
+    covered = 0
+    report = []
+    for name, g_ref in ref.items():
+        off, size = net.param_span(name.split('/', 1)[1])
+        g = grads[off:off + size].reshape(g_ref.shape)
+        covered += size
+        denom = np.linalg.norm(g_ref) + 1e-12
+        rel = np.linalg.norm(g - g_ref) / denom
+        cos = float((g * g_ref).sum() / (np.linalg.norm(g) * denom + 1e-20))
+        report.append('%s rel=%.3f cos=%.4f' % (name, rel, cos))
+        assert cos > 0.98 and rel < 0.2, report[-1]
+    assert covered == total
+    print('\n'.join(report))
+
+
+def test_head_only_training_leaves_encoder_gradients_zero(dev):
+    rng = np.random.default_rng(7)
+    net, params, x, labels = _setup(dev, rng)
+    net.train_begin()
+    grads, _ = net.train_gradients(cuda(x), cuda(labels), train_encoder=False)
+    grads = grads.cpu().numpy()
+    off, size = net.param_span('conv3_2/kernel')
+    assert not grads[off:off + size].any()
+    off, size = net.param_span('score_conv4/kernel')
+    assert grads[off:off + size].any()
+
+
+def test_adam_steps_follow_the_oracle_and_reduce_the_loss(dev):
+    rng = np.random.default_rng(11)
+    net, params, x, labels = _setup(dev, rng)
+    net.train_begin()
+    lr = 1e-4
+    p_ref = {k: v.copy() for k, v in params.items()}
+    m, v = {}, {}
+    losses, ref_losses = [], []
+    for step in range(1, 9):
+        grads, loss = net.train_gradients(cuda(x), cuda(labels))
+        l = loss.cpu().numpy()
+        losses.append(l[0] / l[1])
+        net.adam_step(grads, learning_rate=lr)
+        ref_loss, g_ref = loss_and_grads(p_ref, 'm', x, labels, C)
+        ref_losses.append(ref_loss)
+        adam_update(p_ref, g_ref, m, v, step, learning_rate=lr)
+    assert losses[-1] < losses[0]
+    np.testing.assert_allclose(losses, ref_losses, rtol=5e-2)
+    flat = net.get_params()
+    off, size = net.param_span('score/kernel')
+    np.testing.assert_allclose(flat[off:off + size].reshape(1, 1, NU, C), p_ref['m/score/kernel'],
+                               atol=2.5 * lr * 5)      # |Adam step| <= ~lr per iteration
+
+
+def test_simple_fcn_fit_api(tmp_path):
+    from xview.models import get_model
+    rng = np.random.default_rng(3)
+    desc = ({'rgb': np.float32, 'labels': np.int32}, {'rgb': (None, None, 3),
+                                                      'labels': (None, None)}, C)
+    data = {'rgb': rng.uniform(0, 1, size=(4, 32, 32, 3)).astype(np.float32),
+            'labels': rng.integers(0, C, size=(4, 32, 32)).astype(np.int32)}
+    with get_model('fcn')('rgb', desc, 'rgb', num_units=NU, batch_normalization=False,
+                          learning_rate=1e-3, batchsize=2, seed=5,
+                          output_dir=str(tmp_path)) as net:
+        before = {k: v.copy() for k, v in net.variables.items()}
+        m0, _ = net.score(data)
+        net.fit(data, 12, validation_dataset=data, validation_interval=4, output=False)
+        assert net.global_step == 12
+        assert net.loss_history[-1] < net.loss_history[0]
+        assert not np.array_equal(net.variables['rgb/conv1_1/kernel'], before['rgb/conv1_1/kernel'])
+        np.testing.assert_array_equal(net.variables['rgb/upscore/kernel'],
+                                      before['rgb/upscore/kernel'])      # never trained
+        path = net.export_weights()
+        assert path.endswith('SimpleFCN_weights_12.npz')
+        pred = net.predict({'rgb': data['rgb']})
+    # a fresh model loaded from the exported file predicts the same
+    with get_model('fcn')('rgb', desc, 'rgb', num_units=NU, batch_normalization=False) as net2:
+        net2.import_weights(path, warnings=False)
+        np.testing.assert_array_equal(net2.predict({'rgb': data['rgb']}), pred)
+        assert net2.global_step == 12

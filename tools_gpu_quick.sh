@@ -1,3 +1,25 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_fusion.py -q -m gpu -x -k "dirichlet" 2>&1 | tail -5
-python tools/fusion_bench.py 2>&1 | grep -E "dirichlet_fuse"
+timeout 900 python -m pytest tests/test_gpu_training.py -q -m gpu -x 2>&1 | tail -30
+python - <<'PY'
+import sys, time
+sys.path.insert(0,'.')
+import numpy as np, torch, oracle
+from modular_semantic_segmentation_b200 import device as dev
+dev.init()
+rng=np.random.default_rng(0)
+params=oracle.glorot_fcn_params('m',1,64,12,rng,gain=1.4)
+net=dev.FcnExpert(1,64,12,precision='bf16'); net.set_params({k.split('/',1)[1]:v for k,v in params.items()})
+net.train_begin()
+for N in (4,16):
+    x=torch.rand((N,384,768,1),device='cuda'); lab=torch.randint(0,12,(N,384,768),device='cuda',dtype=torch.int32)
+    g=l=None
+    for _ in range(2):
+        g,l=net.train_gradients(x,lab,grads=g,loss=l); net.adam_step(g)
+    torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        g,l=net.train_gradients(x,lab,grads=g,loss=l); net.adam_step(g)
+    e1.record(); torch.cuda.synchronize()
+    ms=e0.elapsed_time(e1)/3
+    print('fit step N=%d 384x768 depth stream: %.1f ms/step, %.1f frames/s'%(N,ms,N/ms*1e3))
+PY
