@@ -35,7 +35,7 @@ struct IgemmSample {
 static bool g_profile = false;
 static std::vector<IgemmSample> g_samples;
 
-static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer
+static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients
 
 static DeviceInfo g_dev;
 const DeviceInfo& device_info() { return g_dev; }
@@ -1302,6 +1302,42 @@ static int repack_layer(xv_fcn* net, TrainState* ts, TrainLayer& tl, cudaStream_
   return 0;
 }
 
+// tensor-core weight gradient; the split of the pixel tiles over CTAs is chosen to fill whole waves
+static int run_wgrad_tc(xv_fcn* net, const void* x, const void* dy, float* dw, int B, int H, int W,
+                        int cin, int cout, cudaStream_t s) {
+  ConvWgradParams p;
+  std::memset(&p, 0, sizeof(p));
+  choose_tile(H, W, &p.th, &p.tw);
+  XV_TRY(get_tmap(net, &p.tmap_x, x, B, H, W, cin, p.th, p.tw));
+  XV_TRY(get_tmap(net, &p.tmap_dy, dy, B, H, W, cout, p.th, p.tw));
+  p.dw = dw;
+  p.N = B;
+  p.H = H;
+  p.W = W;
+  p.cin = cin;
+  p.cout = cout;
+  p.tiles_x = div_up(W, p.tw);
+  p.tiles_y = div_up(H, p.th);
+  p.m_blocks = div_up(cout, 128);
+  p.total_atoms = 9 * cin / 64;
+  p.n_groups = div_up(p.total_atoms, 4);
+  const int base = p.m_blocks * p.n_groups;
+  const int tiles = B * p.tiles_x * p.tiles_y;
+  const int sms = g_dev.num_sms;
+  int best_k = 1;
+  double best_cost = 1e30;
+  for (int k = 1; k <= 64 && k <= tiles; ++k) {
+    const double waves = std::ceil(static_cast<double>(base) * k / sms);
+    const double cost = waves * (std::ceil(static_cast<double>(tiles) / k) + 6.0);  // + epilogue
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_k = k;
+    }
+  }
+  p.k_splits = best_k;
+  return launch_conv_wgrad_tc(p, s);
+}
+
 struct Backward {
   xv_fcn* net;
   TrainState* ts;
@@ -1330,9 +1366,13 @@ struct Backward {
     const size_t npix = static_cast<size_t>(dy.B) * dy.H * dy.W;
     XV_TRY(launch_bias_grad_bf16(static_cast<const __nv_bfloat16*>(dy.p), grads + tl->b_off, npix,
                                  tl->cout, s));
-    XV_TRY(launch_conv_wgrad(static_cast<const __nv_bfloat16*>(x.p),
-                             static_cast<const __nv_bfloat16*>(dy.p), grads + tl->w_off, dy.B, dy.H,
-                             dy.W, tl->cin, tl->cout, s));
+    if (tl->cin % 64 == 0 && !(g_debug_flags & 8)) {
+      XV_TRY(run_wgrad_tc(net, x.p, dy.p, grads + tl->w_off, dy.B, dy.H, dy.W, tl->cin, tl->cout, s));
+    } else {
+      XV_TRY(launch_conv_wgrad(static_cast<const __nv_bfloat16*>(x.p),
+                               static_cast<const __nv_bfloat16*>(dy.p), grads + tl->w_off, dy.B,
+                               dy.H, dy.W, tl->cin, tl->cout, s));
+    }
     if (need_dx) XV_TRY(run_igemm(net, *tl->bwd, dy.p, dy.B, dy.H, dy.W, dx->p, false, s));
     return 0;
   }

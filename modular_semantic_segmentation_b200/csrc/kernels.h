@@ -35,6 +35,20 @@ int launch_conv_igemm_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t str
 // 2x2 max pool (then tmap_out describes the pooled tensor, box {64,8,8,1}; else {64,16,8,1}).
 int launch_conv_igemm_t(const ConvIgemmParams& p, bool pool, cudaStream_t stream);
 
+// conv_wgrad_sm100.cu: tensor-core weight gradient of a 3x3 'same' convolution
+struct ConvWgradParams {
+  CUtensorMap tmap_x;     // bf16 [N,H,W,Cin]  box {64, tw, th, 1}, SW128
+  CUtensorMap tmap_dy;    // bf16 [N,H,W,Cout] box {64, tw, th, 1}, SW128
+  float* dw;              // fp32 [9][Cin][Cout], accumulated into
+  int N, H, W, cin, cout;
+  int th, tw, tiles_x, tiles_y;
+  int m_blocks;           // ceil(Cout / 128)
+  int total_atoms;        // 9 * Cin / 64  ((tap, 64-channel chunk) pairs)
+  int n_groups;           // ceil(total_atoms / 4)
+  int k_splits;           // pixel tiles are dealt round-robin to k_splits CTAs
+};
+int launch_conv_wgrad_tc(const ConvWgradParams& p, cudaStream_t stream);
+
 // ------------------------------------------------------------- layers.cu
 int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, int cin,
                      cudaStream_t s);

@@ -53,6 +53,22 @@ def test_gradients_match_autograd(dev, cin):
     print('\n'.join(report))
 
 
+def test_tensor_core_weight_gradient_equals_cuda_core_reference(dev):
+    """Same bf16 operands, fp32 accumulation: the tcgen05 wgrad kernel and the CUDA-core kernel
+    must agree to accumulation-order noise."""
+    rng = np.random.default_rng(5)
+    net, params, x, labels = _setup(dev, rng, n=3, h=48, w=80)
+    net.train_begin()
+    g_tc = net.train_gradients(cuda(x), cuda(labels))[0].cpu().numpy()
+    dev.set_debug_flags(8)
+    g_cc = net.train_gradients(cuda(x), cuda(labels))[0].cpu().numpy()
+    dev.set_debug_flags(0)
+    for layer in ('conv1_2', 'conv2_1', 'conv3_2', 'conv4_3', 'conv5_1'):
+        off, size = net.param_span(layer + '/kernel')
+        a, b = g_tc[off:off + size], g_cc[off:off + size]
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-3 * np.abs(b).max(), err_msg=layer)
+
+
 def test_head_only_training_leaves_encoder_gradients_zero(dev):
     rng = np.random.default_rng(7)
     net, params, x, labels = _setup(dev, rng)
