@@ -1363,9 +1363,7 @@ struct Backward {
     XV_CHECK(tl != nullptr, "no train layer " + name);
     if (need_dx) *dx = make(DType::BF16, dy.B, dy.H, dy.W, tl->cin);
     if (dry) return 0;
-    const size_t npix = static_cast<size_t>(dy.B) * dy.H * dy.W;
-    XV_TRY(launch_bias_grad_bf16(static_cast<const __nv_bfloat16*>(dy.p), grads + tl->b_off, npix,
-                                 tl->cout, s));
+    // (the bias gradient was accumulated by the kernel that produced dy)
     if (tl->cin % 64 == 0 && !(g_debug_flags & 8)) {
       XV_TRY(run_wgrad_tc(net, x.p, dy.p, grads + tl->w_off, dy.B, dy.H, dy.W, tl->cin, tl->cout, s));
     } else {
@@ -1376,21 +1374,30 @@ struct Backward {
     if (need_dx) XV_TRY(run_igemm(net, *tl->bwd, dy.p, dy.B, dy.H, dy.W, dx->p, false, s));
     return 0;
   }
-  int relu_bwd(const Act& da, const Act* db, const Act& y, Act* out) {
+  // gradient wrt the pre-ReLU output of conv `name` (+ its bias gradient) from the gradient wrt
+  // its post-ReLU output `da`
+  int relu_bwd(const std::string& name, const Act& da, const Act& y, Act* out) {
+    TrainLayer* tl = find_layer(ts, name);
     *out = make(DType::BF16, y.B, y.H, y.W, y.C);
     if (dry) return 0;
-    return launch_relu_bwd_bf16(static_cast<const __nv_bfloat16*>(da.p),
-                                db ? static_cast<const __nv_bfloat16*>(db->p) : nullptr,
+    return launch_relu_bwd_bf16(static_cast<const __nv_bfloat16*>(da.p), nullptr,
                                 static_cast<const __nv_bfloat16*>(y.p),
-                                static_cast<__nv_bfloat16*>(out->p), y.elems(), s);
+                                static_cast<__nv_bfloat16*>(out->p), y.elems(), y.C,
+                                grads + tl->b_off, s);
   }
-  int pool_bwd(const Act& dp, const Act& y, const Act& p, Act* out) {
+  // same through the 2x2 max pool that follows conv `name` (dp = gradient wrt the pooled map,
+  // extra = optional second gradient wrt the un-pooled map)
+  int pool_relu_bwd(const std::string& name, const Act& dp, const Act& y, const Act& p,
+                    const Act* extra, Act* out) {
+    TrainLayer* tl = find_layer(ts, name);
     *out = make(DType::BF16, y.B, y.H, y.W, y.C);
     if (dry) return 0;
-    return launch_maxpool_bwd_bf16(static_cast<const __nv_bfloat16*>(dp.p),
-                                   static_cast<const __nv_bfloat16*>(y.p),
-                                   static_cast<const __nv_bfloat16*>(p.p),
-                                   static_cast<__nv_bfloat16*>(out->p), y.B, y.H, y.W, y.C, s);
+    return launch_pool_relu_bwd_bf16(static_cast<const __nv_bfloat16*>(dp.p),
+                                     static_cast<const __nv_bfloat16*>(y.p),
+                                     static_cast<const __nv_bfloat16*>(p.p),
+                                     extra ? static_cast<const __nv_bfloat16*>(extra->p) : nullptr,
+                                     static_cast<__nv_bfloat16*>(out->p), y.B, y.H, y.W, y.C,
+                                     grads + tl->b_off, s);
   }
   // 1x1 head conv with fp32 ReLU output y: returns the un-masked gradient wrt its bf16 input
   int head_bwd(const std::string& name, const Act& x, const Act& y, const Act& dy, Act* dx) {
@@ -1449,40 +1456,34 @@ int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, in
   if (!train_encoder) return 0;
   // encoder, last layer first
   Act g, dx, dp;
-  XV_TRY(relu_bwd(d53, nullptr, c53, &g));
+  XV_TRY(relu_bwd("conv5_3", d53, c53, &g));
   XV_TRY(conv_bwd("conv5_3", layer("conv5_2"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv5_2"), &g));
+  XV_TRY(relu_bwd("conv5_2", dx, layer("conv5_2"), &g));
   XV_TRY(conv_bwd("conv5_2", layer("conv5_1"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv5_1"), &g));
+  XV_TRY(relu_bwd("conv5_1", dx, layer("conv5_1"), &g));
   XV_TRY(conv_bwd("conv5_1", layer("pool4"), g, true, &dp));
-  XV_TRY(pool_bwd(dp, c43, layer("pool4"), &dx));
-  XV_TRY(relu_bwd(dx, &d43a, c43, &g));
+  XV_TRY(pool_relu_bwd("conv4_3", dp, c43, layer("pool4"), &d43a, &g));
   XV_TRY(conv_bwd("conv4_3", layer("conv4_2"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv4_2"), &g));
+  XV_TRY(relu_bwd("conv4_2", dx, layer("conv4_2"), &g));
   XV_TRY(conv_bwd("conv4_2", layer("conv4_1"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv4_1"), &g));
+  XV_TRY(relu_bwd("conv4_1", dx, layer("conv4_1"), &g));
   XV_TRY(conv_bwd("conv4_1", layer("pool3"), g, true, &dp));
-  XV_TRY(pool_bwd(dp, layer("conv3_3"), layer("pool3"), &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv3_3"), &g));
+  XV_TRY(pool_relu_bwd("conv3_3", dp, layer("conv3_3"), layer("pool3"), nullptr, &g));
   XV_TRY(conv_bwd("conv3_3", layer("conv3_2"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv3_2"), &g));
+  XV_TRY(relu_bwd("conv3_2", dx, layer("conv3_2"), &g));
   XV_TRY(conv_bwd("conv3_2", layer("conv3_1"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv3_1"), &g));
+  XV_TRY(relu_bwd("conv3_1", dx, layer("conv3_1"), &g));
   XV_TRY(conv_bwd("conv3_1", layer("pool2"), g, true, &dp));
-  XV_TRY(pool_bwd(dp, layer("conv2_2"), layer("pool2"), &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv2_2"), &g));
+  XV_TRY(pool_relu_bwd("conv2_2", dp, layer("conv2_2"), layer("pool2"), nullptr, &g));
   XV_TRY(conv_bwd("conv2_2", layer("conv2_1"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv2_1"), &g));
+  XV_TRY(relu_bwd("conv2_1", dx, layer("conv2_1"), &g));
   XV_TRY(conv_bwd("conv2_1", layer("pool1"), g, true, &dp));
-  XV_TRY(pool_bwd(dp, layer("conv1_2"), layer("pool1"), &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv1_2"), &g));
+  XV_TRY(pool_relu_bwd("conv1_2", dp, layer("conv1_2"), layer("pool1"), nullptr, &g));
   XV_TRY(conv_bwd("conv1_2", layer("conv1_1"), g, true, &dx));
-  XV_TRY(relu_bwd(dx, nullptr, layer("conv1_1"), &g));
+  XV_TRY(relu_bwd("conv1_1", dx, layer("conv1_1"), &g));
   // conv1_1: weight + bias gradients only (its input is the image)
   TrainLayer* t11 = find_layer(ts, "conv1_1");
   if (!dry) {
-    XV_TRY(launch_bias_grad_bf16(static_cast<const __nv_bfloat16*>(g.p), grads + t11->b_off, npix,
-                                 t11->cout, s));
     XV_TRY(launch_conv_wgrad_c1(x, static_cast<const __nv_bfloat16*>(g.p), grads + t11->w_off, N, H,
                                 W, t11->cin, t11->cout, s));
   }

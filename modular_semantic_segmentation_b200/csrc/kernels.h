@@ -151,9 +151,11 @@ int launch_upscore2_bwd(const float* dfused, const float* up5, const float* g, f
 int launch_relu_mask_f32(const float* dy, const float* y, float* dpre, __nv_bfloat16* dpre_bf16,
                          size_t npix, int c, int c_pad, cudaStream_t s);
 int launch_relu_bwd_bf16(const __nv_bfloat16* da, const __nv_bfloat16* db, const __nv_bfloat16* y,
-                         __nv_bfloat16* dy, size_t n, cudaStream_t s);
-int launch_maxpool_bwd_bf16(const __nv_bfloat16* dp, const __nv_bfloat16* y, const __nv_bfloat16* p,
-                            __nv_bfloat16* dy, int N, int H, int W, int C, cudaStream_t s);
+                         __nv_bfloat16* dy, size_t n, int cout, float* bias_grad, cudaStream_t s);
+int launch_pool_relu_bwd_bf16(const __nv_bfloat16* dp, const __nv_bfloat16* y,
+                              const __nv_bfloat16* p, const __nv_bfloat16* extra,
+                              __nv_bfloat16* dy, int N, int H, int W, int C, float* bias_grad,
+                              cudaStream_t s);
 int launch_bias_grad_bf16(const __nv_bfloat16* dy, float* db, size_t npix, int cout,
                           cudaStream_t s);
 int launch_bias_grad_f32(const float* dy, float* db, size_t npix, int cout, cudaStream_t s);

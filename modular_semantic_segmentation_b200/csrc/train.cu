@@ -209,61 +209,111 @@ __global__ void relu_mask_f32_kernel(const float* __restrict__ dy, const float* 
   }
 }
 
-// dy <- (y > 0) ? (da [+ db]) : 0   (bf16, 8 elements per thread)
-__global__ void relu_bwd_bf16_kernel(const uint4* __restrict__ da, const uint4* __restrict__ db,
-                                     const uint4* __restrict__ y, uint4* __restrict__ dy, size_t n8) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const uint4 a = da[i], yy = y[i];
-    uint4 b = make_uint4(0, 0, 0, 0);
-    if (db) b = db[i];
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w},
-                   yw[4] = {yy.x, yy.y, yy.z, yy.w};
-    uint32_t o[4];
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
-      const __nv_bfloat162 bv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
-      const __nv_bfloat162 yv = *reinterpret_cast<const __nv_bfloat162*>(&yw[j]);
-      const float lo = __bfloat162float(yv.x) > 0.f
-                           ? __bfloat162float(av.x) + __bfloat162float(bv.x) : 0.f;
-      const float hi = __bfloat162float(yv.y) > 0.f
-                           ? __bfloat162float(av.y) + __bfloat162float(bv.y) : 0.f;
-      o[j] = pack_bf16x2(lo, hi);
-    }
-    dy[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    f[2 * j] = __bfloat162float(t.x);
+    f[2 * j + 1] = __bfloat162float(t.y);
   }
 }
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+// per-thread partial channel sums -> block shared memory -> global (fused bias gradient)
+__device__ __forceinline__ void flush_bias(const float (&acc)[8], int octet, int cout,
+                                           float* __restrict__ bias_grad) {
+  extern __shared__ float s_bias[];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) s_bias[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&s_bias[octet * 8 + j], acc[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) atomicAdd(bias_grad + i, s_bias[i]);
+}
 
-// 2x2/2 max pool backward: the gradient of a pooled element goes to the FIRST window position
-// holding the maximum (row-major), everything else gets 0.  One thread = one pooled element.
-__global__ void maxpool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dp,
-                                        const __nv_bfloat16* __restrict__ y,
-                                        const __nv_bfloat16* __restrict__ p,
-                                        __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C) {
+// dy <- (y > 0) ? (da [+ db]) : 0  (bf16, one thread = 8 channels of one pixel); optionally
+// bias_grad[c] += sum over pixels of dy[., c] (a thread keeps the same channel octet because the
+// grid stride is a multiple of cout/8).
+__global__ void __launch_bounds__(kThreads)
+relu_bwd_bf16_kernel(const uint4* __restrict__ da, const uint4* __restrict__ db,
+                     const uint4* __restrict__ y, uint4* __restrict__ dy, size_t n8, int cout,
+                     float* __restrict__ bias_grad) {
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float a[8], yy[8], o[8];
+    unpack8(da[i], a);
+    unpack8(y[i], yy);
+    if (db) {
+      float b[8];
+      unpack8(db[i], b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = yy[j] > 0.f ? a[j] : 0.f;
+      acc[j] += o[j];
+    }
+    dy[i] = pack8(o);
+  }
+  if (bias_grad) flush_bias(acc, threadIdx.x % (cout / 8), cout, bias_grad);
+}
+
+// Fused 2x2/2 max-pool backward + ReLU backward (+ optional second gradient source + bias grad):
+// the gradient of a pooled element goes to the FIRST window position holding the maximum
+// (row-major); dy = (y > 0) ? (pool-routed dp [+ extra]) : 0.  One thread = one pooled pixel x 8
+// channels; y / extra / dy are full resolution.
+__global__ void __launch_bounds__(kThreads)
+pool_relu_bwd_bf16_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ y,
+                          const uint4* __restrict__ p, const uint4* __restrict__ extra,
+                          uint4* __restrict__ dy, int N, int H, int W, int C8, int cout,
+                          float* __restrict__ bias_grad) {
   const int Ho = H / 2, Wo = W / 2;
-  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % C);
-    size_t t = idx / C;
+    const int c = static_cast<int>(idx % C8);
+    size_t t = idx / C8;
     const int xo = static_cast<int>(t % Wo);
     t /= Wo;
     const int yo = static_cast<int>(t % Ho);
     const size_t n = t / Ho;
-    const size_t base = ((n * H + 2 * yo) * W + 2 * xo) * C + c;
-    const size_t offs[4] = {base, base + C, base + static_cast<size_t>(W) * C,
-                            base + static_cast<size_t>(W) * C + C};
-    const float pv = __bfloat162float(p[idx]);
-    const __nv_bfloat16 g = dp[idx];
-    bool given = false;
+    const size_t base = ((n * H + 2 * yo) * W + 2 * xo) * C8 + c;
+    const size_t offs[4] = {base, base + C8, base + static_cast<size_t>(W) * C8,
+                            base + static_cast<size_t>(W) * C8 + C8};
+    float g[8], pv[8];
+    unpack8(dp[idx], g);
+    unpack8(p[idx], pv);
+    bool given[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool hit = !given && __bfloat162float(y[offs[j]]) == pv;
-      dy[offs[j]] = hit ? g : __float2bfloat16_rn(0.f);
-      given = given || hit;
+    for (int j = 0; j < 8; ++j) given[j] = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float yy[8], o[8], e[8];
+      unpack8(y[offs[q]], yy);
+      if (extra) unpack8(extra[offs[q]], e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool hit = !given[j] && yy[j] == pv[j];
+        given[j] = given[j] || hit;
+        float v = hit ? g[j] : 0.f;
+        if (extra) v += e[j];
+        o[j] = yy[j] > 0.f ? v : 0.f;
+        acc[j] += o[j];
+      }
+      dy[offs[q]] = pack8(o);
     }
   }
+  if (bias_grad) flush_bias(acc, threadIdx.x % C8, cout, bias_grad);
 }
 
 // ------------------------------------------------------------------ weight / bias gradients
@@ -374,30 +424,40 @@ conv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
       atomicAdd(dw + (static_cast<size_t>(t) * cin + ci0 + ci) * cout + co0 + cog * 8 + j, acc[t][j]);
 }
 
-// conv1_1 weight gradient: raw fp32 input with cin <= 3 channels; thread = (k = tap*cin+ci, co)
+// conv1_1 weight gradient (raw fp32 input, CIN <= 3): thread = (output channel, pixel lane) keeps
+// the 9*CIN partial sums of its channel in registers over a contiguous pixel range; the input
+// neighbourhood loads are warp-uniform broadcasts, the dy loads are coalesced over channels.
+template <int CIN>
 __global__ void __launch_bounds__(kThreads)
 conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                     float* __restrict__ dw, int N, int H, int W, int cin, int cout) {
-  const int entries = 9 * cin * cout;
+                     float* __restrict__ dw, int N, int H, int W, int cout) {
+  constexpr int K = 9 * CIN;
+  const int lanes = kThreads / cout;                       // cout = 64 -> 4 pixel lanes
+  const int co = threadIdx.x % cout, lane = threadIdx.x / cout;
   const size_t npix = static_cast<size_t>(N) * H * W;
   const size_t per_block = (npix + gridDim.x - 1) / gridDim.x;
   const size_t p0 = blockIdx.x * per_block;
   const size_t p1 = p0 + per_block < npix ? p0 + per_block : npix;
-  for (int e = threadIdx.x; e < entries; e += kThreads) {
-    const int co = e % cout, k = e / cout;
-    const int ci = k % cin, tap = k / cin;
-    const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
-    float acc = 0.f;
-    for (size_t p = p0; p < p1; ++p) {
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  if (lane < lanes) {
+    for (size_t p = p0 + lane; p < p1; p += lanes) {
+      const float d = __bfloat162float(dy[p * cout + co]);
       const int px = static_cast<int>(p % W);
       const int py = static_cast<int>((p / W) % H);
-      const int yy = py + dyy, xx = px + dxx;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
       const size_t img = p / (static_cast<size_t>(W) * H);
-      acc = fmaf(__ldg(x + ((img * H + yy) * W + xx) * cin + ci),
-                 __bfloat162float(dy[p * cout + co]), acc);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float* src = x + ((img * H + yy) * W + xx) * CIN;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) acc[tap * CIN + ci] = fmaf(__ldg(src + ci), d, acc[tap * CIN + ci]);
+      }
     }
-    atomicAdd(dw + e, acc);
+#pragma unroll
+    for (int k = 0; k < K; ++k) atomicAdd(dw + k * cout + co, acc[k]);
   }
 }
 
@@ -518,17 +578,24 @@ int launch_relu_mask_f32(const float* dy, const float* y, float* dpre, __nv_bflo
   XV_LAUNCHED();
 }
 int launch_relu_bwd_bf16(const __nv_bfloat16* da, const __nv_bfloat16* db, const __nv_bfloat16* y,
-                         __nv_bfloat16* dy, size_t n, cudaStream_t s) {
-  XV_CHECK(n % 8 == 0, "relu_bwd: element count must be a multiple of 8");
-  relu_bwd_bf16_kernel<<<grid_for(n / 8), kThreads, 0, s>>>(
+                         __nv_bfloat16* dy, size_t n, int cout, float* bias_grad, cudaStream_t s) {
+  XV_CHECK(n % 8 == 0 && cout % 8 == 0 && kThreads % (cout / 8) == 0,
+           "relu_bwd: channel count must be a multiple of 8 dividing 2048");
+  relu_bwd_bf16_kernel<<<grid_for(n / 8), kThreads, cout * sizeof(float), s>>>(
       reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(db),
-      reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(dy), n / 8);
+      reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(dy), n / 8, cout, bias_grad);
   XV_LAUNCHED();
 }
-int launch_maxpool_bwd_bf16(const __nv_bfloat16* dp, const __nv_bfloat16* y, const __nv_bfloat16* p,
-                            __nv_bfloat16* dy, int N, int H, int W, int C, cudaStream_t s) {
-  maxpool_bwd_bf16_kernel<<<grid_for(static_cast<size_t>(N) * (H / 2) * (W / 2) * C), kThreads, 0,
-                            s>>>(dp, y, p, dy, N, H, W, C);
+int launch_pool_relu_bwd_bf16(const __nv_bfloat16* dp, const __nv_bfloat16* y,
+                              const __nv_bfloat16* p, const __nv_bfloat16* extra,
+                              __nv_bfloat16* dy, int N, int H, int W, int C, float* bias_grad,
+                              cudaStream_t s) {
+  XV_CHECK(C % 8 == 0 && kThreads % (C / 8) == 0, "pool_relu_bwd: unsupported channel count");
+  const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+  pool_relu_bwd_bf16_kernel<<<grid_for(total), kThreads, C * sizeof(float), s>>>(
+      reinterpret_cast<const uint4*>(dp), reinterpret_cast<const uint4*>(y),
+      reinterpret_cast<const uint4*>(p), reinterpret_cast<const uint4*>(extra),
+      reinterpret_cast<uint4*>(dy), N, H, W, C / 8, C, bias_grad);
   XV_LAUNCHED();
 }
 int launch_bias_grad_bf16(const __nv_bfloat16* dy, float* db, size_t npix, int cout,
@@ -557,7 +624,11 @@ int launch_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
 }
 int launch_conv_wgrad_c1(const float* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W,
                          int cin, int cout, cudaStream_t s) {
-  conv_wgrad_c1_kernel<<<device_info().num_sms * 4, kThreads, 0, s>>>(x, dy, dw, N, H, W, cin, cout);
+  XV_CHECK(cout <= kThreads && cin >= 1 && cin <= 3, "conv_wgrad_c1: Cin <= 3, Cout <= 256");
+  const int grid = device_info().num_sms * 8;
+  if (cin == 1) conv_wgrad_c1_kernel<1><<<grid, kThreads, 0, s>>>(x, dy, dw, N, H, W, cout);
+  if (cin == 2) conv_wgrad_c1_kernel<2><<<grid, kThreads, 0, s>>>(x, dy, dw, N, H, W, cout);
+  if (cin == 3) conv_wgrad_c1_kernel<3><<<grid, kThreads, 0, s>>>(x, dy, dw, N, H, W, cout);
   XV_LAUNCHED();
 }
 int launch_scale_by_count(float* g, size_t n, const double* loss, cudaStream_t s) {

@@ -1,25 +1,18 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_training.py -q -m gpu -x 2>&1 | tail -30
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 160 --csv --log-file gpurun_out/launches_train.csv python tools/train_probe.py 16 1 > gpurun_out/train_ncu.log 2>&1
 python - <<'PY'
-import sys, time
-sys.path.insert(0,'.')
-import numpy as np, torch, oracle
-from modular_semantic_segmentation_b200 import device as dev
-dev.init()
-rng=np.random.default_rng(0)
-params=oracle.glorot_fcn_params('m',1,64,12,rng,gain=1.4)
-net=dev.FcnExpert(1,64,12,precision='bf16'); net.set_params({k.split('/',1)[1]:v for k,v in params.items()})
-net.train_begin()
-for N in (4,16):
-    x=torch.rand((N,384,768,1),device='cuda'); lab=torch.randint(0,12,(N,384,768),device='cuda',dtype=torch.int32)
-    g=l=None
-    for _ in range(2):
-        g,l=net.train_gradients(x,lab,grads=g,loss=l); net.adam_step(g)
-    torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        g,l=net.train_gradients(x,lab,grads=g,loss=l); net.adam_step(g)
-    e1.record(); torch.cuda.synchronize()
-    ms=e0.elapsed_time(e1)/3
-    print('fit step N=%d 384x768 depth stream: %.1f ms/step, %.1f frames/s'%(N,ms,N/ms*1e3))
+import csv, collections
+rows=[r for r in csv.reader(open('gpurun_out/launches_train.csv')) if len(r)>5]
+hdr=rows[0]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value'); ui=hdr.index('Metric Unit')
+agg=collections.OrderedDict(); tot=0
+for r in rows[1:]:
+    try: v=float(r[vi].replace(',',''))
+    except: continue
+    if r[ui]=='ns': v/=1e3
+    name=r[ki].replace('void ','').replace('<unnamed>::','').split('(')[0][:55]
+    a=agg.setdefault(name,[0,0.0]); a[0]+=1; a[1]+=v; tot+=v
+print('launches',sum(a[0] for a in agg.values()),'total us',round(tot,1))
+for k,(n,t) in sorted(agg.items(), key=lambda kv:-kv[1][1])[:25]:
+    print('%-57s n=%3d  %9.1f us  %5.1f%%'%(k,n,t,100*t/tot))
 PY
