@@ -30,8 +30,18 @@ with get_model('bayes_fusion')(confusion_matrices=cms, data_description=desc,
                                seed=3) as net:
     measures, cm = net.score(data)
     pred = net.predict({'rgb': data['rgb'], 'depth': data['depth']})
+# data-parallel fit(): every rank trains on its share of each batch, gradients are summed
+fdesc = ({'rgb': np.float32, 'labels': np.int32}, {'rgb': (None, None, 3), 'labels': (None, None)}, c)
+train = {'rgb': data['rgb'][:6] / 255.0, 'labels': np.clip(data['labels'][:6], 0, None)}
+with get_model('fcn')('rgb', fdesc, 'rgb', num_units=8, batch_normalization=False,
+                      learning_rate=1e-4, batchsize=4 // world, seed=9) as fnet:  # same global batch
+    fnet.fit(train, 6)
+    trained = fnet.variables['rgb/conv4_2/kernel'].copy()
+    trained_head = fnet.variables['rgb/score/kernel'].copy()
+    final_loss = fnet.loss
 if rank == 0:
-    np.savez(os.environ['XV_OUT'], cm=cm, pred=pred, miou=measures['mean_IoU'])
+    np.savez(os.environ['XV_OUT'], cm=cm, pred=pred, miou=measures['mean_IoU'], trained=trained,
+             trained_head=trained_head, final_loss=final_loss)
 dist.destroy_process_group()
 '''
 
@@ -71,3 +81,12 @@ def test_two_gpu_score_and_predict_equal_single_gpu(tmp_path):
     np.testing.assert_array_equal(results[2]['pred'], results[1]['pred'])
     assert results[2]['miou'] == results[1]['miou']
     assert results[1]['pred'].shape == (n, h, w)
+    # 2-rank data-parallel training follows the 1-rank trajectory (same global batches; the
+    # gradient sums differ only by fp32 accumulation order)
+    np.testing.assert_allclose(results[2]['final_loss'], results[1]['final_loss'], rtol=2e-2)
+    # Adam normalises every step to ~lr, so entries whose gradient is fp32 noise may move in
+    # opposite directions: bound by 2 * lr * steps, and require the bulk to agree closely
+    for key in ('trained_head', 'trained'):
+        diff = np.abs(results[2][key] - results[1][key])
+        assert diff.max() <= 2 * 1e-4 * 6 + 1e-6, (key, diff.max())
+        assert np.median(diff) < 2e-5, (key, np.median(diff))
