@@ -1118,7 +1118,7 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(h, w, &p.th, &p.tw);
-  XV_TRY(make_tmap_act(&p.tmap_in, in.p, n, h, w, cin, p.th, p.tw));
+  if (cin % 64 == 0) XV_TRY(make_tmap_act(&p.tmap_in, in.p, n, h, w, cin, p.th, p.tw));
   XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
   XV_TRY(make_tmap_act(&p.tmap_out, out.p, n, h, w, cout, p.th, p.tw));
   p.bias = static_cast<const float*>(L.bias_pad.p);
@@ -1128,6 +1128,24 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
   cudaEvent_t e0, e1;
   XV_CUDA(cudaEventCreate(&e0));
   XV_CUDA(cudaEventCreate(&e1));
+  if (k == 3 && cin <= 3) {   // conv1_1 path: raw fp32 input, operand packing inside the kernel
+    DevBuf xraw;
+    XV_TRY(xraw.ensure(npix * cin * 4));
+    XV_CUDA(cudaMemset(xraw.p, 0x3c, npix * cin * 4));
+    p.x_raw = static_cast<const float*>(xraw.p);
+    p.tmap_in = p.tmap_out;
+    p.cin = 64;
+    p.n_blocks = 1;
+    XV_TRY(launch_conv_igemm_c1(p, cin, 0));
+    XV_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) XV_TRY(launch_conv_igemm_c1(p, cin, 0));
+    XV_CUDA(cudaEventRecord(e1, 0));
+    XV_CUDA(cudaEventSynchronize(e1));
+    float ms1 = 0.f;
+    XV_CUDA(cudaEventElapsedTime(&ms1, e0, e1));
+    *ms_out = ms1 / iters;
+    return 0;
+  }
   const bool use_t = (flags & 512) != 0 && L.use_t;
   const bool t_pool = (flags & 1024) != 0;
   auto once = [&]() -> int {

@@ -32,7 +32,8 @@ constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kOutBufBytes = kBlockM * 128;      // one 64-channel bf16 output chunk
 constexpr int kThreads = 192;
-constexpr int kPackThreads = 256;                // conv1_1 mode: two groups of 128 operand packers
+constexpr int kPackGroups = 4;                    // conv1_1 mode: groups of 128 operand packers
+constexpr int kPackThreads = 128 * kPackGroups;
 constexpr int kPrefetchTiles = 2;               // L2 prefetch distance in tiles per CTA
 
 template <int BLOCK_N>
@@ -98,7 +99,7 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
     tma_prefetch_desc(&p.tmap_w);
     if (!OUT_F32) tma_prefetch_desc(&p.tmap_out);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], C1 > 0 ? 129 : 1);   // + 128 operand-packing threads
+      mbar_init(&full_bar[s], C1 > 0 ? 2 : 1);     // + one arrival per operand-packing group
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -207,19 +208,25 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
     // ------------------------------------------------------------- conv1_1 operand packing
     constexpr int CIN = C1 > 0 ? C1 : 1;
     constexpr int K9 = 9 * CIN;
-    // two groups of 128 threads alternate tiles so the global loads of one tile overlap the
-    // packing / barrier wait of the previous one
+    // kPackGroups groups of 128 threads take tiles round-robin so the global-load latency of one
+    // tile overlaps the packing / barrier wait of the others
     const int group = (threadIdx.x - kThreads) >> 7;
     const int row = (threadIdx.x - kThreads) & 127;     // pixel index inside the tile
     const int py = row / p.tw;
     const int px = row - py * p.tw;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      if ((local & 1) != group) continue;
+      if ((local % kPackGroups) != group) continue;
       const uint32_t stage = static_cast<uint32_t>(local) % kStages;
       const uint32_t phase = (static_cast<uint32_t>(local) / kStages) & 1u;
       const TileCoord c = decode_tile(p, tile, BLOCK_N);
       const int y = c.y0 + py, x = c.x0 + px;
+      if (p.debug_flags & 1) {                  // experiment: no operand packing work
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        named_bar_sync(2 + group, 128);
+        if (row == 0) mbar_arrive(&full_bar[stage]);
+        continue;
+      }
       float hi[K9], lo[K9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -254,7 +261,8 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
             make_uint4(packed[0], packed[1], packed[2], packed[3]);
       }
       fence_proxy_async_smem();                 // generic-proxy writes -> visible to the MMA
-      mbar_arrive(&full_bar[stage]);
+      named_bar_sync(2 + group, 128);           // whole group done: one mbarrier arrival, not 128
+      if (row == 0) mbar_arrive(&full_bar[stage]);
     }
   } else {
     // ------------------------------------------------------------- epilogue (128 threads)

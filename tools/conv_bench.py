@@ -4,7 +4,7 @@ sys.path.insert(0, '.')
 import torch
 from modular_semantic_segmentation_b200 import _abi, device
 device.init()
-LAYERS = [('conv1_2', 768, 384, 64, 64), ('conv2_1', 384, 192, 64, 128), ('conv2_2', 384, 192, 128, 128),
+LAYERS = [('conv1_1', 768, 384, 3, 64), ('conv1_2', 768, 384, 64, 64), ('conv2_1', 384, 192, 64, 128), ('conv2_2', 384, 192, 128, 128),
           ('conv3_1', 192, 96, 128, 256), ('conv3_2', 192, 96, 256, 256), ('conv4_2', 96, 48, 512, 512),
           ('conv5_1', 48, 24, 512, 512)]
 flags_list = [int(f) for f in sys.argv[1].split(',')] if len(sys.argv) > 1 else [0]
