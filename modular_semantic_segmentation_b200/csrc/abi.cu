@@ -35,7 +35,7 @@ struct IgemmSample {
 static bool g_profile = false;
 static std::vector<IgemmSample> g_samples;
 
-static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients
+static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients, bit4: use the 2-CTA weight-multicast kernel
 
 static DeviceInfo g_dev;
 const DeviceInfo& device_info() { return g_dev; }
@@ -358,7 +358,16 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   p.tiles_y = div_up(H, p.th);
   p.n_blocks = L.cout_pad / L.block_n;
   p.relu = L.relu;
-  if (!g_profile) return launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+  // Optional cluster variant (debug bit4): the two CTAs of a pair share each weight tile by TMA
+  // multicast.  Measured gain on B200 is only 1-2 % - the Cout >= 256 layers are bound by shared-
+  // memory bandwidth (TMA fill + MMA operand reads), not by L2 traffic - so it is off by default.
+  const bool mc = (L.block_n == 256 && !out_f32 && (g_debug_flags & 16));
+  if (mc) XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
+  auto launch = [&]() -> int {
+    return mc ? launch_conv_igemm_mc(p, L.taps, s)
+              : launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+  };
+  if (!g_profile) return launch();
   IgemmSample smp;
   XV_CUDA(cudaEventCreate(&smp.e0));
   XV_CUDA(cudaEventCreate(&smp.e1));
@@ -366,7 +375,7 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   smp.flops = 2.0 * B * H * W * static_cast<double>(L.cout) * L.k * L.k * L.cin;
   smp.block_n = L.block_n;
   XV_CUDA(cudaEventRecord(smp.e0, s));
-  const int rc = launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+  const int rc = launch();
   XV_CUDA(cudaEventRecord(smp.e1, s));
   g_samples.push_back(smp);
   return rc;
@@ -1144,6 +1153,18 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
     float ms1 = 0.f;
     XV_CUDA(cudaEventElapsedTime(&ms1, e0, e1));
     *ms_out = ms1 / iters;
+    return 0;
+  }
+  if ((flags & 2048) && L.block_n == 256) {
+    XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
+    XV_TRY(launch_conv_igemm_mc(p, L.taps, 0));
+    XV_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) XV_TRY(launch_conv_igemm_mc(p, L.taps, 0));
+    XV_CUDA(cudaEventRecord(e1, 0));
+    XV_CUDA(cudaEventSynchronize(e1));
+    float ms2 = 0.f;
+    XV_CUDA(cudaEventElapsedTime(&ms2, e0, e1));
+    *ms_out = ms2 / iters;
     return 0;
   }
   const bool use_t = (flags & 512) != 0 && L.use_t;

@@ -31,6 +31,10 @@ int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_
 // [hi taps | lo taps | 0] are built in shared memory by producer warps (no im2col buffer).
 int launch_conv_igemm_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t stream);
 
+// conv_igemm_mc_sm100.cu: BLOCK_N = 256 with 2-CTA clusters sharing the weight tile by TMA
+// multicast (tmap_w box {64, 128}); bf16 epilogue only.
+int launch_conv_igemm_mc(const ConvIgemmParams& p, int taps, cudaStream_t stream);
+
 // conv_igemm_t_sm100.cu: 3x3, Cout <= 128 per block of 128, 16x16 pixel tiles, optional fused
 // 2x2 max pool (then tmap_out describes the pooled tensor, box {64,8,8,1}; else {64,16,8,1}).
 int launch_conv_igemm_t(const ConvIgemmParams& p, bool pool, cudaStream_t stream);

@@ -50,6 +50,12 @@ def test_conv2d_tcgen05_matches_oracle(dev, n, h, w, cin, cout, k, relu):
     # identical bf16 operands, fp32 accumulation; the bf16 epilogue rounds the result once
     tol = (2.0 ** -8 if cout % 64 == 0 else 1e-5) * scale
     np.testing.assert_allclose(got, ref, rtol=0, atol=tol)
+    if cout >= 256:
+        # 2-CTA cluster kernel with TMA-multicast weight tiles (debug bit4): same numbers
+        dev.set_debug_flags(16)
+        alt = dev.conv2d(cuda(xb), kb, bias, relu=relu, precision='bf16').cpu().numpy()
+        dev.set_debug_flags(0)
+        np.testing.assert_array_equal(alt, got)
     if cout <= 128 and cout % 64 == 0 and k == 3:
         # same layer through the pixel-major kernel (debug bit1) must agree to bf16 rounding
         dev.set_debug_flags(2)

@@ -1,3 +1,3 @@
 #!/bin/bash
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:conv_igemm -c 45 --csv --log-file gpurun_out/c1.csv python tools/perf_probe.py 16 1 3 > /dev/null 2>&1
-grep -E "64, 1, 0, 3|igemm_t_kernel<1>" gpurun_out/c1.csv | awk -F'","' '{print $5, $(NF)}' | tr -d '"' | head -8
+timeout 120 python tools/conv_bench.py 0,2048 conv3_1,conv3_2,conv4_2,conv5_1 2>&1 | tail -10
+timeout 300 python -m pytest tests/test_gpu_layers.py -q -m gpu -x 2>&1 | tail -5
