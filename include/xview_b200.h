@@ -106,6 +106,18 @@ typedef struct xv_fcn_outputs {
 
 int xv_fcn_create(xv_fcn** out, int cin, int num_units, int num_classes, int batchnorm,
                   int precision);
+/* Mid-level fusion network (fusion_fcn.py:11-40 over vgg16.py:7-51): one encoder-only handle per
+ * modality (role XV_ROLE_ENCODER) plus one head handle (role XV_ROLE_HEAD, head_cin = 512 * number
+ * of towers) that owns score_conv4/5 on the channel-concatenated conv4_3 / conv5_3, the bilinear
+ * transposed convolutions and the final score layer. */
+#define XV_ROLE_EXPERT 0
+#define XV_ROLE_ENCODER 1
+#define XV_ROLE_HEAD 2
+int xv_fcn_create_ex(xv_fcn** out, int cin, int num_units, int num_classes, int batchnorm,
+                     int precision, int role, int head_cin);
+int xv_fcn_forward_encoder(xv_fcn* net, const float* x, int n, int h, int w, void* stream);
+int xv_fcn_forward_head(xv_fcn* head, xv_fcn* const* towers_host, int num_towers,
+                        const xv_fcn_outputs* outputs, void* stream);
 int xv_fcn_destroy(xv_fcn* net);
 /* `name` is the variable name below the expert prefix, e.g. "conv1_1/kernel", "score/bias",
  * "upscore/kernel", "conv3_2/moving_variance" (layout: SURVEY.md Appendix B;

@@ -63,6 +63,9 @@ PROTOTYPES = {
     'xv_memset': [_P, _I, _Z, _P],
     'xv_stream_sync': [_P],
     'xv_fcn_create': [_PP, _I, _I, _I, _I, _I],
+    'xv_fcn_create_ex': [_PP, _I, _I, _I, _I, _I, _I, _I],
+    'xv_fcn_forward_encoder': [_P, _P, _I, _I, _I, _P],
+    'xv_fcn_forward_head': [_P, _PP, _I, C.POINTER(FcnOutputs), _P],
     'xv_fcn_destroy': [_P],
     'xv_fcn_set_param_host': [_P, C.c_char_p, _P, C.POINTER(_L), _I],
     'xv_fcn_finalize': [_P],

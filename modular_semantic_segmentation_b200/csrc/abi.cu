@@ -189,6 +189,8 @@ using namespace xv;
 
 struct xv_fcn {
   int cin = 0, nu = 0, C = 0, batchnorm = 0, precision = 0;
+  int role = 0;        // 0 = whole expert, 1 = VGG16 encoder only, 2 = head + decoder only
+  int head_cin = 512;  // input channels of score_conv4/5 (1024 for the two-tower fusion_fcn head)
   bool finalized = false;
   std::map<std::string, HostParam> params;
   std::vector<std::unique_ptr<ConvLayer>> convs;   // conv1_1..conv5_3, score_conv4, score_conv5, score
@@ -545,11 +547,22 @@ struct Forward {
   }
 
   int run(const float* x, int N, int H, int W, const xv_fcn_outputs* o);
+  int run_encoder(const float* x, int N, int H, int W, Act* c43_out, Act* c53_out,
+                  bool* replicated_out);
+  int run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o);
 };
 
 int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
+  Act c43, c53;
+  bool replicated = false;
+  XV_TRY(run_encoder(x, N, H, W, &c43, &c53, &replicated));
+  if (net->role == 1) return 0;
+  return run_head(c43, c53, replicated, o);
+}
+
+int Forward::run_encoder(const float* x, int N, int H, int W, Act* c43_out, Act* c53_out,
+                         bool* replicated_out) {
   const uint32_t sites = drop ? drop->sites : 0u;
-  const bool mc = T > 1;
   Act cur, t;
   if (bf16() && !(g_debug_flags & 4)) {
     // conv1_1 straight from the raw fp32 input (operand packing fused into the GEMM producer)
@@ -598,6 +611,16 @@ int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
   XV_TRY(conv("conv5_2", t, &cur));
   Act c53;
   XV_TRY(conv("conv5_3", cur, &c53));
+  *c43_out = c43;
+  *c53_out = c53;
+  *replicated_out = replicated;
+  return 0;
+}
+
+int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o) {
+  const uint32_t sites = drop ? drop->sites : 0u;
+  const bool mc = T > 1;
+  Act t;
   Act s4in = c43, s5in = c53;
   const bool branch_sites = (sites & (XV_DROP_CONV4_3 | XV_DROP_CONV5_3)) != 0;
   if (branch_sites) {
@@ -849,6 +872,79 @@ int xv_fcn_create(xv_fcn** out, int cin, int num_units, int num_classes, int bat
   return 0;
 }
 
+int xv_fcn_create_ex(xv_fcn** out, int cin, int num_units, int num_classes, int batchnorm,
+                     int precision, int role, int head_cin) {
+  XV_CHECK(role >= 0 && role <= 2, "xv_fcn_create_ex: role must be 0, 1 or 2");
+  XV_CHECK(head_cin >= 64 && head_cin % 64 == 0, "xv_fcn_create_ex: head_cin must be a multiple of 64");
+  XV_TRY(xv_fcn_create(out, role == 2 ? 1 : cin, num_units, num_classes, batchnorm, precision));
+  (*out)->role = role;
+  (*out)->head_cin = head_cin;
+  return 0;
+}
+
+// One VGG16 tower (role 1): runs conv1_1..conv5_3 and keeps conv4_3 / conv5_3 for the head.
+int xv_fcn_forward_encoder(xv_fcn* net, const float* x, int n, int h, int w, void* stream) {
+  XV_CHECK(net && x, "xv_fcn_forward_encoder: NULL argument");
+  XV_CHECK(net->finalized && net->role == 1, "xv_fcn_forward_encoder: needs a finalized encoder");
+  XV_CHECK(n >= 1 && h >= 16 && w >= 16 && h % 16 == 0 && w % 16 == 0,
+           "xv_fcn_forward_encoder: H and W must be positive multiples of 16");
+  xv_fcn_outputs none;
+  std::memset(&none, 0, sizeof(none));
+  Forward plan{net, Arena(), XV_STREAM(stream), true, 1, nullptr};
+  XV_TRY(plan.run(x, n, h, w, &none));
+  XV_TRY(net->arena_buf.ensure(plan.arena.off + 1024));
+  Forward real{net, Arena(), XV_STREAM(stream), false, 1, nullptr};
+  real.arena.base = static_cast<char*>(net->arena_buf.p);
+  net->layers.clear();
+  return real.run(x, n, h, w, &none);
+}
+
+// Mid-level fusion head (role 2, fusion_fcn.py:24-39): channel-concatenates conv4_3 / conv5_3 of
+// the towers' LAST forward_encoder calls, then score_conv4/5 -> upscore_conv5 + add -> decoder.
+int xv_fcn_forward_head(xv_fcn* head, xv_fcn* const* towers, int num_towers,
+                        const xv_fcn_outputs* outputs, void* stream) {
+  XV_CHECK(head && towers && outputs, "xv_fcn_forward_head: NULL argument");
+  XV_CHECK(head->finalized && head->role == 2, "xv_fcn_forward_head: needs a finalized head");
+  XV_CHECK(num_towers >= 1 && num_towers * 512 == head->head_cin,
+           "xv_fcn_forward_head: head_cin must equal 512 * number of towers");
+  cudaStream_t s = XV_STREAM(stream);
+  Act c43s[4], c53s[4];
+  XV_CHECK(num_towers <= 4, "xv_fcn_forward_head: at most 4 towers");
+  for (int m = 0; m < num_towers; ++m) {
+    auto i4 = towers[m]->layers.find("conv4_3");
+    auto i5 = towers[m]->layers.find("conv5_3");
+    XV_CHECK(i4 != towers[m]->layers.end() && i5 != towers[m]->layers.end() && i4->second.p,
+             "xv_fcn_forward_head: run xv_fcn_forward_encoder on every tower first");
+    c43s[m] = i4->second;
+    c53s[m] = i5->second;
+    XV_CHECK(c43s[m].B == c43s[0].B && c43s[m].H == c43s[0].H && c43s[m].W == c43s[0].W,
+             "xv_fcn_forward_head: towers ran on different shapes");
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool dry = pass == 0;
+    Forward f{head, Arena(), s, dry, 1, nullptr};
+    if (!dry) {
+      f.arena.base = static_cast<char*>(head->arena_buf.p);
+      head->layers.clear();
+    }
+    Act cat4 = f.make("concat_conv4", DType::BF16, c43s[0].B, c43s[0].H, c43s[0].W, head->head_cin);
+    Act cat5 = f.make("concat_conv5", DType::BF16, c53s[0].B, c53s[0].H, c53s[0].W, head->head_cin);
+    if (!dry) {
+      for (int m = 0; m < num_towers; ++m) {
+        XV_TRY(launch_concat_bf16(static_cast<const __nv_bfloat16*>(c43s[m].p),
+                                  static_cast<__nv_bfloat16*>(cat4.p), cat4.elems() / cat4.C, 512,
+                                  head->head_cin, m * 512, s));
+        XV_TRY(launch_concat_bf16(static_cast<const __nv_bfloat16*>(c53s[m].p),
+                                  static_cast<__nv_bfloat16*>(cat5.p), cat5.elems() / cat5.C, 512,
+                                  head->head_cin, m * 512, s));
+      }
+    }
+    XV_TRY(f.run_head(cat4, cat5, false, outputs));
+    if (dry) XV_TRY(head->arena_buf.ensure(f.arena.off + 1024));
+  }
+  return 0;
+}
+
 int xv_fcn_destroy(xv_fcn* net) {
   xv_fcn_train_end(net);
   delete net;
@@ -903,12 +999,18 @@ int xv_fcn_finalize(xv_fcn* net) {
     net->convs.push_back(std::move(L));
     return 0;
   };
-  for (int i = 0; i < 13; ++i) {
-    XV_TRY(add_conv(kConvNames[i], 3, cin, kConvCout[i], 1));
-    cin = kConvCout[i];
+  if (net->role != 2) {
+    for (int i = 0; i < 13; ++i) {
+      XV_TRY(add_conv(kConvNames[i], 3, cin, kConvCout[i], 1));
+      cin = kConvCout[i];
+    }
   }
-  XV_TRY(add_conv("score_conv4", 1, 512, nu, 1));
-  XV_TRY(add_conv("score_conv5", 1, 512, nu, 1));
+  if (net->role == 1) {     // encoder only (one tower of fusion_fcn): no heads, no decoder
+    net->finalized = true;
+    return 0;
+  }
+  XV_TRY(add_conv("score_conv4", 1, net->head_cin, nu, 1));
+  XV_TRY(add_conv("score_conv5", 1, net->head_cin, nu, 1));
   {
     // final 1x1 score conv: fp32 weights are always kept (generic decoder); the fast decoder
     // uses the [nu,C] matrix directly

@@ -80,6 +80,8 @@ int launch_conv_f32(const float* x, const float* w_hwio, const float* bias, floa
 int launch_deconv_f32(const float* x, const float* w_khkwoi, float* out, int N, int hin, int win,
                       int cin, int cout, int k, int stride, int relu, const float* addend,
                       cudaStream_t s);
+int launch_concat_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, size_t npix, int c_src,
+                       int c_dst, int offset, cudaStream_t s);
 int launch_add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t s);
 int launch_affine_f32(float* x, const float* scale, const float* shift, size_t npix, int C,
                       int relu, cudaStream_t s);

@@ -271,6 +271,18 @@ __global__ void affine_f32_kernel(float* __restrict__ x, const float* __restrict
   }
 }
 
+// dst[p][offset .. offset+c_src) = src[p][0 .. c_src)   (bf16, 16-byte pieces)
+__global__ void concat_bf16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                   size_t npix, int src8, int dst8, int off8) {
+  const size_t total = npix * src8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = i / src8;
+    const int c = static_cast<int>(i - pix * src8);
+    dst[pix * dst8 + off8 + c] = __ldg(src + i);
+  }
+}
+
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                float* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -670,6 +682,16 @@ int launch_deconv_f32(const float* x, const float* w, float* out, int N, int hin
   const size_t total = static_cast<size_t>(N) * hin * stride * win * stride * cout;
   deconv_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(x, w, out, N, hin, win, cin, cout, k,
                                                          stride, relu, addend);
+  XV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+int launch_concat_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, size_t npix, int c_src,
+                       int c_dst, int offset, cudaStream_t s) {
+  XV_CHECK(c_src % 8 == 0 && c_dst % 8 == 0 && offset % 8 == 0, "concat: channels must be multiples of 8");
+  concat_bf16_kernel<<<grid_for(npix * (c_src / 8)), kThreads, 0, s>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), npix, c_src / 8, c_dst / 8,
+      offset / 8);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

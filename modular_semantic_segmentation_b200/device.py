@@ -68,14 +68,21 @@ class FcnExpert(object):
     """One VGG16-FCN expert on the device (xv_fcn handle): the `fcn()` of
     xview/models/simple_fcn.py:137-170 plus softmax/argmax of basic_fusion_model.py:21-22."""
 
-    def __init__(self, cin, num_units, num_classes, batchnorm=False, precision='bf16'):
+    ROLES = {'expert': 0, 'encoder': 1, 'head': 2}
+
+    def __init__(self, cin, num_units, num_classes, batchnorm=False, precision='bf16',
+                 role='expert', head_cin=512):
+        """role 'encoder' / 'head' are the pieces of the mid-level fusion net (fusion_fcn.py):
+        one VGG16 tower per modality and one head on the concatenated conv4_3 / conv5_3."""
         init()
         self.cin, self.num_units, self.num_classes = cin, num_units, num_classes
         self.batchnorm = bool(batchnorm)
         self.precision = precision
+        self.role = role
         handle = C.c_void_p()
-        call('xv_fcn_create', C.byref(handle), cin, num_units, num_classes, int(self.batchnorm),
-             {'bf16': _abi.XV_PRECISION_BF16, 'fp32': _abi.XV_PRECISION_FP32}[precision])
+        call('xv_fcn_create_ex', C.byref(handle), cin, num_units, num_classes, int(self.batchnorm),
+             {'bf16': _abi.XV_PRECISION_BF16, 'fp32': _abi.XV_PRECISION_FP32}[precision],
+             self.ROLES[role], head_cin)
         self._h = handle
         self._dirty = True
 
@@ -155,6 +162,41 @@ class FcnExpert(object):
              C.byref(o), stream_ptr())
         if keep_alive:
             torch.cuda.current_stream().synchronize()
+        return out
+
+    # ------------------------------------------------------------------ mid-level fusion net
+    def forward_encoder(self, x):
+        """Encoder-only handle: runs conv1_1..conv5_3 on x (float32 CUDA [N,H,W,cin])."""
+        if self._dirty:
+            self.finalize()
+        n, h, w, _ = x.shape
+        call('xv_fcn_forward_encoder', self._h, ptr(x.contiguous()), n, h, w, stream_ptr())
+        self._last_shape = (n, h, w)
+
+    def forward_head(self, towers, want=('label',), label_dtype=torch.int64):
+        """Head handle: fuses the towers' last encoder passes (fusion_fcn.py:24-39)."""
+        if self._dirty:
+            self.finalize()
+        n, h, w = towers[0]._last_shape
+        c = self.num_classes
+        dev = torch.device('cuda', torch.cuda.current_device())
+        out = {}
+        o = _abi.FcnOutputs()
+        if 'score' in want:
+            out['score'] = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+            o.score = out['score'].data_ptr()
+        if 'prob' in want:
+            out['prob'] = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+            o.prob = out['prob'].data_ptr()
+        if 'label' in want:
+            out['label'] = torch.empty((n, h, w), dtype=label_dtype, device=dev)
+            if label_dtype == torch.int64:
+                o.label_i64 = out['label'].data_ptr()
+            else:
+                o.label_u8 = out['label'].data_ptr()
+        handles = (C.c_void_p * len(towers))(*[t._h for t in towers])
+        call('xv_fcn_forward_head', self._h, C.cast(handles, C.POINTER(C.c_void_p)), len(towers),
+             C.byref(o), stream_ptr())
         return out
 
     # ------------------------------------------------------------------ training

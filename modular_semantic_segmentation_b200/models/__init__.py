@@ -4,13 +4,16 @@ from .bayes_mix import BayesFusion
 from .dirichlet_mix import DirichletFusion
 from .average_mix import AverageFusion
 from .variance_mix import VarianceFusion
+from .fusion_fcn import FusionFCN
 
 
 def get_model(name):
-    """xview/models/__init__.py:10-26.  'fusion_fcn' and 'adapnet' are outside the hot path
-    built so far and are reported exactly like an unknown model."""
+    """xview/models/__init__.py:10-26.  'adapnet' is outside the hot path built so far
+     and is reported exactly like an unknown model."""
     if name == 'fcn':
         return SimpleFCN
+    elif name == 'fusion_fcn':
+        return FusionFCN
     elif name in ['bayes_mix', 'bayes_fusion']:
         return BayesFusion
     elif name in ['dirichlet_mix', 'dirichlet_fusion']:

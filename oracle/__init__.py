@@ -29,7 +29,8 @@ Pinning status:
 
 from .fcn import (bilinear_kernel_1d, bilinear_filter, glorot_fcn_params, fcn_param_shapes,
                   conv2d, deconv2d, max_pool2x2, dropout, encoder, decoder, fcn,
-                  softmax, argmax_first, test_pipeline, cross_entropy)
+                  softmax, argmax_first, test_pipeline, cross_entropy, vgg16_tower,
+                  fusion_fcn, fusion_fcn_params)
 from .fusion import (bayes_conditionals, bayes_prior, bayes_fusion, bayes_decision_matrix,
                      dirichlet_log_norm, dirichlet_fusion, dirichlet_prior,
                      dirichlet_uncertainty_fusion,

@@ -256,3 +256,53 @@ def cross_entropy(score, labels, num_classes):
     idx = np.where(valid, labels, 0)
     picked = np.take_along_axis(logp, idx[..., None], axis=-1)[..., 0]
     return float(-(picked * valid).sum() / (1e-20 + valid.sum()))
+
+
+def vgg16_tower(x, params, prefix):
+    """xview/models/vgg16.py:7-51: un-scoped variable names `<prefix>_conv1_1/kernel`."""
+    l = {}
+    cur = x
+    for name, _ in CONV_LAYERS:
+        cur = conv2d(cur, params, '%s_%s' % (prefix, name))
+        l[name] = cur
+        if name in ('conv1_2', 'conv2_2', 'conv3_3', 'conv4_3'):
+            cur = max_pool2x2(cur)
+            l['pool' + name[4]] = cur
+    return l
+
+
+def fusion_fcn(inputs, params, prefixes, num_units, num_classes):
+    """xview/models/fusion_fcn.py:11-40: two VGG16 towers, channel concat of conv4_3 / conv5_3,
+    1x1 score convs, bilinear upscore + add, decoder with prefix 'fused'."""
+    layers = {m: vgg16_tower(inputs[m], params, prefix) for m, prefix in prefixes.items()}
+    layers['concat_conv4'] = np.concatenate([layers[m]['conv4_3'] for m in prefixes], axis=3)
+    layers['concat_conv5'] = np.concatenate([layers[m]['conv5_3'] for m in prefixes], axis=3)
+    layers['score_conv4'] = conv2d(layers['concat_conv4'], params, 'fused_score_conv4')
+    layers['score_conv5'] = conv2d(layers['concat_conv5'], params, 'fused_score_conv5')
+    layers['upscore_conv5'] = deconv2d(layers['score_conv5'], params, 'fused_upscore_conv5', 2)
+    layers['features'] = layers['score_conv4'] + layers['upscore_conv5']
+    layers.update(decoder(layers['features'], params, 'fused', num_units, num_classes))
+    return layers
+
+
+def fusion_fcn_params(prefixes, channels, num_units, num_classes, rng, gain=1.0, bias_scale=0.0):
+    """Random init of fusion_fcn's variables under the names the reference gives them."""
+    params = {}
+    for m, prefix in prefixes.items():
+        tower = glorot_fcn_params('x', channels[m], num_units, num_classes, rng, gain, bias_scale)
+        for name, _ in CONV_LAYERS:
+            for leaf in ('kernel', 'bias'):
+                params['%s_%s/%s' % (prefix, name, leaf)] = tower['x/%s/%s' % (name, leaf)]
+    cin = 512 * len(prefixes)
+    for name in ('fused_score_conv4', 'fused_score_conv5'):
+        limit = gain * np.sqrt(6.0 / (cin + num_units))
+        params[name + '/kernel'] = rng.uniform(-limit, limit, size=(1, 1, cin, num_units)).astype(
+            np.float32)
+        params[name + '/bias'] = (bias_scale * rng.standard_normal(num_units)).astype(np.float32)
+    params['fused_upscore_conv5/kernel'] = bilinear_filter((4, 4, num_units, num_units))
+    params['fused/upscore/kernel'] = bilinear_filter((16, 16, num_units, num_units))
+    limit = gain * np.sqrt(6.0 / (num_units + num_classes))
+    params['fused/score/kernel'] = rng.uniform(-limit, limit, size=(1, 1, num_units, num_classes)
+                                               ).astype(np.float32)
+    params['fused/score/bias'] = (bias_scale * rng.standard_normal(num_classes)).astype(np.float32)
+    return params

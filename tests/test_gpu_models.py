@@ -197,3 +197,33 @@ def test_average_and_variance_fusion_models():
     assert fused.shape == (n, h, w)
     np.testing.assert_allclose(score.sum(-1), 1.0, atol=1e-4)   # convex mix of probabilities
     np.testing.assert_array_equal(fused, np.argmax(score, -1))
+
+
+def test_fusion_fcn_mid_level_fusion_net():
+    """fusion_fcn (two VGG16 towers, concat of conv4_3 / conv5_3) against
+    the oracle, through the model class, the functional API and the legacy variable names."""
+    from xview.models import get_model
+    from xview.models.fusion_fcn import fusion_fcn
+    c, n, h, w = 6, 2, 48, 64
+    rng = np.random.default_rng(8)
+    data = _data(rng, n, h, w, c)
+    prefixes = {'rgb': 'rgb', 'depth': 'depth'}
+    channels = {'rgb': 3, 'depth': 1}
+    params = oracle.fusion_fcn_params(prefixes, channels, NU, c, rng, gain=1.45, bias_scale=0.05)
+    params['rgb_conv1_1/kernel'] /= np.float32(255.0)
+    params['depth_conv1_1/kernel'] /= np.float32(65535.0)
+    ref = oracle.fusion_fcn(data, params, prefixes, NU, c)
+    ref_prob = oracle.softmax(ref['score'])
+    with get_model('fusion_fcn')(_description(c), prefixes, channels, NU, batchsize=2) as net:
+        assert set(net.variables) == set(params)
+        _load(net, params)
+        prob = net.predict(data, output_attr='prob')
+        pred = net.predict({'rgb': data['rgb'], 'depth': data['depth']})
+        measures, cm = net.score(data)
+    np.testing.assert_allclose(prob, ref_prob, rtol=0, atol=2e-2)
+    assert (pred == np.argmax(ref_prob, -1)).mean() > 0.97
+    np.testing.assert_array_equal(cm, oracle.confusion_matrix(data['labels'], pred, c))
+    out = fusion_fcn({m: torch.from_numpy(data[m]).cuda() for m in prefixes}, prefixes, NU, c,
+                     want=('score',), params=params)
+    np.testing.assert_allclose(out['score'].cpu().numpy(), ref['score'], rtol=0,
+                               atol=0.05 * np.abs(ref['score']).max())

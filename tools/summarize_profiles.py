@@ -116,7 +116,7 @@ for r in rows:
 # ---- timing sweep, fit
 t = json.load(open(os.path.join(G, '%s_timing_sweep.json' % R)))
 json.dump(t, open(os.path.join(P, '%s_timing_sweep.json' % R), 'w'), indent=1)
-ref = {'time_rgb_fcn': 0.0219, 'time_depth_fcn': 0.0218, 'time_average_fcn': 0.0432, 'time_bayes_fcn': 0.0461,
+ref = {'time_fusion_fcn': 0.0720, 'time_rgb_fcn': 0.0219, 'time_depth_fcn': 0.0218, 'time_average_fcn': 0.0432, 'time_bayes_fcn': 0.0461,
        'time_dirichlet_fcn': 0.0517, 'time_variance_fcn': 0.3064}
 md.append('\n## Batch-1 latency sweep, protocol of experiments/timing.py (`tools/timing.py`)\n')
 md.append('| command | impl | mean s (first call included) | warm median s | CUDA-graph replay s | reference (GTX 1080 Ti, TF 1.x) s |\n|---|---|---|---|---|---|')

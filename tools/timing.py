@@ -53,6 +53,12 @@ def gpu_commands():
         [dp['rgb'], dp['depth']], 1.0, class_prior_from_counts(dp['class_counts'], 'data'))]
     kw = dict(trainable=False, batchnorm=False)
 
+    from xview.models.fusion_fcn import fusion_fcn
+
+    def fusion_fcn_cmd():                            # timing.py:23-46
+        return fusion_fcn({'rgb': rgb, 'depth': depth}, {'rgb': 'rgb', 'depth': 'depth'}, NU, C,
+                          trainable=False, want=('label',))['label']
+
     def rgb_fcn():                                   # timing.py:266-287
         return fcn(rgb, 'rgb', NU, C, want=('label',), **kw)['label']
 
@@ -88,7 +94,8 @@ def gpu_commands():
             probs.append(fcn(x, m, NU, C, want=('prob',), **kw)['prob'])
         return dev.variance_fuse(probs, variances)[1]
 
-    return {'rgb_fcn': rgb_fcn, 'depth_fcn': depth_fcn, 'average_fcn': average_fcn,
+    return {'fusion_fcn': fusion_fcn_cmd, 'rgb_fcn': rgb_fcn, 'depth_fcn': depth_fcn,
+            'average_fcn': average_fcn,
             'bayes_fcn': bayes_fcn, 'bayes_lookup_fcn': bayes_lookup_fcn,
             'dirichlet_fcn': dirichlet_fcn, 'variance_fcn': variance_fcn}
 
