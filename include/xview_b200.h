@@ -69,6 +69,11 @@ int xv_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream);
 int xv_memset(void* dst, int value, size_t bytes, void* stream);
 int xv_stream_sync(void* stream);
 
+/* ---- input pipeline step (xview/datasets/data_baseclass.py:64-79: stack + astype('float32')) -- */
+/* Raw sensor values -> float32 on the device, after the host->device copy.
+ * src_dtype: 0 = uint8 (rgb), 1 = uint16 (depth), 2 = int16, 3 = int32. */
+int xv_convert_to_f32(const void* src, int src_dtype, int64_t n, float* dst, void* stream);
+
 /* ---- FCN expert (xview/models/simple_fcn.py:137-170 `fcn`, :10-87 encoder, :90-134 decoder) */
 typedef struct xv_fcn xv_fcn;
 

@@ -62,6 +62,7 @@ PROTOTYPES = {
     'xv_memcpy_d2h': [_P, _P, _Z, _P],
     'xv_memset': [_P, _I, _Z, _P],
     'xv_stream_sync': [_P],
+    'xv_convert_to_f32': [_P, _I, _L, _P, _P],
     'xv_fcn_create': [_PP, _I, _I, _I, _I, _I],
     'xv_fcn_create_ex': [_PP, _I, _I, _I, _I, _I, _I, _I],
     'xv_fcn_forward_encoder': [_P, _P, _I, _I, _I, _P],

@@ -1199,6 +1199,12 @@ int xv_deconv2d(const float* x, const float* w_host, int n, int h, int w, int ci
   return 0;
 }
 
+int xv_convert_to_f32(const void* src, int src_dtype, int64_t n, float* dst, void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(src && dst && n >= 0, "xv_convert_to_f32: bad argument");
+  return launch_to_f32(src, src_dtype, dst, static_cast<size_t>(n), XV_STREAM(stream));
+}
+
 int xv_maxpool2x2(const float* x, int n, int h, int w, int c, float* out, void* stream) {
   XV_TRY(ensure_init());
   return launch_maxpool_f32(x, out, n, h, w, c, XV_STREAM(stream));

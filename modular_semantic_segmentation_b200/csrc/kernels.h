@@ -56,6 +56,7 @@ int launch_conv_wgrad_tc(const ConvWgradParams& p, cudaStream_t stream);
 // ------------------------------------------------------------- layers.cu
 int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, int cin,
                      cudaStream_t s);
+int launch_to_f32(const void* in, int src_dtype, float* out, size_t n, cudaStream_t s);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t s);
 int launch_maxpool_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int H, int W, int C,

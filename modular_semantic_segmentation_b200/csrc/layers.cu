@@ -69,6 +69,29 @@ im2col_c1_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, i
   }
 }
 
+// raw sensor dtypes -> float32 (the cast of data_baseclass.py:77-78, done after the H2D copy so
+// that uint8 rgb / uint16 depth cross PCIe at 1 / 2 bytes per value)
+template <typename T>
+__global__ void to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<float>(in[i]);
+}
+__global__ void u8x16_to_f32_kernel(const uint4* __restrict__ in, float4* __restrict__ out,
+                                    size_t n16) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldg(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      out[i * 4 + j] = make_float4(static_cast<float>(w[j] & 0xffu),
+                                   static_cast<float>((w[j] >> 8) & 0xffu),
+                                   static_cast<float>((w[j] >> 16) & 0xffu),
+                                   static_cast<float>(w[j] >> 24));
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                    size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -615,6 +638,27 @@ int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, in
   if (cin == 1) im2col_c1_kernel<1><<<grid, kThreads, 0, s>>>(x, out, N, H, W);
   if (cin == 2) im2col_c1_kernel<2><<<grid, kThreads, 0, s>>>(x, out, N, H, W);
   if (cin == 3) im2col_c1_kernel<3><<<grid, kThreads, 0, s>>>(x, out, N, H, W);
+  XV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+int launch_to_f32(const void* in, int src_dtype, float* out, size_t n, cudaStream_t s) {
+  if (src_dtype == 0) {
+    if (n % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+      u8x16_to_f32_kernel<<<grid_for(n / 16), kThreads, 0, s>>>(
+          reinterpret_cast<const uint4*>(in), reinterpret_cast<float4*>(out), n / 16);
+    } else {
+      to_f32_kernel<uint8_t><<<grid_for(n), kThreads, 0, s>>>(static_cast<const uint8_t*>(in), out, n);
+    }
+  } else if (src_dtype == 1) {
+    to_f32_kernel<uint16_t><<<grid_for(n), kThreads, 0, s>>>(static_cast<const uint16_t*>(in), out, n);
+  } else if (src_dtype == 2) {
+    to_f32_kernel<int16_t><<<grid_for(n), kThreads, 0, s>>>(static_cast<const int16_t*>(in), out, n);
+  } else if (src_dtype == 3) {
+    to_f32_kernel<int32_t><<<grid_for(n), kThreads, 0, s>>>(static_cast<const int32_t*>(in), out, n);
+  } else {
+    return fail("to_f32: src_dtype must be 0 (uint8), 1 (uint16), 2 (int16) or 3 (int32)");
+  }
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -51,6 +51,17 @@ def to_device(a, dtype=None):
     return a.cuda(non_blocking=True).contiguous()
 
 
+_RAW_DTYPES = {torch.uint8: 0, torch.uint16: 1, torch.int16: 2, torch.int32: 3}
+
+
+def convert_to_f32(t):
+    """uint8 / uint16 / int16 / int32 CUDA tensor -> float32 CUDA tensor of the same shape."""
+    init()
+    out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+    call('xv_convert_to_f32', ptr(t), _RAW_DTYPES[t.dtype], t.numel(), ptr(out), stream_ptr())
+    return out
+
+
 def _label_bytes(t):
     if t.dtype == torch.int64:
         return 8

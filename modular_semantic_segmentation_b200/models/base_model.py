@@ -20,6 +20,7 @@ import torch
 
 from .. import device as dev
 from .. import sharding
+from ..input_pipeline import crop_multiple
 from ..sharding import dist_or_none as _dist
 
 
@@ -203,10 +204,16 @@ class BaseModel(object):
         for key, value in batch.items():
             if isinstance(value, np.ndarray):
                 value = torch.from_numpy(np.ascontiguousarray(value))
+            # spatial size must be a multiple of 16 (crop_multiple, augmentation.py:244-262)
+            value = crop_multiple(value, batched=True)
             if key == 'labels':
                 if value.dim() == 4:        # one-hot labels of the training pipeline
                     value = value.argmax(-1)
                 out[key] = value.to(device='cuda', dtype=torch.int32, non_blocking=True)
+            elif value.dtype in (torch.uint8, torch.uint16, torch.int16, torch.int32):
+                # raw sensor dtype: copy the narrow values, cast to float32 on the device
+                out[key] = dev.convert_to_f32(value.contiguous().to(device='cuda',
+                                                                    non_blocking=True))
             else:
                 out[key] = value.to(device='cuda', dtype=torch.float32, non_blocking=True)
         return out

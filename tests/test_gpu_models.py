@@ -227,3 +227,30 @@ def test_fusion_fcn_mid_level_fusion_net():
                      want=('score',), params=params)
     np.testing.assert_allclose(out['score'].cpu().numpy(), ref['score'], rtol=0,
                                atol=0.05 * np.abs(ref['score']).max())
+
+
+def test_raw_sensor_dtypes_and_crop_multiple():
+    """uint8 rgb / uint16 depth inputs of arbitrary size are cropped to
+    multiples of 16 and cast on the device; results equal the float32 path exactly."""
+    from xview.models import get_model
+    c, n, h, w = 6, 3, 37, 52
+    rng = np.random.default_rng(12)
+    raw = {'rgb': rng.integers(0, 256, size=(n, h, w, 3)).astype(np.uint8),
+           'depth': rng.integers(0, 65536, size=(n, h, w, 1)).astype(np.uint16),
+           'labels': rng.integers(-1, c, size=(n, h, w)).astype(np.int32)}
+    as_float = {'rgb': raw['rgb'][:, :32, :48].astype(np.float32),
+                'depth': raw['depth'][:, :32, :48].astype(np.float32),
+                'labels': raw['labels'][:, :32, :48]}
+    cms = {m: rng.integers(1, 50, size=(c, c)).astype(np.float64) + 100 * np.eye(c)
+           for m in ('rgb', 'depth')}
+    with get_model('bayes_fusion')(
+            confusion_matrices=cms, data_description=_description(c),
+            prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn', num_units=NU,
+            num_channels={'rgb': 3, 'depth': 1}, batchsize=2, seed=4) as net:
+        a = net.predict({'rgb': raw['rgb'], 'depth': raw['depth']})
+        b = net.predict({'rgb': as_float['rgb'], 'depth': as_float['depth']})
+        _, cm_a = net.score(raw)
+        _, cm_b = net.score(as_float)
+    assert a.shape == (n, 32, 48)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(cm_a, cm_b)

@@ -167,3 +167,18 @@ def test_get_model_names():
     assert get_model('variance_mix').__name__ == 'VarianceFusion'
     with pytest.raises(UserWarning):
         get_model('nope')
+
+
+def test_input_pipeline_crop_and_collate():
+    from modular_semantic_segmentation_b200.input_pipeline import collate, crop_multiple
+    img = np.zeros((37, 50, 3), np.uint8)
+    assert crop_multiple(img).shape == (32, 48, 3)
+    assert crop_multiple(np.zeros((4, 37, 50)), batched=True).shape == (4, 32, 48)
+    assert crop_multiple(np.zeros((32, 48, 1))).shape == (32, 48, 1)
+    assert crop_multiple(5) == 5
+    items = [{'rgb': np.full((33, 40, 3), i, np.uint8), 'depth': np.full((33, 40, 1), i, np.uint16),
+              'labels': np.full((33, 40), i, np.int64)} for i in range(3)]
+    batch = collate(items)
+    assert batch['rgb'].shape == (3, 32, 32, 3) and batch['rgb'].dtype == np.uint8
+    assert batch['depth'].dtype == np.uint16 and batch['labels'].dtype == np.int32
+    assert collate(items, keep_raw_dtype=False)['rgb'].dtype == np.float32

@@ -1,2 +1,4 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_models.py tests/test_gpu_fcn.py -q -m gpu -x 2>&1 | tail -15
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_models.py -q -m gpu -x 2>&1 | tail -5
+timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_latest.json
