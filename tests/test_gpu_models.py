@@ -254,3 +254,26 @@ def test_raw_sensor_dtypes_and_crop_multiple():
     assert a.shape == (n, 32, 48)
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(cm_a, cm_b)
+
+
+def test_expert_predictions_dump(tmp_path):
+    """predictions.npz of experiments/ibcc_fusion.py:18-42."""
+    from modular_semantic_segmentation_b200.records import dump_expert_predictions
+    c, h, w = 5, 32, 32
+    rng = np.random.default_rng(2)
+
+    def split(n):
+        return {'rgb': rng.normal(size=(n, h, w, 3)).astype(np.float32),
+                'depth': rng.normal(size=(n, h, w, 1)).astype(np.float32),
+                'labels': rng.integers(0, c, size=(n, h, w)).astype(np.int32)}
+    measure, test = split(3), split(2)
+    net_config = {'expert_model': 'fcn', 'prefixes': {'rgb': 'rgb', 'depth': 'depth'},
+                  'num_units': NU, 'num_channels': {'rgb': 3, 'depth': 1}, 'batchsize': 2,
+                  'seed': 5, 'batch_normalization': False}
+    out = dump_expert_predictions(net_config, _description(c), measure, test, str(tmp_path))
+    with np.load(out) as archive:
+        assert sorted(archive.files) == ['measure_depth', 'measure_gt', 'measure_rgb',
+                                         'test_depth', 'test_gt', 'test_rgb']
+        assert archive['measure_rgb'].shape == (3, h, w) and archive['test_depth'].shape == (2, h, w)
+        assert archive['measure_rgb'].dtype == np.int64
+        np.testing.assert_array_equal(archive['test_gt'], test['labels'])

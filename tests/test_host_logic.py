@@ -182,3 +182,29 @@ def test_input_pipeline_crop_and_collate():
     assert batch['rgb'].shape == (3, 32, 32, 3) and batch['rgb'].dtype == np.uint8
     assert batch['depth'].dtype == np.uint16 and batch['labels'].dtype == np.int32
     assert collate(items, keep_raw_dtype=False)['rgb'].dtype == np.float32
+
+
+def test_experiment_records_roundtrip(tmp_path):
+    from modular_semantic_segmentation_b200.records import (ExperimentData, decode_record,
+                                                           write_experiment)
+    cms = {'rgb': np.arange(9.0).reshape(3, 3), 'depth': np.eye(3)}
+    config = {'net_config': {'num_units': 8, 'prefixes': {'rgb': 'rgb', 'depth': 'depth'}},
+              'starting_weights': {'rgb': 12, 'depth': 13}}
+    for as_zip, exp_id in ((False, 868), (True, 869)):
+        write_experiment(str(tmp_path), exp_id, config, {'confusion_matrices': cms},
+                         captured_out='done', as_zip=as_zip)
+        exp = ExperimentData(exp_id, str(tmp_path))
+        record = exp.get_record()
+        assert record['config']['net_config']['num_units'] == 8
+        assert record['captured_out'] == 'done'
+        got = exp.get_confusion_matrices()
+        np.testing.assert_array_equal(got['rgb'], cms['rgb'])
+        np.testing.assert_array_equal(record['info']['confusion_matrices']['depth'], cms['depth'])
+        assert exp.get_artifact('cout.txt').read() == b'done'
+    with pytest.raises(UserWarning):
+        ExperimentData(1, str(tmp_path))
+    with pytest.raises(UserWarning):
+        ExperimentData(869, str(tmp_path)).get_weights()
+    assert decode_record({'py/tuple': [1, 2]}) == [1, 2]
+    assert decode_record('[1, 2]') == [1, 2]
+    assert decode_record({'a': {'values': [3]}}) == {'a': [3]}
