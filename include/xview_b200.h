@@ -120,6 +120,16 @@ int xv_fcn_create(xv_fcn** out, int cin, int num_units, int num_classes, int bat
 #define XV_ROLE_HEAD 2
 int xv_fcn_create_ex(xv_fcn** out, int cin, int num_units, int num_classes, int batchnorm,
                      int precision, int role, int head_cin);
+/* Adapnet expert (xview/models/adapnet.py:99-173: ResNet-50 style blocks with atrous stage-2
+ * convolutions, two batch-normalised transposed convolutions), test-time graph with batch norm on
+ * its moving statistics - what the fusion models build with expert_model='adapnet'
+ * (basic_fusion_model.py:13-16).  Returns the same handle type: parameters are set with
+ * xv_fcn_set_param_host under the names below the prefix ("block_layer_4/stage_2/kernel",
+ * ".../gamma", "first_deconvolution_upconv/kernel" [4,4,num_units,2048], ...), then
+ * xv_fcn_finalize / xv_fcn_forward (drop = NULL; score, prob and label outputs) /
+ * xv_fcn_get_layer_host ("block_0_1" .. "block_16", "shortcut", "merge", "score") /
+ * xv_fcn_destroy.  cin <= 3 in bf16 precision. */
+int xv_adapnet_create(xv_fcn** out, int cin, int num_units, int num_classes, int precision);
 int xv_fcn_forward_encoder(xv_fcn* net, const float* x, int n, int h, int w, void* stream);
 int xv_fcn_forward_head(xv_fcn* head, xv_fcn* const* towers_host, int num_towers,
                         const xv_fcn_outputs* outputs, void* stream);

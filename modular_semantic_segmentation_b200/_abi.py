@@ -65,6 +65,7 @@ PROTOTYPES = {
     'xv_convert_to_f32': [_P, _I, _L, _P, _P],
     'xv_fcn_create': [_PP, _I, _I, _I, _I, _I],
     'xv_fcn_create_ex': [_PP, _I, _I, _I, _I, _I, _I, _I],
+    'xv_adapnet_create': [_PP, _I, _I, _I, _I],
     'xv_fcn_forward_encoder': [_P, _P, _I, _I, _I, _P],
     'xv_fcn_forward_head': [_P, _PP, _I, C.POINTER(FcnOutputs), _P],
     'xv_fcn_destroy': [_P],

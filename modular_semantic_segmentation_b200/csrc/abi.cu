@@ -9,9 +9,7 @@
 #include <tuple>
 #include <vector>
 
-#include "../../include/xview_b200.h"
-#include "common.cuh"
-#include "kernels.h"
+#include "net.h"
 
 namespace xv {
 
@@ -46,7 +44,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
-static int ensure_init() {
+int debug_flags() { return g_debug_flags; }
+
+int ensure_init() {
   if (g_dev.device >= 0) return 0;
   int dev = 0;
   XV_CUDA(cudaGetDevice(&dev));
@@ -67,12 +67,12 @@ static int ensure_init() {
 }
 
 // ------------------------------------------------------------------ TMA descriptors
-static int make_tmap_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int th,
-                         int tw) {
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
-                        static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
-                           static_cast<cuuint64_t>(H) * W * C * 2};
+static int make_tmap_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int pitch,
+                         int sample, int th, int tw) {
+  const cuuint64_t px = static_cast<cuuint64_t>(pitch) * 2;       // bytes per physical pixel
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(div_up(W, sample)),
+                        static_cast<cuuint64_t>(div_up(H, sample)), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {px * sample, px * W * sample, px * W * H};
   cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
@@ -84,14 +84,10 @@ static int make_tmap_act(CUtensorMap* m, const void* ptr, int N, int H, int W, i
 }
 
 static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n);
-static int get_tmap(struct xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W,
-                    int C, int th, int tw);
-static int get_tmap_w(struct xv_fcn* net, CUtensorMap* out, const void* ptr, int kdim, int cout_pad,
-                      int block_n);
 
 // in: bf16 [B,H,W,cin]; out: bf16 [B,H,W,cout] or, with pool, [B,H/2,W/2,cout]
-static int run_igemm_t(struct xv_fcn* net, const struct ConvLayer& L, const void* in, int B, int H,
-                       int W, void* out, bool pool, cudaStream_t s);
+static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
+                       void* out, bool pool, cudaStream_t s);
 
 static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n) {
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(cout_pad)};
@@ -123,91 +119,9 @@ static void choose_tile(int H, int W, int* th, int* tw) {
   }
 }
 
-// ------------------------------------------------------------------ device buffers
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-  int ensure(size_t n) {
-    if (n <= bytes) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    XV_CUDA(cudaMalloc(&p, n));
-    bytes = n;
-    return 0;
-  }
-  template <typename T>
-  int upload(const std::vector<T>& v) {
-    XV_TRY(ensure(v.size() * sizeof(T)));
-    XV_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return 0;
-  }
-};
-
-struct Arena {
-  char* base = nullptr;
-  size_t off = 0;
-  void* alloc(size_t bytes) {
-    off = (off + 1023) & ~static_cast<size_t>(1023);
-    void* p = base ? base + off : nullptr;
-    off += bytes;
-    return p;
-  }
-};
-
-struct HostParam {
-  std::vector<int64_t> shape;
-  std::vector<float> data;
-};
-
-struct ConvLayer {
-  std::string name;
-  int k = 3, cin = 0, cout = 0, relu = 1;
-  // bf16 path
-  int taps = 9, kdim = 0, cin_gemm = 0, cout_pad = 0, block_n = 0;
-  bool use_t = false;   // few output channels: transposed-role kernel (conv_igemm_t_sm100.cu)
-  DevBuf w_packed, bias_pad;
-  // fp32 path
-  DevBuf w_f32, bias_f32, bn_scale, bn_shift;
-  bool has_bn = false;
-};
-
-enum class DType { F32, BF16, U8 };
-struct Act {
-  void* p = nullptr;
-  DType dt = DType::F32;
-  int B = 0, H = 0, W = 0, C = 0;
-  size_t elems() const { return static_cast<size_t>(B) * H * W * C; }
-};
-
 }  // namespace xv
 
 using namespace xv;
-
-struct xv_fcn {
-  int cin = 0, nu = 0, C = 0, batchnorm = 0, precision = 0;
-  int role = 0;        // 0 = whole expert, 1 = VGG16 encoder only, 2 = head + decoder only
-  int head_cin = 512;  // input channels of score_conv4/5 (1024 for the two-tower fusion_fcn head)
-  bool finalized = false;
-  std::map<std::string, HostParam> params;
-  std::vector<std::unique_ptr<ConvLayer>> convs;   // conv1_1..conv5_3, score_conv4, score_conv5, score
-  // decoder
-  bool fast_up5 = false, fast_up = false;
-  DevBuf g4, g16, w_score_nuxc, b_score;           // fast paths
-  DevBuf w_up5, w_up, up5_scale, up5_shift, up_scale, up_shift;   // generic paths
-  DevBuf arena_buf;
-  std::map<std::string, Act> layers;
-  std::map<std::tuple<const void*, int, int, int, int, int, int>, CUtensorMap> tmaps;
-
-  ConvLayer* conv(const std::string& n) {
-    for (auto& c : convs)
-      if (c->name == n) return c.get();
-    return nullptr;
-  }
-};
 
 namespace xv {
 
@@ -216,7 +130,7 @@ static const char* kConvNames[13] = {"conv1_1", "conv1_2", "conv2_1", "conv2_2",
                                      "conv5_1", "conv5_2", "conv5_3"};
 static const int kConvCout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
 
-static int get_param(xv_fcn* net, const std::string& name, std::vector<int64_t> shape,
+int get_param(xv_fcn* net, const std::string& name, std::vector<int64_t> shape,
                      const HostParam** out) {
   auto it = net->params.find(name);
   XV_CHECK(it != net->params.end(), "parameter '" + name + "' was never set");
@@ -227,11 +141,11 @@ static int get_param(xv_fcn* net, const std::string& name, std::vector<int64_t> 
 
 // BN folding factors: y = scale * conv + shift (test-time tf.layers.batch_normalization,
 // epsilon 1e-3, custom_layers.py:116,132-134)
-static int bn_factors(xv_fcn* net, const std::string& layer, int cout, std::vector<float>* scale,
-                      std::vector<float>* shift) {
+int bn_factors_of(xv_fcn* net, const std::string& layer, int cout, bool enabled,
+                  std::vector<float>* scale, std::vector<float>* shift) {
   scale->assign(cout, 1.f);
   shift->assign(cout, 0.f);
-  if (!net->batchnorm) return 0;
+  if (!enabled) return 0;
   const HostParam *g, *b, *m, *v;
   XV_TRY(get_param(net, layer + "/gamma", {cout}, &g));
   XV_TRY(get_param(net, layer + "/beta", {cout}, &b));
@@ -245,6 +159,11 @@ static int bn_factors(xv_fcn* net, const std::string& layer, int cout, std::vect
   return 0;
 }
 
+static int bn_factors(xv_fcn* net, const std::string& layer, int cout, std::vector<float>* scale,
+                      std::vector<float>* shift) {
+  return bn_factors_of(net, layer, cout, net->batchnorm != 0, scale, shift);
+}
+
 static inline uint16_t f2bf(float f) {
   uint32_t u;
   std::memcpy(&u, &f, 4);
@@ -255,7 +174,7 @@ static inline uint16_t f2bf(float f) {
 
 // Packs one conv layer for both precisions.  `special_c1`: conv1_1 operand layout
 // [hi taps | lo taps | 0] with K = 64 (see layers.cu im2col_c1_kernel).
-static int pack_conv(xv_fcn* net, ConvLayer* L, const float* w_hwio, const float* bias,
+int pack_conv(xv_fcn* net, ConvLayer* L, const float* w_hwio, const float* bias,
                      const std::vector<float>& scale, const std::vector<float>& shift,
                      bool bn) {
   const int k = L->k, cin = L->cin, cout = L->cout, taps = k * k;
@@ -280,7 +199,8 @@ static int pack_conv(xv_fcn* net, ConvLayer* L, const float* w_hwio, const float
   L->kdim = L->taps * L->cin_gemm;
   L->block_n = conv_igemm_block_n(cout);
   L->cout_pad = div_up(cout, L->block_n) * L->block_n;
-  L->use_t = (k == 3 && !special_c1 && cout <= 128 && cout % 64 == 0);
+  L->use_t = ((k == 3 || L->generic) && !special_c1 && cout <= 128 && cout % 64 == 0);
+  L->macs_per_pixel = static_cast<double>(taps) * cin * cout;
   if (L->use_t) L->cout_pad = div_up(cout, 128) * 128;   // weight rows padded to the M block
   std::vector<uint16_t> wp(static_cast<size_t>(L->cout_pad) * L->kdim, 0);
   std::vector<float> bp(L->cout_pad, 0.f);
@@ -303,9 +223,10 @@ static int pack_conv(xv_fcn* net, ConvLayer* L, const float* w_hwio, const float
   return 0;
 }
 
-static int get_tmap(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W, int C,
-                    int th, int tw) {
-  auto key = std::make_tuple(ptr, N, H, W, C, th, tw);
+int get_tmap_ex(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W, int C,
+                int pitch, int sample, int th, int tw) {
+  const std::array<long long, 9> key = {static_cast<long long>(reinterpret_cast<uintptr_t>(ptr)),
+                                        N, H, W, C, pitch, sample, th, tw};
   if (net) {
     auto it = net->tmaps.find(key);
     if (it != net->tmaps.end()) {
@@ -313,14 +234,20 @@ static int get_tmap(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H
       return 0;
     }
   }
-  XV_TRY(make_tmap_act(out, ptr, N, H, W, C, th, tw));
+  XV_TRY(make_tmap_act(out, ptr, N, H, W, C, pitch, sample, th, tw));
   if (net) net->tmaps[key] = *out;
   return 0;
 }
 
-static int get_tmap_w(xv_fcn* net, CUtensorMap* out, const void* ptr, int kdim, int cout_pad,
-                      int block_n) {
-  auto key = std::make_tuple(ptr, kdim, cout_pad, block_n, -1, -1, -1);
+int get_tmap(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W, int C, int th,
+             int tw) {
+  return get_tmap_ex(net, out, ptr, N, H, W, C, C, 1, th, tw);
+}
+
+int get_tmap_w(xv_fcn* net, CUtensorMap* out, const void* ptr, int kdim, int cout_pad,
+               int block_n) {
+  const std::array<long long, 9> key = {static_cast<long long>(reinterpret_cast<uintptr_t>(ptr)),
+                                        kdim, cout_pad, block_n, -1, -1, -1, -1, -1};
   if (net) {
     auto it = net->tmaps.find(key);
     if (it != net->tmaps.end()) {
@@ -419,8 +346,8 @@ static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, i
 }
 
 // conv1_1 on the raw fp32 input: operand rows are packed inside the kernel
-static int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, int H, int W,
-                        void* out, cudaStream_t s) {
+int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, int H, int W, void* out,
+                 cudaStream_t s) {
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
@@ -446,6 +373,83 @@ static int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, 
   smp.block_n = 64;
   XV_CUDA(cudaEventRecord(smp.e0, s));
   const int rc = launch_conv_igemm_c1(p, L.cin, s);
+  XV_CUDA(cudaEventRecord(smp.e1, s));
+  g_samples.push_back(smp);
+  return rc;
+}
+
+// Adapnet layers: any square filter with dilation / padding offset, optional stride-2 sampling
+// of the input and channel-sliced input / output tensors (concat without a copy).
+int run_conv_generic(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
+                     int in_pitch, void* out, int out_pitch, bool out_f32, cudaStream_t s,
+                     const void* residual) {
+  const int step = L.stride2 ? 2 : L.sample;
+  const int Ho = div_up(H, step), Wo = div_up(W, step);
+  const bool t_kernel = L.use_t && !out_f32 && (L.stride2 || !(g_debug_flags & 2));
+  XV_CHECK(!L.stride2 || (t_kernel && H % 2 == 0 && W % 2 == 0),
+           "stride-2 filters run on the transposed-role kernel (Cout <= 128) on even sizes");
+  XV_CHECK(residual == nullptr || (!t_kernel && !out_f32 && L.block_n == 256),
+           "the residual epilogue needs the pixel-major bf16 kernel with BLOCK_N = 256");
+  ConvIgemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  if (t_kernel) {
+    p.th = p.tw = 16;
+  } else {
+    choose_tile(Ho, Wo, &p.th, &p.tw);
+  }
+  if (L.stride2) {
+    // parity (vy, vx): pixels (2i + vy, 2j + vx) of the input
+    for (int v = 0; v < 4; ++v) {
+      const char* base = static_cast<const char*>(in) +
+                         (static_cast<size_t>(v >> 1) * W + (v & 1)) * in_pitch * 2;
+      XV_TRY(get_tmap_ex(net, &p.tmap_in_par[v], base, B, H, W, L.cin_gemm, in_pitch, 2, p.th,
+                         p.tw));
+    }
+    p.tmap_in = p.tmap_in_par[0];
+    p.stride2 = 1;
+  } else {
+    XV_TRY(get_tmap_ex(net, &p.tmap_in, in, B, H, W, L.cin_gemm, in_pitch, L.sample, p.th, p.tw));
+  }
+  if (residual) {
+    p.has_residual = 1;
+    XV_TRY(get_tmap_ex(net, &p.tmap_res, residual, B, Ho, Wo, L.cout, L.cout, 1, p.th, p.tw));
+  }
+  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, t_kernel ? 128 : L.block_n));
+  if (out_f32) {
+    p.tmap_out = p.tmap_in;
+    p.out_f32 = static_cast<float*>(out);
+  } else if (t_kernel) {
+    XV_TRY(get_tmap_ex(net, &p.tmap_out, out, B, Ho, Wo, L.cout, out_pitch, 1, 8, 16));
+  } else {
+    XV_CHECK(L.cout % 8 == 0, "bf16 epilogue needs Cout % 8 == 0");
+    XV_TRY(get_tmap_ex(net, &p.tmap_out, out, B, Ho, Wo, L.cout, out_pitch, 1, p.th, p.tw));
+  }
+  p.bias = static_cast<const float*>(L.bias_pad.p);
+  p.N = B;
+  p.H = Ho;
+  p.W = Wo;
+  p.cin = L.cin_gemm;
+  p.cout = L.cout;
+  p.tiles_x = div_up(Wo, p.tw);
+  p.tiles_y = div_up(Ho, p.th);
+  p.n_blocks = L.cout_pad / (t_kernel ? 128 : L.block_n);
+  p.relu = L.relu;
+  p.taps = L.taps;
+  p.kw = L.k;
+  p.dil = L.dil;
+  p.pad = L.pad;
+  auto launch = [&]() -> int {
+    return t_kernel ? launch_conv_igemm_t_generic(p, s)
+                    : launch_conv_igemm(p, L.block_n, 0, out_f32, s);
+  };
+  if (!g_profile) return launch();
+  IgemmSample smp;
+  XV_CUDA(cudaEventCreate(&smp.e0));
+  XV_CUDA(cudaEventCreate(&smp.e1));
+  smp.flops = 2.0 * B * Ho * Wo * L.macs_per_pixel;
+  smp.block_n = t_kernel ? 0 : L.block_n;
+  XV_CUDA(cudaEventRecord(smp.e0, s));
+  const int rc = launch();
   XV_CUDA(cudaEventRecord(smp.e1, s));
   g_samples.push_back(smp);
   return rc;
@@ -882,6 +886,14 @@ int xv_fcn_create_ex(xv_fcn** out, int cin, int num_units, int num_classes, int 
   return 0;
 }
 
+// Adapnet expert (adapnet.py:99-173): same handle type and the same set_param / finalize /
+// forward / get_layer_host / destroy calls as the FCN expert.
+int xv_adapnet_create(xv_fcn** out, int cin, int num_units, int num_classes, int precision) {
+  XV_TRY(xv_fcn_create(out, cin, num_units, num_classes, 1, precision));
+  (*out)->arch = 1;
+  return 0;
+}
+
 // One VGG16 tower (role 1): runs conv1_1..conv5_3 and keeps conv4_3 / conv5_3 for the head.
 int xv_fcn_forward_encoder(xv_fcn* net, const float* x, int n, int h, int w, void* stream) {
   XV_CHECK(net && x, "xv_fcn_forward_encoder: NULL argument");
@@ -978,6 +990,7 @@ static bool deconv_is_diagonal(const HostParam& w, int k, int nu) {
 int xv_fcn_finalize(xv_fcn* net) {
   XV_CHECK(net != nullptr, "xv_fcn_finalize: NULL handle");
   XV_TRY(ensure_init());
+  if (net->arch == 1) return adapnet_finalize(net);
   net->convs.clear();
   net->tmaps.clear();
   const int nu = net->nu, C = net->C;
@@ -1086,6 +1099,10 @@ int xv_fcn_forward(xv_fcn* net, const float* x, int n, int h, int w, const xv_dr
   XV_CHECK(net->finalized, "xv_fcn_forward: call xv_fcn_finalize first");
   XV_CHECK(n >= 1 && h >= 16 && w >= 16 && h % 16 == 0 && w % 16 == 0,
            "xv_fcn_forward: H and W must be positive multiples of 16");
+  if (net->arch == 1) {
+    XV_CHECK(!drop || drop->sites == 0, "xv_fcn_forward: adapnet has no dropout sites");
+    return adapnet_forward(net, x, n, h, w, outputs, XV_STREAM(stream));
+  }
   xv_dropout_cfg cfg;
   const xv_dropout_cfg* d = nullptr;
   int T = 1;
@@ -1235,9 +1252,9 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(h, w, &p.th, &p.tw);
-  if (cin % 64 == 0) XV_TRY(make_tmap_act(&p.tmap_in, in.p, n, h, w, cin, p.th, p.tw));
+  if (cin % 64 == 0) XV_TRY(make_tmap_act(&p.tmap_in, in.p, n, h, w, cin, cin, 1, p.th, p.tw));
   XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
-  XV_TRY(make_tmap_act(&p.tmap_out, out.p, n, h, w, cout, p.th, p.tw));
+  XV_TRY(make_tmap_act(&p.tmap_out, out.p, n, h, w, cout, cout, 1, p.th, p.tw));
   p.bias = static_cast<const float*>(L.bias_pad.p);
   p.N = n; p.H = h; p.W = w; p.cin = cin; p.cout = cout;
   p.tiles_x = div_up(w, p.tw); p.tiles_y = div_up(h, p.th);

@@ -36,15 +36,18 @@ constexpr int kPackGroups = 4;                    // conv1_1 mode: groups of 128
 constexpr int kPackThreads = 128 * kPackGroups;
 constexpr int kPrefetchTiles = 2;               // L2 prefetch distance in tiles per CTA
 
-template <int BLOCK_N>
+// RES: two extra 16 KB buffers receive the residual operand tiles (one pipeline stage less)
+template <int BLOCK_N, bool RES = false>
 struct IgemmCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 196608 / kStageBytes;   // 4 / 6 / 8 for N = 256 / 128 / 64
+  static constexpr int kOutBufs = RES ? 4 : 2;           // 2 output staging (+ 2 residual) buffers
+  // 4 / 6 / 8 stages for N = 256 / 128 / 64 (3 for N = 256 with the residual buffers)
+  static constexpr int kStages = (196608 - (kOutBufs - 2) * kOutBufBytes) / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;          // two accumulator stages
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes =
-      1024 /*align slack*/ + kStages * kStageBytes + 2 * kOutBufBytes + kBarBytes;
+      1024 /*align slack*/ + kStages * kStageBytes + kOutBufs * kOutBufBytes + kBarBytes;
 };
 
 struct TileCoord {
@@ -69,10 +72,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvIgemmParams& p, int t
 // C1 > 0: conv1_1 mode with C1 raw input channels - warps 6..9 build the A operand rows from the
 // fp32 input (3x3 neighbourhood split into hi + lo bf16 halves, see layers.cu), TMA loads only
 // the 8 KB weight tile.
-template <int BLOCK_N, int TAPS, bool OUT_F32, int C1 = 0>
+template <int BLOCK_N, int TAPS, bool OUT_F32, int C1 = 0, bool RES = false>
 __global__ void __launch_bounds__(C1 > 0 ? kThreads + kPackThreads : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
-  using Cfg = IgemmCfg<BLOCK_N>;
+  using Cfg = IgemmCfg<BLOCK_N, RES>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -81,18 +84,20 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
   uint8_t* smem_out = smem + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 2 * kOutBufBytes);
+  uint8_t* smem_res = smem_out + 2 * kOutBufBytes;          // RES only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::kOutBufs * kOutBufBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* res_full_bar = bars + 2 * kStages + 5;          // RES only, two barriers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_blocks;
   const int cin_chunks = p.cin / kBlockK;
-  const int num_kb = TAPS * cin_chunks;
+  const int num_kb = (TAPS == 0 ? p.taps : TAPS) * cin_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_in);
@@ -105,7 +110,9 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 128);
+      if (RES) mbar_init(&res_full_bar[s], 1);
     }
+    if (RES) tma_prefetch_desc(&p.tmap_res);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -136,8 +143,13 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / cin_chunks;
         const int cc = kb - tap * cin_chunks;
-        const int dy = (TAPS == 9) ? tap / 3 - 1 : 0;
-        const int dx = (TAPS == 9) ? tap % 3 - 1 : 0;
+        int dy = (TAPS == 9) ? tap / 3 - 1 : 0;
+        int dx = (TAPS == 9) ? tap % 3 - 1 : 0;
+        if (TAPS == 0) {
+          const int ty = tap / p.kw;
+          dy = ty * p.dil - p.pad;
+          dx = (tap - ty * p.kw) * p.dil - p.pad;
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (C1 > 0) {
           if (elect_one_sync()) {
@@ -272,6 +284,22 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
     const int px = row - py * p.tw;
     const bool issuer = (threadIdx.x == 64);
     uint32_t acc = 0, acc_phase = 0, gchunk = 0;
+    // RES: TMA load of the residual tile of this CTA's g-th output chunk into rbuf[g & 1]
+    auto request_residual = [&](uint32_t g) {
+      constexpr uint32_t kChunks = BLOCK_N / 64;
+      const int t = blockIdx.x + static_cast<int>(g / kChunks) * static_cast<int>(gridDim.x);
+      if (t >= total_tiles) return;
+      const TileCoord rc = decode_tile(p, t, BLOCK_N);
+      mbar_arrive_expect_tx(&res_full_bar[g & 1], kOutBufBytes);
+      tma_load_4d(smem_res + (g & 1) * kOutBufBytes, &p.tmap_res, &res_full_bar[g & 1],
+                  rc.n0 + static_cast<int>(g % kChunks) * 64, rc.x0, rc.y0, rc.img);
+    };
+    if constexpr (RES) {
+      if (issuer) {
+        request_residual(0);
+        request_residual(1);
+      }
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile(p, tile, BLOCK_N);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -284,27 +312,58 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
           uint8_t* buf = smem_out + (gchunk & 1) * kOutBufBytes;
           if (issuer) tma_store_wait_read<1>();   // the store that last used `buf` has drained
           named_bar_sync(1, 128);
+          if constexpr (RES) {
+            // the residual tile of this chunk was requested two chunks ago (or in the prologue)
+            mbar_wait(&res_full_bar[gchunk & 1], (gchunk >> 1) & 1);
+          }
+          const uint8_t* rbuf = smem_res + (gchunk & 1) * kOutBufBytes;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_row + chunk * 64 + half * 32, r);
             tmem_ld_wait();
-            const float* bias = p.bias + c.n0 + chunk * 64 + half * 32;
+            const float4* bias4 =
+                reinterpret_cast<const float4*>(p.bias + c.n0 + chunk * 64 + half * 32);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t packed[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float v0 = __uint_as_float(r[j * 8 + e * 2]) + __ldg(bias + j * 8 + e * 2);
-                float v1 =
-                    __uint_as_float(r[j * 8 + e * 2 + 1]) + __ldg(bias + j * 8 + e * 2 + 1);
-                if (p.relu) {
-                  v0 = fmaxf(v0, 0.f);
-                  v1 = fmaxf(v1, 0.f);
-                }
-                packed[e] = pack_bf16x2(v0, v1);
-              }
               const int piece = (half * 4 + j) ^ (row & 7);   // 128B swizzle
+              const float4 b_lo = __ldg(bias4 + j * 2), b_hi = __ldg(bias4 + j * 2 + 1);
+              const float bb[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+              if constexpr (RES) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + row * 128 + piece * 16);
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float v0 = __uint_as_float(r[j * 8 + e * 2]) + bb[e * 2];
+                  float v1 = __uint_as_float(r[j * 8 + e * 2 + 1]) + bb[e * 2 + 1];
+                  if (p.relu) {
+                    v0 = fmaxf(v0, 0.f);
+                    v1 = fmaxf(v1, 0.f);
+                  }
+                  const float2 a = __bfloat1622float2(
+                      *reinterpret_cast<const __nv_bfloat162*>(&rw[e]));
+                  packed[e] = pack_bf16x2(fmaxf(v0 + a.x, 0.f), fmaxf(v1 + a.y, 0.f));
+                }
+              } else {
+                // two outputs per instruction: packed fp32 add, packed bf16 convert, packed max
+                // (ReLU after the rounding gives the same bits as before it)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float v0, v1;
+                  asm("{\n\t.reg .b64 a, b;\n\t"
+                      "mov.b64 a, {%2, %3};\n\t"
+                      "mov.b64 b, {%4, %5};\n\t"
+                      "add.rn.f32x2 a, a, b;\n\t"
+                      "mov.b64 {%0, %1}, a;\n\t}"
+                      : "=f"(v0), "=f"(v1)
+                      : "r"(r[j * 8 + e * 2]), "r"(r[j * 8 + e * 2 + 1]), "f"(bb[e * 2]),
+                        "f"(bb[e * 2 + 1]));
+                  __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                  if (p.relu) h = __hmax2(h, __floats2bfloat162_rn(0.f, 0.f));
+                  packed[e] = *reinterpret_cast<uint32_t*>(&h);
+                }
+              }
               *reinterpret_cast<uint4*>(buf + row * 128 + piece * 16) =
                   make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
@@ -314,6 +373,9 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
           if (issuer && !(p.debug_flags & 4)) {
             tma_store_4d(&p.tmap_out, buf, c.n0 + chunk * 64, c.x0, c.y0, c.img);
             tma_store_commit();
+          }
+          if constexpr (RES) {
+            if (issuer) request_residual(gchunk + 2);   // everybody is done with rbuf
           }
         } else {
           const int y = c.y0 + py, x = c.x0 + px;
@@ -354,10 +416,10 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   }
 }
 
-template <int BLOCK_N, int TAPS, bool OUT_F32>
+template <int BLOCK_N, int TAPS, bool OUT_F32, bool RES = false>
 int launch_one(const ConvIgemmParams& p, cudaStream_t stream) {
-  using Cfg = IgemmCfg<BLOCK_N>;
-  auto kernel = conv_igemm_kernel<BLOCK_N, TAPS, OUT_F32>;
+  using Cfg = IgemmCfg<BLOCK_N, RES>;
+  auto kernel = conv_igemm_kernel<BLOCK_N, TAPS, OUT_F32, 0, RES>;
   static bool configured = false;
   if (!configured) {
     XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -410,9 +472,21 @@ int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_
                       cudaStream_t stream) {
   XV_CHECK(p.th * p.tw == kBlockM, "conv_igemm: tile must hold 128 pixels");
   XV_CHECK(p.cin % kBlockK == 0, "conv_igemm: Cin must be a multiple of 64");
-  XV_CHECK(taps == 1 || taps == 9, "conv_igemm: only 1x1 and 3x3 kernels");
+  XV_CHECK(taps == 0 || taps == 1 || taps == 9,
+           "conv_igemm: taps must be 1, 9 or 0 (geometry from the parameter block)");
+  if (taps == 0)
+    XV_CHECK(p.taps > 0 && p.kw > 0 && p.dil > 0, "conv_igemm: generic geometry not set");
+  if (p.has_residual) {
+    XV_CHECK(taps == 0 && block_n == 256 && !out_f32,
+             "conv_igemm: the residual epilogue exists for generic bf16 layers with BLOCK_N = 256");
+    return launch_one<256, 0, false, true>(p, stream);
+  }
 #define XV_IGEMM_CASE(BN)                                                              \
   if (block_n == BN) {                                                                 \
+    if (taps == 0) {                                                                   \
+      return out_f32 ? launch_one<BN, 0, true>(p, stream)                              \
+                     : launch_one<BN, 0, false>(p, stream);                            \
+    }                                                                                  \
     if (taps == 9) {                                                                   \
       return out_f32 ? launch_one<BN, 9, true>(p, stream)                              \
                      : launch_one<BN, 9, false>(p, stream);                            \

@@ -31,7 +31,7 @@ constexpr int kStagingBytes = 32768;               // 2 channel chunks x 128 row
 constexpr int kThreads = 192;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
 
-template <bool POOL>
+template <bool POOL, bool GEN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -51,7 +51,7 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_blocks;
   const int cin_chunks = p.cin / kBlockK;
-  const int num_kb = 9 * cin_chunks;
+  const int num_kb = (GEN ? p.taps : 9) * cin_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_in);
@@ -94,11 +94,23 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / cin_chunks;
         const int cc = kb - tap * cin_chunks;
+        int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const CUtensorMap* tmap_x = &p.tmap_in;
+        if (GEN) {
+          const int ty = tap / p.kw;
+          dy = ty * p.dil - p.pad;
+          dx = (tap - ty * p.kw) * p.dil - p.pad;
+          if (p.stride2) {
+            tmap_x = &p.tmap_in_par[(dy & 1) * 2 + (dx & 1)];
+            dy >>= 1;
+            dx >>= 1;
+          }
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_4d(smem_x + stage * kXBytes, &p.tmap_in, &full_bar[stage], cc * kBlockK,
-                      x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+          tma_load_4d(smem_x + stage * kXBytes, tmap_x, &full_bar[stage], cc * kBlockK,
+                      x0 + dx, y0 + dy, img);
           tma_load_2d(smem_w + stage * kWBytes, &p.tmap_w, &full_bar[stage],
                       tap * p.cin + cc * kBlockK, n0);
         }
@@ -242,9 +254,9 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
   }
 }
 
-template <bool POOL>
+template <bool POOL, bool GEN>
 int launch_t(const ConvIgemmParams& p, cudaStream_t stream) {
-  auto kernel = conv_igemm_t_kernel<POOL>;
+  auto kernel = conv_igemm_t_kernel<POOL, GEN>;
   static bool configured = false;
   if (!configured) {
     XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -268,7 +280,14 @@ int launch_conv_igemm_t(const ConvIgemmParams& p, bool pool, cudaStream_t stream
   XV_CHECK(p.cin % kBlockK == 0, "conv_igemm_t: Cin must be a multiple of 64");
   XV_CHECK(p.cout % 64 == 0, "conv_igemm_t: Cout must be a multiple of 64");
   XV_CHECK(!pool || (p.H % 2 == 0 && p.W % 2 == 0), "conv_igemm_t: pooling needs even H, W");
-  return pool ? launch_t<true>(p, stream) : launch_t<false>(p, stream);
+  return pool ? launch_t<true, false>(p, stream) : launch_t<false, false>(p, stream);
+}
+
+int launch_conv_igemm_t_generic(const ConvIgemmParams& p, cudaStream_t stream) {
+  XV_CHECK(p.cin % kBlockK == 0, "conv_igemm_t: Cin must be a multiple of 64");
+  XV_CHECK(p.cout % 64 == 0, "conv_igemm_t: Cout must be a multiple of 64");
+  XV_CHECK(p.taps > 0 && p.kw > 0 && p.dil > 0, "conv_igemm_t: generic geometry not set");
+  return launch_t<false, true>(p, stream);
 }
 
 }  // namespace xv

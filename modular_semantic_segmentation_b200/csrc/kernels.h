@@ -23,6 +23,20 @@ struct ConvIgemmParams {
   int relu;
   int debug_flags;        // timing experiments only (xv_bench_conv_igemm); 0 in production
   const float* x_raw;     // conv1_1 mode: raw fp32 input [N,H,W,cin_raw] (operand packed on the fly)
+  // generic filter geometry (taps template argument 0): tap t reads the input shifted by
+  // ((t / kw) * dil - pad, (t % kw) * dil - pad); covers dilated 3x3 (adapnet.py:83-86) and the
+  // 4x4 form of the stride-2 7x7 convolution on the space-to-depth input (adapnet.py:121)
+  int taps, kw, dil, pad;
+  // bf16 epilogue of the pixel-major kernel (BLOCK_N = 256): out = relu(act(conv + bias) +
+  // residual), the block output of adapnet.py:49,96; tmap_res describes the residual tensor
+  // exactly like tmap_out describes the output
+  int has_residual;
+  CUtensorMap tmap_res;
+  // stride-2 filters on the transposed-role kernel (7x7 of adapnet.py:121): the input is read
+  // through four descriptors that each sample every second pixel, one per (row, column) parity;
+  // tap offset e = t * dil - pad selects parity e & 1 and coordinate shift e >> 1
+  int stride2;
+  CUtensorMap tmap_in_par[4];
 };
 int conv_igemm_block_n(int cout);
 int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,
@@ -38,6 +52,8 @@ int launch_conv_igemm_mc(const ConvIgemmParams& p, int taps, cudaStream_t stream
 // conv_igemm_t_sm100.cu: 3x3, Cout <= 128 per block of 128, 16x16 pixel tiles, optional fused
 // 2x2 max pool (then tmap_out describes the pooled tensor, box {64,8,8,1}; else {64,16,8,1}).
 int launch_conv_igemm_t(const ConvIgemmParams& p, bool pool, cudaStream_t stream);
+// any filter geometry (p.taps / kw / dil / pad), no pool
+int launch_conv_igemm_t_generic(const ConvIgemmParams& p, cudaStream_t stream);
 
 // conv_wgrad_sm100.cu: tensor-core weight gradient of a 3x3 'same' convolution
 struct ConvWgradParams {
@@ -86,6 +102,26 @@ int launch_concat_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, size_t npix
 int launch_add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t s);
 int launch_affine_f32(float* x, const float* scale, const float* shift, size_t npix, int C,
                       int relu, cudaStream_t s);
+
+// adapnet_kernels.cu: the memory-bound steps between Adapnet's convolutions
+int launch_space_to_depth2_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W,
+                                int C, cudaStream_t s);
+int launch_add_relu_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out,
+                         size_t n, cudaStream_t s);
+int launch_add_relu_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t s);
+// transposed convolution, gather half: col [B,hin,win,k*k*cout] (fp32 or bf16) -> out
+// [B,hin*stride,win*stride,cout] = sum of the overlapping taps + shift[co] (+ addend); fp32 output
+// and / or bf16 output zero-padded to pad_c channels
+int launch_col2im(const void* col, bool col_bf16, const float* shift, const float* addend,
+                  float* out_f32, __nv_bfloat16* out_bf16, int pad_c, int B, int hin, int win,
+                  int cout, int k, int stride, cudaStream_t s);
+// d2s bf16 [B,h8,w8,64*C], channel (py*8+px)*C+c -> full-resolution score / softmax / argmax
+int launch_d2s_softmax_argmax(const __nv_bfloat16* d2s, int B, int h8, int w8, int C, float* score,
+                              float* prob, int64_t* label_i64, uint8_t* label_u8, cudaStream_t s);
+// fp32 convolution with TF 'SAME' padding for any stride / dilation (validation mode)
+int launch_conv_f32_ex(const float* x, const float* w_hwio, const float* bias, float* out, int N,
+                       int H, int W, int cin, int cout, int k, int stride, int dil, int relu,
+                       cudaStream_t s);
 
 // fast decoder pieces (channel-diagonal transposed convolutions)
 // fused = s4 + relu(sum_taps g[ky,kx,u] * s5[tap,u]);  s4 [N,2h,2w,nu], s5 [N,h,w,nu]

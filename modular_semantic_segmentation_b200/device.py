@@ -82,18 +82,25 @@ class FcnExpert(object):
     ROLES = {'expert': 0, 'encoder': 1, 'head': 2}
 
     def __init__(self, cin, num_units, num_classes, batchnorm=False, precision='bf16',
-                 role='expert', head_cin=512):
+                 role='expert', head_cin=512, arch='fcn'):
         """role 'encoder' / 'head' are the pieces of the mid-level fusion net (fusion_fcn.py):
-        one VGG16 tower per modality and one head on the concatenated conv4_3 / conv5_3."""
+        one VGG16 tower per modality and one head on the concatenated conv4_3 / conv5_3.
+        arch 'adapnet' builds the Adapnet expert (adapnet.py:99-173) behind the same calls."""
         init()
         self.cin, self.num_units, self.num_classes = cin, num_units, num_classes
-        self.batchnorm = bool(batchnorm)
+        self.batchnorm = bool(batchnorm) or arch == 'adapnet'
         self.precision = precision
         self.role = role
+        self.arch = arch
         handle = C.c_void_p()
-        call('xv_fcn_create_ex', C.byref(handle), cin, num_units, num_classes, int(self.batchnorm),
-             {'bf16': _abi.XV_PRECISION_BF16, 'fp32': _abi.XV_PRECISION_FP32}[precision],
-             self.ROLES[role], head_cin)
+        prec = {'bf16': _abi.XV_PRECISION_BF16, 'fp32': _abi.XV_PRECISION_FP32}[precision]
+        if arch == 'adapnet':
+            call('xv_adapnet_create', C.byref(handle), cin, num_units, num_classes, prec)
+        elif arch == 'fcn':
+            call('xv_fcn_create_ex', C.byref(handle), cin, num_units, num_classes,
+                 int(self.batchnorm), prec, self.ROLES[role], head_cin)
+        else:
+            raise ValueError('unknown expert architecture %r' % (arch,))
         self._h = handle
         self._dirty = True
 

@@ -5,13 +5,15 @@ from .dirichlet_mix import DirichletFusion
 from .average_mix import AverageFusion
 from .variance_mix import VarianceFusion
 from .fusion_fcn import FusionFCN
+from .adapnet import Adapnet
 
 
 def get_model(name):
-    """xview/models/__init__.py:10-26.  'adapnet' is outside the hot path built so far
-     and is reported exactly like an unknown model."""
+    """xview/models/__init__.py:10-26."""
     if name == 'fcn':
         return SimpleFCN
+    elif name == 'adapnet':
+        return Adapnet
     elif name == 'fusion_fcn':
         return FusionFCN
     elif name in ['bayes_mix', 'bayes_fusion']:

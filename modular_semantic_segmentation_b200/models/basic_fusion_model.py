@@ -3,12 +3,17 @@ import numpy as np
 import torch
 
 from .base_model import BaseModel
+from .adapnet import build_adapnet
 from .simple_fcn import build_expert
 
 
 def build_test_pipeline(prefix, channels, **config):
-    """basic_fusion_model.py:9-23: the expert network behind `test_pipeline`.  Only the FCN
-    expert is on the B200 path."""
+    """basic_fusion_model.py:9-23: the expert network behind `test_pipeline`, 'adapnet' or
+    'fcn'."""
+    if config['expert_model'] == 'adapnet':
+        return build_adapnet(prefix, channels, config['num_units'], config['num_classes'],
+                             precision=config.get('precision', 'bf16'),
+                             rng=np.random.default_rng(config.get('seed')))
     if config['expert_model'] == 'fcn':
         return build_expert(prefix, channels, config['num_units'], config['num_classes'],
                             batchnorm=False, precision=config.get('precision', 'bf16'),

@@ -21,6 +21,9 @@ Pinning status:
   * bilinear kernel -- PINNED on the closed form custom_layers.py:13-21.
   * npz key layout -- PINNED on the 34-name list printed in
     ``Synthia Rand Cityscapes Examples.ipynb`` (tests/golden/fcn_weight_keys.json).
+  * Adapnet forward numerics (oracle/adapnet.py) -- **PARITY UNPINNED** for the same reason;
+    TF 'SAME' padding of the strided / atrous convolutions follows its documented rule and
+    is checked on hand-computed cases (tests/test_oracle_golden.py).
   * FCN forward numerics (conv / pool / transposed conv / softmax at the TensorFlow
     boundary) -- **PARITY UNPINNED**: TensorFlow 1.x is not installable in the build image
     and the reference's own tests assert nothing numeric.  The restatement follows the
@@ -31,6 +34,8 @@ from .fcn import (bilinear_kernel_1d, bilinear_filter, glorot_fcn_params, fcn_pa
                   conv2d, deconv2d, max_pool2x2, dropout, encoder, decoder, fcn,
                   softmax, argmax_first, test_pipeline, cross_entropy, vgg16_tower,
                   fusion_fcn, fusion_fcn_params)
+from .adapnet import (adapnet, adapnet_params, adapnet_param_shapes, same_padding, conv_bn,
+                      block_a, block_b)
 from .fusion import (bayes_conditionals, bayes_prior, bayes_fusion, bayes_decision_matrix,
                      dirichlet_log_norm, dirichlet_fusion, dirichlet_prior,
                      dirichlet_uncertainty_fusion,

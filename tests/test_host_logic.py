@@ -208,3 +208,12 @@ def test_experiment_records_roundtrip(tmp_path):
     assert decode_record({'py/tuple': [1, 2]}) == [1, 2]
     assert decode_record('[1, 2]') == [1, 2]
     assert decode_record({'a': {'values': [3]}}) == {'a': [3]}
+
+
+def test_adapnet_variable_layout_matches_oracle():
+    from modular_semantic_segmentation_b200.models.adapnet import init_adapnet_variables
+    mine = init_adapnet_variables('depth', 1, 20, 14, np.random.default_rng(0))
+    shapes = oracle.adapnet_param_shapes('depth', 1, 20, 14)
+    assert {k: v.shape for k, v in mine.items()} == {k: tuple(s) for k, s in shapes.items()}
+    up = mine['depth/second_deconvolution_upconv/kernel']
+    assert up.shape == (16, 16, 14, 20) and up[:, :, 3, 3].max() > 0 and up[:, :, 3, 4].max() == 0

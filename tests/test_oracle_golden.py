@@ -118,3 +118,32 @@ def test_fcn_shapes_and_relu_identity_of_bilinear_upscore():
     up = oracle.deconv2d(lowres - params['rgb/score/bias'], p2, 'rgb/upscore', 8,
                          activation=False) + params['rgb/score/bias']
     np.testing.assert_allclose(up, out['score'], rtol=1e-4, atol=1e-5)
+
+
+def test_adapnet_oracle_geometry():
+    """TF 'SAME' padding rule (smaller half first) and the layer shapes of adapnet.py:99-173."""
+    from oracle.adapnet import same_padding
+    assert same_padding(6, 7, 2, 1) == (2, 3)      # 7x7 stride 2 on an even size
+    assert same_padding(5, 3, 2, 1) == (1, 1)
+    assert same_padding(8, 1, 2, 1) == (0, 0)      # 1x1 stride 2 picks pixels 0, 2, 4, ...
+    assert same_padding(8, 3, 1, 4) == (4, 4)      # atrous 3x3 rate 4
+    assert same_padding(7, 2, 2, 1) == (0, 1)
+    # strided case by hand: x = 0..5, w = ones(3), stride 2 -> out = 3, pad_total = 1 -> (0, 1):
+    # windows [0,1,2], [2,3,4], [4,5,pad] -> 3, 9, 9
+    assert same_padding(6, 3, 2, 1) == (0, 1)
+    x = np.arange(6, dtype=np.float32).reshape(1, 6, 1, 1)
+    kernel = np.zeros((3, 3, 1, 1), np.float32)
+    kernel[:, 1] = 1                               # acts along the height axis only
+    unit = {'s/kernel': kernel, 's/gamma': np.ones(1, np.float32),
+            's/beta': np.zeros(1, np.float32), 's/moving_mean': np.zeros(1, np.float32),
+            's/moving_variance': np.full(1, 1 - 1e-3, np.float32)}
+    y = oracle.conv_bn(x, unit, 's', stride=2)
+    np.testing.assert_allclose(y[0, :, 0, 0], [3.0, 9.0, 9.0], rtol=1e-6)
+    rng = np.random.default_rng(0)
+    p = oracle.adapnet_params('rgb', 3, 20, 14, rng)
+    assert len(p) == 334 and p['rgb/first_deconvolution_upconv/kernel'].shape == (4, 4, 20, 2048)
+    assert 'rgb/block_layer_1/stage_1/bias' not in p and 'rgb/shortcut/bias' in p
+    out = oracle.adapnet(rng.normal(size=(1, 32, 48, 3)).astype(np.float32), p, 'rgb', 20, 14)
+    assert out['block_0_2'].shape == (1, 16, 24, 64) and out['block_3'].shape == (1, 8, 12, 256)
+    assert out['block_7'].shape == (1, 4, 6, 512) and out['block_16'].shape == (1, 2, 3, 2048)
+    assert out['merge'].shape == (1, 4, 6, 20) and out['score'].shape == (1, 32, 48, 14)
