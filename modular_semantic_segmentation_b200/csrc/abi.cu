@@ -85,6 +85,23 @@ static int make_tmap_act(CUtensorMap* m, const void* ptr, int N, int H, int W, i
 
 static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n);
 
+// fp32 input [N,H,W,cin] viewed as (W*cin, H, N): box = one input patch {patch_w, rows, 1}
+static int make_tmap_patch(CUtensorMap* m, const void* ptr, int N, int H, int W, int cin,
+                           int patch_w, int rows) {
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(W) * cin * 4;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(W) * cin, static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[2] = {row_bytes, row_bytes * H};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(patch_w), static_cast<cuuint32_t>(rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(input patch) failed: " + std::to_string(r));
+  return 0;
+}
+
 // in: bf16 [B,H,W,cin]; out: bf16 [B,H,W,cout] or, with pool, [B,H/2,W/2,cout]
 static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
                        void* out, bool pool, cudaStream_t s);
@@ -351,9 +368,26 @@ int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, int H, 
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
+  // debug bit5: previous variant (operand rows built from global loads inside conv_igemm_kernel)
+  const bool staged = !(g_debug_flags & 32) && (W * L.cin) % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                      conv_c1_patch_fits(p.th, p.tw, L.cin, &p.patch_w);
   XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
   XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, p.th, p.tw));
-  p.tmap_in = p.tmap_out;            // unused in this mode, kept valid for the descriptor prefetch
+  if (staged) {
+    const std::array<long long, 9> key = {
+        static_cast<long long>(reinterpret_cast<uintptr_t>(x)), B, H, W, L.cin, p.patch_w,
+        p.th + 2, -2, -2};
+    auto it = net ? net->tmaps.find(key) : std::map<std::array<long long, 9>, CUtensorMap>::iterator();
+    if (net && it != net->tmaps.end()) {
+      p.tmap_in = it->second;
+    } else {
+      XV_TRY(make_tmap_patch(&p.tmap_in, x, B, H, W, L.cin, p.patch_w, p.th + 2));
+      if (net) net->tmaps[key] = p.tmap_in;
+    }
+  } else {
+    p.tmap_in = p.tmap_out;          // unused in that mode, kept valid for the descriptor prefetch
+  }
   p.bias = static_cast<const float*>(L.bias_pad.p);
   p.x_raw = x;
   p.N = B;
@@ -365,14 +399,17 @@ int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, int H, 
   p.tiles_y = div_up(H, p.th);
   p.n_blocks = 1;
   p.relu = L.relu;
-  if (!g_profile) return launch_conv_igemm_c1(p, L.cin, s);
+  auto launch = [&]() -> int {
+    return staged ? launch_conv_c1(p, L.cin, s) : launch_conv_igemm_c1(p, L.cin, s);
+  };
+  if (!g_profile) return launch();
   IgemmSample smp;
   XV_CUDA(cudaEventCreate(&smp.e0));
   XV_CUDA(cudaEventCreate(&smp.e1));
   smp.flops = 2.0 * B * H * W * static_cast<double>(L.cout) * L.k * L.k * L.cin;
   smp.block_n = 64;
   XV_CUDA(cudaEventRecord(smp.e0, s));
-  const int rc = launch_conv_igemm_c1(p, L.cin, s);
+  const int rc = launch();
   XV_CUDA(cudaEventRecord(smp.e1, s));
   g_samples.push_back(smp);
   return rc;
@@ -1270,9 +1307,15 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
     p.tmap_in = p.tmap_out;
     p.cin = 64;
     p.n_blocks = 1;
-    XV_TRY(launch_conv_igemm_c1(p, cin, 0));
+    // flag 4096: the previous variant (global loads in the packers); else conv_c1_sm100.cu
+    const bool staged = !(flags & 4096) && conv_c1_patch_fits(p.th, p.tw, cin, &p.patch_w);
+    if (staged) XV_TRY(make_tmap_patch(&p.tmap_in, xraw.p, n, h, w, cin, p.patch_w, p.th + 2));
+    auto run = [&]() -> int {
+      return staged ? launch_conv_c1(p, cin, 0) : launch_conv_igemm_c1(p, cin, 0);
+    };
+    XV_TRY(run());
     XV_CUDA(cudaEventRecord(e0, 0));
-    for (int i = 0; i < iters; ++i) XV_TRY(launch_conv_igemm_c1(p, cin, 0));
+    for (int i = 0; i < iters; ++i) XV_TRY(run());
     XV_CUDA(cudaEventRecord(e1, 0));
     XV_CUDA(cudaEventSynchronize(e1));
     float ms1 = 0.f;

@@ -37,6 +37,7 @@ struct ConvIgemmParams {
   // tap offset e = t * dil - pad selects parity e & 1 and coordinate shift e >> 1
   int stride2;
   CUtensorMap tmap_in_par[4];
+  int patch_w;            // conv_c1_sm100.cu: floats per row of the input patch
 };
 int conv_igemm_block_n(int cout);
 int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,
@@ -44,6 +45,11 @@ int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_
 // conv1_1: 3x3 conv of the raw fp32 input (cin_raw <= 3) as a K=64 GEMM whose A rows
 // [hi taps | lo taps | 0] are built in shared memory by producer warps (no im2col buffer).
 int launch_conv_igemm_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t stream);
+// conv_c1_sm100.cu: same layer with the fp32 input patch (tile + halo) staged by TMA and the
+// weights resident in shared memory; tmap_in = fp32 input viewed as (W*Cin, H, N) with box
+// {patch_w, th + 2, 1}.  conv_c1_patch_fits tells whether a tile shape is supported.
+bool conv_c1_patch_fits(int th, int tw, int cin_raw, int* patch_w);
+int launch_conv_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t stream);
 
 // conv_igemm_mc_sm100.cu: BLOCK_N = 256 with 2-CTA clusters sharing the weight tile by TMA
 // multicast (tmap_w box {64, 128}); bf16 epilogue only.

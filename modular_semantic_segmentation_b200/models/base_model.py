@@ -167,8 +167,10 @@ class BaseModel(object):
             return dev_batch, event
 
         def pieces():
-            # a large host batch is uploaded in `upload_split` pieces so that its own copy
-            # overlaps its own kernels (matters when score() is called one batch at a time)
+            # A large host batch is uploaded in pieces so that its own copy overlaps its own
+            # kernels (matters when score() is called one batch at a time).  The first piece
+            # is small - its copy is the only one nothing can hide - and the following ones
+            # grow: [n/8, 3n/8, n/2] for `upload_split` = 2 (the default).
             split = int(self.config.get('upload_split', 2))
             for blob in self._batches(data):
                 count = len(next(iter(blob.values())))
@@ -176,8 +178,11 @@ class BaseModel(object):
                                   for v in blob.values())
                 if on_host and split > 1 and count >= 8 * split:
                     step = (count + split - 1) // split
-                    for start in range(0, count, step):
-                        yield {k: v[start:start + step] for k, v in blob.items()}
+                    bounds = list(range(0, count, step)) + [count]
+                    lead = max(1, step // 4)
+                    bounds.insert(1, lead)
+                    for start, stop in zip(bounds[:-1], bounds[1:]):
+                        yield {k: v[start:stop] for k, v in blob.items()}
                 else:
                     yield blob
 

@@ -1,6 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
-timeout 300 python tools/adapnet_bench.py 16 10 2>&1 | tail -1
-timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_latest.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 207 -c 69 --csv --log-file gpurun_out/adapnet_launches.csv python tools/adapnet_bench.py 16 2 > gpurun_out/adapnet_ncu.log 2>&1
+timeout 300 python tools/c1_debug.py 3 2>&1 | tail -1
+timeout 300 python tools/c1_debug.py 1 2>&1 | tail -1
+timeout 300 python tools/conv_bench.py 0,1,8,13 conv1_1 2>&1 | tail -12
+timeout 900 python -m pytest tests/test_gpu_fcn.py tests/test_gpu_layers.py tests/test_gpu_adapnet.py -q -m gpu -x 2>&1 | tail -3
