@@ -332,8 +332,12 @@ static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, i
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   p.th = p.tw = 16;
-  XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, 16, 16));
-  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
+  // debug bit6: previous variant (nine shifted 16x16 tiles per channel chunk instead of three
+  // column-shifted 18x16 patches)
+  p.halo = (g_debug_flags & 64) ? 0 : 1;
+  XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, p.halo ? 18 : 16, 16));
+  p.w_rows = L.cout <= 64 ? 64 : 128;
+  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, p.w_rows));
   if (pool) {
     XV_TRY(get_tmap(net, &p.tmap_out, out, B, H / 2, W / 2, L.cout, 8, 8));
   } else {
@@ -451,7 +455,9 @@ int run_conv_generic(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
     p.has_residual = 1;
     XV_TRY(get_tmap_ex(net, &p.tmap_res, residual, B, Ho, Wo, L.cout, L.cout, 1, p.th, p.tw));
   }
-  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, t_kernel ? 128 : L.block_n));
+  p.w_rows = L.cout <= 64 ? 64 : 128;
+  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad,
+                    t_kernel ? p.w_rows : L.block_n));
   if (out_f32) {
     p.tmap_out = p.tmap_in;
     p.out_f32 = static_cast<float*>(out);

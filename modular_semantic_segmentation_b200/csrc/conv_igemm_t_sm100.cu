@@ -30,22 +30,37 @@ constexpr int kStages = 4;
 constexpr int kStagingBytes = 32768;               // 2 channel chunks x 128 rows x 128 B
 constexpr int kThreads = 192;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+// HALO variant (3x3, dilation 1): the producer loads three column-shifted copies of the
+// (16 + 2) x 16 pixel patch per input-channel chunk instead of nine shifted 16 x 16 tiles; the
+// three row shifts are a 2 KB offset in the operand descriptor.  Shared-memory fill traffic per
+// tile drops from 9 x 32 KB to 3 x 36 KB - this kernel is bound by shared-memory bandwidth
+// (TMA writes + MMA operand reads = 96 KB per K block against 128 B / cycle).
+constexpr int kCopyRows = kTile + 2;
+constexpr int kCopyBytes = kCopyRows * kTile * 128;        // 36 KB
+constexpr int kXCopies = 3;
+constexpr int kWStages = 4;
+constexpr int kHaloSmemBytes =
+    1024 + kXCopies * kCopyBytes + kWStages * kWBytes + kStagingBytes + 256;
 
-template <bool POOL, bool GEN = false>
+template <bool POOL, bool GEN = false, bool HALO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
+  static_assert(!(GEN && HALO), "the halo variant is for plain 3x3 filters");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_w = smem;
-  uint8_t* smem_x = smem + kStages * kWBytes;
-  uint8_t* staging = smem + kStages * kStageBytes;
+  // plain: kStages x (W 16 KB) | kStages x (X 32 KB); halo: kXCopies x 36 KB | kWStages x 16 KB
+  uint8_t* smem_w = HALO ? smem + kXCopies * kCopyBytes : smem;
+  uint8_t* smem_x = HALO ? smem : smem + kStages * kWBytes;
+  uint8_t* staging = HALO ? smem_w + kWStages * kWBytes : smem + kStages * kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* x_full_bar = bars + 2 * kStages + 5;      // HALO only: kXCopies + kXCopies barriers
+  uint64_t* x_empty_bar = x_full_bar + kXCopies;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -65,9 +80,27 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 128);
     }
+    if (HALO) {
+      for (int s = 0; s < kXCopies; ++s) {
+        mbar_init(&x_full_bar[s], 1);
+        mbar_init(&x_empty_bar[s], 1);
+      }
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  // Cout <= 64: the weight box holds 64 rows; rows 64..127 of every weight stage stay zero for
+  // the whole kernel instead of being zero-filled by TMA for every K block
+  const uint32_t w_bytes = static_cast<uint32_t>(p.w_rows) * 128;
+  if (p.w_rows < kBlockM) {
+    constexpr int kNumW = HALO ? kWStages : kStages;
+    for (int i = threadIdx.x; i < kNumW * (kWBytes / 2 / 16); i += kThreads) {
+      const int st = i / (kWBytes / 2 / 16), off = i % (kWBytes / 2 / 16);
+      *reinterpret_cast<uint4*>(smem_w + st * kWBytes + kWBytes / 2 + off * 16) =
+          make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -88,6 +121,41 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     uint32_t stage = 0, phase = 0;
+    if constexpr (HALO) {
+      uint32_t xs = 0, xphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int img, y0, x0, n0;
+        decode(tile, img, y0, x0, n0);
+        for (int cc = 0; cc < cin_chunks; ++cc) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&x_empty_bar[xs], xphase ^ 1);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&x_full_bar[xs], kCopyBytes);
+              tma_load_4d(smem_x + xs * kCopyBytes, &p.tmap_in, &x_full_bar[xs], cc * kBlockK,
+                          x0 + dxi - 1, y0 - 1, img);
+            }
+            __syncwarp();
+            if (++xs == kXCopies) {
+              xs = 0;
+              xphase ^= 1;
+            }
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&full_bar[stage], w_bytes);
+                tma_load_2d(smem_w + stage * kWBytes, &p.tmap_w, &full_bar[stage],
+                            (dyi * 3 + dxi) * p.cin + cc * kBlockK, n0);
+              }
+              __syncwarp();
+              if (++stage == kWStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    } else {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int img, y0, x0, n0;
       decode(tile, img, y0, x0, n0);
@@ -108,7 +176,7 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
         }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], kXBytes + w_bytes);
           tma_load_4d(smem_x + stage * kXBytes, tmap_x, &full_bar[stage], cc * kBlockK,
                       x0 + dx, y0 + dy, img);
           tma_load_2d(smem_w + stage * kWBytes, &p.tmap_w, &full_bar[stage],
@@ -121,14 +189,52 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
         }
       }
     }
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kPixels);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    uint32_t xs = 0, xphase = 0;                 // HALO: position in the ring of patch copies
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kPixels;
+      if constexpr (HALO) {
+        int first = 1;
+        for (int cc = 0; cc < cin_chunks; ++cc) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&x_full_bar[xs], xphase);
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              if (elect_one_sync()) {
+                const uint32_t w_addr = smem_u32(smem_w + stage * kWBytes);
+                // rows dyi .. dyi + 15 of the 18-row copy: 16 pixel rows of 128 B each = 2 KB step
+                const uint32_t x_addr = smem_u32(smem_x + xs * kCopyBytes) + dyi * (kTile * 128);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  umma_bf16(d_tmem, umma_desc_sw128(w_addr + k * 32, 1024, 0),
+                            umma_desc_sw128(x_addr + k * 32, 1024, 0), idesc,
+                            (first && k == 0) ? 0u : 1u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (dyi == 2) umma_commit(&x_empty_bar[xs]);
+                if (cc == cin_chunks - 1 && dxi == 2 && dyi == 2) umma_commit(&tmem_full_bar[acc]);
+              }
+              __syncwarp();
+              first = 0;
+              if (++stage == kWStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            if (++xs == kXCopies) {
+              xs = 0;
+              xphase ^= 1;
+            }
+          }
+        }
+      } else {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -149,6 +255,7 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
           stage = 0;
           phase ^= 1;
         }
+      }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -254,18 +361,18 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
   }
 }
 
-template <bool POOL, bool GEN>
+template <bool POOL, bool GEN, bool HALO = false>
 int launch_t(const ConvIgemmParams& p, cudaStream_t stream) {
-  auto kernel = conv_igemm_t_kernel<POOL, GEN>;
+  auto kernel = conv_igemm_t_kernel<POOL, GEN, HALO>;
+  constexpr int kBytes = HALO ? kHaloSmemBytes : kSmemBytes;
   static bool configured = false;
   if (!configured) {
-    XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSmemBytes));
+    XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
     configured = true;
   }
   const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_blocks;
   const int grid = total_tiles < device_info().num_sms ? total_tiles : device_info().num_sms;
-  kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  kernel<<<grid, kThreads, kBytes, stream>>>(p);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -280,6 +387,10 @@ int launch_conv_igemm_t(const ConvIgemmParams& p, bool pool, cudaStream_t stream
   XV_CHECK(p.cin % kBlockK == 0, "conv_igemm_t: Cin must be a multiple of 64");
   XV_CHECK(p.cout % 64 == 0, "conv_igemm_t: Cout must be a multiple of 64");
   XV_CHECK(!pool || (p.H % 2 == 0 && p.W % 2 == 0), "conv_igemm_t: pooling needs even H, W");
+  XV_CHECK(p.w_rows == 64 || p.w_rows == 128, "conv_igemm_t: weight box must hold 64 or 128 rows");
+  if (p.halo) {   // tmap_in box {64, 16, 18, 1}
+    return pool ? launch_t<true, false, true>(p, stream) : launch_t<false, false, true>(p, stream);
+  }
   return pool ? launch_t<true, false>(p, stream) : launch_t<false, false>(p, stream);
 }
 
@@ -287,6 +398,7 @@ int launch_conv_igemm_t_generic(const ConvIgemmParams& p, cudaStream_t stream) {
   XV_CHECK(p.cin % kBlockK == 0, "conv_igemm_t: Cin must be a multiple of 64");
   XV_CHECK(p.cout % 64 == 0, "conv_igemm_t: Cout must be a multiple of 64");
   XV_CHECK(p.taps > 0 && p.kw > 0 && p.dil > 0, "conv_igemm_t: generic geometry not set");
+  XV_CHECK(p.w_rows == 64 || p.w_rows == 128, "conv_igemm_t: weight box must hold 64 or 128 rows");
   return launch_t<false, true>(p, stream);
 }
 

@@ -38,6 +38,8 @@ struct ConvIgemmParams {
   int stride2;
   CUtensorMap tmap_in_par[4];
   int patch_w;            // conv_c1_sm100.cu: floats per row of the input patch
+  int halo;               // conv_igemm_t: halo variant, tmap_in box {64, 16, 18, 1}
+  int w_rows;             // conv_igemm_t: rows of the weight box, 64 (Cout <= 64) or 128
 };
 int conv_igemm_block_n(int cout);
 int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,

@@ -1,5 +1,10 @@
 #!/bin/bash
-timeout 300 python tools/c1_debug.py 3 2>&1 | tail -1
-timeout 300 python tools/c1_debug.py 1 2>&1 | tail -1
-timeout 300 python tools/conv_bench.py 0,1,8,13 conv1_1 2>&1 | tail -12
-timeout 900 python -m pytest tests/test_gpu_fcn.py tests/test_gpu_layers.py tests/test_gpu_adapnet.py -q -m gpu -x 2>&1 | tail -3
+timeout 300 python tools/halo_bench.py 2>&1 | tail -8
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
+timeout 300 python tools/adapnet_bench.py 16 10 2>&1 | tail -1
+timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_latest.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_latest.json'))
+print('value',d['value'],'e2e',d['e2e']['value'],'raw',d['e2e']['raw_dtype_inputs']['value'],'roof',d['roofline']['achieved'],d['roofline']['frac'])
+PY
