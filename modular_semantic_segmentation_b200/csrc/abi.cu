@@ -285,7 +285,12 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
-  XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, p.th, p.tw));
+  // halo variant (debug bit6 selects the nine-shifted-tiles one): three (th + 2) x tw patch copies
+  p.halo = (L.taps == 9 && !out_f32 && !(g_debug_flags & (64 | 16)) && (p.tw == 8 || p.tw == 16) &&
+            (p.th + 2) * p.tw * 128 <= 20480)
+               ? 1
+               : 0;
+  XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, p.halo ? p.th + 2 : p.th, p.tw));
   XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
   if (!out_f32) {
     XV_CHECK(L.cout % 64 == 0, "bf16 epilogue needs Cout % 64 == 0");
@@ -1295,13 +1300,16 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(h, w, &p.th, &p.tw);
-  if (cin % 64 == 0) XV_TRY(make_tmap_act(&p.tmap_in, in.p, n, h, w, cin, cin, 1, p.th, p.tw));
+  // flag 8192: halo variant of the pixel-major kernel
+  p.halo = ((flags & 8192) && k == 3 && cin % 64 == 0 && (p.tw == 8 || p.tw == 16)) ? 1 : 0;
+  if (cin % 64 == 0)
+    XV_TRY(make_tmap_act(&p.tmap_in, in.p, n, h, w, cin, cin, 1, p.halo ? p.th + 2 : p.th, p.tw));
   XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
   XV_TRY(make_tmap_act(&p.tmap_out, out.p, n, h, w, cout, cout, 1, p.th, p.tw));
   p.bias = static_cast<const float*>(L.bias_pad.p);
   p.N = n; p.H = h; p.W = w; p.cin = cin; p.cout = cout;
   p.tiles_x = div_up(w, p.tw); p.tiles_y = div_up(h, p.th);
-  p.n_blocks = L.cout_pad / L.block_n; p.relu = 1; p.debug_flags = flags;
+  p.n_blocks = L.cout_pad / L.block_n; p.relu = 1; p.debug_flags = flags & ~8192;
   cudaEvent_t e0, e1;
   XV_CUDA(cudaEventCreate(&e0));
   XV_CUDA(cudaEventCreate(&e1));

@@ -36,18 +36,30 @@ constexpr int kPackGroups = 4;                    // conv1_1 mode: groups of 128
 constexpr int kPackThreads = 128 * kPackGroups;
 constexpr int kPrefetchTiles = 2;               // L2 prefetch distance in tiles per CTA
 
-// RES: two extra 16 KB buffers receive the residual operand tiles (one pipeline stage less)
-template <int BLOCK_N, bool RES = false>
+// RES: two extra 16 KB buffers receive the residual operand tiles (one pipeline stage less).
+// HALO (3x3, dilation 1): the pixel operand is loaded as three column-shifted copies of the
+// (th + 2) x tw patch per input-channel chunk instead of nine shifted tiles (the row shift is an
+// offset of tw rows in the operand descriptor), the weights stream through their own ring.  The
+// kernel is bound by shared-memory bandwidth, so 2.4x less pixel fill traffic is time.
+constexpr int kACopies = 3;
+constexpr int kACopyBytes = 20480;               // (8 + 2) x 16 or (16 + 2) x 8 pixel rows of 128 B
+template <int BLOCK_N, bool RES = false, bool HALO = false>
 struct IgemmCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBufs = RES ? 4 : 2;           // 2 output staging (+ 2 residual) buffers
-  // 4 / 6 / 8 stages for N = 256 / 128 / 64 (3 for N = 256 with the residual buffers)
-  static constexpr int kStages = (196608 - (kOutBufs - 2) * kOutBufBytes) / kStageBytes;
+  // plain: 4 / 6 / 8 stages for N = 256 / 128 / 64 (3 for N = 256 with the residual buffers);
+  // halo: that many weight stages next to the three patch copies
+  static constexpr int kHaloStages =
+      (196608 - kACopies * kACopyBytes) / kBBytes > 8 ? 8 : (196608 - kACopies * kACopyBytes) / kBBytes;
+  static constexpr int kStages =
+      HALO ? kHaloStages : (196608 - (kOutBufs - 2) * kOutBufBytes) / kStageBytes;
+  static constexpr int kPipeBytes =
+      HALO ? kACopies * kACopyBytes + kStages * kBBytes : kStages * kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;          // two accumulator stages
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes =
-      1024 /*align slack*/ + kStages * kStageBytes + kOutBufs * kOutBufBytes + kBarBytes;
+      1024 /*align slack*/ + kPipeBytes + kOutBufs * kOutBufBytes + kBarBytes;
 };
 
 struct TileCoord {
@@ -72,18 +84,19 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvIgemmParams& p, int t
 // C1 > 0: conv1_1 mode with C1 raw input channels - warps 6..9 build the A operand rows from the
 // fp32 input (3x3 neighbourhood split into hi + lo bf16 halves, see layers.cu), TMA loads only
 // the 8 KB weight tile.
-template <int BLOCK_N, int TAPS, bool OUT_F32, int C1 = 0, bool RES = false>
+template <int BLOCK_N, int TAPS, bool OUT_F32, int C1 = 0, bool RES = false, bool HALO = false>
 __global__ void __launch_bounds__(C1 > 0 ? kThreads + kPackThreads : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
-  using Cfg = IgemmCfg<BLOCK_N, RES>;
+  static_assert(!HALO || (TAPS == 9 && !OUT_F32 && C1 == 0 && !RES), "halo: plain 3x3 bf16 layers");
+  using Cfg = IgemmCfg<BLOCK_N, RES, HALO>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* smem_out = smem + kStages * Cfg::kStageBytes;
+  uint8_t* smem_a = smem;                                  // HALO: the three patch copies
+  uint8_t* smem_b = smem + (HALO ? kACopies * kACopyBytes : kStages * kABytes);
+  uint8_t* smem_out = smem + Cfg::kPipeBytes;
   uint8_t* smem_res = smem_out + 2 * kOutBufBytes;          // RES only
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::kOutBufs * kOutBufBytes);
   uint64_t* full_bar = bars;
@@ -92,6 +105,8 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   uint64_t* res_full_bar = bars + 2 * kStages + 5;          // RES only, two barriers
+  uint64_t* a_full_bar = bars + 2 * kStages + 7;            // HALO only, kACopies + kACopies
+  uint64_t* a_empty_bar = a_full_bar + kACopies;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,6 +127,12 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
       mbar_init(&tmem_empty_bar[s], 128);
       if (RES) mbar_init(&res_full_bar[s], 1);
     }
+    if (HALO) {
+      for (int s = 0; s < kACopies; ++s) {
+        mbar_init(&a_full_bar[s], 1);
+        mbar_init(&a_empty_bar[s], 1);
+      }
+    }
     if (RES) tma_prefetch_desc(&p.tmap_res);
     fence_mbar_init();
   }
@@ -128,7 +149,41 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    if constexpr (HALO) {
+      uint32_t as = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile, BLOCK_N);
+        for (int cc = 0; cc < cin_chunks; ++cc) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&a_empty_bar[as], aphase ^ 1);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&a_full_bar[as], static_cast<uint32_t>((p.th + 2) * p.tw) * 128);
+              tma_load_4d(smem_a + as * kACopyBytes, &p.tmap_in, &a_full_bar[as], cc * kBlockK,
+                          c.x0 + dxi - 1, c.y0 - 1, c.img);
+            }
+            __syncwarp();
+            if (++as == kACopies) {
+              as = 0;
+              aphase ^= 1;
+            }
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+                tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmap_w, &full_bar[stage],
+                            (dyi * 3 + dxi) * p.cin + cc * kBlockK, c.n0);
+              }
+              __syncwarp();
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int tile = blockIdx.x; !HALO && tile < total_tiles; tile += gridDim.x) {
       if (p.debug_flags & 256) break;       // experiment: MMA warp free-runs, no smem pipeline
       const TileCoord c = decode_tile(p, tile, BLOCK_N);
       if (p.debug_flags & 128) {            // experiment: L2 prefetch of a later tile
@@ -186,11 +241,49 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
     // ------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    uint32_t as = 0, aphase = 0;                 // HALO: position in the ring of patch copies
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      if constexpr (HALO) {
+        int first = 1;
+        for (int cc = 0; cc < cin_chunks; ++cc) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&a_full_bar[as], aphase);
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              if (elect_one_sync()) {
+                // tile rows dyi .. dyi + th - 1 of the (th + 2)-row copy: tw pixel rows per step
+                const uint32_t a_addr =
+                    smem_u32(smem_a + as * kACopyBytes) + static_cast<uint32_t>(dyi * p.tw) * 128;
+                const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 1024, 0),
+                            umma_desc_sw128(b_addr + k * 32, 1024, 0), idesc,
+                            (first && k == 0) ? 0u : 1u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (dyi == 2) umma_commit(&a_empty_bar[as]);
+                if (cc == cin_chunks - 1 && dxi == 2 && dyi == 2) umma_commit(&tmem_full_bar[acc]);
+              }
+              __syncwarp();
+              first = 0;
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            if (++as == kACopies) {
+              as = 0;
+              aphase ^= 1;
+            }
+          }
+        }
+      }
+      for (int kb = 0; !HALO && kb < num_kb; ++kb) {
         if (!(p.debug_flags & 256)) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -416,10 +509,10 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   }
 }
 
-template <int BLOCK_N, int TAPS, bool OUT_F32, bool RES = false>
+template <int BLOCK_N, int TAPS, bool OUT_F32, bool RES = false, bool HALO = false>
 int launch_one(const ConvIgemmParams& p, cudaStream_t stream) {
-  using Cfg = IgemmCfg<BLOCK_N, RES>;
-  auto kernel = conv_igemm_kernel<BLOCK_N, TAPS, OUT_F32, 0, RES>;
+  using Cfg = IgemmCfg<BLOCK_N, RES, HALO>;
+  auto kernel = conv_igemm_kernel<BLOCK_N, TAPS, OUT_F32, 0, RES, HALO>;
   static bool configured = false;
   if (!configured) {
     XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -476,6 +569,14 @@ int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_
            "conv_igemm: taps must be 1, 9 or 0 (geometry from the parameter block)");
   if (taps == 0)
     XV_CHECK(p.taps > 0 && p.kw > 0 && p.dil > 0, "conv_igemm: generic geometry not set");
+  if (p.halo) {   // tmap_in box {64, tw, th + 2, 1}
+    XV_CHECK(taps == 9 && !out_f32 && !p.has_residual && (p.tw == 8 || p.tw == 16) &&
+                 (p.th + 2) * p.tw * 128 <= kACopyBytes,
+             "conv_igemm: the halo variant needs a 3x3 bf16 layer and an 8x16 or 16x8 tile");
+    if (block_n == 64) return launch_one<64, 9, false, false, true>(p, stream);
+    if (block_n == 128) return launch_one<128, 9, false, false, true>(p, stream);
+    if (block_n == 256) return launch_one<256, 9, false, false, true>(p, stream);
+  }
   if (p.has_residual) {
     XV_CHECK(taps == 0 && block_n == 256 && !out_f32,
              "conv_igemm: the residual epilogue exists for generic bf16 layers with BLOCK_N = 256");

@@ -1,7 +1,5 @@
 #!/bin/bash
-timeout 300 python tools/halo_bench.py 2>&1 | tail -8
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
-timeout 300 python tools/adapnet_bench.py 16 10 2>&1 | tail -1
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -8
 timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_latest.json
 python - <<'PY'
 import json
