@@ -82,6 +82,30 @@ def test_fcn_bf16_tcgen05_matches_oracle(dev, cin, h, w, fused_pool):
     dev.set_debug_flags(0)
 
 
+@pytest.mark.parametrize('cin', [3, 1])
+def test_fcn_kernel_variants_agree(dev, cin):
+    """The previous kernel variants (debug bit5: conv1_1 packers reading global memory, bit6:
+    nine shifted tiles instead of three patch copies) compute the same network up to summation
+    order and bf16 rounding."""
+    rng = np.random.default_rng(40 + cin)
+    net, params = _net(dev, 'bf16', cin, rng)
+    hi = 255.0 if cin == 3 else 65535.0
+    x = cuda(rng.integers(0, int(hi) + 1, size=(2, 48, 80, cin)).astype(np.float32))
+    net.set_param('conv1_1/kernel', params['m/conv1_1/kernel'] / np.float32(hi))
+    base = net.forward(x, want=('prob', 'label'))
+    base_c11 = net.layer('conv1_1')
+    for flags in (32, 64, 96):
+        dev.set_debug_flags(flags)
+        alt = net.forward(x, want=('prob', 'label'))
+        alt_c11 = net.layer('conv1_1')
+        dev.set_debug_flags(0)
+        # conv1_1: the bias enters as hi + lo bf16 inside the MMA vs an fp32 add
+        np.testing.assert_allclose(alt_c11, base_c11, rtol=0, atol=2.0 ** -7 * np.abs(base_c11).max())
+        np.testing.assert_allclose(alt['prob'].cpu().numpy(), base['prob'].cpu().numpy(), rtol=0,
+                                   atol=1e-2)
+        assert (alt['label'] == base['label']).float().mean().item() > 0.99
+
+
 def test_fcn_batchnorm_fp32(dev):
     rng = np.random.default_rng(5)
     net, params = _net(dev, 'fp32', 3, rng, batchnorm=True)

@@ -38,6 +38,7 @@ rows = [r for r in csv.reader(open(os.path.join(G, '%s_bench_launches.csv' % R))
 hdr = rows[0]
 ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
 agg, tot, seq = collections.OrderedDict(), 0.0, []
+allrows = []
 for r in rows[1:]:
     try:
         v = float(r[vi].replace(',', ''))
@@ -46,6 +47,16 @@ for r in rows[1:]:
     if r[ui] == 'ns':
         v /= 1e3
     name = r[ki].replace('void ', '').replace('<unnamed>::', '').replace('xv::', '').split('(')[0]
+    allrows.append((name, v))
+# the capture holds every launch of the process; a step ends with confusion_kernel, the run does
+# 3 warm-up steps and then the 2 timed device-resident steps (bench.py --steps 2 --warmup 1)
+steps, cur = [], []
+for name, v in allrows:
+    cur.append((name, v))
+    if name.startswith('confusion_kernel'):
+        steps.append(cur)
+        cur = []
+for name, v in steps[3] + steps[4]:
     seq.append((name, v))
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
@@ -55,11 +66,11 @@ with open(os.path.join(P, '%s_bench_launches.csv' % R), 'w') as f:
     f.write('kernel,duration_us\n')
     for n, v in seq:
         f.write('"%s",%.1f\n' % (n, v))
-md.append('## ncu launch list of `bench.py --steps 2 --warmup 1` (%d launches = 2 steps; cold-cache, serialised)\n' % len(seq))
+md.append('## ncu launch list of `bench.py --steps 2 --warmup 1` (%d launches = the 2 timed device-resident steps; cold-cache, serialised)\n' % len(seq))
 md.append('| kernel | launches | total us | share |\n|---|---|---|---|')
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     md.append('| `%s` | %d | %.1f | %.1f%% |' % (k, n, t, 100 * t / tot))
-conv_share = sum(t for k, (n, t) in agg.items() if 'conv_igemm' in k) / tot
+conv_share = sum(t for k, (n, t) in agg.items() if 'conv_igemm' in k or 'conv_c1' in k) / tot
 md.append('\ntensor-core conv kernels: %.1f%% of the serialised step (bench.py live measurement: %.1f%%)\n' % (100 * conv_share, 100 * b['roofline']['kernel_share_of_step']))
 
 # ---- ncu --set full of the conv kernels (one stream forward)
@@ -68,10 +79,9 @@ want = [('Kernel Name', 'kernel'), ('gpu__time_duration.sum', 'us'), ('dram__byt
         ('dram__bytes_write.sum', 'dram wr MB'), ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %'),
         ('l1tex__m_xbar2l1tex_read_bytes.sum', 'L2->SM GB'), ('launch__registers_per_thread', 'regs')]
 idx = [(col(hdr, k), t) for k, t in want if col(hdr, k) is not None]
-# the capture (-s 16 -c 16 over conv launches; 15 per forward) starts at conv1_2 of the 2nd forward
-layer_names = ['conv1_2+pool1', 'conv2_1', 'conv2_2+pool2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv4_1', 'conv4_2',
-               'conv4_3', 'conv5_1', 'conv5_2', 'conv5_3', 'score_conv4', 'score_conv5', 'conv1_1 (next forward)',
-               'conv1_2+pool1 (next forward)']
+# the capture (-s 15 -c 15 over the conv launches, 15 per forward) is the 2nd forward
+layer_names = ['conv1_1', 'conv1_2+pool1', 'conv2_1', 'conv2_2+pool2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv4_1',
+               'conv4_2', 'conv4_3', 'conv5_1', 'conv5_2', 'conv5_3', 'score_conv4', 'score_conv5']
 md.append('## ncu --set full, tensor-core conv kernels of one stream forward\n')
 md.append('| layer | ' + ' | '.join(t for _, t in idx) + ' |\n|' + '---|' * (len(idx) + 1))
 traffic = []
@@ -84,7 +94,7 @@ for n, r in enumerate(rows):
         vals.append(v)
     md.append('| %s | ' % (layer_names[n] if n < len(layer_names) else '') + ' | '.join(vals) + ' |')
     ir, iw = col(hdr, 'dram__bytes_read.sum'), col(hdr, 'dram__bytes_write.sum')
-    if n < 12 or n == 14:
+    if n < 13:
         traffic.append((float(r[ir]) + float(r[iw])) * 1e6)
 json.dump({'conv_igemm_dram_bytes_per_launch': sum(traffic) / len(traffic),
            'note': 'mean dram__bytes_read+write over the 13 conv layers of one stream forward (batch 16), ncu --set full'},
@@ -127,5 +137,43 @@ for r in t['rows']:
 fb = json.load(open(os.path.join(P, '%s_fit_bench.json' % R)))
 md.append('\n## fit() (`tools/fit_bench.py`, depth stream 384x768, batch 16, Adam)\n')
 md.append('* %.0f frames/s on 1 GPU, %.1f ms per step (forward + backward + Adam), %d parameters, %.0f MB gradient bucket' % (fb['value'], fb['ms_per_step'], fb['params'], fb['allreduce_bytes_per_step'] / 1e6))
+# ---- Adapnet expert
+ap = os.path.join(G, '%s_adapnet_bench.json' % R)
+if os.path.exists(ap):
+    a = json.loads(open(ap).read().strip().splitlines()[-1])
+    json.dump(a, open(os.path.join(P, '%s_adapnet_bench.json' % R), 'w'), indent=1)
+    md.append('\n## Adapnet expert (`tools/adapnet_bench.py`, rgb 768x384, batch 16, num_units 64, 12 classes)\n')
+    md.append('* %.0f frames/s per expert, %.2f ms per forward, %d launches; tensor-core convs %.0f GFLOP/frame at %.0f TFLOP/s' % (
+        a['frames_per_s'], a['ms_per_forward'], a['launches_per_forward'], a['conv_gflop_per_frame'], a['conv_tflops']))
+    lp = os.path.join(G, '%s_adapnet_launches.csv' % R)
+    if os.path.exists(lp):
+        rows = [r for r in csv.reader(open(lp)) if len(r) > 5]
+        hdr = rows[0]
+        ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+        agg, tot = collections.OrderedDict(), 0.0
+        with open(os.path.join(P, '%s_adapnet_launches.csv' % R), 'w') as f:
+            f.write('kernel,duration_us\n')
+            for r in rows[1:]:
+                try:
+                    v = float(r[vi].replace(',', ''))
+                except ValueError:
+                    continue
+                if r[ui] == 'ns':
+                    v /= 1e3
+                name = r[ki].replace('void ', '').replace('<unnamed>::', '').replace('xv::', '').split('(')[0]
+                f.write('"%s",%.1f\n' % (name, v))
+                e = agg.setdefault(name, [0, 0.0])
+                e[0] += 1
+                e[1] += v
+                tot += v
+        md.append('\n| kernel (ncu launch list of one forward) | launches | total us | share |\n|---|---|---|---|')
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            md.append('| `%s` | %d | %.1f | %.1f%% |' % (k, n, t, 100 * t / tot))
+for extra in ('bench_8gpu', 'bench_2gpu'):
+    ep = os.path.join(P, '%s_%s.json' % (R, extra))
+    if os.path.exists(ep):
+        e = json.loads(open(ep).read().strip().splitlines()[-1])
+        md.append('\n## bench.py --gpus %d\n' % e['n_gpus'])
+        md.append('* value %.0f frames/s (%.3f ms per step), e2e %.0f frames/s' % (e['value'], e['ms_per_step'], e['e2e']['value']))
 open(os.path.join(P, 'README.md'), 'w').write('\n'.join(md) + '\n')
 print('\n'.join(md))
