@@ -46,8 +46,9 @@ int xv_device_sm_count(int* out);
  * operand buffer instead of in-kernel packing, bit3 = weight gradients on the CUDA cores instead
  * of the tensor-core kernel, bit4 = use the 2-CTA weight-multicast conv kernel, bit5 = conv1_1
  * with global loads in the operand packers instead of TMA-staged input patches, bit6 = 3x3
- * convolutions load nine shifted tiles per channel chunk instead of three patch copies.
- * 0 = production behaviour. */
+ * convolutions load nine shifted tiles per channel chunk instead of three patch copies,
+ * bit7 = single-CTA MMAs for the Cout >= 256 layers instead of the CTA-pair (cta_group::2)
+ * kernel.  0 = production behaviour. */
 int xv_set_debug_flags(int flags);
 /* Number of kernels this library has launched since it was loaded. */
 int xv_launch_count(int64_t* out);

@@ -291,7 +291,9 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
                ? 1
                : 0;
   XV_TRY(get_tmap(net, &p.tmap_in, in, B, H, W, L.cin_gemm, p.halo ? p.th + 2 : p.th, p.tw));
-  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n));
+  // CTA-pair kernel (cta_group::2) for the 256-wide layers; debug bit7 keeps the single-CTA one
+  const bool pair = p.halo && L.block_n == 256 && !(g_debug_flags & 128);
+  XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, pair ? 128 : L.block_n));
   if (!out_f32) {
     XV_CHECK(L.cout % 64 == 0, "bf16 epilogue needs Cout % 64 == 0");
     XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, p.th, p.tw));
@@ -315,6 +317,7 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   const bool mc = (L.block_n == 256 && !out_f32 && (g_debug_flags & 16));
   if (mc) XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
   auto launch = [&]() -> int {
+    if (pair) return launch_conv_igemm_2cta(p, s);
     return mc ? launch_conv_igemm_mc(p, L.taps, s)
               : launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
   };
@@ -1351,7 +1354,12 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
   }
   const bool use_t = (flags & 512) != 0 && L.use_t;
   const bool t_pool = (flags & 1024) != 0;
+  // flag 16384 (with 8192): CTA-pair kernel
+  const bool pair = (flags & 16384) && p.halo && L.block_n == 256;
+  if (pair) XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
+  p.debug_flags = flags & ~(8192 | 16384);
   auto once = [&]() -> int {
+    if (pair) return launch_conv_igemm_2cta(p, 0);
     if (use_t) return run_igemm_t(nullptr, L, in.p, n, h, w, out.p, t_pool, 0);
     return launch_conv_igemm(p, L.block_n, L.taps, false, 0);
   };

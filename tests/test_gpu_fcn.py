@@ -85,8 +85,8 @@ def test_fcn_bf16_tcgen05_matches_oracle(dev, cin, h, w, fused_pool):
 @pytest.mark.parametrize('cin', [3, 1])
 def test_fcn_kernel_variants_agree(dev, cin):
     """The previous kernel variants (debug bit5: conv1_1 packers reading global memory, bit6:
-    nine shifted tiles instead of three patch copies) compute the same network up to summation
-    order and bf16 rounding."""
+    nine shifted tiles instead of three patch copies, bit7: single-CTA instead of cta_group::2
+    MMAs) compute the same network up to summation order and bf16 rounding."""
     rng = np.random.default_rng(40 + cin)
     net, params = _net(dev, 'bf16', cin, rng)
     hi = 255.0 if cin == 3 else 65535.0
@@ -94,7 +94,7 @@ def test_fcn_kernel_variants_agree(dev, cin):
     net.set_param('conv1_1/kernel', params['m/conv1_1/kernel'] / np.float32(hi))
     base = net.forward(x, want=('prob', 'label'))
     base_c11 = net.layer('conv1_1')
-    for flags in (32, 64, 96):
+    for flags in (32, 64, 96, 128):     # bit7: single-CTA kernel instead of the CTA-pair one
         dev.set_debug_flags(flags)
         alt = net.forward(x, want=('prob', 'label'))
         alt_c11 = net.layer('conv1_1')

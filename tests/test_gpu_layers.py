@@ -59,9 +59,14 @@ def test_conv2d_tcgen05_matches_oracle(dev, n, h, w, cin, cout, k, relu):
         # nine-shifted-tiles variant of the default kernel (debug bit6)
         dev.set_debug_flags(64)
         alt2 = dev.conv2d(cuda(xb), kb, bias, relu=relu, precision='bf16').cpu().numpy()
+        # single-CTA halo kernel (debug bit7) vs the default CTA-pair (cta_group::2) kernel: same
+        # operands, same summation order
+        dev.set_debug_flags(128)
+        alt3 = dev.conv2d(cuda(xb), kb, bias, relu=relu, precision='bf16').cpu().numpy()
         dev.set_debug_flags(0)
         np.testing.assert_array_equal(alt, alt2)
         np.testing.assert_allclose(alt, got, rtol=0, atol=tol)
+        np.testing.assert_array_equal(alt3, got)
     if cout <= 128 and cout % 64 == 0 and k == 3:
         # same layer through the pixel-major kernel (debug bit1) must agree to bf16 rounding
         dev.set_debug_flags(2)

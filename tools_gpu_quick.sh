@@ -1,5 +1,9 @@
 #!/bin/bash
-mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r01_bench_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r01_bench_under_ncu.log 2>&1
-tail -2 gpurun_out/r01_bench_under_ncu.log | cut -c1-200
-timeout 600 python -m pytest tests/test_gpu_fcn.py -q -m gpu -x -k variants 2>&1 | tail -3
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
+timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_latest.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_latest.json'))
+print('value',d['value'],'e2e',d['e2e']['value'],'raw',d['e2e']['raw_dtype_inputs']['value'],'roof',d['roofline']['achieved'],d['roofline']['frac'], d['clocks'])
+PY
+timeout 300 python tools/adapnet_bench.py 16 10 2>&1 | tail -1
