@@ -317,7 +317,7 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   const bool mc = (L.block_n == 256 && !out_f32 && (g_debug_flags & 16));
   if (mc) XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
   auto launch = [&]() -> int {
-    if (pair) return launch_conv_igemm_2cta(p, s);
+    if (pair) return launch_conv_igemm_2cta(p, 256, s);
     return mc ? launch_conv_igemm_mc(p, L.taps, s)
               : launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
   };
@@ -1355,11 +1355,14 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
   const bool use_t = (flags & 512) != 0 && L.use_t;
   const bool t_pool = (flags & 1024) != 0;
   // flag 16384 (with 8192): CTA-pair kernel
-  const bool pair = (flags & 16384) && p.halo && L.block_n == 256;
-  if (pair) XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
+  const bool pair = (flags & 16384) && p.halo;
+  if (pair) {
+    XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, L.block_n / 2));
+    p.n_blocks = div_up(cout, L.block_n);
+  }
   p.debug_flags = flags & ~(8192 | 16384);
   auto once = [&]() -> int {
-    if (pair) return launch_conv_igemm_2cta(p, 0);
+    if (pair) return launch_conv_igemm_2cta(p, L.block_n, 0);
     if (use_t) return run_igemm_t(nullptr, L, in.p, n, h, w, out.p, t_pool, 0);
     return launch_conv_igemm(p, L.block_n, L.taps, false, 0);
   };

@@ -26,16 +26,20 @@ namespace xv {
 namespace {
 
 constexpr int kBlockM = 128;                      // pixels per CTA
-constexpr int kBlockN = 256;                      // output channels per tile pair
 constexpr int kBlockK = 64;
 constexpr int kACopies = 3;
 constexpr int kACopyBytes = 20480;                // (8 + 2) x 16 or (16 + 2) x 8 pixel rows
-constexpr int kBHalfBytes = (kBlockN / 2) * 128;  // 16 KB: this CTA's half of a weight slice
 constexpr int kBStages = 6;
 constexpr int kOutBufBytes = kBlockM * 128;
 constexpr int kThreads = 192;
-constexpr int kSmemBytes =
-    1024 + kACopies * kACopyBytes + kBStages * kBHalfBytes + 2 * kOutBufBytes + 256;
+// BLOCK_N = output channels per tile pair (256, or 128 / 64 for the narrow layers); every CTA holds
+// BLOCK_N / 2 weight rows of a K block
+template <int BLOCK_N>
+struct PairCfg {
+  static constexpr int kBHalfBytes = (BLOCK_N / 2) * 128;
+  static constexpr int kSmemBytes =
+      1024 + kACopies * kACopyBytes + kBStages * kBHalfBytes + 2 * kOutBufBytes + 256;
+};
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;    // shared::cluster address -> same offset in CTA 0
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -108,7 +112,8 @@ struct PairTile {
   int img, y0, x0, n0;
 };
 
-__device__ __forceinline__ PairTile decode_pair(const ConvIgemmParams& p, int pt, int rank) {
+__device__ __forceinline__ PairTile decode_pair(const ConvIgemmParams& p, int pt, int rank,
+                                                int block_n) {
   PairTile c;
   const int nb = pt % p.n_blocks;
   const int mt = 2 * (pt / p.n_blocks) + rank;           // this CTA's 128-pixel tile
@@ -118,12 +123,16 @@ __device__ __forceinline__ PairTile decode_pair(const ConvIgemmParams& p, int pt
   c.img = rest / p.tiles_y;       // == N for the padding half of an odd last pair: every TMA box is
   c.y0 = ty * p.th;               // then out of bounds (zero-filled loads, clipped stores)
   c.x0 = tx * p.tw;
-  c.n0 = nb * kBlockN;
+  c.n0 = nb * block_n;
   return c;
 }
 
+template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
+  constexpr int kBlockN = BLOCK_N;
+  constexpr int kBHalfBytes = PairCfg<BLOCK_N>::kBHalfBytes;
+  constexpr int kTmemCols = 2 * BLOCK_N;        // two accumulator stages (128 / 256 / 512)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -168,7 +177,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();             // the peer's barriers exist before anything is signalled remotely
@@ -179,7 +188,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
     // ------------------------------------------------------------- TMA producer (both CTAs)
     uint32_t bs = 0, bphase = 0, as = 0, aphase = 0;
     for (int pt = pair_id; pt < total_pairs; pt += num_pairs) {
-      const PairTile c = decode_pair(p, pt, rank);
+      const PairTile c = decode_pair(p, pt, rank, kBlockN);
       for (int cc = 0; cc < cin_chunks; ++cc) {
         for (int dxi = 0; dxi < 3; ++dxi) {
           mbar_wait(&a_empty[as], aphase ^ 1);
@@ -265,7 +274,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
     uint32_t acc = 0, acc_phase = 0, gchunk = 0;
     const uint32_t zero2 = 0u;
     for (int pt = pair_id; pt < total_pairs; pt += num_pairs) {
-      const PairTile c = decode_pair(p, pt, rank);
+      const PairTile c = decode_pair(p, pt, rank, kBlockN);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
@@ -333,33 +342,42 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
   cluster_sync_all();             // nobody leaves while the peer may still signal or read
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_pair(tmem_base, 512);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
 }  // namespace
 
-// p.tmap_in box {64, tw, th + 2, 1}; p.tmap_w box {64, 128}; p.tmap_out box {64, tw, th, 1};
-// p.n_blocks = CoutPad / 256.
-int launch_conv_igemm_2cta(const ConvIgemmParams& p, cudaStream_t stream) {
-  XV_CHECK(p.th * p.tw == kBlockM && (p.tw == 8 || p.tw == 16) &&
-               (p.th + 2) * p.tw * 128 <= kACopyBytes,
-           "conv_igemm_2cta: needs an 8x16 or 16x8 pixel tile");
-  XV_CHECK(p.cin % kBlockK == 0, "conv_igemm_2cta: Cin must be a multiple of 64");
+// p.tmap_in box {64, tw, th + 2, 1}; p.tmap_w box {64, BLOCK_N / 2}; p.tmap_out box
+// {64, tw, th, 1}; p.n_blocks = ceil(Cout / BLOCK_N).
+template <int BLOCK_N>
+static int launch_pair(const ConvIgemmParams& p, cudaStream_t stream) {
+  auto kernel = conv_igemm_2cta_kernel<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    XV_CUDA(cudaFuncSetAttribute(conv_igemm_2cta_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 PairCfg<BLOCK_N>::kSmemBytes));
     configured = true;
   }
   const int pixel_tiles = p.N * p.tiles_y * p.tiles_x;
   const int total_pairs = ((pixel_tiles + 1) / 2) * p.n_blocks;
   const int max_pairs = device_info().num_sms / 2;
   const int pairs = total_pairs < max_pairs ? total_pairs : max_pairs;
-  conv_igemm_2cta_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(p);
+  kernel<<<2 * pairs, kThreads, PairCfg<BLOCK_N>::kSmemBytes, stream>>>(p);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+int launch_conv_igemm_2cta(const ConvIgemmParams& p, int block_n, cudaStream_t stream) {
+  XV_CHECK(p.th * p.tw == kBlockM && (p.tw == 8 || p.tw == 16) &&
+               (p.th + 2) * p.tw * 128 <= kACopyBytes,
+           "conv_igemm_2cta: needs an 8x16 or 16x8 pixel tile");
+  XV_CHECK(p.cin % kBlockK == 0, "conv_igemm_2cta: Cin must be a multiple of 64");
+  if (block_n == 256) return launch_pair<256>(p, stream);
+  if (block_n == 128) return launch_pair<128>(p, stream);
+  if (block_n == 64) return launch_pair<64>(p, stream);
+  return fail("conv_igemm_2cta: BLOCK_N must be 64, 128 or 256");
 }
 
 }  // namespace xv

@@ -59,7 +59,7 @@ int launch_conv_igemm_mc(const ConvIgemmParams& p, int taps, cudaStream_t stream
 
 // conv_igemm_2cta_sm100.cu: CTA-pair (cta_group::2) 3x3 kernel for Cout multiples of 256, halo
 // operands; tmap_in box {64, tw, th + 2, 1}, tmap_w box {64, 128}, n_blocks = CoutPad / 256.
-int launch_conv_igemm_2cta(const ConvIgemmParams& p, cudaStream_t stream);
+int launch_conv_igemm_2cta(const ConvIgemmParams& p, int block_n, cudaStream_t stream);
 
 // conv_igemm_t_sm100.cu: 3x3, Cout <= 128 per block of 128, 16x16 pixel tiles, optional fused
 // 2x2 max pool (then tmap_out describes the pooled tensor, box {64,8,8,1}; else {64,16,8,1}).
