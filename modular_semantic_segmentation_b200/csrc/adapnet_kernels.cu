@@ -15,28 +15,6 @@ inline int grid_for(size_t work, int threads = kThreads) {
   return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
-// [B,H,W,C] -> [B,H/2,W/2,4C], channel index (vy*2+vx)*C + c: turns the stride-2 7x7 convolution
-// (adapnet.py:121) into a stride-1 4x4 convolution.  One thread moves 8 channels (16 B).
-__global__ void space_to_depth2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
-                                       int H, int W, int c8) {
-  const int H2 = H / 2, W2 = W / 2;
-  const size_t total = static_cast<size_t>(B) * H * W * c8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    // enumerate in OUTPUT order so that the stores are fully coalesced
-    const int c = static_cast<int>(i % c8);
-    size_t t = i / c8;
-    const int v = static_cast<int>(t % 4);
-    t /= 4;
-    const int x2 = static_cast<int>(t % W2);
-    t /= W2;
-    const int y2 = static_cast<int>(t % H2);
-    const size_t b = t / H2;
-    const int y = 2 * y2 + (v >> 1), x = 2 * x2 + (v & 1);
-    out[i] = __ldg(in + ((b * H + y) * W + x) * c8 + c);
-  }
-}
-
 __device__ __forceinline__ uint32_t add_relu_bf16x2(uint32_t a, uint32_t b) {
   const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(&a);
   const __nv_bfloat162 vb = *reinterpret_cast<const __nv_bfloat162*>(&b);
@@ -289,17 +267,6 @@ __global__ void conv_f32_ex_kernel(const float* __restrict__ x, const float* __r
 }
 
 }  // namespace
-
-int launch_space_to_depth2_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W,
-                                int C, cudaStream_t s) {
-  XV_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "space_to_depth2: needs C % 8 == 0, even H, W");
-  const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
-  space_to_depth2_kernel<<<grid_for(total), kThreads, 0, s>>>(
-      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
-  XV_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
-}
 
 int launch_add_relu_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out,
                          size_t n, cudaStream_t s) {

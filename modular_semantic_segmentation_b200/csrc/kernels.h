@@ -116,8 +116,6 @@ int launch_affine_f32(float* x, const float* scale, const float* shift, size_t n
                       int relu, cudaStream_t s);
 
 // adapnet_kernels.cu: the memory-bound steps between Adapnet's convolutions
-int launch_space_to_depth2_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W,
-                                int C, cudaStream_t s);
 int launch_add_relu_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out,
                          size_t n, cudaStream_t s);
 int launch_add_relu_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t s);
