@@ -147,3 +147,64 @@ def test_adapnet_oracle_geometry():
     assert out['block_0_2'].shape == (1, 16, 24, 64) and out['block_3'].shape == (1, 8, 12, 256)
     assert out['block_7'].shape == (1, 4, 6, 512) and out['block_16'].shape == (1, 2, 3, 2048)
     assert out['merge'].shape == (1, 4, 6, 20) and out['score'].shape == (1, 32, 48, 14)
+
+
+def test_oracle_layer_ops_match_their_definitions():
+    """The torch-CPU calls inside the oracle against direct numpy loops over the documented
+    tf.layers definitions: 'same' conv as a correlation with symmetric
+    zero padding, conv2d_transpose 'SAME' as out[s*i + k - (K-s)/2] += x[i] * w[k] with the
+    [kh,kw,Cout,Cin] kernel and no flip, 2x2/2 'valid' max pooling, softmax over the last axis
+    and first-index argmax."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((1, 5, 6, 3))
+    w = rng.standard_normal((3, 3, 3, 4))
+    b = rng.standard_normal(4)
+    got = oracle.conv2d(x, {'l/kernel': w, 'l/bias': b}, 'l', activation=False)
+    xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    want = np.zeros((1, 5, 6, 4))
+    for y in range(5):
+        for xx in range(6):
+            want[0, y, xx] = np.einsum('abi,abio->o', xp[0, y:y + 3, xx:xx + 3], w) + b
+    np.testing.assert_allclose(got, want, atol=1e-12)
+
+    for k, s in ((4, 2), (16, 8)):
+        xin = rng.standard_normal((1, 3, 2, 2))
+        wt = rng.standard_normal((k, k, 3, 2))           # [kh, kw, Cout, Cin]
+        got = oracle.deconv2d(xin, {'l/kernel': wt}, 'l', s, activation=False)
+        pad = (k - s) // 2
+        want = np.zeros((1, 3 * s, 2 * s, 3))
+        for iy in range(3):
+            for ix in range(2):
+                for ky in range(k):
+                    for kx in range(k):
+                        oy, ox = s * iy + ky - pad, s * ix + kx - pad
+                        if 0 <= oy < 3 * s and 0 <= ox < 2 * s:
+                            want[0, oy, ox] += wt[ky, kx] @ xin[0, iy, ix]
+        np.testing.assert_allclose(got, want, atol=1e-12)
+
+    p = oracle.max_pool2x2(x[:, :4])
+    assert p.shape == (1, 2, 3, 3) and p[0, 1, 2, 1] == x[0, 2:4, 4:6, 1].max()
+    sm = oracle.softmax(x)
+    np.testing.assert_allclose(sm, np.exp(x) / np.exp(x).sum(-1, keepdims=True), atol=1e-12)
+    tie = np.array([[1.0, 3.0, 3.0, 2.0]])
+    assert oracle.argmax_first(tie)[0] == 1
+
+    # Adapnet's strided / atrous convolution with TF 'SAME' (smaller padding half first)
+    xs = rng.standard_normal((1, 6, 8, 2))
+    ws = rng.standard_normal((3, 3, 2, 3))
+    unit = {'s/kernel': ws, 's/gamma': np.ones(3), 's/beta': np.zeros(3),
+            's/moving_mean': np.zeros(3), 's/moving_variance': np.full(3, 1 - 1e-3)}
+    for stride, dil in ((2, 1), (1, 2)):
+        got = oracle.conv_bn(xs, unit, 's', stride=stride, dilation=dil, activation=False)
+        ho, wo = -(-6 // stride), -(-8 // stride)
+        pt = max((ho - 1) * stride + 2 * dil + 1 - 6, 0) // 2
+        pl = max((wo - 1) * stride + 2 * dil + 1 - 8, 0) // 2
+        want = np.zeros((1, ho, wo, 3))
+        for oy in range(ho):
+            for ox in range(wo):
+                for ky in range(3):
+                    for kx in range(3):
+                        yy, xx = oy * stride + ky * dil - pt, ox * stride + kx * dil - pl
+                        if 0 <= yy < 6 and 0 <= xx < 8:
+                            want[0, oy, ox] += xs[0, yy, xx] @ ws[ky, kx]
+        np.testing.assert_allclose(got, want, atol=1e-10)
