@@ -240,6 +240,13 @@ int pack_conv(xv_fcn* net, ConvLayer* L, const float* w_hwio, const float* bias,
   return 0;
 }
 
+// Descriptors are cached per network, keyed by address and geometry.  Activations live in the
+// network's arena (stable addresses); caller-owned inputs may move, so the cache is bounded.
+static void cache_tmap(xv_fcn* net, const std::array<long long, 9>& key, const CUtensorMap& m) {
+  if (net->tmaps.size() >= 4096) net->tmaps.clear();
+  net->tmaps[key] = m;
+}
+
 int get_tmap_ex(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W, int C,
                 int pitch, int sample, int th, int tw) {
   const std::array<long long, 9> key = {static_cast<long long>(reinterpret_cast<uintptr_t>(ptr)),
@@ -252,7 +259,7 @@ int get_tmap_ex(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, in
     }
   }
   XV_TRY(make_tmap_act(out, ptr, N, H, W, C, pitch, sample, th, tw));
-  if (net) net->tmaps[key] = *out;
+  if (net) cache_tmap(net, key, *out);
   return 0;
 }
 
@@ -273,7 +280,7 @@ int get_tmap_w(xv_fcn* net, CUtensorMap* out, const void* ptr, int kdim, int cou
     }
   }
   XV_TRY(make_tmap_w(out, ptr, kdim, cout_pad, block_n));
-  if (net) net->tmaps[key] = *out;
+  if (net) cache_tmap(net, key, *out);
   return 0;
 }
 
@@ -390,12 +397,17 @@ int run_igemm_c1(xv_fcn* net, const ConvLayer& L, const float* x, int B, int H, 
     const std::array<long long, 9> key = {
         static_cast<long long>(reinterpret_cast<uintptr_t>(x)), B, H, W, L.cin, p.patch_w,
         p.th + 2, -2, -2};
-    auto it = net ? net->tmaps.find(key) : std::map<std::array<long long, 9>, CUtensorMap>::iterator();
-    if (net && it != net->tmaps.end()) {
-      p.tmap_in = it->second;
-    } else {
+    bool cached = false;
+    if (net) {
+      auto it = net->tmaps.find(key);
+      if (it != net->tmaps.end()) {
+        p.tmap_in = it->second;
+        cached = true;
+      }
+    }
+    if (!cached) {
       XV_TRY(make_tmap_patch(&p.tmap_in, x, B, H, W, L.cin, p.patch_w, p.th + 2));
-      if (net) net->tmaps[key] = p.tmap_in;
+      if (net) cache_tmap(net, key, p.tmap_in);
     }
   } else {
     p.tmap_in = p.tmap_out;          // unused in that mode, kept valid for the descriptor prefetch

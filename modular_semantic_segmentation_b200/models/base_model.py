@@ -43,6 +43,37 @@ def measures_from_confusion_matrix(confusion_matrix):
     return measures
 
 
+class _DeviceBatch(dict):
+    """Batch of CUDA tensors whose uploads may still be in flight on the copy stream: reading an
+    entry makes the compute stream wait for that entry's copy only."""
+
+    def __init__(self, tensors, events, stream):
+        dict.__init__(self, tensors)
+        self._events = dict(events)
+        self._stream = stream
+
+    def _arrived(self, key=None):
+        for k in ([key] if key is not None else list(self._events)):
+            event = self._events.pop(k, None)
+            if event is not None:
+                self._stream.wait_event(event)
+
+    def __getitem__(self, key):
+        self._arrived(key)
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        self._arrived()
+        return dict.items(self)
+
+    def values(self):
+        self._arrived()
+        return dict.values(self)
+
+
 class BaseModel(object):
     """Structure for network models.  Subclasses implement `_build_graph()` (create the
     experts and register their variables) and `_run_batch(batch, fetch)`."""
@@ -158,33 +189,44 @@ class BaseModel(object):
             if all(isinstance(v, torch.Tensor) and v.is_cuda for v in host_batch.values()):
                 return self._to_device(host_batch), None
             copy.wait_stream(compute)          # never overwrite buffers the kernels still read
+            tensors, events = {}, {}
             with torch.cuda.stream(copy):
-                dev_batch = self._to_device(host_batch)
-                event = torch.cuda.Event()
-                event.record(copy)
-            for t in dev_batch.values():
+                # images first, labels last; one event per array, so the first expert starts as
+                # soon as ITS modality has arrived (see _DeviceBatch)
+                for key in sorted(host_batch, key=lambda k: k == 'labels'):
+                    tensors.update(self._to_device({key: host_batch[key]}))
+                    events[key] = torch.cuda.Event()
+                    events[key].record(copy)
+            for t in tensors.values():
                 t.record_stream(compute)
-            return dev_batch, event
+            return _DeviceBatch(tensors, events, compute), None
 
         def pieces():
             # A large host batch is uploaded in pieces so that its own copy overlaps its own
-            # kernels (matters when score() is called one batch at a time).  The first piece
-            # is small - its copy is the only one nothing can hide - and the following ones
-            # grow: [n/8, 3n/8, n/2] for `upload_split` = 2 (the default).
+            # kernels (matters when score() is called one batch at a time): [n/4, 3n/4] for
+            # `upload_split` = 2 (the default), or the explicit sizes of `upload_pieces`.
             split = int(self.config.get('upload_split', 2))
+            explicit = self.config.get('upload_pieces')      # e.g. [4, 12]: sizes of the pieces
             for blob in self._batches(data):
                 count = len(next(iter(blob.values())))
                 on_host = not all(isinstance(v, torch.Tensor) and v.is_cuda
                                   for v in blob.values())
-                if on_host and split > 1 and count >= 8 * split:
-                    step = (count + split - 1) // split
-                    bounds = list(range(0, count, step)) + [count]
-                    lead = max(1, step // 4)
-                    bounds.insert(1, lead)
-                    for start, stop in zip(bounds[:-1], bounds[1:]):
-                        yield {k: v[start:stop] for k, v in blob.items()}
+                if on_host and explicit and sum(explicit) == count:
+                    bounds = [0]
+                    for size in explicit:
+                        bounds.append(bounds[-1] + int(size))
+                elif on_host and split > 1 and count >= 8 * split:
+                    # every piece costs ~0.5 ms of launch / tail overhead (measured), so few
+                    # pieces; the first one - whose copy nothing can hide - is a quarter
+                    lead = max(1, count // (2 * split))
+                    rest = count - lead
+                    bounds = [0] + [lead + (rest * i + split - 2) // (split - 1)
+                                    for i in range(split)]
                 else:
                     yield blob
+                    continue
+                for start, stop in zip(bounds[:-1], bounds[1:]):
+                    yield {k: v[start:stop] for k, v in blob.items()}
 
         it = iter(pieces())
         try:
