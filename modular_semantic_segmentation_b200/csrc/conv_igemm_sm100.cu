@@ -481,13 +481,35 @@ conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
             tmem_ld_32x32b_x32(t_row + chunk * 64 + half * 32, r);
             tmem_ld_wait();
             const int col0 = c.n0 + chunk * 64 + half * 32;
+            if (valid && (p.cout & 3) == 0) {
+              // 16-byte stores (Cout % 4 == 0: every pixel row of the output is 16-byte aligned)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              if (valid && col < p.cout) {
-                float v = __uint_as_float(r[j]) + __ldg(p.bias + col);
-                if (p.relu) v = fmaxf(v, 0.f);
-                dst[col] = v;
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const int col = col0 + j4 * 4;
+                if (col < p.cout) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                  float4 v = make_float4(__uint_as_float(r[j4 * 4]) + b4.x,
+                                         __uint_as_float(r[j4 * 4 + 1]) + b4.y,
+                                         __uint_as_float(r[j4 * 4 + 2]) + b4.z,
+                                         __uint_as_float(r[j4 * 4 + 3]) + b4.w);
+                  if (p.relu) {
+                    v.x = fmaxf(v.x, 0.f);
+                    v.y = fmaxf(v.y, 0.f);
+                    v.z = fmaxf(v.z, 0.f);
+                    v.w = fmaxf(v.w, 0.f);
+                  }
+                  *reinterpret_cast<float4*>(dst + col) = v;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = col0 + j;
+                if (valid && col < p.cout) {
+                  float v = __uint_as_float(r[j]) + __ldg(p.bias + col);
+                  if (p.relu) v = fmaxf(v, 0.f);
+                  dst[col] = v;
+                }
               }
             }
           }

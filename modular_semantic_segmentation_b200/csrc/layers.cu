@@ -581,12 +581,76 @@ decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__
   }
 }
 
+// Label-only decode (what score() asks for).  One thread = 4 horizontally adjacent output pixels:
+// they share their four low-resolution cells ((ox + 4) >> 3 is constant over an aligned group of
+// 4), so the cells are read once per group - the one-pixel-per-thread version was bound by L1
+// bandwidth.  Same tap order and fmaf chain as decode_upsample8_kernel: identical scores / argmax.
+template <int C>
+__global__ void __launch_bounds__(256)
+decode_upsample8_labels_kernel(const float* __restrict__ low, const float* __restrict__ g,
+                               const float* __restrict__ bias, int h, int w,
+                               uint8_t* __restrict__ label_u8, int64_t* __restrict__ label_i64) {
+  const int H = 8 * h, W = 8 * w;
+  const int ox0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+  const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int img = blockIdx.z;
+  if (ox0 >= W || oy >= H) return;
+  const int ay = (oy + 4) >> 3, ry = (oy + 4) & 7;   // taps: (iy=ay, ky=ry), (iy=ay-1, ky=ry+8)
+  const int ax = (ox0 + 4) >> 3, rx0 = (ox0 + 4) & 7;   // rx0 is 0 or 4
+  float s[4][C];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < C; ++c) s[i][c] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int iy = ay - a, ky = ry + 8 * a;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ix = ax - b;
+      if (ix < 0 || ix >= w) continue;
+      const float4 wg = __ldg(reinterpret_cast<const float4*>(g + ky * 16 + rx0 + 8 * b));
+      const float wgt[4] = {wg.x, wg.y, wg.z, wg.w};
+      const float* lp = low + ((static_cast<size_t>(img) * h + iy) * w + ix) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float v = __ldg(lp + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i][c] = fmaf(wgt[i], v, s[i][c]);
+      }
+    }
+  }
+  uint32_t packed = 0;
+  const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int best = 0;
+    float bestv = s[i][0] + __ldg(bias);
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+      const float v = s[i][c] + __ldg(bias + c);
+      if (v > bestv) {
+        bestv = v;
+        best = c;
+      }
+    }
+    packed |= static_cast<uint32_t>(best) << (8 * i);
+    if (label_i64) label_i64[pix + i] = best;
+  }
+  if (label_u8) *reinterpret_cast<uint32_t*>(label_u8 + pix) = packed;
+}
+
 template <int C>
 int decode_dispatch(bool mc, const float* low, const float* g, const float* bias, int T, int N,
                     int h, int w, const DecodeOut& out, float* mean_prob, float* var_prob,
                     float* mean_var, cudaStream_t s) {
   dim3 grid(div_up(8 * w, 16), div_up(8 * h, 16), N);
-  if (mc)
+  if (!mc && !out.prob && !out.score) {
+    dim3 lgrid(div_up(8 * w, 256), div_up(8 * h, 4), N);
+    decode_upsample8_labels_kernel<C><<<lgrid, 256, 0, s>>>(low, g, bias, h, w, out.label_u8,
+                                                            out.label_i64);
+  } else if (mc)
     decode_upsample8_kernel<C, true><<<grid, 256, 0, s>>>(low, g, bias, T, N, h, w, out,
                                                            mean_prob, var_prob, mean_var);
   else if (out.prob)
