@@ -1,4 +1,10 @@
 #!/bin/bash
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:decode_upsample8' -c 3 --csv --log-file gpurun_out/tail_launches.csv python tools/perf_probe.py 16 1 3 > gpurun_out/tail_ncu.log 2>&1
-grep -E "decode" gpurun_out/tail_launches.csv | awk -F'","' '{print $NF}'
-timeout 900 python -m pytest tests/test_gpu_fcn.py tests/test_gpu_models.py tests/test_gpu_fullsize.py -q -m gpu -x 2>&1 | tail -3
+mkdir -p gpurun_out
+timeout 900 python bench.py --steps 50 --warmup 5 2>&1 | tail -1 > gpurun_out/r01_bench.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r01_bench.json'))
+print('value',d['value'],'e2e',d['e2e']['value'],'raw',d['e2e']['raw_dtype_inputs']['value'],'roof',d['roofline']['achieved'],d['roofline']['frac'], d['clocks'])
+PY
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r01_bench_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r01_bench_under_ncu.log 2>&1
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
