@@ -169,7 +169,7 @@ if os.path.exists(ap):
         md.append('\n| kernel (ncu launch list of one forward) | launches | total us | share |\n|---|---|---|---|')
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             md.append('| `%s` | %d | %.1f | %.1f%% |' % (k, n, t, 100 * t / tot))
-for extra in ('bench_8gpu', 'bench_2gpu'):
+for extra in ('bench_2gpu', 'bench_4gpu', 'bench_8gpu'):
     ep = os.path.join(P, '%s_%s.json' % (R, extra))
     if os.path.exists(ep):
         e = json.loads(open(ep).read().strip().splitlines()[-1])
