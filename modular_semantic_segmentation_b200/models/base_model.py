@@ -43,6 +43,23 @@ def measures_from_confusion_matrix(confusion_matrix):
     return measures
 
 
+def upload_bounds(count, split=2, explicit=None):
+    """Where a host batch of `count` images is cut for uploading, or None for one upload.
+    Every piece costs ~0.5 ms of launch / tail overhead (measured: a fused step takes about
+    0.5 + 0.26 n ms for n frames), so there are few pieces; the first one - whose copy nothing
+    can hide - is the smallest: [n/4, 3n/4] for split = 2.  `explicit` gives the piece sizes."""
+    if explicit and sum(explicit) == count:
+        bounds = [0]
+        for size in explicit:
+            bounds.append(bounds[-1] + int(size))
+        return bounds
+    if split > 1 and count >= 8 * split:
+        lead = max(1, count // (2 * split))
+        rest = count - lead
+        return [0] + [lead + (rest * i + split - 2) // (split - 1) for i in range(split)]
+    return None
+
+
 class _DeviceBatch(dict):
     """Batch of CUDA tensors whose uploads may still be in flight on the copy stream: reading an
     entry makes the compute stream wait for that entry's copy only."""
@@ -211,18 +228,8 @@ class BaseModel(object):
                 count = len(next(iter(blob.values())))
                 on_host = not all(isinstance(v, torch.Tensor) and v.is_cuda
                                   for v in blob.values())
-                if on_host and explicit and sum(explicit) == count:
-                    bounds = [0]
-                    for size in explicit:
-                        bounds.append(bounds[-1] + int(size))
-                elif on_host and split > 1 and count >= 8 * split:
-                    # every piece costs ~0.5 ms of launch / tail overhead (measured), so few
-                    # pieces; the first one - whose copy nothing can hide - is a quarter
-                    lead = max(1, count // (2 * split))
-                    rest = count - lead
-                    bounds = [0] + [lead + (rest * i + split - 2) // (split - 1)
-                                    for i in range(split)]
-                else:
+                bounds = upload_bounds(count, split, explicit) if on_host else None
+                if bounds is None:
                     yield blob
                     continue
                 for start, stop in zip(bounds[:-1], bounds[1:]):

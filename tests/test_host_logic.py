@@ -217,3 +217,17 @@ def test_adapnet_variable_layout_matches_oracle():
     assert {k: v.shape for k, v in mine.items()} == {k: tuple(s) for k, s in shapes.items()}
     up = mine['depth/second_deconvolution_upconv/kernel']
     assert up.shape == (16, 16, 14, 20) and up[:, :, 3, 3].max() > 0 and up[:, :, 3, 4].max() == 0
+
+
+def test_upload_bounds():
+    from modular_semantic_segmentation_b200.models.base_model import upload_bounds
+    assert upload_bounds(16) == [0, 4, 16]            # a quarter first, then the rest
+    assert upload_bounds(32, 2) == [0, 8, 32]
+    assert upload_bounds(24, 3) == [0, 4, 14, 24]
+    assert upload_bounds(15) is None                  # small batches go up in one piece
+    assert upload_bounds(16, 1) is None
+    assert upload_bounds(16, 2, [2, 6, 8]) == [0, 2, 8, 16]
+    assert upload_bounds(16, 2, [4, 4]) == [0, 4, 16]     # sizes that do not add up are ignored
+    for n in range(16, 70):
+        b = upload_bounds(n)
+        assert b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:]))
