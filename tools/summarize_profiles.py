@@ -77,7 +77,12 @@ md.append('\ntensor-core conv kernels: %.1f%% of the serialised step (bench.py l
 hdr, rows = raw(os.path.join(G, '%s_conv_igemm.ncu-rep' % R))
 want = [('Kernel Name', 'kernel'), ('gpu__time_duration.sum', 'us'), ('dram__bytes_read.sum', 'dram rd MB'),
         ('dram__bytes_write.sum', 'dram wr MB'), ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %'),
-        ('l1tex__m_xbar2l1tex_read_bytes.sum', 'L2->SM GB'), ('launch__registers_per_thread', 'regs')]
+        ('l1tex__m_xbar2l1tex_read_bytes.sum', 'L2->SM GB'),
+        ('l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed', 'smem bank rd %'),
+        ('l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed', 'smem bank wr %'),
+        ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'L2 %'),
+        ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM %'),
+        ('launch__registers_per_thread', 'regs')]
 idx = [(col(hdr, k), t) for k, t in want if col(hdr, k) is not None]
 # the capture (-s 15 -c 15 over the conv launches, 15 per forward) is the 2nd forward
 layer_names = ['conv1_1', 'conv1_2+pool1', 'conv2_1', 'conv2_2+pool2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv4_1',
@@ -91,6 +96,11 @@ for n, r in enumerate(rows):
         v = r[i]
         if t == 'kernel':
             v = '`' + v.replace('void ', '').replace('<unnamed>::', '').split('(')[0][-34:] + '`'
+        else:
+            try:
+                v = '%.1f' % float(v)
+            except ValueError:
+                pass
         vals.append(v)
     md.append('| %s | ' % (layer_names[n] if n < len(layer_names) else '') + ' | '.join(vals) + ' |')
     ir, iw = col(hdr, 'dram__bytes_read.sum'), col(hdr, 'dram__bytes_write.sum')
