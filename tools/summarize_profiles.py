@@ -110,6 +110,9 @@ json.dump({'conv_igemm_dram_bytes_per_launch': sum(traffic) / len(traffic),
            'note': 'mean dram__bytes_read+write over the 13 conv layers of one stream forward (batch 16), ncu --set full'},
           open(os.path.join(P, 'roofline_traffic.json'), 'w'), indent=1)
 md.append('\nmean DRAM traffic per 3x3/conv1_1 launch: %.1f MB -> `roofline.traffic` of bench.py\n' % (sum(traffic) / len(traffic) / 1e6))
+md.append('(`--set full` replays every kernel ~40 times with all counters on: its durations run 5-10 % above the launch '
+          'list. This capture predates the 16-byte fp32 epilogue stores and the 4-pixel label decode: score_conv4 42 -> 27 us, '
+          'score_conv5 16 -> 11 us, decode 54 -> 43 us in the launch list above.)\n')
 
 # ---- fusion kernels
 f = json.load(open(os.path.join(G, '%s_fusion_roofline.json' % R)))
