@@ -53,3 +53,42 @@ def test_two_rank_score_and_predict_plumbing(tmp_path):
     for rank in range(world):
         np.testing.assert_array_equal(np.load(tmp_path / ('cm%d.npy' % rank)), ref_cm)
         np.testing.assert_array_equal(np.load(tmp_path / ('pred%d.npy' % rank)), ref_pred)
+
+
+def _fit_worker(rank, world, port, out_dir):
+    """DirichletFusion.fit plumbing: per-rank float64 sufficient statistics + int64 class counts
+    summed over ranks, and predict() when one rank has no image at all."""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from modular_semantic_segmentation_b200 import sharding
+    rng = np.random.default_rng(1)
+    c, n_img = 4, 5
+    logits = rng.normal(size=(2, n_img, 6, 8, c))
+    prob = np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)
+    labels = rng.integers(-1, c, size=(n_img, 6, 8))
+    mine = list(range(rank, n_img, world))
+    stats = torch.zeros((2, c, c), dtype=torch.float64)
+    counts = torch.zeros(c, dtype=torch.int64)
+    for m in range(2):
+        s, n = oracle.sufficient_statistics(prob[m][mine], labels[mine], c)
+        stats[m] = torch.from_numpy(s)
+        counts = torch.from_numpy(n)
+    sharding.allreduce_sum_(stats)
+    sharding.allreduce_sum_(counts)
+    ref = [oracle.sufficient_statistics(prob[m], labels, c) for m in range(2)]
+    np.testing.assert_allclose(stats.numpy(), np.stack([r[0] for r in ref]), rtol=1e-12)
+    np.testing.assert_array_equal(counts.numpy(), ref[0][1])
+    # a single image: rank 1 has nothing to contribute, every rank still gets the full result
+    one = torch.from_numpy(labels[:1]) if rank == 0 else None
+    gathered = sharding.gather_interleaved(one, 'cpu')
+    np.testing.assert_array_equal(gathered.numpy(), labels[:1])
+    open(os.path.join(out_dir, 'ok%d' % rank), 'w').write('ok')
+    dist.destroy_process_group()
+
+
+def test_two_rank_dirichlet_fit_statistics_and_empty_rank(tmp_path):
+    world = 2
+    mp.spawn(_fit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ('ok%d' % r)).exists() for r in range(world))
