@@ -139,6 +139,39 @@ def _oracle_frame_fn(rng):
     return frame, torch.get_num_threads()
 
 
+def cpu_sweep_commands(num_units, num_classes, height, width, cms, dirichlet_params):
+    """CPU leg of the batch-1 latency sweep (tools/timing.py --cpu): the oracle restatement of
+    the commands of experiments/timing.py on the host cores.  Lives here because bench.py is the
+    only non-test module that may execute oracle/."""
+    import torch
+    import oracle
+    torch.set_num_threads(os.cpu_count())
+    rng = np.random.default_rng(0)
+    params = {}
+    for m, cin in (('rgb', 3), ('depth', 1)):
+        params.update(oracle.glorot_fcn_params(m, cin, num_units, num_classes, rng))
+    rgb = np.ones((1, height, width, 3), np.float32)
+    depth = np.ones((1, height, width, 1), np.float32)
+
+    def expert(x, m):
+        return oracle.test_pipeline(x, params, m, num_units, num_classes)
+
+    def rgb_fcn():
+        return expert(rgb, 'rgb')['classification']
+
+    def bayes_fcn():
+        cls = [expert(rgb, 'rgb')['classification'], expert(depth, 'depth')['classification']]
+        return oracle.argmax_first(oracle.bayes_fusion(cls, cms)[0])
+
+    def dirichlet_fcn():
+        p = [expert(rgb, 'rgb')['prob'], expert(depth, 'depth')['prob']]
+        return oracle.argmax_first(oracle.dirichlet_fusion(
+            p, [dirichlet_params['rgb'], dirichlet_params['depth']],
+            oracle.dirichlet_prior(dirichlet_params['class_counts'])))
+
+    return {'rgb_fcn': rgb_fcn, 'bayes_fcn': bayes_fcn, 'dirichlet_fcn': dirichlet_fcn}
+
+
 def cpu_baseline(rng, frames=2):
     frame, threads = _oracle_frame_fn(rng)
     frame()                                    # warm-up (thread pools, allocator)

@@ -52,6 +52,17 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r'^\s*(import|from)\s+oracle', src, re.M), f
 
 
+def test_tools_do_not_import_the_oracle():
+    """Outside tests/ only __graft_entry__.smoke() and bench.py's CPU legs may execute oracle/;
+    the xview facade and the scripts under tools/ must not."""
+    for folder in ('tools', 'xview'):
+        for base, _, files in os.walk(os.path.join(ROOT, folder)):
+            for f in files:
+                if f.endswith('.py'):
+                    src = open(os.path.join(base, f)).read()
+                    assert not re.search(r'^\s*(import|from)\s+oracle', src, re.M), f
+
+
 def test_variable_layout_matches_reference_key_list():
     from modular_semantic_segmentation_b200.models.simple_fcn import init_fcn_variables
     keys = json.load(open(os.path.join(GOLDEN, 'fcn_weight_keys.json')))

@@ -2,7 +2,6 @@
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
-import oracle
 from modular_semantic_segmentation_b200 import device as dev
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16
@@ -10,7 +9,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 cin = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev.init()
 rng = np.random.default_rng(0)
-params = oracle.glorot_fcn_params('m', cin, 64, 12, rng, gain=1.4)
+from modular_semantic_segmentation_b200.models.simple_fcn import init_fcn_variables
+params = init_fcn_variables('m', cin, 64, 12, rng=rng)
 net = dev.FcnExpert(cin, 64, 12, precision='bf16')
 net.set_params({k.split('/', 1)[1]: v for k, v in params.items()})
 x = torch.rand((N, 768, 384, cin), device='cuda')

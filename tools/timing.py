@@ -101,34 +101,11 @@ def gpu_commands():
 
 
 def cpu_commands():
-    import torch
-    import oracle
-    torch.set_num_threads(os.cpu_count())
-    rng = np.random.default_rng(0)
-    params = {}
-    for m, cin in (('rgb', 3), ('depth', 1)):
-        params.update(oracle.glorot_fcn_params(m, cin, NU, C, rng))
-    rgb = np.ones((1, H, W, 3), np.float32)
-    depth = np.ones((1, H, W, 1), np.float32)
-    cms = _cms()
-    dp = _dirichlet_params(rng)
-
-    def expert(x, m):
-        return oracle.test_pipeline(x, params, m, NU, C)
-
-    def rgb_fcn():
-        return expert(rgb, 'rgb')['classification']
-
-    def bayes_fcn():
-        cls = [expert(rgb, 'rgb')['classification'], expert(depth, 'depth')['classification']]
-        return oracle.argmax_first(oracle.bayes_fusion(cls, cms)[0])
-
-    def dirichlet_fcn():
-        p = [expert(rgb, 'rgb')['prob'], expert(depth, 'depth')['prob']]
-        return oracle.argmax_first(oracle.dirichlet_fusion(
-            p, [dp['rgb'], dp['depth']], oracle.dirichlet_prior(dp['class_counts'])))
-
-    return {'rgb_fcn': rgb_fcn, 'bayes_fcn': bayes_fcn, 'dirichlet_fcn': dirichlet_fcn}
+    """The oracle on the host cores; the code lives in bench.py (the only non-test module that
+    may execute oracle/)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.cpu_sweep_commands(NU, C, H, W, _cms(), _dirichlet_params(np.random.default_rng(0)))
 
 
 def time_command(fn, repetitions, to_host):
