@@ -242,3 +242,64 @@ def test_upload_bounds():
     for n in range(16, 70):
         b = upload_bounds(n)
         assert b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:]))
+
+
+def test_device_batch_waits_per_array():
+    """_DeviceBatch: reading one entry makes the compute stream wait for that entry's upload
+    only; iterating waits for everything; nothing is waited for twice."""
+    from modular_semantic_segmentation_b200.models.base_model import _DeviceBatch
+
+    class Stream(object):
+        def __init__(self):
+            self.waited = []
+
+        def wait_event(self, event):
+            self.waited.append(event)
+
+    stream = Stream()
+    batch = _DeviceBatch({'rgb': 1, 'depth': 2, 'labels': 3},
+                         {'rgb': 'e_rgb', 'depth': 'e_depth', 'labels': 'e_labels'}, stream)
+    assert 'rgb' in batch and len(batch) == 3 and stream.waited == []
+    assert batch['rgb'] == 1 and stream.waited == ['e_rgb']
+    assert batch['rgb'] == 1 and stream.waited == ['e_rgb']
+    assert batch.get('depth') == 2 and stream.waited == ['e_rgb', 'e_depth']
+    assert batch.get('missing', 7) == 7
+    assert sorted(batch.values()) == [1, 2, 3]
+    assert stream.waited == ['e_rgb', 'e_depth', 'e_labels']
+    assert dict(batch.items()) == {'rgb': 1, 'depth': 2, 'labels': 3}
+    assert stream.waited == ['e_rgb', 'e_depth', 'e_labels']
+
+
+def test_dump_expert_predictions_layout(tmp_path, monkeypatch):
+    """predictions.npz of experiments/ibcc_fusion.py:18-42 with a stand-in expert model (the GPU
+    version of this test runs the real experts)."""
+    from modular_semantic_segmentation_b200 import models, records
+
+    class FakeExpert(object):
+        def __init__(self, data_description=None, **config):
+            self.offset = {'rgb': 1, 'depth': 2}[config['modality']]
+            assert config['prefix'] == 'p_' + config['modality']
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *args):
+            return False
+
+        def import_weights(self, path):
+            self.path = path
+
+        def predict(self, data):
+            return (np.asarray(data['labels']) + self.offset).astype(np.int64)
+
+    monkeypatch.setattr(models, 'get_model', lambda name: FakeExpert)
+    measure = {'labels': np.zeros((3, 4, 4), np.int32)}
+    test = {'labels': np.ones((2, 4, 4), np.int32)}
+    out = records.dump_expert_predictions(
+        {'expert_model': 'fcn', 'prefixes': {'rgb': 'p_rgb', 'depth': 'p_depth'}}, None, measure,
+        test, str(tmp_path / 'out'), starting_weights={'p_rgb': 'a.npz', 'p_depth': 'b.npz'})
+    with np.load(out) as archive:
+        assert sorted(archive.files) == ['measure_depth', 'measure_gt', 'measure_rgb',
+                                         'test_depth', 'test_gt', 'test_rgb']
+        assert (archive['measure_rgb'] == 1).all() and (archive['test_depth'] == 3).all()
+        np.testing.assert_array_equal(archive['test_gt'], test['labels'])
