@@ -98,7 +98,14 @@ typedef struct xv_dropout_cfg {
   /* optional external keep-masks (uint8, one byte per element of the [T*N,h,w,c] activation):
    * order pool3, pool4, conv4_3, conv5_3, features.  NULL = fused Philox.                   */
   const uint8_t* ext_mask[5];
+  /* XV_DROP_FLAG_*.  KEEP_FIRST: the dropout-free network rides along as an extra leading
+   * sample that shares the trunk and every weight load (variance_mix.py:68-69 takes the
+   * probabilities from a separate no-dropout pass): score / prob / label then describe that
+   * dropout-free pass ([N,...]) and the moments are taken over the num_samples dropout passes;
+   * external masks still cover the num_samples dropout passes only.                            */
+  uint32_t flags;
 } xv_dropout_cfg;
+#define XV_DROP_FLAG_KEEP_FIRST 1u
 
 typedef struct xv_fcn_outputs {
   /* T == 1 (or no dropout): per-image results; T > 1: per-sample results, batch = T*N        */
@@ -213,7 +220,20 @@ int xv_bayes_fuse_score(const void* const* labels_host, int num_experts, int lab
 int xv_dirichlet_fuse(const float* const* probs_host, int num_experts, const float* alpha_m1,
                       const float* log_norm, const float* log_prior, int num_classes,
                       int64_t npix, float* score, void* label, int label_bytes, void* stream);
-/* average_mix.py:18-21 */
+/* Same rule with a bit-exact argmax: label (and score, if requested) equal the float32 statement
+ * of dirichlet_mix.py:100-113 with the fixed operation order documented in DESIGN.md 4.3
+ * (sequential sums, IEEE division, correctly rounded logarithm, separately rounded products and
+ * sums; oracle.dirichlet_fusion_f32).  Pixels whose two best fast scores differ by more than a
+ * rigorous bound on |fast - exact| keep the fast result (same argmax); the others are re-evaluated
+ * in the exact arithmetic; with score != NULL every pixel is.  abs_alpha_m1_max =
+ * max_c sum_{m,k} |alpha_m1[m][k][c]|, abs_norm_max = max_c sum_m |log_norm[m][c]| + max_c
+ * |log_prior[c]| (host-side table magnitudes that scale the bound).  num_exact (device int64, may
+ * be NULL) is incremented by the number of re-evaluated pixels. */
+int xv_dirichlet_fuse_exact(const float* const* probs_host, int num_experts, const float* alpha_m1,
+                            const float* log_norm, const float* log_prior, int num_classes,
+                            int64_t npix, float abs_alpha_m1_max, float abs_norm_max, float* score,
+                            void* label, int label_bytes, int64_t* num_exact, void* stream);
+/* average_mix.py:18-21; every sum and quotient individually rounded (bit-exact vs float32 numpy) */
 int xv_average_fuse(const float* const* probs_host, int num_experts, int num_classes,
                     int64_t npix, float* score, void* label, int label_bytes, void* stream);
 /* variance_mix.py:7-15; vars_host[m]: device float32 [npix] */

@@ -16,6 +16,7 @@ XV_DROP_POOL3 = 1
 XV_DROP_CONV4_3 = 2
 XV_DROP_CONV5_3 = 4
 XV_DROP_FEATURES = 8
+XV_DROP_FLAG_KEEP_FIRST = 1
 DROPOUT_SITES = {'pool3': XV_DROP_POOL3, 'conv4_3': XV_DROP_CONV4_3,
                  'conv5_3': XV_DROP_CONV5_3, 'features': XV_DROP_FEATURES}
 # order of xv_dropout_cfg.ext_mask
@@ -28,7 +29,7 @@ class XViewError(RuntimeError):
 
 class DropoutCfg(C.Structure):
     _fields_ = [('rate', C.c_float), ('sites', C.c_uint32), ('num_samples', C.c_int32),
-                ('seed', C.c_uint64), ('ext_mask', C.c_void_p * 5)]
+                ('seed', C.c_uint64), ('ext_mask', C.c_void_p * 5), ('flags', C.c_uint32)]
 
 
 class FcnOutputs(C.Structure):
@@ -87,6 +88,8 @@ PROTOTYPES = {
     'xv_bayes_fuse_lut': [_PP, _I, _I, _P, _I, _L, _P, _P],
     'xv_bayes_fuse_score': [_PP, _I, _I, _P, _P, _I, _L, _P, _P, _P],
     'xv_dirichlet_fuse': [_PP, _I, _P, _P, _P, _I, _L, _P, _P, _I, _P],
+    'xv_dirichlet_fuse_exact': [_PP, _I, _P, _P, _P, _I, _L, C.c_float, C.c_float, _P, _P, _I, _P,
+                                _P],
     'xv_average_fuse': [_PP, _I, _I, _L, _P, _P, _I, _P],
     'xv_variance_fuse': [_PP, _PP, _I, _I, _L, _P, _P, _I, _P],
     'xv_mc_moments': [_P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P],

@@ -524,9 +524,13 @@ struct Forward {
   Arena arena;
   cudaStream_t s;
   bool dry;
-  int T = 1;
+  int T = 1;                 // copies made at the first active dropout site (MC samples + the
+                             // optional dropout-free leading sample)
   const xv_dropout_cfg* drop = nullptr;
   bool training = false;     // keep every activation (no pool fusion), materialise score + up5
+  int N0 = 0;                // images of the call (set by run)
+  bool keep_first() const { return drop && (drop->flags & XV_DROP_FLAG_KEEP_FIRST); }
+  int mc_samples() const { return keep_first() ? T - 1 : T; }
 
   bool bf16() const { return net->precision == XV_PRECISION_BF16; }
   size_t esize(DType d) const { return d == DType::F32 ? 4 : (d == DType::BF16 ? 2 : 1); }
@@ -602,6 +606,9 @@ struct Forward {
     d.ext_mask = active ? drop->ext_mask[idx] : nullptr;
     d.seed = drop ? drop->seed : 0;
     d.offset = static_cast<uint64_t>(idx + 1) << 40;
+    // the dropout-free leading sample: the first N0 images of the (replicated) output
+    if (keep_first() && active)
+      d.pass_elems = in.elems() / static_cast<size_t>(in.B) * static_cast<size_t>(N0);
     if (!active) {
       static const uint8_t* none = nullptr;
       d.ext_mask = none;
@@ -620,6 +627,7 @@ struct Forward {
 };
 
 int Forward::run(const float* x, int N, int H, int W, const xv_fcn_outputs* o) {
+  N0 = N;
   Act c43, c53;
   bool replicated = false;
   XV_TRY(run_encoder(x, N, H, W, &c43, &c53, &replicated));
@@ -686,7 +694,11 @@ int Forward::run_encoder(const float* x, int N, int H, int W, Act* c43_out, Act*
 
 int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o) {
   const uint32_t sites = drop ? drop->sites : 0u;
-  const bool mc = T > 1;
+  const int Tmc = mc_samples();
+  const bool mc = Tmc > 1;
+  // with a dropout-free leading sample the per-image outputs describe that sample only and
+  // the moments skip it
+  const bool lead = keep_first() && N0 > 0;
   Act t;
   Act s4in = c43, s5in = c53;
   const bool branch_sites = (sites & (XV_DROP_CONV4_3 | XV_DROP_CONV5_3)) != 0;
@@ -756,6 +768,8 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
       o = &train_out;
     }
     const bool want_samples = o->score || o->prob || o->label_i64 || o->label_u8;
+    const int b_samples = lead ? N0 : B;
+    const size_t lead_low = lead ? static_cast<size_t>(N0) * feat.H * feat.W * C : 0;
     if (!dry) {
       XV_TRY(launch_score_lowres(static_cast<const float*>(feat.p),
                                  static_cast<const float*>(net->w_score_nuxc.p),
@@ -769,15 +783,15 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
         d.score = o->score;
         XV_TRY(launch_decode_upsample8(static_cast<const float*>(low.p),
                                        static_cast<const float*>(net->g16.p),
-                                       static_cast<const float*>(net->b_score.p), B, feat.H,
-                                       feat.W, C, d, s));
+                                       static_cast<const float*>(net->b_score.p), b_samples,
+                                       feat.H, feat.W, C, d, s));
       }
       if (want_moments)
-        XV_TRY(launch_decode_upsample8_mc(static_cast<const float*>(low.p),
+        XV_TRY(launch_decode_upsample8_mc(static_cast<const float*>(low.p) + lead_low,
                                           static_cast<const float*>(net->g16.p),
-                                          static_cast<const float*>(net->b_score.p), T, B / T,
-                                          feat.H, feat.W, C, o->mean_prob, o->var_prob,
-                                          o->mean_var, s));
+                                          static_cast<const float*>(net->b_score.p), Tmc,
+                                          (B - (lead ? N0 : 0)) / Tmc, feat.H, feat.W, C,
+                                          o->mean_prob, o->var_prob, o->mean_var, s));
     }
     return 0;
   }
@@ -813,14 +827,30 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
   }
   Act prob_tmp;
   float* prob_ptr = o->prob;
-  if (want_moments && !prob_ptr) {
+  if (want_moments && (!prob_ptr || lead)) {
     prob_tmp = make("prob_samples", DType::F32, B, Hf, Wf, C);
     prob_ptr = static_cast<float*>(prob_tmp.p);
   }
   if (!dry) {
+    const size_t npix_lead = lead ? static_cast<size_t>(N0) * Hf * Wf : 0;
+    const size_t npix_out = lead ? npix_lead : npix;
     if (o->score)
-      XV_CUDA(cudaMemcpyAsync(o->score, sc.p, npix * C * sizeof(float), cudaMemcpyDeviceToDevice,
-                              s));
+      XV_CUDA(cudaMemcpyAsync(o->score, sc.p, npix_out * C * sizeof(float),
+                              cudaMemcpyDeviceToDevice, s));
+    if (lead) {
+      // dropout-free sample -> the per-image outputs; dropout samples -> scratch probabilities
+      if (want_samples)
+        XV_TRY(launch_softmax_argmax(static_cast<const float*>(sc.p), npix_lead, C, o->prob,
+                                     o->label_i64, o->label_u8, s));
+      if (want_moments) {
+        float* mc_prob = static_cast<float*>(prob_tmp.p);
+        XV_TRY(launch_softmax_argmax(static_cast<const float*>(sc.p) + npix_lead * C,
+                                     npix - npix_lead, C, mc_prob, nullptr, nullptr, s));
+        XV_TRY(launch_mc_moments(mc_prob, Tmc, (npix - npix_lead) / Tmc, C, o->mean_prob,
+                                 o->var_prob, o->mean_var, nullptr, nullptr, nullptr, s));
+      }
+      return 0;
+    }
     if (want_samples || want_moments)
       XV_TRY(launch_softmax_argmax(static_cast<const float*>(sc.p), npix, C, prob_ptr,
                                    o->label_i64, o->label_u8, s));
@@ -1173,7 +1203,7 @@ int xv_fcn_forward(xv_fcn* net, const float* x, int n, int h, int w, const xv_dr
     cfg = *drop;
     XV_CHECK(cfg.rate >= 0.f && cfg.rate < 1.f, "xv_fcn_forward: dropout rate must be in [0,1)");
     XV_CHECK(cfg.num_samples >= 1, "xv_fcn_forward: num_samples must be >= 1");
-    T = cfg.num_samples;
+    T = cfg.num_samples + ((cfg.flags & XV_DROP_FLAG_KEEP_FIRST) ? 1 : 0);
     d = &cfg;
   }
   Forward plan{net, Arena(), XV_STREAM(stream), true, T, d};
@@ -1428,7 +1458,21 @@ int xv_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m1,
   XV_TRY(ensure_init());
   XV_TRY(check_label_bytes(label_bytes));
   return launch_dirichlet_fuse(probs, M, alpha_m1, log_norm, log_prior, C, npix, score, label,
-                               label_bytes, XV_STREAM(stream));
+                               label_bytes, -1.f, 0.f, nullptr, XV_STREAM(stream));
+}
+
+int xv_dirichlet_fuse_exact(const float* const* probs, int M, const float* alpha_m1,
+                            const float* log_norm, const float* log_prior, int C, int64_t npix,
+                            float abs_alpha_m1_max, float abs_norm_max, float* score, void* label,
+                            int label_bytes, int64_t* num_exact, void* stream) {
+  XV_TRY(ensure_init());
+  XV_TRY(check_label_bytes(label_bytes));
+  XV_CHECK(abs_alpha_m1_max >= 0.f && abs_norm_max >= 0.f,
+           "xv_dirichlet_fuse_exact: the table magnitudes must be non-negative");
+  return launch_dirichlet_fuse(probs, M, alpha_m1, log_norm, log_prior, C, npix, score, label,
+                               label_bytes, abs_alpha_m1_max, abs_norm_max,
+                               reinterpret_cast<unsigned long long*>(num_exact),
+                               XV_STREAM(stream));
 }
 
 int xv_average_fuse(const float* const* probs, int M, int C, int64_t npix, float* score,

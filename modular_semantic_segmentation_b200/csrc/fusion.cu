@@ -20,6 +20,20 @@ namespace {
 constexpr int kPix = 256;   // threads per block, one pixel per thread and iteration
 constexpr int kMaxM = 4;    // experts per fusion call
 
+// Bound on |fast - exact| of one Dirichlet class score, used by the two-tier exact mode
+// (DESIGN.md 4.3).  With A = max_c sum_{m,k} |alpha_m1[m][k][c]| (passed as exact_amax) and
+// Lmax = max |log x| of the pixel:
+//   kLogErr  per-logarithm difference: lg2.approx (rel. 2^-22 of |log2 x| <= 66.5, i.e. <= 1.1e-5
+//            abs) + p*inv vs p/sum and sum order ((C+3) ulp of x) + the exact log's half ulp
+//   kAccErr  per-term rounding of the two accumulation chains (FMA chain: 1 rounding per term,
+//            product+sum chain: 2), relative to |a||L| <= |a| Lmax: 3 * 2^-24, doubled for slack
+//   kTailErr roundings of  - lognorm, + next expert, + logprior  (identical operations in both
+//            modes, each propagating <= 1 ulp of a partial result <= A Lmax + exact_tail, where
+//            exact_tail = max_c sum_m |lognorm[m][c]| + max_c |logprior[c]|)
+constexpr float kLogErr = 3.0e-5f;
+constexpr float kAccErr = 3.6e-7f;
+constexpr float kTailErr = 1.0e-6f;
+
 struct PtrPack {
   const void* p[kMaxM];
 };
@@ -285,12 +299,58 @@ bayes_score_kernel(PtrPack labels, int M, int label_bytes, const float* __restri
 // score[c] = sum_m ( sum_k am1[m][k][c] * log(1e-20 + p_m[k]/sum p_m) - lognorm[m][c] ) + logprior[c]
 // The (alpha-1) tables sit in shared memory with rows padded to a multiple of 4 floats so one
 // broadcast LDS.128 feeds four FMAs.
+//
+// Two arithmetic modes:
+//   fast   one reciprocal per expert, MUFU lg2 logarithm, packed fused multiply-adds.
+//   exact  the fixed float32 operation order of oracle.dirichlet_fusion_f32 (sequential sums,
+//          IEEE division, correctly rounded logarithm, separately rounded products and sums) so
+//          that the argmax is bit-exact against that oracle.  The kernel evaluates the fast
+//          form first; only pixels whose two best fast scores are closer than a rigorous bound on
+//          |fast - exact| are re-evaluated in the exact arithmetic (`exact_amax` >= 0 enables
+//          this; see dirichlet_fast_bound).  With `score` requested every pixel takes the exact
+//          path so that the returned scores are the exact ones too.
+
+// Correctly rounded float32 logarithm (round-once from the float64 value).
+__device__ __forceinline__ float log_rn(float x) { return static_cast<float>(log(static_cast<double>(x))); }
+
+// Exact-mode score of one pixel; p_m read again from global memory (this path is rare).
+template <int C>
+__device__ __noinline__ void dirichlet_exact_pixel(const PtrPack& probs, int M, int64_t pix,
+                                                   const float* __restrict__ s_am1,
+                                                   const float* __restrict__ s_norm,
+                                                   const float* __restrict__ s_prior,
+                                                   float* __restrict__ total) {
+  constexpr int CP = (C + 3) & ~3;
+  for (int m = 0; m < M; ++m) {
+    const float* p = reinterpret_cast<const float*>(probs.p[m]) + pix * C;
+    float lx[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) lx[k] = __ldg(p + k);
+    float sum = lx[0];
+#pragma unroll
+    for (int k = 1; k < C; ++k) sum = __fadd_rn(sum, lx[k]);
+#pragma unroll
+    for (int k = 0; k < C; ++k) lx[k] = log_rn(__fadd_rn(1e-20f, __fdiv_rn(lx[k], sum)));
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float acc = __fmul_rn(lx[0], s_am1[(m * C) * CP + c]);
+#pragma unroll
+      for (int k = 1; k < C; ++k) acc = __fadd_rn(acc, __fmul_rn(lx[k], s_am1[(m * C + k) * CP + c]));
+      const float t = __fsub_rn(acc, s_norm[m * C + c]);
+      total[c] = (m == 0) ? t : __fadd_rn(total[c], t);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) total[c] = __fadd_rn(total[c], s_prior[c]);
+}
+
 template <int C>
 __global__ void __launch_bounds__(kPix)
 dirichlet_fuse_kernel(PtrPack probs, int M, const float* __restrict__ alpha_m1,
                       const float* __restrict__ lognorm, const float* __restrict__ logprior,
                       int64_t npix, float* __restrict__ score, void* __restrict__ label_out,
-                      int label_bytes) {
+                      int label_bytes, float exact_amax, float exact_tail,
+                      unsigned long long* __restrict__ n_exact) {
   constexpr int CP = (C + 3) & ~3;
   __shared__ __align__(16) float s_am1[kMaxM * C * CP];
   __shared__ float s_norm[kMaxM * C];
@@ -304,55 +364,85 @@ dirichlet_fuse_kernel(PtrPack probs, int M, const float* __restrict__ alpha_m1,
   __shared__ float s_stage[WarpStage<C>::kFloats];
   float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
   const int lane = threadIdx.x & 31;
+  const bool exact = exact_amax >= 0.f;
+  const bool exact_all = exact && score != nullptr;
+  unsigned int exact_count = 0;
   __syncthreads();
   XV_WARP_LOOP(base, cnt, npix) {
     const int64_t pix = base + lane;
     const bool live = lane < cnt;
     float total[C];
-    for (int m = 0; m < M; ++m) {
-      float lx[C];
+    float lmax = 0.f;               // largest |log| of the pixel: scales the rounding bound
+    if (!exact_all) {
+      for (int m = 0; m < M; ++m) {
+        float lx[C];
 #pragma unroll
-      for (int k = 0; k < C; ++k) lx[k] = 1.f;
-      px_load<C>(reinterpret_cast<const float*>(probs.p[m]), base, cnt, slice, lx);
-      float sum = 0.f;
+        for (int k = 0; k < C; ++k) lx[k] = 1.f;
+        px_load<C>(reinterpret_cast<const float*>(probs.p[m]), base, cnt, slice, lx);
+        float sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < C; ++k) sum += lx[k];
-      // one reciprocal per expert, MUFU lg2 for the logarithm (|error| ~1e-6 relative to the
-      // score scale; the parity tests bound it)
-      const float inv = 1.f / sum;
+        for (int k = 0; k < C; ++k) sum += lx[k];
+        const float inv = 1.f / sum;
 #pragma unroll
-      for (int k = 0; k < C; ++k) lx[k] = __logf(1e-20f + lx[k] * inv);
-      // packed fp32 FMAs (fma.rn.f32x2, sm_100): one broadcast LDS.128 feeds two 2-wide FMAs
-      unsigned long long ll2[CP / 2];
+        for (int k = 0; k < C; ++k) {
+          lx[k] = __logf(1e-20f + lx[k] * inv);
+          lmax = fmaxf(lmax, fabsf(lx[k]));
+        }
+        // packed fp32 FMAs (fma.rn.f32x2, sm_100): one broadcast LDS.128 feeds two 2-wide FMAs
+        unsigned long long ll2[CP / 2];
 #pragma unroll
-      for (int c = 0; c < CP / 2; ++c) ll2[c] = 0ull;
+        for (int c = 0; c < CP / 2; ++c) ll2[c] = 0ull;
 #pragma unroll
-      for (int k = 0; k < C; ++k) {
-        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(s_am1 + (m * C + k) * CP);
-        unsigned long long xx;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(lx[k]));
+        for (int k = 0; k < C; ++k) {
+          const ulonglong2* row = reinterpret_cast<const ulonglong2*>(s_am1 + (m * C + k) * CP);
+          unsigned long long xx;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(lx[k]));
 #pragma unroll
-        for (int c4 = 0; c4 < CP / 4; ++c4) {
-          const ulonglong2 a = row[c4];
-          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ll2[2 * c4]) : "l"(xx), "l"(a.x));
-          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ll2[2 * c4 + 1]) : "l"(xx), "l"(a.y));
+          for (int c4 = 0; c4 < CP / 4; ++c4) {
+            const ulonglong2 a = row[c4];
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ll2[2 * c4]) : "l"(xx), "l"(a.x));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ll2[2 * c4 + 1]) : "l"(xx), "l"(a.y));
+          }
+        }
+        float ll[CP];
+#pragma unroll
+        for (int c = 0; c < CP / 2; ++c)
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(ll[2 * c]), "=f"(ll[2 * c + 1]) : "l"(ll2[c]));
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float t = ll[c] - s_norm[m * C + c];
+          total[c] = (m == 0) ? t : total[c] + t;
         }
       }
-      float ll[CP];
 #pragma unroll
-      for (int c = 0; c < CP / 2; ++c)
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(ll[2 * c]), "=f"(ll[2 * c + 1]) : "l"(ll2[c]));
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float t = ll[c] - s_norm[m * C + c];
-        total[c] = (m == 0) ? t : total[c] + t;
-      }
+      for (int c = 0; c < C; ++c) total[c] += s_prior[c];
     }
+    int best = 0;
+    if (live) {
+      bool redo = exact_all;
+      if (!exact_all) {
+        best = argmax_first<C>(total);
+        if (exact) {
+          // margin between the two best fast scores against 2 * bound on |fast - exact|
+          float second = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < C; ++c) total[c] += s_prior[c];
-    if (label_out && live) store_label(label_out, label_bytes, pix, argmax_first<C>(total));
+          for (int c = 0; c < C; ++c)
+            if (c != best) second = fmaxf(second, total[c]);
+          const float bound = exact_amax * (kLogErr + kAccErr * static_cast<float>(C) * lmax) +
+                              kTailErr * (exact_amax * lmax + exact_tail);
+          redo = !(total[best] - second > 2.f * bound);   // also catches NaN / inf
+        }
+      }
+      if (redo) {
+        dirichlet_exact_pixel<C>(probs, M, pix, s_am1, s_norm, s_prior, total);
+        best = argmax_first<C>(total);
+        ++exact_count;
+      }
+      if (label_out) store_label(label_out, label_bytes, pix, best);
+    }
     if (score) px_store<C>(score, base, cnt, slice, total);
   }
+  if (n_exact != nullptr && exact_count) atomicAdd(n_exact, static_cast<unsigned long long>(exact_count));
 }
 
 // ------------------------------------------------------------------ average / variance fusion
@@ -374,18 +464,23 @@ mean_fuse_kernel(PtrPack probs, PtrPack vars, int M, int64_t npix, float* __rest
       for (int c = 0; c < C; ++c) v[c] = 0.f;
       px_load<C>(reinterpret_cast<const float*>(probs.p[m]), base, cnt, slice, v);
       float wgt = 1.f;
+      // every product, sum and quotient is rounded on its own (no FMA contraction, IEEE
+      // division): bit-exact against the float32 numpy statement of the rule
       if (VAR) {   // certainty = 1 / (1e-20 + variance), variance_mix.py:11
-        wgt = 1.f / (1e-20f + (live ? __ldg(reinterpret_cast<const float*>(vars.p[m]) + pix) : 1.f));
-        csum = (m == 0) ? wgt : csum + wgt;
+        wgt = __fdiv_rn(1.f, __fadd_rn(1e-20f, live ? __ldg(reinterpret_cast<const float*>(
+                                                                 vars.p[m]) + pix)
+                                                    : 1.f));
+        csum = (m == 0) ? wgt : __fadd_rn(csum, wgt);
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float t = wgt * v[c];
-        acc[c] = (m == 0) ? t : acc[c] + t;
+        const float t = VAR ? __fmul_rn(wgt, v[c]) : v[c];
+        acc[c] = (m == 0) ? t : __fadd_rn(acc[c], t);
       }
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = VAR ? acc[c] / csum : acc[c] / static_cast<float>(M);
+    for (int c = 0; c < C; ++c)
+      acc[c] = VAR ? __fdiv_rn(acc[c], csum) : __fdiv_rn(acc[c], static_cast<float>(M));
     if (label_out && live) store_label(label_out, label_bytes, pix, argmax_first<C>(acc));
     if (score) px_store<C>(score, base, cnt, slice, acc);
   }
@@ -639,11 +734,13 @@ int launch_bayes_score(const void* const* labels, int M, int label_bytes, const 
 
 int launch_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m1,
                           const float* lognorm, const float* logprior, int C, int64_t npix,
-                          float* score, void* label_out, int label_bytes, cudaStream_t s) {
+                          float* score, void* label_out, int label_bytes, float exact_amax,
+                          float exact_tail, unsigned long long* n_exact, cudaStream_t s) {
   PtrPack pk;
   XV_TRY(pack_ptrs(reinterpret_cast<const void* const*>(probs), M, &pk));
   XV_DISPATCH_C(C, (dirichlet_fuse_kernel<kC><<<tiles_grid(npix), kPix, 0, s>>>(
-                       pk, M, alpha_m1, lognorm, logprior, npix, score, label_out, label_bytes)));
+                       pk, M, alpha_m1, lognorm, logprior, npix, score, label_out, label_bytes,
+                       exact_amax, exact_tail, n_exact)));
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

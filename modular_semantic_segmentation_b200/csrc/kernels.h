@@ -96,6 +96,8 @@ struct DropoutSpec {
   const uint8_t* ext_mask = nullptr;  // optional keep-mask, one byte per OUTPUT element
   uint64_t seed = 0;              // Philox key
   uint64_t offset = 0;            // Philox counter offset (distinct per site)
+  size_t pass_elems = 0;          // leading output elements copied through without dropout;
+                                  // ext_mask / Philox indices start after them
 };
 // out[r * n + i] = dropout(in[i]) for r in [0, replicate); n elements per copy.
 int launch_dropout_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, int replicate,
@@ -167,6 +169,8 @@ int launch_bayes_score(const void* const* labels_dev, int M, int label_bytes,
 int launch_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m1 /*[M,C,C]*/,
                           const float* lognorm /*[M,C]*/, const float* logprior /*[C]*/, int C,
                           int64_t npix, float* score, void* label_out, int label_bytes,
+                          float exact_amax /* < 0: fast arithmetic only */, float exact_tail,
+                          unsigned long long* n_exact /* += pixels re-evaluated exactly */,
                           cudaStream_t s);
 int launch_average_fuse(const float* const* probs, int M, int C, int64_t npix, float* score,
                         void* label_out, int label_bytes, cudaStream_t s);

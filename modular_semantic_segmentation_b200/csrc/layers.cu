@@ -173,15 +173,28 @@ __device__ __forceinline__ float u01(uint32_t r) { return (r >> 8) * (1.0f / 167
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n,
                                int replicate, float rate, const uint8_t* __restrict__ ext_mask,
-                               uint64_t seed, uint64_t offset) {
+                               uint64_t seed, uint64_t offset, size_t pass_elems) {
   const float keep = 1.f - rate;
   const size_t total = n * static_cast<size_t>(replicate);
-  const size_t groups = (total + 3) / 4;
+  // leading `pass_elems` outputs are plain copies (the dropout-free sample); the dropout region
+  // behind them has its own group / mask indexing, so its masks do not depend on pass_elems
+  const size_t groups_a = (pass_elems + 3) / 4;
+  const size_t total_b = total - pass_elems;
+  const size_t groups = groups_a + (total_b + 3) / 4;
   for (size_t gidx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; gidx < groups;
        gidx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (gidx < groups_a) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const size_t i = gidx * 4 + e;
+        if (i < pass_elems) out[i] = in[i % n];
+      }
+      continue;
+    }
+    const size_t g = gidx - groups_a;
     uint4 rnd = make_uint4(0, 0, 0, 0);
     if (ext_mask == nullptr) {
-      const uint64_t c = gidx + offset;
+      const uint64_t c = g + offset;
       rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32),
                                      0x58564231u, 0u),
                           make_uint2(static_cast<uint32_t>(seed),
@@ -190,9 +203,10 @@ __global__ void dropout_kernel(const T* __restrict__ in, T* __restrict__ out, si
     const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const size_t i = gidx * 4 + e;
-      if (i < total) {
-        const bool kept = ext_mask ? (ext_mask[i] != 0) : (u01(rr[e]) >= rate);
+      const size_t j = g * 4 + e;
+      if (j < total_b) {
+        const size_t i = j + pass_elems;
+        const bool kept = ext_mask ? (ext_mask[j] != 0) : (u01(rr[e]) >= rate);
         const float v = static_cast<float>(in[i % n]);
         out[i] = static_cast<T>(kept ? v / keep : 0.f);
       }
@@ -758,18 +772,18 @@ int launch_maxpool_f32(const float* in, float* out, int N, int H, int W, int C, 
 }
 int launch_dropout_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, int replicate,
                         const DropoutSpec& d, cudaStream_t s) {
-  const size_t groups = (n * replicate + 3) / 4;
+  const size_t groups = (n * replicate + 3) / 4 + 1;
   dropout_kernel<__nv_bfloat16><<<grid_for(groups), kThreads, 0, s>>>(
-      in, out, n, replicate, d.rate, d.ext_mask, d.seed, d.offset);
+      in, out, n, replicate, d.rate, d.ext_mask, d.seed, d.offset, d.pass_elems);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 int launch_dropout_f32(const float* in, float* out, size_t n, int replicate,
                        const DropoutSpec& d, cudaStream_t s) {
-  const size_t groups = (n * replicate + 3) / 4;
-  dropout_kernel<float><<<grid_for(groups), kThreads, 0, s>>>(in, out, n, replicate, d.rate,
-                                                               d.ext_mask, d.seed, d.offset);
+  const size_t groups = (n * replicate + 3) / 4 + 1;
+  dropout_kernel<float><<<grid_for(groups), kThreads, 0, s>>>(
+      in, out, n, replicate, d.rate, d.ext_mask, d.seed, d.offset, d.pass_elems);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

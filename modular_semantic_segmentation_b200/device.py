@@ -122,7 +122,11 @@ class FcnExpert(object):
     def forward(self, x, want=('label',), dropout=None, label_dtype=torch.int64):
         """x: float32 CUDA tensor [N,H,W,cin].  want: any of 'score','prob','label',
         'mean_prob','var_prob','mean_var'.  dropout: None or dict(rate, layers, num_samples,
-        seed, masks={site: uint8 CUDA tensor}).  Returns a dict of CUDA tensors."""
+        seed, masks={site: uint8 CUDA tensor}, with_deterministic=False).  With
+        `with_deterministic` the dropout-free network runs as an extra leading sample sharing the
+        trunk: 'score'/'prob'/'label' are then its [N,...] outputs and the moments cover the
+        num_samples dropout passes (variance_mix.py:62-69 in one call).  Returns a dict of CUDA
+        tensors."""
         if self._dirty:
             self.finalize()
         assert x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == self.cin
@@ -139,6 +143,8 @@ class FcnExpert(object):
                 cfg.sites |= _abi.DROPOUT_SITES[site]
             cfg.num_samples = int(dropout.get('num_samples', 1))
             cfg.seed = int(dropout.get('seed', 0))
+            cfg.flags = (_abi.XV_DROP_FLAG_KEEP_FIRST if dropout.get('with_deterministic')
+                         else 0)
             masks = dropout.get('masks') or {}
             for i, site in enumerate(_abi.MASK_ORDER):
                 m = masks.get(site)
@@ -149,7 +155,8 @@ class FcnExpert(object):
                 else:
                     cfg.ext_mask[i] = None
             t_samples = cfg.num_samples
-        b = n * t_samples
+        lead = cfg is not None and bool(cfg.flags & _abi.XV_DROP_FLAG_KEEP_FIRST)
+        b = n if lead else n * t_samples
         c = self.num_classes
         dev = x.device
         out = {}
@@ -351,16 +358,36 @@ def bayes_fuse_score(labels, log_cond, log_prior, want_score=True):
     return score, out
 
 
+def dirichlet_table_magnitudes(alpha_m1, log_norm, log_prior):
+    """The two table magnitudes that scale the |fast - exact| bound of xv_dirichlet_fuse_exact:
+    max_c sum_{m,k} |alpha_m1[m][k][c]| and max_c sum_m |log_norm[m][c]| + max_c |log_prior[c]|
+    (accepts numpy arrays or tensors; evaluated on the host)."""
+    a, n, p = (np.abs(np.asarray(t.detach().cpu() if isinstance(t, torch.Tensor) else t,
+                                 dtype=np.float64)) for t in (alpha_m1, log_norm, log_prior))
+    return float(a.sum(axis=(0, 1)).max()), float(n.sum(axis=0).max() + p.max())
+
+
 def dirichlet_fuse(probs, alpha_m1, log_norm, log_prior, want_score=False,
-                   label_dtype=torch.int64):
+                   label_dtype=torch.int64, exact=False, magnitudes=None, num_exact=None):
+    """dirichlet_mix.py:14-36 on the device.  exact=True: argmax (and score) bit-exact against
+    the fixed-order float32 statement (oracle.dirichlet_fusion_f32); `magnitudes` =
+    dirichlet_table_magnitudes(...) (computed here if omitted - a device->host copy of the
+    tables); `num_exact`: optional int64 CUDA scalar that counts the re-evaluated pixels."""
     init()
     c = probs[0].shape[-1]
     npix = probs[0].numel() // c
     arr, keep = _abi.ptr_array([t.data_ptr() for t in probs])
     score = torch.empty_like(probs[0]) if want_score else None
     label = _new_label(probs[0].shape[:-1], label_dtype, probs[0].device)
-    call('xv_dirichlet_fuse', arr, len(probs), ptr(alpha_m1), ptr(log_norm), ptr(log_prior), c,
-         npix, ptr(score), ptr(label), _label_bytes(label), stream_ptr())
+    if exact:
+        if magnitudes is None:
+            magnitudes = dirichlet_table_magnitudes(alpha_m1, log_norm, log_prior)
+        call('xv_dirichlet_fuse_exact', arr, len(probs), ptr(alpha_m1), ptr(log_norm),
+             ptr(log_prior), c, npix, C.c_float(magnitudes[0]), C.c_float(magnitudes[1]),
+             ptr(score), ptr(label), _label_bytes(label), ptr(num_exact), stream_ptr())
+    else:
+        call('xv_dirichlet_fuse', arr, len(probs), ptr(alpha_m1), ptr(log_norm), ptr(log_prior),
+             c, npix, ptr(score), ptr(label), _label_bytes(label), stream_ptr())
     del keep
     return score, label
 

@@ -41,13 +41,16 @@ def class_prior_from_counts(class_counts, class_prior):
     return prior / prior.sum()
 
 
-def dirichlet_fusion(probs, dirichlet_params, prior, sigma=1.0, want_score=True):
+def dirichlet_fusion(probs, dirichlet_params, prior, sigma=1.0, want_score=True, exact=True):
     """dirichlet_mix.py:14-36 on the device.  probs: list of CUDA float32 [N,H,W,C] softmax
     outputs; dirichlet_params: list of [C,C] numpy arrays; prior: [C] or scalar.  Returns the
-    fused score [N,H,W,C] (argmax over the last axis is the fused classification)."""
+    fused score [N,H,W,C] (argmax over the last axis is the fused classification).
+    exact=True (default): the fixed-order float32 arithmetic whose argmax is bit-exact."""
     alpha_m1, log_norm, log_prior = dirichlet_tables(dirichlet_params, sigma, prior)
-    score, label = dev.dirichlet_fuse(probs, dev.to_device(alpha_m1), dev.to_device(log_norm),
-                                      dev.to_device(log_prior), want_score=want_score)
+    score, label = dev.dirichlet_fuse(
+        probs, dev.to_device(alpha_m1), dev.to_device(log_norm), dev.to_device(log_prior),
+        want_score=want_score, exact=exact,
+        magnitudes=dev.dirichlet_table_magnitudes(alpha_m1, log_norm, log_prior))
     return score if want_score else label
 
 
@@ -88,23 +91,40 @@ class DirichletFusion(BaseModel):
             tables = dirichlet_tables([self.dirichlet_params[m] for m in self.modalities],
                                       self.config['sigma'], prior)
             self._tables = [dev.to_device(t) for t in tables]
+            self._magnitudes = dev.dirichlet_table_magnitudes(*tables)
             self.prediction = 'prediction'
         else:
             self._tables = None
             self.prediction = 0     # dirichlet_mix.py:166-167: nothing to fuse before fit()
 
     def _probs(self, batch):
-        return [self._experts[m].forward(batch[m], want=('prob',))['prob']
-                for m in self.modalities]
+        """Expert outputs that enter the fusion.  `num_samples` > 1 (BASELINE configs[2]):
+        the mean softmax of that many MC-dropout passes per modality (dropout at
+        `dropout_layers`, default after pool3 as variance_mix.py:56), all samples sharing one
+        weight load; otherwise the dropout-free softmax of dirichlet_mix.py:98."""
+        num_samples = int(self.config.get('num_samples', 1))
+        if num_samples <= 1:
+            return [self._experts[m].forward(batch[m], want=('prob',))['prob']
+                    for m in self.modalities]
+        from .variance_mix import mc_dropout_seed
+        return [self._experts[m].forward(batch[m], want=('mean_prob',), dropout={
+            'rate': self.config.get('dropout_rate', 0.5),
+            'layers': list(self.config.get('dropout_layers', ['pool3'])),
+            'num_samples': num_samples, 'seed': mc_dropout_seed(self, i)})['mean_prob']
+                for i, m in enumerate(self.modalities)]
 
     def _run_batch(self, batch, fetch='prediction'):
         if self._tables is None:
             raise UserWarning('ERROR: DirichletFusion has to be fitted before inference')
         label_dtype = torch.uint8 if fetch == 'prediction_compact' else torch.int64
         self.probs = dict(zip(self.modalities, self._probs(batch)))
+        # `exact_fusion` (default True): bit-exact argmax of the fixed-order float32 rule; the
+        # fast arithmetic is kept for pixels whose decision margin exceeds the error bound
         score, label = dev.dirichlet_fuse([self.probs[m] for m in self.modalities],
                                           *self._tables, want_score=(fetch == 'fused_score'),
-                                          label_dtype=label_dtype)
+                                          label_dtype=label_dtype,
+                                          exact=bool(self.config.get('exact_fusion', True)),
+                                          magnitudes=self._magnitudes)
         return score if fetch == 'fused_score' else label
 
     def _get_sufficient_statistic(self, data):

@@ -11,6 +11,18 @@ def variance_fusion(probs, variances, want_score=True):
     return dev.variance_fuse(probs, variances, want_score=want_score)[0 if want_score else 1]
 
 
+def mc_dropout_seed(model, stream_index):
+    """Philox key of one MC-dropout call.  The reference draws fresh masks in every sess.run;
+    here every `_run_batch` call advances a per-model counter that is folded into the seed
+    (config `deterministic_dropout=True` freezes the masks, for tests)."""
+    calls = getattr(model, '_mc_calls', 0)
+    if stream_index == 0 and not model.config.get('deterministic_dropout', False):
+        calls += 1
+        model._mc_calls = calls
+    base = int(model.config.get('seed') or 0)
+    return (base * 1000003 + calls * 8191 + stream_index) & 0xFFFFFFFFFFFFFFFF
+
+
 class VarianceFusion(FusionModel):
     """variance_mix.py:18-83: MC-dropout (dropout after pool3, `num_samples` samples sharing
     one weight load) gives the per-pixel variance, a dropout-free pass gives the
@@ -31,12 +43,14 @@ class VarianceFusion(FusionModel):
         probs, variances = [], []
         for i, m in enumerate(self.modalities):
             expert = self._experts[self._expert_prefix(m)]
-            probs.append(expert.forward(batch[m], want=('prob',))['prob'])
-            mc = expert.forward(batch[m], want=('mean_var',), dropout={
+            # one call: the dropout-free pass (probabilities, variance_mix.py:68-69) rides along
+            # as a leading sample of the MC batch, so conv1_1..pool3 run once for both
+            out = expert.forward(batch[m], want=('prob', 'mean_var'), dropout={
                 'rate': self.config['dropout_rate'], 'layers': ['pool3'],
-                'num_samples': self.config['num_samples'],
-                'seed': self.config.get('seed', 0) + i})
-            variances.append(mc['mean_var'])
+                'num_samples': self.config['num_samples'], 'with_deterministic': True,
+                'seed': mc_dropout_seed(self, i)})
+            probs.append(out['prob'])
+            variances.append(out['mean_var'])
         score, label = dev.variance_fuse(probs, variances, want_score=(fetch == 'fused_score'),
                                          label_dtype=label_dtype)
         return score if fetch == 'fused_score' else label

@@ -37,7 +37,7 @@ from .fcn import (bilinear_kernel_1d, bilinear_filter, glorot_fcn_params, fcn_pa
 from .adapnet import (adapnet, adapnet_params, adapnet_param_shapes, same_padding, conv_bn,
                       block_a, block_b)
 from .fusion import (bayes_conditionals, bayes_prior, bayes_fusion, bayes_decision_matrix,
-                     dirichlet_log_norm, dirichlet_fusion, dirichlet_prior,
+                     dirichlet_log_norm, dirichlet_fusion, dirichlet_fusion_f32, dirichlet_prior,
                      dirichlet_uncertainty_fusion,
                      average_fusion, variance_fusion, mc_moments, normed_entropy,
                      sampling_uncertainty, sufficient_statistics)

@@ -118,6 +118,48 @@ def dirichlet_fusion(probs, dirichlet_params, prior, sigma=1.0, dtype=np.float32
     return total + np.log(np.asarray(1e-20, dtype) + np.asarray(prior, dtype))
 
 
+def _log_f32(x):
+    """Correctly rounded float32 logarithm: evaluate in float64, round once."""
+    with np.errstate(divide='ignore'):
+        return np.log(x.astype(np.float64)).astype(np.float32)
+
+
+def dirichlet_fusion_f32(probs, dirichlet_params, prior, sigma=1.0):
+    """dirichlet_mix.py:14-36,100-113 in float32 with a FIXED operation order - the definition
+    the device's exact mode reproduces bit for bit (TensorFlow's own reduction order is not
+    observable offline, so the order is fixed here and documented in DESIGN.md):
+      s      = p_0 + p_1 + ... + p_{C-1}                  sequential, one rounding per add
+      x_k    = 1e-20 + p_k / s                            IEEE division, then the add
+      L_k    = RN(log x_k)                                correctly rounded float32 logarithm
+      u_c    = (..((a_0c L_0) + (a_1c L_1)) + ...)        a_kc = sigma*alpha_kc - 1; every product
+                                                          and every sum rounded (no fused FMA)
+      ll_c   = u_c - lbeta(sigma*alpha[:, c])
+      score  = ((ll^0 + ll^1) + ...) + log(1e-20 + prior) experts in order, prior last
+    All arrays float32; returns the fused score [..., C]."""
+    f32 = np.float32
+    total = None
+    for p, params in zip(probs, dirichlet_params):
+        p = np.asarray(p, f32)
+        c_out = p.shape[-1]
+        alpha = f32(sigma) * np.asarray(params).astype(f32)
+        am1 = (alpha - f32(1)).astype(f32)
+        log_norm = dirichlet_log_norm(alpha.astype(np.float64)).astype(f32)
+        s = p[..., 0].copy()
+        for k in range(1, c_out):
+            s = s + p[..., k]
+        logx = _log_f32(f32(1e-20) + p / s[..., None])
+        acc = logx[..., 0:1] * am1[0]
+        for k in range(1, c_out):
+            acc = acc + logx[..., k:k + 1] * am1[k]
+        ll = acc - log_norm
+        total = ll if total is None else total + ll
+    with np.errstate(divide='ignore'):
+        log_prior = np.log(f32(1e-20) + np.broadcast_to(np.asarray(prior, f32),
+                                                         (total.shape[-1],))).astype(f32)
+    assert total.dtype == f32
+    return total + log_prior
+
+
 def dirichlet_uncertainty_fusion(probs, conditional_params, uncertainties, prior,
                                  dtype=np.float64):
     """uncertainty_dirichlet_mix.py:18-52: per pixel alpha = cond*(1-mix) + mix*(I+1) with

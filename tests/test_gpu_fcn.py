@@ -164,6 +164,33 @@ def test_mc_dropout_with_shared_masks(dev, precision, sites):
                                atol=1e-7)
 
 
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+def test_mc_dropout_with_dropout_free_leading_sample(dev, precision):
+    """XV_DROP_FLAG_KEEP_FIRST: the dropout-free pass of variance_mix.py:68-69 rides along as a
+    leading sample.  Its outputs equal a plain forward call bit for bit and the moments equal
+    those of a separate MC call with the same external masks."""
+    rng = np.random.default_rng(77)
+    t, n, h, w, rate = 3, 2, 32, 48, 0.3
+    net, params = _net(dev, precision, 3, rng)
+    x = cuda(rng.uniform(0, 1, size=(n, h, w, 3)).astype(np.float32))
+    masks = _masks(rng, t, n, h, w, rate, ['pool3'])
+    cfg = {'rate': rate, 'layers': ['pool3'], 'num_samples': t, 'masks': masks}
+    plain = net.forward(x, want=('prob', 'label', 'score'))
+    mc = net.forward(x, want=('mean_prob', 'var_prob', 'mean_var'), dropout=cfg)
+    both = net.forward(x, want=('prob', 'label', 'score', 'mean_prob', 'var_prob', 'mean_var'),
+                       dropout=dict(cfg, with_deterministic=True))
+    assert both['prob'].shape == (n, h, w, C)
+    for key in ('prob', 'label', 'score'):
+        assert torch.equal(both[key], plain[key]), key
+    for key in ('mean_prob', 'var_prob', 'mean_var'):
+        assert torch.equal(both[key], mc[key]), key
+    # Philox masks: the leading sample stays dropout-free
+    philox = net.forward(x, want=('prob',), dropout={'rate': rate, 'layers': ['pool3'],
+                                                     'num_samples': t, 'seed': 3,
+                                                     'with_deterministic': True})
+    assert torch.equal(philox['prob'], plain['prob'])
+
+
 def test_fused_philox_dropout_statistics(dev):
     """Without external masks the fused Philox generator must drop ~rate of the units,
     independently per sample, and be reproducible for a fixed seed."""

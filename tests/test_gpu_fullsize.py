@@ -1,9 +1,15 @@
-"""GPU checks at the full sizes of BASELINE.json's configs (768x384 frames, num_units 64, 12
-classes) through size-independent properties: the oracle would need minutes per frame there, so
-these tests assert what must hold at any size - invariance to how a data set is split into batches
-and uploads, additivity of the confusion matrix, its checksum, permutation equivariance, and
-agreement of the fused labels with the oracle's fusion rule applied to the device's own expert
-outputs."""
+"""GPU checks at the full sizes of BASELINE.json's configs (768x384 / 384x768 frames, num_units 64,
+12 classes).
+
+Two kinds of test:
+  * oracle parity at full size (`test_config2_*`, `test_config3_*`): one frame per modality
+    through the CPU oracle (about 0.3 s per stream-frame on the box's host cores) against the
+    CUDA path - bf16 probabilities <= 2e-2 abs, fp32 validation mode <= 1e-4 abs, fused labels
+    >= 0.97 agreement, mIoU within 0.1 point (north_star tolerances), plus bit-exact fusion on
+    the device's own expert outputs;
+  * size-independent properties on more frames than the oracle should be asked for: invariance
+    to how a data set is split into batches and uploads, additivity of the confusion matrix, its
+    checksum, permutation equivariance."""
 import numpy as np
 import pytest
 import torch
@@ -129,3 +135,129 @@ def test_mc_dropout_full_size_properties():
     assert pred.shape == (2, 768, 384) and pred.dtype == np.int64
     assert pred.min() >= 0 and pred.max() < C
     np.testing.assert_array_equal(cm, oracle.confusion_matrix(data['labels'], pred, C))
+
+
+# ----------------------------------------------------------------- oracle parity at full size
+def _trained_like(rng, gain=1.45):
+    """Glorot weights of the named architecture (nu = 64, C = 12) with the input range folded
+    into conv1_1 so that the logits are O(1) (SURVEY.md 8d "trained-like" variant)."""
+    params = {}
+    for m, cin, hi in (('rgb', 3, 255.0), ('depth', 1, 65535.0)):
+        p = oracle.glorot_fcn_params(m, cin, NU, C, rng, gain=gain, bias_scale=0.05)
+        p[m + '/conv1_1/kernel'] /= np.float32(hi)
+        params.update(p)
+    return params
+
+
+def _noisy_labels(rng, fused_ref):
+    """Ground truth correlated with the prediction (so that mIoU is far from chance level):
+    the oracle's fused labels with 25 % of the pixels re-drawn and 5 % set to -1 (ignore)."""
+    labels = fused_ref.astype(np.int32).copy()
+    redraw = rng.random(labels.shape) < 0.25
+    labels[redraw] = rng.integers(0, C, size=int(redraw.sum()))
+    labels[rng.random(labels.shape) < 0.05] = -1
+    return labels
+
+
+@pytest.mark.parametrize('h,w', [(768, 384), (384, 768)])
+def test_config2_bayes_fusion_matches_oracle_at_full_size(h, w):
+    """BASELINE configs[1] against the oracle end to end: two-stream VGG16-FCN (nu = 64, C = 12)
+    + confusion-matrix Bayes fusion + score() on 768x384 and 384x768 frames
+    (basic_fusion_model.py:9-23, simple_fcn.py:137-170, bayes_mix.py:12-58, base_model.py:294-331).
+    bf16: probabilities <= 2e-2 abs; fp32 validation mode: <= 1e-4 abs; fused labels >= 0.97;
+    mIoU within 0.1 point."""
+    from xview.models import get_model
+    rng = np.random.default_rng(h + 1)
+    n = 1
+    data = _data(rng, n, h, w)
+    params = _trained_like(rng)
+    cms = _cms(rng)
+    ref = {m: oracle.test_pipeline(data[m], params, m, NU, C) for m in ('rgb', 'depth')}
+    tables = [cms[m].astype('float32').T for m in ('rgb', 'depth')]
+    fused_ref = oracle.argmax_first(oracle.bayes_fusion(
+        [ref['rgb']['classification'], ref['depth']['classification']], tables)[0])
+    data['labels'] = _noisy_labels(rng, fused_ref)
+    miou_ref = oracle.score_measures(oracle.confusion_matrix(data['labels'], fused_ref, C))['mean_IoU']
+    report = {}
+    for precision, tol in (('bf16', 2e-2), ('fp32', 1e-4)):
+        with _bayes(cms, n, precision=precision) as net:
+            for name, value in params.items():
+                net.variables[name] = value
+            net._push_variables()
+            fused = net.predict({k: data[k] for k in ('rgb', 'depth')})
+            measures, cm = net.score(data)
+            experts = net.expert_outputs
+            for m in ('rgb', 'depth'):
+                out = net._experts[m].forward(torch.from_numpy(data[m]).cuda(), want=('prob', 'label'))
+                err = float(np.abs(out['prob'].cpu().numpy() - ref[m]['prob']).max())
+                agree = float((out['label'].cpu().numpy() == ref[m]['classification']).mean())
+                report['%s %s' % (precision, m)] = (err, agree)
+                assert err <= tol, report
+                assert agree > 0.97, report
+            dev_labels = [experts[m]['classification'].cpu().numpy().astype(np.int64)
+                          for m in ('rgb', 'depth')]
+        agree = float((fused == fused_ref).mean())
+        report['%s fused' % precision] = agree
+        assert agree >= 0.97, report
+        # integer work on the device's own expert labels is bit-exact
+        want = oracle.argmax_first(oracle.bayes_fusion(dev_labels, tables)[0])
+        np.testing.assert_array_equal(fused, want)
+        np.testing.assert_array_equal(cm, oracle.confusion_matrix(data['labels'], fused, C))
+        assert abs(measures['mean_IoU'] - miou_ref) < 1e-3, (measures['mean_IoU'], miou_ref)
+        report['%s mIoU' % precision] = (float(measures['mean_IoU']), float(miou_ref))
+    print('config2 %dx%d: %s' % (h, w, report))
+
+
+def _mc_masks(rng, t, n, h, w, rate):
+    return {'pool3': (rng.random((t * n, h // 8, w // 8, 256)) >= rate).astype(np.uint8),
+            'pool4': (rng.random((t * n, h // 16, w // 16, 512)) >= rate).astype(np.uint8)}
+
+
+def test_config3_mc_dropout_dirichlet_fusion_matches_oracle_at_full_size():
+    """BASELINE configs[2] shape against the oracle: per modality T MC-dropout samples (dropout
+    after pool3, shared external keep-masks so that device and oracle drop the same units;
+    variance_mix.py:46-69), the mean of the per-sample softmax, then Dirichlet fusion
+    (dirichlet_mix.py:14-36,100-113) of the two means; 768x384, nu = 64, C = 12, T = 4."""
+    from modular_semantic_segmentation_b200 import device as dev
+    from modular_semantic_segmentation_b200.models.dirichlet_mix import dirichlet_tables
+    from modular_semantic_segmentation_b200.models.simple_fcn import build_expert
+    rng = np.random.default_rng(33)
+    t, n, h, w, rate = 4, 1, 768, 384, 0.3
+    data = _data(rng, n, h, w)
+    params = _trained_like(rng)
+    alphas = [1.0 + rng.gamma(2.0, 2.0, size=(C, C)) + 6.0 * np.eye(C) for _ in range(2)]
+    counts = rng.integers(100, 10000, size=C)
+    prior = oracle.dirichlet_prior(counts)
+    mean_dev, mean_ref = [], []
+    for m, cin in (('rgb', 3), ('depth', 1)):
+        masks = _mc_masks(rng, t, n, h, w, rate)
+        samples = []
+        for i in range(t):
+            mk = {s: v[i * n:(i + 1) * n] for s, v in masks.items()}
+            samples.append(oracle.test_pipeline(data[m], params, m, NU, C, dropout_rate=rate,
+                                                dropout_layers=['pool3'], masks=mk)['prob'])
+        mean_ref.append(np.mean(np.stack(samples), axis=0).astype(np.float32))
+        expert, _ = build_expert(m, cin, NU, C)
+        expert.set_params({k[len(m) + 1:]: v for k, v in params.items() if k.startswith(m + '/')})
+        out = expert.forward(torch.from_numpy(data[m]).cuda(), want=('prob', 'mean_prob'),
+                             dropout={'rate': rate, 'layers': ['pool3'], 'num_samples': t,
+                                      'masks': masks})
+        got = out['prob'].cpu().numpy().reshape(t, n, h, w, C)
+        err = float(np.abs(got - np.stack(samples)).max())
+        assert err <= 2e-2, (m, err)
+        mean_dev.append(out['mean_prob'])
+        assert float(np.abs(out['mean_prob'].cpu().numpy() - mean_ref[-1]).max()) <= 2e-2
+        expert.close()
+    fused_ref = oracle.argmax_first(oracle.dirichlet_fusion_f32(mean_ref, alphas, prior))
+    tables = [dev.to_device(a) for a in dirichlet_tables(alphas, 1.0, prior)]
+    _, fused = dev.dirichlet_fuse(mean_dev, *tables, exact=True)
+    fused = fused.cpu().numpy()
+    assert (fused == fused_ref).mean() >= 0.97
+    # the fusion rule itself, on the device's own means: bit-exact against the fp32 oracle
+    own = oracle.argmax_first(oracle.dirichlet_fusion_f32([p.cpu().numpy() for p in mean_dev],
+                                                          alphas, prior))
+    np.testing.assert_array_equal(fused, own)
+    labels = _noisy_labels(rng, fused_ref)
+    miou = [oracle.score_measures(oracle.confusion_matrix(labels, f, C))['mean_IoU']
+            for f in (fused, fused_ref)]
+    assert abs(miou[0] - miou[1]) < 1e-3, miou

@@ -105,6 +105,106 @@ def test_dirichlet_fusion_exact_on_decisive_inputs(dev):
     np.testing.assert_array_equal(label.cpu().numpy()[decisive], np.argmax(ref32, -1)[decisive])
 
 
+def _flip_report(name, fast, exact, redone, total):
+    flips = int((fast != exact).sum())
+    print('%s: fast-mode flips %d of %d pixels (%.3g), exact re-evaluations %d (%.3g)'
+          % (name, flips, total, flips / total, redone, redone / total))
+    return flips
+
+
+def test_dirichlet_fusion_exact_mode_is_bit_exact_at_full_size(dev):
+    """north_star: fusion argmax bit-exact.  16 x 768 x 384 random softmax outputs (the batch of
+    BASELINE configs[1]/[2]) through the exact mode: labels AND scores must equal the fixed-order
+    float32 oracle (dirichlet_mix.py:14-36,100-113 restated in oracle.dirichlet_fusion_f32) to
+    the last bit; the flip rate of the fast arithmetic is printed."""
+    c = 12
+    rng = np.random.default_rng(2024)
+    shape = (16, 768, 384, c)
+    probs = [softmax_probs(rng, shape), softmax_probs(rng, shape)]
+    params = [1 + rng.gamma(2, 2, size=(c, c)) + 4 * np.eye(c) for _ in range(2)]
+    prior = oracle.dirichlet_prior(rng.integers(100, 100000, size=c))
+    ref = oracle.dirichlet_fusion_f32(probs, params, prior)
+    ref_label = oracle.argmax_first(ref)
+    tables = [cuda(t) for t in _dirichlet_tables(params, 1.0, prior)]
+    dp = [cuda(p) for p in probs]
+    redone = torch.zeros(1, dtype=torch.int64, device='cuda')
+    _, label = dev.dirichlet_fuse(dp, *tables, exact=True, num_exact=redone)
+    np.testing.assert_array_equal(label.cpu().numpy(), ref_label)
+    score, label_all = dev.dirichlet_fuse(dp, *tables, want_score=True, exact=True)
+    np.testing.assert_array_equal(label_all.cpu().numpy(), ref_label)
+    np.testing.assert_array_equal(score.cpu().numpy(), ref)
+    _, fast = dev.dirichlet_fuse(dp, *tables, label_dtype=torch.uint8)
+    npix = ref_label.size
+    _flip_report('dirichlet C=12 16x768x384', fast.cpu().numpy(), ref_label, int(redone.item()), npix)
+    # the two-tier scheme must re-evaluate only a small share of the pixels
+    assert int(redone.item()) < 0.05 * npix
+
+
+@pytest.mark.parametrize('c', [12, 13, 5])
+def test_dirichlet_fusion_exact_mode_on_adversarial_near_ties(dev, c):
+    """Class columns that are exact copies of each other (exact ties: the first index must
+    win), copies nudged by one ulp, and pixels that are duplicates of each other up to one ulp
+    of one probability: the exact mode must still reproduce the oracle argmax bit for bit."""
+    rng = np.random.default_rng(70 + c)
+    shape = (3, 96, 80, c)
+    probs = [softmax_probs(rng, shape, 1.0), softmax_probs(rng, shape, 1.0)]
+    # near-duplicate pixels: pixel 2i+1 = pixel 2i with one probability moved by one ulp
+    for p in probs:
+        flat = p.reshape(-1, c)
+        flat[1::2] = flat[0::2]
+        idx = rng.integers(0, c, size=flat[1::2].shape[0])
+        rows = np.arange(1, flat.shape[0], 2)
+        flat[rows, idx] = np.nextafter(flat[rows, idx], np.float32(1))
+    params = [1 + rng.gamma(2, 2, size=(c, c)) for _ in range(2)]
+    for a in params:
+        a[:, 2] = a[:, 0]                                   # exact tie between classes 0 and 2
+        a[:, 3] = a[:, 1]
+        a[0, 3] = np.nextafter(np.float32(a[0, 3]), np.float32(100))   # 1-ulp near tie 1 vs 3
+        if c > 4:
+            a[:, 4] = a[:, 0] * (1 + 1e-6)
+    counts = np.full(c, 50.0)
+    prior = oracle.dirichlet_prior(counts)                  # equal priors keep the ties exact
+    ref = oracle.dirichlet_fusion_f32(probs, params, prior)
+    ref_label = oracle.argmax_first(ref)
+    tables = [cuda(t) for t in _dirichlet_tables(params, 1.0, prior)]
+    dp = [cuda(p) for p in probs]
+    redone = torch.zeros(1, dtype=torch.int64, device='cuda')
+    for dtype in (torch.int64, torch.uint8):
+        _, label = dev.dirichlet_fuse(dp, *tables, exact=True, label_dtype=dtype, num_exact=redone)
+        np.testing.assert_array_equal(label.cpu().numpy().astype(np.int64), ref_label)
+    score, _ = dev.dirichlet_fuse(dp, *tables, want_score=True, exact=True)
+    np.testing.assert_array_equal(score.cpu().numpy(), ref)
+    # the construction really produces ties: classes 0 and 2 have identical scores everywhere
+    np.testing.assert_array_equal(ref[..., 0], ref[..., 2])
+    assert not (ref_label == 2).any()
+    _, fast = dev.dirichlet_fuse(dp, *tables)
+    _flip_report('dirichlet adversarial C=%d' % c, fast.cpu().numpy(), ref_label,
+                 int(redone.item()) // 2, ref_label.size)
+
+
+def test_average_and_variance_fusion_bit_exact_at_full_size(dev):
+    """average_mix.py:18-21 and variance_mix.py:7-15 on 16 x 768 x 384 probabilities: every device
+    operation is individually rounded in numpy's order, so scores and labels are bit-exact."""
+    c = 12
+    rng = np.random.default_rng(99)
+    shape = (16, 768, 384, c)
+    probs = [softmax_probs(rng, shape), softmax_probs(rng, shape)]
+    probs[1][0, :8] = probs[0][0, :8]                       # rows of exact ties after averaging
+    dp = [cuda(p) for p in probs]
+    ref = oracle.average_fusion(probs)
+    assert ref.dtype == np.float32
+    score, label = dev.average_fuse(dp, want_score=True)
+    np.testing.assert_array_equal(score.cpu().numpy(), ref)
+    np.testing.assert_array_equal(label.cpu().numpy(), oracle.argmax_first(ref))
+    variances = [(rng.random(shape[:-1] + (1,)) * 1e-2).astype(np.float32) for _ in range(2)]
+    variances[0][0, 0, :5] = 0.0
+    refv = oracle.variance_fusion(probs, variances)
+    assert refv.dtype == np.float32
+    score, label = dev.variance_fuse(dp, [cuda(v[..., 0]) for v in variances], want_score=True)
+    np.testing.assert_array_equal(score.cpu().numpy(), refv)
+    np.testing.assert_array_equal(label.cpu().numpy(), oracle.argmax_first(refv))
+
+
 def test_average_and_variance_fusion(dev):
     c = 12
     rng = np.random.default_rng(11)

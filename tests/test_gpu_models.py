@@ -169,6 +169,12 @@ def test_dirichlet_fusion_fit_and_predict():
     scale = np.abs(ref).max()
     np.testing.assert_allclose(score, ref, rtol=0, atol=3e-5 * scale)
     assert_labels_match(fused, ref, 6e-5 * scale)
+    # the model runs the exact fusion mode by default: scores and labels are bit-exact against
+    # the fixed-order float32 statement of the rule
+    ref32 = oracle.dirichlet_fusion_f32([probs['rgb'], probs['depth']],
+                                        [fit['rgb'], fit['depth']], prior, sigma=0.8)
+    np.testing.assert_array_equal(score, ref32)
+    np.testing.assert_array_equal(fused, oracle.argmax_first(ref32))
     # a second model constructed from the fitted parameters gives the same prediction
     with get_model('dirichlet_mix')(dirichlet_params=fit, **config) as net2:
         _load(net2, params)
@@ -190,13 +196,37 @@ def test_average_and_variance_fusion_models():
         probs = [net.expert_outputs[m]['prob'].cpu().numpy() for m in net.modalities]
     assert_labels_match(fused, oracle.average_fusion(probs), 1e-6)
     with get_model('variance_fusion')(modalities=['rgb', 'depth'], dropout_rate=0.3,
-                                      num_samples=6, **common) as net:
+                                      num_samples=6, deterministic_dropout=True, seed=5,
+                                      **common) as net:
         _load(net, params)
         fused = net.predict(data)
         score = net.predict(data, output_attr='fused_score')
+        # the pieces the model fuses, recomputed through the expert API with the model's seeds:
+        # dropout-free probabilities and the MC-dropout variance (variance_mix.py:62-69)
+        from modular_semantic_segmentation_b200.models.variance_mix import mc_dropout_seed
+        probs, variances = [], []
+        for i, m in enumerate(net.modalities):
+            x = torch.from_numpy(data[m]).cuda()
+            expert = net._experts[m]
+            probs.append(expert.forward(x, want=('prob',))['prob'].cpu().numpy())
+            mc = expert.forward(x, want=('mean_var',), dropout={
+                'rate': 0.3, 'layers': ['pool3'], 'num_samples': 6,
+                'seed': mc_dropout_seed(net, i)})
+            variances.append(mc['mean_var'].cpu().numpy()[..., None])
     assert fused.shape == (n, h, w)
     np.testing.assert_allclose(score.sum(-1), 1.0, atol=1e-4)   # convex mix of probabilities
     np.testing.assert_array_equal(fused, np.argmax(score, -1))
+    # the shared-trunk call equals the two separate passes, and the fusion rule is bit-exact
+    ref = oracle.variance_fusion(probs, variances)
+    np.testing.assert_array_equal(score, ref)
+    np.testing.assert_array_equal(fused, oracle.argmax_first(ref))
+    # without `deterministic_dropout` every call draws fresh masks (the reference's behaviour)
+    with get_model('variance_fusion')(modalities=['rgb', 'depth'], dropout_rate=0.3,
+                                      num_samples=6, seed=5, **common) as net:
+        _load(net, params)
+        a = net.predict(data, output_attr='fused_score')
+        b = net.predict(data, output_attr='fused_score')
+    assert not np.array_equal(a, b)
 
 
 def test_fusion_fcn_mid_level_fusion_net():
