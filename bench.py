@@ -14,11 +14,23 @@ data-path collective ("weak" scaling: 16 frames per GPU per step), the only coll
 the int64 confusion-matrix all-reduce at the end of score().
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  value     device-resident throughput: inputs already in HBM when the timed region starts
+  value     device-resident throughput: inputs already in HBM when the timed region starts;
+            the timed K steps follow W warm-up steps and an untimed soak of the same step
+            (`soak_s`, >= 2 s) so that clocks and power have settled
   e2e       the same metric through the public API `net.score(host arrays)`: pinned host
-            buffers, H2D of rgb/depth/labels every step, D2H of the confusion matrix
+            buffers, H2D of rgb/depth/labels every step, D2H of the confusion matrix;
+            `e2e.dataset_call` = ONE net.score() over K x 16 frames with batchsize 16 (the
+            reference's API shape, base_model.py:294-313)
   roofline  tensor-core stack (all tcgen05 conv launches): algorithmic FLOPs / CUDA-event time
-            measured live in the timed region, against MEASURED_PEAKS.json
+            measured live in the timed region, against both MEASURED_PEAKS.json figures
+            (`frac` = sustained, `frac_burst` = burst)
+  fusion_hbm  HBM fraction of every per-pixel fusion / score kernel (algorithmic bytes /
+            CUDA-event time / measured copy bandwidth), batch-16 sizes
+  dirichlet_mc_T20  BASELINE configs[2]: Dirichlet fusion of T = 20 MC-dropout samples per
+            modality, frames/s (device-resident)
+  fit       BASELINE configs[4]: data-parallel fit() of the depth stream, frames/s
+  sharded_check  N > 1: the same global batch through score() with images sharded over the
+            ranks equals rank 0's single-rank confusion matrix
   cpu_baseline  the oracle (CPU restatement of the reference; TensorFlow is not installable)
             timed on this box's host cores on a bounded sample
 """
@@ -59,60 +71,104 @@ def _confusion_matrices(rng):
 
 
 def _peaks():
+    """(sustained bf16 TFLOP/s, burst bf16 TFLOP/s, HBM GB/s, 'measured' | 'fallback')."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         p = json.load(open(path))
-        return p.get('bf16_tflops_sustained', 1400.0), p.get('hbm_gbs', 6650.0), 'measured'
-    return 1400.0, 6650.0, 'fallback'
+        return (p.get('bf16_tflops_sustained', 1400.0), p.get('bf16_tflops', 1590.0),
+                p.get('hbm_gbs', 6650.0), 'measured')
+    return 1400.0, 1590.0, 6650.0, 'fallback'
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock + throttle reasons sampled during the timed region: NVML polled every 10 ms from
+    a thread (a 20-step timed region lasts ~0.1 s), nvidia-smi -lms as the fallback."""
 
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40),
+               ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
     QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []            # (time, sm_mhz, sm_max_mhz, [reasons])
         self.proc = None
+        self._stop = False
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if visible:
+                ids = [v for v in visible.split(',') if v.strip() != '']
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self.source = 'nvml'
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '200'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = 'nvidia-smi'
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll(self):
+        nv = self._nvml
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+                self.rows.append((time.time(), mhz, self._max,
+                                  [name for name, bit in self.REASONS if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for t, line in self.rows:
-            if t < t0 - 0.2 or t > t1 + 0.2:
-                continue
+    def _read(self):
+        names = [n for n, _ in self.REASONS]
+        for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(',')]
             try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
+                self.rows.append((time.time(), float(parts[0]), float(parts[1]),
+                                  [n for n, f in zip(names, parts[3:7])
+                                   if f.lower().startswith('active')]))
             except (ValueError, IndexError):
                 continue
-            for name, flag in zip(names, parts[3:7]):
-                if flag.lower().startswith('active'):
-                    reasons.add(name)
-        if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)),
-                'reasons': sorted(reasons), 'samples': len(sm)}
+
+    def stop(self, t0, t1):
+        if self.source is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no clock source'],
+                    'samples': 0}
+        time.sleep(0.06)
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        if len(inside) < 5:       # widen slightly rather than report too few samples
+            inside = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+        if not inside:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'], 'samples': 0,
+                    'source': self.source}
+        reasons = sorted({name for r in inside for name in r[3]})
+        return {'sm_mhz': float(np.median([r[1] for r in inside])),
+                'sm_min_mhz': float(min(r[1] for r in inside)),
+                'sm_max_mhz': float(max(r[2] for r in inside)),
+                'reasons': reasons, 'samples': len(inside), 'source': self.source}
 
 
 # ------------------------------------------------------------------------------- CPU arm
@@ -213,6 +269,156 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------- GPU arm
+def _event_ms(fn, iters, warm=3):
+    """Mean CUDA-event milliseconds of fn() on the current stream after `warm` warm-up calls."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def fusion_hbm_rows(peak_gbs):
+    """HBM roofline of the per-pixel fusion / score kernels at the batch-16 768x384 size.
+    Algorithmic bytes per pixel: SURVEY.md 8(d) / DESIGN.md 4.3; inputs (>= 226 MB per expert)
+    are far larger than the 126 MB L2; CUDA events on the launching stream."""
+    import torch
+    from modular_semantic_segmentation_b200 import device as dev
+    n, m = BATCH, 2
+    npix = n * H * W
+    g = torch.Generator(device='cuda').manual_seed(0)
+    probs = [torch.softmax(2 * torch.randn((n, H, W, C), device='cuda', generator=g), -1)
+             .contiguous() for _ in range(m)]
+    score = torch.randn((n, H, W, C), device='cuda', generator=g)
+    l64 = [torch.randint(0, C, (n, H, W), device='cuda', generator=g) for _ in range(m)]
+    l8 = [t.to(torch.uint8) for t in l64]
+    # segmentation-like maps: 32x32-pixel blocks of one class, prediction agrees on 90 %
+    blocks = torch.randint(-1, C, (n, H // 32, W // 32), device='cuda', generator=g,
+                           dtype=torch.int32)
+    gt = blocks.repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous()
+    gt_rand = torch.randint(-1, C, (n, H, W), device='cuda', generator=g, dtype=torch.int32)
+    pred = torch.where(torch.rand((n, H, W), device='cuda', generator=g) < 0.9,
+                       gt.clamp(min=0).to(torch.int64), l64[0])
+    pred8 = pred.to(torch.uint8)
+    lut = torch.randint(0, C, (C, C), device='cuda', generator=g, dtype=torch.int32)
+    am1 = torch.rand((m, C, C), device='cuda', generator=g) * 3
+    lognorm = torch.rand((m, C), device='cuda', generator=g)
+    logprior = torch.log(torch.full((C,), 1.0 / C, device='cuda'))
+    mags = dev.dirichlet_table_magnitudes(am1, lognorm, logprior)
+    var = [torch.rand((n, H, W), device='cuda', generator=g) * 1e-2 for _ in range(m)]
+    cm = torch.zeros((C, C), dtype=torch.int64, device='cuda')
+    stats = torch.zeros((C, C), dtype=torch.float64, device='cuda')
+    cnt = torch.zeros(C, dtype=torch.int64, device='cuda')
+    cases = [
+        ('softmax_argmax prob+i64', 8 * C + 8, lambda: dev.softmax_argmax(score)),
+        ('softmax_argmax u8', 4 * C + 1,
+         lambda: dev.softmax_argmax(score, want_prob=False, label_dtype=torch.uint8)),
+        ('bayes_fuse_lut i64', 8 * m + 8, lambda: dev.bayes_fuse_lut(l64, lut, C)),
+        ('bayes_fuse_lut u8', m + 1, lambda: dev.bayes_fuse_lut(l8, lut, C)),
+        ('dirichlet_fuse fast u8', 4 * C * m + 1,
+         lambda: dev.dirichlet_fuse(probs, am1, lognorm, logprior, label_dtype=torch.uint8)),
+        ('dirichlet_fuse exact u8', 4 * C * m + 1,
+         lambda: dev.dirichlet_fuse(probs, am1, lognorm, logprior, label_dtype=torch.uint8,
+                                    exact=True, magnitudes=mags)),
+        ('average_fuse i64', 4 * C * m + 8, lambda: dev.average_fuse(probs)),
+        ('variance_fuse i64', 4 * C * m + 4 * m + 8, lambda: dev.variance_fuse(probs, var)),
+        ('confusion i64 blocky', 12, lambda: dev.confusion_accumulate(pred, gt, cm)),
+        ('confusion u8 blocky', 5, lambda: dev.confusion_accumulate(pred8, gt, cm)),
+        ('confusion i64 random', 12, lambda: dev.confusion_accumulate(l64[0], gt_rand, cm)),
+        ('suffstats blocky', 4 * C + 4, lambda: dev.dirichlet_suffstats(probs[0], gt, stats, cnt)),
+        ('suffstats random', 4 * C + 4,
+         lambda: dev.dirichlet_suffstats(probs[0], gt_rand, stats, cnt)),
+    ]
+    rows = {}
+    for name, bytes_px, fn in cases:
+        ms = _event_ms(fn, 10)
+        gbs = bytes_px * npix / ms / 1e6
+        rows[name] = {'bytes_per_pixel': bytes_px, 'ms': round(ms, 4), 'gbs': round(gbs, 1),
+                      'frac': round(gbs / peak_gbs, 3)}
+    return rows
+
+
+def dirichlet_mc_bench(world, rank, steps=3, batch=8, num_samples=20):
+    """BASELINE configs[2]: per modality T = 20 MC-dropout samples (dropout after pool3, all
+    samples sharing one weight load) -> mean softmax -> Dirichlet fusion (exact argmax) ->
+    confusion matrix; images sharded over the ranks (`batch` frames per GPU and step)."""
+    import torch
+    import torch.distributed as dist
+    from xview.models import get_model
+    rng = np.random.default_rng(77)
+    params = {m: 1.0 + rng.gamma(2.0, 2.0, size=(C, C)) + 4.0 * np.eye(C) for m in ('rgb', 'depth')}
+    params['class_counts'] = rng.integers(1000, 100000, size=C).astype(np.float64)
+    net = get_model('dirichlet_mix')(
+        data_description=_data_description(), modalities=['rgb', 'depth'], expert_model='fcn',
+        num_units=NU, num_channels={'rgb': 3, 'depth': 1}, batchsize=batch, seed=7,
+        dirichlet_params=params, num_samples=num_samples, dropout_rate=0.5,
+        dropout_layers=['pool3'], shard_images=False)
+    g = torch.Generator(device='cuda').manual_seed(100 + rank)
+    sets = [{'rgb': torch.randint(0, 256, (batch, H, W, 3), device='cuda', generator=g).float(),
+             'depth': torch.randint(0, 65536, (batch, H, W, 1), device='cuda', generator=g).float(),
+             'labels': torch.randint(-1, C, (batch, H, W), device='cuda', generator=g,
+                                     dtype=torch.int32)} for _ in range(2)]
+    cm = torch.zeros((C, C), dtype=torch.int64, device='cuda')
+    it = [0]
+
+    def step():
+        net.score_batch_on_device(sets[it[0] % 2], cm)
+        it[0] += 1
+
+    ms = _event_ms(step, steps, warm=2)
+    if world > 1:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    labelled = sum(int((s['labels'] >= 0).sum()) for s in sets)
+    net.close()
+    del sets
+    torch.cuda.empty_cache()
+    # T passes of conv4_1..conv5_3 + heads and one pass of the trunk, per modality (App. D)
+    gflop = 2 * (109.7 + num_samples * 71.5)
+    return {'value': world * batch / (ms * 1e-3), 'unit': 'frames/s', 'ms_per_step': ms,
+            'frames_per_gpu_per_step': batch, 'num_samples': num_samples, 'steps': steps,
+            'tflops': gflop * batch / ms, 'fusion': 'dirichlet, exact argmax',
+            'labelled_pixels_checksum_ok': bool(int(cm.sum()) > 0 and labelled > 0)}
+
+
+def fit_bench(world, rank, steps=5, batch=16):
+    """BASELINE configs[4]: data-parallel fit() of the VGG16-FCN depth stream on synthetic
+    Cityscapes-shaped data (384x768, 12 classes), Adam lr 1e-4, `batch` frames per GPU: forward +
+    backward + gradient all-reduce over NCCL + Adam, through SimpleFCN's training step."""
+    import torch
+    import torch.distributed as dist
+    from xview.models import get_model
+    desc = ({'depth': np.float32, 'labels': np.int32},
+            {'depth': (None, None, 1), 'labels': (None, None)}, C)
+    net = get_model('fcn')('depth', desc, 'depth', num_units=NU, batch_normalization=False,
+                           learning_rate=1e-4, batchsize=batch, seed=1, shard_images=False)
+    g = torch.Generator(device='cuda').manual_seed(rank)
+    batch_dev = {'depth': torch.rand((batch, W, H, 1), device='cuda', generator=g) * 100.0,
+                 'labels': torch.randint(-1, C, (batch, W, H), device='cuda', generator=g,
+                                         dtype=torch.int32)}
+    trainer = net.make_trainer()
+    ms = _event_ms(lambda: trainer.step(batch_dev), steps, warm=2)
+    if world > 1:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss = trainer.last_loss()
+    num_params = net._experts['depth'].num_params
+    trainer.close()
+    net.close()
+    torch.cuda.empty_cache()
+    return {'value': world * batch / (ms * 1e-3), 'unit': 'frames/s', 'ms_per_step': ms,
+            'frames_per_gpu_per_step': batch, 'steps': steps, 'trainer': 'adam',
+            'allreduce_bytes_per_step': num_params * 4 + 16, 'final_loss': loss}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -226,16 +432,21 @@ def run_gpu(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    _bind_to_local_numa_node(local_rank)
+    warmup = max(args.warmup, 3)
     # sharding inside score() is by image over ranks; the bench gives every rank its own
     # batch-16 shard directly (weak scaling), so the model must not split it again
     rng = np.random.default_rng(1234 + rank)
     cms = _confusion_matrices(np.random.default_rng(0))
-    net = get_model('bayes_fusion')(
-        confusion_matrices=cms, data_description=_data_description(),
-        prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn', num_units=NU,
-        num_channels={'rgb': 3, 'depth': 1}, batchsize=BATCH, seed=7, class_prior='data',
-        shard_images=False)
 
+    def make_net(shard):
+        return get_model('bayes_fusion')(
+            confusion_matrices=cms, data_description=_data_description(),
+            prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn', num_units=NU,
+            num_channels={'rgb': 3, 'depth': 1}, batchsize=BATCH, seed=7, class_prior='data',
+            shard_images=shard)
+
+    net = make_net(False)
     n_sets = 3    # rotate input sets: 3 x 94 MB of inputs + GBs of activations >> 126 MB L2
     host_sets = []
     for _ in range(n_sets):
@@ -248,11 +459,26 @@ def run_gpu(args):
         host_sets.append(blob)
     dev_sets = [{k: v.cuda() for k, v in blob.items()} for blob in host_sets]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+    labelled = [int((b['labels'] >= 0).sum()) for b in host_sets]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def sum_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device='cuda', dtype=torch.int64)
+            dist.all_reduce(t)
+            return int(t.item())
+        return x
 
     cm = torch.zeros((C, C), dtype=torch.int64, device='cuda')
 
@@ -260,10 +486,22 @@ def run_gpu(args):
         net.score_batch_on_device(dev_sets[i % n_sets], cm)
 
     # ---------------- device-resident throughput (value) + live roofline of the conv stack
-    for i in range(max(args.warmup, 3)):
+    for i in range(warmup):
         device_step(i)
     barrier()
+    # untimed soak of the same step: clocks / power settle before anything is timed
+    t_soak = time.time()
+    i = 0
+    while time.time() - t_soak < args.soak:
+        for _ in range(10):
+            device_step(i)
+            i += 1
+        torch.cuda.synchronize()
+    soak_s = time.time() - t_soak
+    barrier()
+    cm.zero_()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.03)
     launches0 = dev.launch_count()
     dev.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,11 +517,11 @@ def run_gpu(args):
     dev.profile_enable(False)
     launches = dev.launch_count() - launches0
     clocks = sampler.stop(t_start, t_end) if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     value = world * BATCH * args.steps / (ms * 1e-3)
+    # checksum of the device-resident loop: every labelled pixel was counted exactly once
+    want_px = sum(labelled[i % n_sets] for i in range(args.steps))
+    assert int(cm.sum().item()) == want_px, (int(cm.sum().item()), want_px)
 
     # ---------------- end to end through the public API with host buffers (e2e)
     # each rank scores its own batch-16 shard (shard_images=False: the dict a rank passes IS
@@ -295,17 +533,26 @@ def run_gpu(args):
     for i in range(args.steps):
         measures, cm_host = net.score(host_sets[i % n_sets])
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * BATCH * args.steps / e2e_s
-    assert int(cm_host.sum()) == int((host_sets[(args.steps - 1) % n_sets]['labels'] >= 0).sum()
-                                     ) * world or world > 1
+    # the all-reduced matrix counts the labelled pixels of every rank's last batch
+    assert int(cm_host.sum()) == sum_over_ranks(labelled[(args.steps - 1) % n_sets])
 
-    # same call with the sensors' own dtypes (uint8 rgb, uint16 depth): the float32 cast of
-    # data_baseclass.py:77-78 then runs on the device after a 2.2x smaller copy (not the headline)
+    # one score() call over the whole data set (K x 16 frames, batchsize 16): the reference's
+    # API shape (base_model.py:294-313); uploads of batch i+1 overlap the kernels of batch i
+    def dataset():
+        for i in range(args.steps):
+            yield host_sets[i % n_sets]
+    net.score(host_sets[0])
+    barrier()
+    t0 = time.perf_counter()
+    _, cm_ds = net.score(dataset())
+    barrier()
+    ds_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(cm_ds.sum()) == sum_over_ranks(want_px)
+
+    # same calls with the sensors' own dtypes (uint8 rgb, uint16 depth): the float32 cast of
+    # data_baseclass.py:77-78 then runs on the device after a 2.2x smaller copy
     raw_sets = [{'rgb': b['rgb'].to(torch.uint8).pin_memory(),
                  'depth': b['depth'].to(torch.uint16).pin_memory(),
                  'labels': b['labels']} for b in host_sets]
@@ -317,18 +564,60 @@ def run_gpu(args):
     for i in range(args.steps):
         _, cm_raw = net.score(raw_sets[i % n_sets])
     barrier()
-    raw_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([raw_s], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        raw_s = float(t.item())
+    raw_s = max_over_ranks(time.perf_counter() - t0)
     assert np.array_equal(cm_raw, cm_host)
+
+    def raw_dataset():
+        for i in range(args.steps):
+            yield raw_sets[i % n_sets]
+    barrier()
+    t0 = time.perf_counter()
+    _, cm_raw_ds = net.score(raw_dataset())
+    barrier()
+    raw_ds_s = max_over_ranks(time.perf_counter() - t0)
+    assert np.array_equal(cm_raw_ds, cm_ds)
+
+    # ---------------- N > 1: the real sharded path, checked against a single-rank evaluation
+    sharded_check = None
+    if world > 1:
+        # every rank passes the SAME global batch (rank 0's set 0); score() shards its images
+        # over the ranks (image i -> rank i mod world) and all-reduces the matrix
+        blob = [host_sets[0]] if rank == 0 else [None]
+        dist.broadcast_object_list(blob, src=0)
+        shared = blob[0]
+        sharded = make_net(True)
+        _, cm_sharded = sharded.score(shared)
+        sharded.close()
+        single = None
+        if rank == 0:
+            cm1 = torch.zeros((C, C), dtype=torch.int64, device='cuda')
+            net.score_batch_on_device({k: v.cuda() for k, v in shared.items()}, cm1)
+            single = cm1.cpu().numpy().astype(np.float64)
+        ok = [bool(np.array_equal(cm_sharded, single))] if rank == 0 else [None]
+        dist.broadcast_object_list(ok, src=0)
+        assert ok[0], 'sharded score() differs from the single-rank confusion matrix'
+        sharded_check = {'images': BATCH, 'ranks': world, 'equal_to_single_rank': True,
+                         'labelled_pixels': int(cm_sharded.sum())}
+
+    net.close()
+    del dev_sets
+    torch.cuda.empty_cache()
+
+    # ---------------- secondary workloads (driver-visible figures for configs[2] and [4])
+    peak_tf, peak_tf_burst, peak_gbs, peak_kind = _peaks()
+    extra = {}
+    if not args.no_extras:
+        extra['dirichlet_mc_T20'] = dirichlet_mc_bench(world, rank)
+        extra['fit'] = fit_bench(world, rank)
+        if rank == 0:
+            extra['fusion_hbm'] = fusion_hbm_rows(peak_gbs)
+            extra['fusion_hbm']['_peak_gbs'] = peak_gbs
+    barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peak_tf, peak_gbs, peak_kind = _peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -336,9 +625,9 @@ def run_gpu(args):
         traffic = json.load(open(prof)).get('conv_igemm_dram_bytes_per_launch')
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+        'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-        'data': 'synthetic',
+        'data': 'synthetic', 'soak_s': round(soak_s, 2),
         'config': {'workload': WORKLOAD, 'global_batch': world * BATCH,
                    'parallelism': 'images sharded over %d GPU(s), no data-path collective' % world,
                    'l2': 'inputs rotate over %d sets (%.0f MB) and every step streams >2 GB of '
@@ -347,28 +636,76 @@ def run_gpu(args):
                               'biases, bilinear transposed convs)'},
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': C * C * 8, 'ms_per_step': e2e_s / args.steps * 1e3,
-                'api': "BayesFusion.score({'rgb','depth','labels'}) on pinned host arrays",
+                'api': "BayesFusion.score({'rgb','depth','labels'}) on pinned host arrays, one "
+                       "call per batch of 16",
+                'dataset_call': {'value': world * BATCH * args.steps / ds_s,
+                                 'frames_per_call': world * BATCH * args.steps,
+                                 'note': 'ONE score() call over steps x 16 frames per GPU, '
+                                         'batchsize 16 (base_model.py:294-313)'},
                 'raw_dtype_inputs': {'value': world * BATCH * args.steps / raw_s,
+                                     'dataset_call': world * BATCH * args.steps / raw_ds_s,
                                      'h2d_bytes_per_step': raw_bytes,
                                      'note': 'uint8 rgb + uint16 depth + int32 labels, cast on '
                                              'the device; same confusion matrix'}},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                     'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic,
+                     'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                     'peak_burst': peak_tf_burst, 'frac_burst': achieved / peak_tf_burst,
+                     'traffic': traffic,
+                     'traffic_source': 'static: ncu --set full capture summarised in '
+                                       'profiles/roofline_traffic.json (not measured in this run)',
                      'kernel': 'conv_igemm_kernel (all %d tcgen05 conv launches of the timed '
                                'region)' % conv_launches,
                      'flops_per_step': conv_flops / args.steps,
                      'kernel_ms_per_step': conv_ms / args.steps,
                      'kernel_share_of_step': conv_ms / ms,
-                     'peak_source': 'bf16_tflops_sustained, %s' % peak_kind,
+                     'peak_source': 'frac: bf16_tflops_sustained, frac_burst: bf16_tflops; %s'
+                                    % peak_kind,
                      'whole_step_tflops': GFLOP_PER_FRAME * BATCH * args.steps / ms},
     }
+    if sharded_check is not None:
+        line['sharded_check'] = sharded_check
+    line.update(extra)
     if world == 1:
         line['cpu_baseline'] = cpu_baseline(np.random.default_rng(0))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _bind_to_local_numa_node(local_rank):
+    """Pins this rank's host threads to the CPUs of the NUMA node its GPU hangs off (pinned
+    staging buffers are then allocated node-locally by first touch).  Best effort: silently
+    does nothing where sysfs / NVML do not tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = local_rank
+        if visible:
+            ids = [v for v in visible.split(',') if v.strip() != '']
+            if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+                phys = int(ids[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node_path = '/sys/bus/pci/devices/%s/numa_node' % bus[-12:].lower()
+        node = int(open(node_path).read().strip())
+        if node < 0:
+            return None
+        cpus = open('/sys/devices/system/node/node%d/cpulist' % node).read().strip()
+        ids = set()
+        for part in cpus.split(','):
+            lo, _, hi = part.partition('-')
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
 
 
 def main():
@@ -377,6 +714,10 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--soak', type=float, default=2.0,
+                    help='seconds of untimed steps before the timed region')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the secondary workloads (fusion kernels, configs[2] and [4])')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -40,29 +40,6 @@ const char* xv_last_error(void);
 int xv_init(int device);
 int xv_device_sm_count(int* out);
 
-/* ---- measurement hooks (no reference counterpart; used by bench.py) ------------------ */
-/* Debug switches for parity tests: bit0 = never fuse max pooling into the conv epilogue,
- * bit1 = never use the transposed-role conv kernel, bit2 = conv1_1 through a materialised
- * operand buffer instead of in-kernel packing, bit3 = weight gradients on the CUDA cores instead
- * of the tensor-core kernel, bit4 = use the 2-CTA weight-multicast conv kernel, bit5 = conv1_1
- * with global loads in the operand packers instead of TMA-staged input patches, bit6 = 3x3
- * convolutions load nine shifted tiles per channel chunk instead of three patch copies,
- * bit7 = single-CTA MMAs for the Cout >= 256 layers instead of the CTA-pair (cta_group::2)
- * kernel.  0 = production behaviour. */
-int xv_set_debug_flags(int flags);
-/* Number of kernels this library has launched since it was loaded. */
-int xv_launch_count(int64_t* out);
-/* on != 0: bracket every tensor-core convolution launch with CUDA events on its stream;
- * on == 0: stop.  Either call discards the samples collected so far. */
-int xv_profile_enable(int on);
-/* Sum over the collected samples: device milliseconds, algorithmic FLOPs (2*MACs), launches. */
-int xv_profile_read(double* ms_out, double* flops_out, int64_t* launches_out);
-
-/* Times `iters` launches of one tensor-core convolution layer on synthetic bf16 data
- * (kernel study only; `flags` selects timing experiments, 0 = the production kernel). */
-int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters, int flags,
-                        float* ms_out);
-
 /* ---- plain memory / stream helpers (session feed/fetch, base_model.py:263-313) ----- */
 int xv_malloc(void** out, size_t bytes);
 int xv_free(void* p);
@@ -126,6 +103,11 @@ int xv_fcn_create(xv_fcn** out, int cin, int num_units, int num_classes, int bat
  * modality (role XV_ROLE_ENCODER) plus one head handle (role XV_ROLE_HEAD, head_cin = 512 * number
  * of towers) that owns score_conv4/5 on the channel-concatenated conv4_3 / conv5_3, the bilinear
  * transposed convolutions and the final score layer. */
+/* `batchnorm` of xv_fcn_create / xv_fcn_create_ex: 0 = none, 1 = every layer (simple_fcn.py
+ * batchnorm=True), XV_BN_DECODER = only the decoder's "upscore" and "score" layers: fusion_fcn.py:39
+ * calls decoder() with its default batchnorm=True (simple_fcn.py:91) although towers and heads
+ * are built without batch norm. */
+#define XV_BN_DECODER 2
 #define XV_ROLE_EXPERT 0
 #define XV_ROLE_ENCODER 1
 #define XV_ROLE_HEAD 2
@@ -179,12 +161,33 @@ int xv_fcn_param_span(xv_fcn* net, const char* name, int64_t* offset_out, int64_
 int xv_fcn_train_gradients(xv_fcn* net, const float* x, const int32_t* labels, int n, int h, int w,
                            int train_encoder, int normalize, float* grads, double* loss_out,
                            void* stream);
+/* Same, for data-parallel training with the gradient all-reduce overlapping the backward pass:
+ * the flat gradient is cut into xv_fcn_grad_buckets() contiguous buckets; bucket_events_host[i]
+ * (a cudaEvent_t, may be NULL) is recorded on `stream` as soon as the i-th bucket IN COMPLETION
+ * ORDER is final - event i covers the flat range [offsets[nb-1-i], offsets[nb-i]) - so the caller
+ * can start that bucket's all-reduce on another stream while the rest of the backward pass runs.
+ * normalize must be 0 (scale with xv_scale_by_count after the all-reduce). */
+int xv_fcn_train_gradients_ex(xv_fcn* net, const float* x, const int32_t* labels, int n, int h,
+                              int w, int train_encoder, int normalize, float* grads,
+                              double* loss_out, void* const* bucket_events_host, int num_events,
+                              void* stream);
+/* offsets_out[0..nb] (ascending, offsets_out[nb] = num_params) of the nb gradient buckets. */
+int xv_fcn_grad_buckets(xv_fcn* net, int64_t* offsets_out, int capacity, int* num_buckets_out);
 /* grads *= 1 / (1e-20 + loss[1]) (after summing un-normalised gradients and counts over ranks). */
 int xv_scale_by_count(float* grads, int64_t n, const double* loss, void* stream);
 /* One Adam step (lr_t = lr sqrt(1-beta2^t)/(1-beta1^t)) on the master parameters followed by a
  * refresh of the bf16 operand copies used by the forward and data-gradient kernels. */
 int xv_fcn_adam_step(xv_fcn* net, const float* grads, float learning_rate, float beta1,
                      float beta2, float epsilon, void* stream);
+/* One step of the trainer named by config['trainer'] (base_model.py:157-162) with the TensorFlow
+ * 1.x defaults: XV_OPT_ADAM (beta1 .9, beta2 .999, eps 1e-8), XV_OPT_ADAGRAD (accumulator starts
+ * at 0.1), XV_OPT_RMSPROP (decay .9, momentum 0, eps 1e-10, mean square starts at 1); then the
+ * same refresh of the bf16 operand copies.  Switching kinds re-initialises the slots. */
+#define XV_OPT_ADAM 0
+#define XV_OPT_ADAGRAD 1
+#define XV_OPT_RMSPROP 2
+int xv_fcn_optimizer_step(xv_fcn* net, const float* grads, int kind, float learning_rate,
+                          void* stream);
 /* Current master parameters (flat) to the host; synchronous. */
 int xv_fcn_get_params_host(xv_fcn* net, float* out_host, int64_t capacity, void* stream);
 int xv_fcn_train_end(xv_fcn* net);

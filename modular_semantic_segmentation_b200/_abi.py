@@ -77,6 +77,9 @@ PROTOTYPES = {
     'xv_fcn_train_begin': [_P, C.POINTER(_L)],
     'xv_fcn_param_span': [_P, C.c_char_p, C.POINTER(_L), C.POINTER(_L)],
     'xv_fcn_train_gradients': [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    'xv_fcn_train_gradients_ex': [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _PP, _I, _P],
+    'xv_fcn_grad_buckets': [_P, C.POINTER(_L), _I, C.POINTER(_I)],
+    'xv_fcn_optimizer_step': [_P, _P, _I, C.c_float, _P],
     'xv_scale_by_count': [_P, _L, _P, _P],
     'xv_fcn_adam_step': [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P],
     'xv_fcn_get_params_host': [_P, _P, _L, _P],

@@ -33,7 +33,7 @@ struct IgemmSample {
 static bool g_profile = false;
 static std::vector<IgemmSample> g_samples;
 
-static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients, bit4: use the 2-CTA weight-multicast kernel
+static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients
 
 static DeviceInfo g_dev;
 const DeviceInfo& device_info() { return g_dev; }
@@ -178,7 +178,9 @@ int bn_factors_of(xv_fcn* net, const std::string& layer, int cout, bool enabled,
 
 static int bn_factors(xv_fcn* net, const std::string& layer, int cout, std::vector<float>* scale,
                       std::vector<float>* shift) {
-  return bn_factors_of(net, layer, cout, net->batchnorm != 0, scale, shift);
+  const bool decoder_layer = layer == "score" || layer == "upscore";
+  return bn_factors_of(net, layer, cout, decoder_layer ? net->bn_decoder() : net->bn_all(), scale,
+                       shift);
 }
 
 static inline uint16_t f2bf(float f) {
@@ -293,7 +295,7 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
   // halo variant (debug bit6 selects the nine-shifted-tiles one): three (th + 2) x tw patch copies
-  p.halo = (L.taps == 9 && !out_f32 && !(g_debug_flags & (64 | 16)) && (p.tw == 8 || p.tw == 16) &&
+  p.halo = (L.taps == 9 && !out_f32 && !(g_debug_flags & 64) && (p.tw == 8 || p.tw == 16) &&
             (p.th + 2) * p.tw * 128 <= 20480)
                ? 1
                : 0;
@@ -318,15 +320,9 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   p.tiles_y = div_up(H, p.th);
   p.n_blocks = L.cout_pad / L.block_n;
   p.relu = L.relu;
-  // Optional cluster variant (debug bit4): the two CTAs of a pair share each weight tile by TMA
-  // multicast.  Measured gain on B200 is only 1-2 % - the Cout >= 256 layers are bound by shared-
-  // memory bandwidth (TMA fill + MMA operand reads), not by L2 traffic - so it is off by default.
-  const bool mc = (L.block_n == 256 && !out_f32 && (g_debug_flags & 16));
-  if (mc) XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
   auto launch = [&]() -> int {
     if (pair) return launch_conv_igemm_2cta(p, 256, s);
-    return mc ? launch_conv_igemm_mc(p, L.taps, s)
-              : launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
+    return launch_conv_igemm(p, L.block_n, L.taps, out_f32, s);
   };
   if (!g_profile) return launch();
   IgemmSample smp;
@@ -724,7 +720,7 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
                                  static_cast<const float*>(net->g4.p),
                                  static_cast<float*>(fused.p), s5.B, s5.H, s5.W, nu, s,
                                  training ? static_cast<float*>(up5.p) : nullptr));
-  } else if (!net->batchnorm) {
+  } else if (!net->bn_all()) {
     if (!dry)
       XV_TRY(launch_deconv_f32(static_cast<const float*>(s5.p),
                                static_cast<const float*>(net->w_up5.p),
@@ -800,7 +796,7 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
   // 1x1 score -> softmax -> argmax (simple_fcn.py:129-133, basic_fusion_model.py:21-22)
   Act up = make("upscore", DType::F32, B, Hf, Wf, nu);
   Act sc;
-  const bool bn = net->batchnorm != 0;
+  const bool bn = net->bn_decoder();
   if (!dry) {
     XV_TRY(launch_deconv_f32(static_cast<const float*>(feat.p),
                              static_cast<const float*>(net->w_up.p), static_cast<float*>(up.p), B,
@@ -1100,8 +1096,7 @@ int xv_fcn_finalize(xv_fcn* net) {
     L->cin = ci;
     L->cout = co;
     L->relu = relu;
-    XV_TRY(pack_conv(net, L.get(), w->data.data(), b->data.data(), scale, shift,
-                     net->batchnorm != 0));
+    XV_TRY(pack_conv(net, L.get(), w->data.data(), b->data.data(), scale, shift, net->bn_all()));
     net->convs.push_back(std::move(L));
     return 0;
   };
@@ -1132,7 +1127,7 @@ int xv_fcn_finalize(xv_fcn* net) {
     L->relu = 0;
     XV_TRY(L->w_f32.upload(w->data));
     XV_TRY(L->bias_f32.upload(b->data));
-    L->has_bn = net->batchnorm != 0;
+    L->has_bn = net->bn_decoder();
     if (L->has_bn) {
       XV_TRY(L->bn_scale.upload(scale));
       XV_TRY(L->bn_shift.upload(shift));
@@ -1146,10 +1141,12 @@ int xv_fcn_finalize(xv_fcn* net) {
   XV_TRY(get_param(net, "upscore/kernel", {16, 16, nu, nu}, &w16));
   XV_TRY(net->w_up5.upload(w5->data));
   XV_TRY(net->w_up.upload(w16->data));
-  if (net->batchnorm) {
+  if (net->bn_all()) {
     XV_TRY(bn_factors(net, "upscore_conv5", nu, &scale, &shift));
     XV_TRY(net->up5_scale.upload(scale));
     XV_TRY(net->up5_shift.upload(shift));
+  }
+  if (net->bn_decoder()) {
     XV_TRY(bn_factors(net, "upscore", nu, &scale, &shift));
     XV_TRY(net->up_scale.upload(scale));
     XV_TRY(net->up_shift.upload(shift));
@@ -1157,15 +1154,15 @@ int xv_fcn_finalize(xv_fcn* net) {
   // Fast decoder paths exist in the bf16 production mode only; the fp32 validation mode keeps
   // the reference op order (dense transposed convolutions).
   net->fast_up5 = net->fast_up = false;
-  if (net->precision == XV_PRECISION_BF16 && !net->batchnorm) {
-    if (deconv_is_diagonal(*w5, 4, nu)) {
+  if (net->precision == XV_PRECISION_BF16) {
+    if (!net->bn_all() && deconv_is_diagonal(*w5, 4, nu)) {
       std::vector<float> g(16 * nu);
       for (int t = 0; t < 16; ++t)
         for (int u = 0; u < nu; ++u) g[t * nu + u] = w5->data[(static_cast<size_t>(t) * nu + u) * nu + u];
       XV_TRY(net->g4.upload(g));
       net->fast_up5 = true;
     }
-    if (deconv_is_diagonal(*w16, 16, nu)) {
+    if (!net->bn_decoder() && deconv_is_diagonal(*w16, 16, nu)) {
       // the 1x1 score conv commutes with the upsampling only if every channel shares one
       // non-negative 16x16 kernel (then ReLU after it is the identity on non-negative input)
       bool shared = true;
@@ -1382,18 +1379,6 @@ int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters
     *ms_out = ms1 / iters;
     return 0;
   }
-  if ((flags & 2048) && L.block_n == 256) {
-    XV_TRY(make_tmap_w(&p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 128));
-    XV_TRY(launch_conv_igemm_mc(p, L.taps, 0));
-    XV_CUDA(cudaEventRecord(e0, 0));
-    for (int i = 0; i < iters; ++i) XV_TRY(launch_conv_igemm_mc(p, L.taps, 0));
-    XV_CUDA(cudaEventRecord(e1, 0));
-    XV_CUDA(cudaEventSynchronize(e1));
-    float ms2 = 0.f;
-    XV_CUDA(cudaEventElapsedTime(&ms2, e0, e1));
-    *ms_out = ms2 / iters;
-    return 0;
-  }
   const bool use_t = (flags & 512) != 0 && L.use_t;
   const bool t_pool = (flags & 1024) != 0;
   // flag 16384 (with 8192): CTA-pair kernel
@@ -1557,6 +1542,11 @@ struct TrainState {
   DevBuf master, m, v;               // fp32 flat
   DevBuf loss;                       // double[2]: sum of -log p, #valid pixels
   int64_t step = 0;
+  int opt_kind = XV_OPT_ADAM;        // whose slot values m / v currently hold
+  // gradient buckets for the overlapped all-reduce: suffixes of the flat vector in the order
+  // the backward pass completes them (conv5_x + heads, conv4_x, conv3_x, conv1_x + conv2_x)
+  std::vector<size_t> bucket_off;    // ascending offsets, bucket_off.back() == total
+  std::vector<cudaEvent_t> bucket_events;   // set per call, recorded when a bucket is complete
 };
 
 static std::map<xv_fcn*, std::unique_ptr<TrainState>> g_train;
@@ -1706,6 +1696,13 @@ struct Backward {
     return run_igemm(net, *tl->bwd, dpre16.p, y.B, y.H, y.W, dx->p, false, s);
   }
 
+  // bucket b of the flat gradient is final: record the caller's event for it (if any)
+  int bucket_done(int b) {
+    if (dry || b >= static_cast<int>(ts->bucket_events.size()) || !ts->bucket_events[b]) return 0;
+    XV_CUDA(cudaEventRecord(ts->bucket_events[b], s));
+    return 0;
+  }
+
   int run(const float* x, const int32_t* labels, int N, int H, int W, int train_encoder);
 };
 
@@ -1741,7 +1738,10 @@ int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, in
   Act d43a, d53;
   XV_TRY(head_bwd("score_conv4", c43, s4, dfused, &d43a));
   XV_TRY(head_bwd("score_conv5", c53, s5, ds5, &d53));
-  if (!train_encoder) return 0;
+  if (!train_encoder) {
+    for (int b = 0; b < 4; ++b) XV_TRY(bucket_done(b));
+    return 0;
+  }
   // encoder, last layer first
   Act g, dx, dp;
   XV_TRY(relu_bwd("conv5_3", d53, c53, &g));
@@ -1750,18 +1750,21 @@ int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, in
   XV_TRY(conv_bwd("conv5_2", layer("conv5_1"), g, true, &dx));
   XV_TRY(relu_bwd("conv5_1", dx, layer("conv5_1"), &g));
   XV_TRY(conv_bwd("conv5_1", layer("pool4"), g, true, &dp));
+  XV_TRY(bucket_done(0));
   XV_TRY(pool_relu_bwd("conv4_3", dp, c43, layer("pool4"), &d43a, &g));
   XV_TRY(conv_bwd("conv4_3", layer("conv4_2"), g, true, &dx));
   XV_TRY(relu_bwd("conv4_2", dx, layer("conv4_2"), &g));
   XV_TRY(conv_bwd("conv4_2", layer("conv4_1"), g, true, &dx));
   XV_TRY(relu_bwd("conv4_1", dx, layer("conv4_1"), &g));
   XV_TRY(conv_bwd("conv4_1", layer("pool3"), g, true, &dp));
+  XV_TRY(bucket_done(1));
   XV_TRY(pool_relu_bwd("conv3_3", dp, layer("conv3_3"), layer("pool3"), nullptr, &g));
   XV_TRY(conv_bwd("conv3_3", layer("conv3_2"), g, true, &dx));
   XV_TRY(relu_bwd("conv3_2", dx, layer("conv3_2"), &g));
   XV_TRY(conv_bwd("conv3_2", layer("conv3_1"), g, true, &dx));
   XV_TRY(relu_bwd("conv3_1", dx, layer("conv3_1"), &g));
   XV_TRY(conv_bwd("conv3_1", layer("pool2"), g, true, &dp));
+  XV_TRY(bucket_done(2));
   XV_TRY(pool_relu_bwd("conv2_2", dp, layer("conv2_2"), layer("pool2"), nullptr, &g));
   XV_TRY(conv_bwd("conv2_2", layer("conv2_1"), g, true, &dx));
   XV_TRY(relu_bwd("conv2_1", dx, layer("conv2_1"), &g));
@@ -1775,7 +1778,7 @@ int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, in
     XV_TRY(launch_conv_wgrad_c1(x, static_cast<const __nv_bfloat16*>(g.p), grads + t11->w_off, N, H,
                                 W, t11->cin, t11->cout, s));
   }
-  return 0;
+  return bucket_done(3);
 }
 
 }  // namespace xv
@@ -1840,6 +1843,9 @@ int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out) {
     std::copy(w->data.begin(), w->data.end(), flat.begin() + tl.w_off);
     std::copy(b->data.begin(), b->data.end(), flat.begin() + tl.b_off);
   }
+  ts->bucket_off = {0, find_layer(ts.get(), "conv3_1")->w_off,
+                    find_layer(ts.get(), "conv4_1")->w_off,
+                    find_layer(ts.get(), "conv5_1")->w_off, ts->total};
   XV_TRY(ts->master.upload(flat));
   std::vector<float> zeros(ts->total, 0.f);
   XV_TRY(ts->m.upload(zeros));
@@ -1873,12 +1879,38 @@ int xv_fcn_param_span(xv_fcn* net, const char* name, int64_t* offset, int64_t* s
 int xv_fcn_train_gradients(xv_fcn* net, const float* x, const int32_t* labels, int n, int h, int w,
                            int train_encoder, int normalize, float* grads, double* loss_out,
                            void* stream) {
+  return xv_fcn_train_gradients_ex(net, x, labels, n, h, w, train_encoder, normalize, grads,
+                                   loss_out, nullptr, 0, stream);
+}
+
+int xv_fcn_grad_buckets(xv_fcn* net, int64_t* offsets_out, int capacity, int* num_buckets_out) {
+  auto it = g_train.find(net);
+  XV_CHECK(it != g_train.end(), "xv_fcn_grad_buckets: call xv_fcn_train_begin first");
+  const auto& off = it->second->bucket_off;
+  XV_CHECK(offsets_out && num_buckets_out && capacity >= static_cast<int>(off.size()),
+           "xv_fcn_grad_buckets: need room for 5 offsets");
+  for (size_t i = 0; i < off.size(); ++i) offsets_out[i] = static_cast<int64_t>(off[i]);
+  *num_buckets_out = static_cast<int>(off.size()) - 1;
+  return 0;
+}
+
+int xv_fcn_train_gradients_ex(xv_fcn* net, const float* x, const int32_t* labels, int n, int h,
+                              int w, int train_encoder, int normalize, float* grads,
+                              double* loss_out, void* const* bucket_events_host, int num_events,
+                              void* stream) {
   auto it = g_train.find(net);
   XV_CHECK(it != g_train.end(), "xv_fcn_train_gradients: call xv_fcn_train_begin first");
   XV_CHECK(x && labels && grads, "xv_fcn_train_gradients: NULL argument");
   XV_CHECK(n >= 1 && h % 16 == 0 && w % 16 == 0, "H and W must be multiples of 16");
   TrainState* ts = it->second.get();
   cudaStream_t s = XV_STREAM(stream);
+  // events are recorded in completion order: event i <-> flat range
+  // [bucket_off[nb-1-i], bucket_off[nb-i])
+  ts->bucket_events.clear();
+  XV_CHECK(num_events == 0 || (bucket_events_host != nullptr && !normalize),
+           "bucket events need un-normalised gradients (scale after the all-reduce)");
+  for (int i = 0; i < num_events; ++i)
+    ts->bucket_events.push_back(reinterpret_cast<cudaEvent_t>(bucket_events_host[i]));
   xv_fcn_outputs none;
   std::memset(&none, 0, sizeof(none));
   Forward plan{net, Arena(), s, true, 1, nullptr};
@@ -1917,12 +1949,48 @@ int xv_fcn_adam_step(xv_fcn* net, const float* grads, float learning_rate, float
   XV_CHECK(it != g_train.end(), "xv_fcn_adam_step: call xv_fcn_train_begin first");
   TrainState* ts = it->second.get();
   cudaStream_t s = XV_STREAM(stream);
+  if (ts->opt_kind != XV_OPT_ADAM) {
+    XV_TRY(launch_fill_f32(static_cast<float*>(ts->v.p), ts->total, 0.f, s));
+    XV_TRY(launch_fill_f32(static_cast<float*>(ts->m.p), ts->total, 0.f, s));
+    ts->opt_kind = XV_OPT_ADAM;
+    ts->step = 0;
+  }
   ts->step += 1;
   const double t = static_cast<double>(ts->step);
   const float lr_t = static_cast<float>(learning_rate * std::sqrt(1.0 - std::pow(beta2, t)) /
                                         (1.0 - std::pow(beta1, t)));
   XV_TRY(launch_adam(static_cast<float*>(ts->master.p), grads, static_cast<float*>(ts->m.p),
                      static_cast<float*>(ts->v.p), ts->total, lr_t, beta1, beta2, epsilon, s));
+  for (auto& tl : ts->layers) XV_TRY(repack_layer(net, ts, tl, s));
+  return 0;
+}
+
+// One step of trainers[config['trainer']] (base_model.py:157-162) with TensorFlow 1.x defaults.
+int xv_fcn_optimizer_step(xv_fcn* net, const float* grads, int kind, float learning_rate,
+                          void* stream) {
+  if (kind == XV_OPT_ADAM)
+    return xv_fcn_adam_step(net, grads, learning_rate, 0.9f, 0.999f, 1e-8f, stream);
+  auto it = g_train.find(net);
+  XV_CHECK(it != g_train.end(), "xv_fcn_optimizer_step: call xv_fcn_train_begin first");
+  XV_CHECK(kind == XV_OPT_ADAGRAD || kind == XV_OPT_RMSPROP, "unknown optimizer kind");
+  TrainState* ts = it->second.get();
+  cudaStream_t s = XV_STREAM(stream);
+  float* v = static_cast<float*>(ts->v.p);
+  float* m = static_cast<float*>(ts->m.p);
+  if (ts->opt_kind != kind) {
+    // slot initial values: Adagrad accumulator 0.1, RMSProp mean square 1 and momentum 0
+    XV_TRY(launch_fill_f32(v, ts->total, kind == XV_OPT_ADAGRAD ? 0.1f : 1.f, s));
+    XV_TRY(launch_fill_f32(m, ts->total, 0.f, s));
+    ts->opt_kind = kind;
+    ts->step = 0;
+  }
+  ts->step += 1;
+  if (kind == XV_OPT_ADAGRAD)
+    XV_TRY(launch_adagrad(static_cast<float*>(ts->master.p), grads, v, ts->total, learning_rate,
+                          s));
+  else
+    XV_TRY(launch_rmsprop(static_cast<float*>(ts->master.p), grads, v, m, ts->total,
+                          learning_rate, 0.9f, 0.f, 1e-10f, s));
   for (auto& tl : ts->layers) XV_TRY(repack_layer(net, ts, tl, s));
   return 0;
 }

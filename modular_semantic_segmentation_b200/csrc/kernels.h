@@ -53,10 +53,6 @@ int launch_conv_igemm_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t str
 bool conv_c1_patch_fits(int th, int tw, int cin_raw, int* patch_w);
 int launch_conv_c1(const ConvIgemmParams& p, int cin_raw, cudaStream_t stream);
 
-// conv_igemm_mc_sm100.cu: BLOCK_N = 256 with 2-CTA clusters sharing the weight tile by TMA
-// multicast (tmap_w box {64, 128}); bf16 epilogue only.
-int launch_conv_igemm_mc(const ConvIgemmParams& p, int taps, cudaStream_t stream);
-
 // conv_igemm_2cta_sm100.cu: CTA-pair (cta_group::2) 3x3 kernel for Cout multiples of 256, halo
 // operands; tmap_in box {64, tw, th + 2, 1}, tmap_w box {64, 128}, n_blocks = CoutPad / 256.
 int launch_conv_igemm_2cta(const ConvIgemmParams& p, int block_n, cudaStream_t stream);
@@ -223,6 +219,10 @@ int launch_conv_wgrad_c1(const float* x, const __nv_bfloat16* dy, float* dw, int
 int launch_scale_by_count(float* g, size_t n, const double* loss, cudaStream_t s);
 int launch_adam(float* w, const float* g, float* m, float* v, size_t n, float lr_t, float b1,
                 float b2, float eps, cudaStream_t s);
+int launch_adagrad(float* w, const float* g, float* acc, size_t n, float lr, cudaStream_t s);
+int launch_rmsprop(float* w, const float* g, float* ms, float* mom, size_t n, float lr,
+                   float decay, float momentum, float eps, cudaStream_t s);
+int launch_fill_f32(float* x, size_t n, float value, cudaStream_t s);
 int launch_pack_weights(const float* w, __nv_bfloat16* fwd, __nv_bfloat16* bwd, int taps, int cin,
                         int cout, int fwd_kdim, int bwd_kdim, int c1_layout, cudaStream_t s);
 

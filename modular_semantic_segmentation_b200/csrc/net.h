@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/xview_b200.h"
+#include "../../include/xview_b200_measure.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -89,7 +90,13 @@ struct Act {
 using namespace xv;
 
 struct xv_fcn {
-  int cin = 0, nu = 0, C = 0, batchnorm = 0, precision = 0;
+  int cin = 0, nu = 0, C = 0, precision = 0;
+  // bit 0: batch norm on every layer (simple_fcn.py `batchnorm`), bit 1 (XV_BN_DECODER): on the
+  // decoder's upscore / score only - fusion_fcn.py:39 calls decoder() with its default
+  // batchnorm=True while the towers and heads are built without
+  int batchnorm = 0;
+  bool bn_all() const { return (batchnorm & 1) != 0; }
+  bool bn_decoder() const { return (batchnorm & 3) != 0; }
   int arch = 0;        // 0 = VGG16-FCN (simple_fcn.py), 1 = Adapnet (adapnet.py)
   int role = 0;        // 0 = whole expert, 1 = VGG16 encoder only, 2 = head + decoder only
   int head_cin = 512;  // input channels of score_conv4/5 (1024 for the two-tower fusion_fcn head)

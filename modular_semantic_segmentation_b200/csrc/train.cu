@@ -635,6 +635,50 @@ int launch_scale_by_count(float* g, size_t n, const double* loss, cudaStream_t s
   scale_kernel<<<grid_for(n), kThreads, 0, s>>>(g, n, loss);
   XV_LAUNCHED();
 }
+// tf.train.AdagradOptimizer: acc += g^2; w -= lr * g / sqrt(acc)   (acc starts at 0.1)
+__global__ void adagrad_kernel(float* __restrict__ w, const float* __restrict__ g,
+                               float* __restrict__ acc, size_t n, float lr) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float a = acc[i] + gi * gi;
+    acc[i] = a;
+    w[i] -= lr * gi * rsqrtf(a);
+  }
+}
+// tf.train.RMSPropOptimizer: ms = decay * ms + (1 - decay) * g^2;
+// mom = momentum * mom + lr * g / sqrt(ms + eps); w -= mom   (ms starts at 1, mom at 0)
+__global__ void rmsprop_kernel(float* __restrict__ w, const float* __restrict__ g,
+                               float* __restrict__ ms, float* __restrict__ mom, size_t n, float lr,
+                               float decay, float momentum, float eps) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float m2 = decay * ms[i] + (1.f - decay) * gi * gi;
+    ms[i] = m2;
+    const float step = momentum * mom[i] + lr * gi / sqrtf(m2 + eps);
+    mom[i] = step;
+    w[i] -= step;
+  }
+}
+__global__ void fill_f32_kernel(float* __restrict__ x, size_t n, float value) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    x[i] = value;
+}
+int launch_adagrad(float* w, const float* g, float* acc, size_t n, float lr, cudaStream_t s) {
+  adagrad_kernel<<<grid_for(n), kThreads, 0, s>>>(w, g, acc, n, lr);
+  XV_LAUNCHED();
+}
+int launch_rmsprop(float* w, const float* g, float* ms, float* mom, size_t n, float lr,
+                   float decay, float momentum, float eps, cudaStream_t s) {
+  rmsprop_kernel<<<grid_for(n), kThreads, 0, s>>>(w, g, ms, mom, n, lr, decay, momentum, eps);
+  XV_LAUNCHED();
+}
+int launch_fill_f32(float* x, size_t n, float value, cudaStream_t s) {
+  fill_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(x, n, value);
+  XV_LAUNCHED();
+}
 int launch_adam(float* w, const float* g, float* m, float* v, size_t n, float lr_t, float b1,
                 float b2, float eps, cudaStream_t s) {
   adam_kernel<<<grid_for(n), kThreads, 0, s>>>(w, g, m, v, n, lr_t, b1, b2, eps);

@@ -89,6 +89,8 @@ class FcnExpert(object):
         init()
         self.cin, self.num_units, self.num_classes = cin, num_units, num_classes
         self.batchnorm = bool(batchnorm) or arch == 'adapnet'
+        # 'decoder': batch norm on the decoder's upscore / score layers only (fusion_fcn head)
+        bn_flag = 2 if batchnorm == 'decoder' else int(self.batchnorm)
         self.precision = precision
         self.role = role
         self.arch = arch
@@ -98,22 +100,27 @@ class FcnExpert(object):
             call('xv_adapnet_create', C.byref(handle), cin, num_units, num_classes, prec)
         elif arch == 'fcn':
             call('xv_fcn_create_ex', C.byref(handle), cin, num_units, num_classes,
-                 int(self.batchnorm), prec, self.ROLES[role], head_cin)
+                 bn_flag, prec, self.ROLES[role], head_cin)
         else:
             raise ValueError('unknown expert architecture %r' % (arch,))
         self._h = handle
         self._dirty = True
+        self._train_live = False
 
-    def set_param(self, name, array):
+    def set_param(self, name, array, keep_train_state=False):
+        """keep_train_state: the array IS the current device master copy (pulled after
+        training), so the optimizer state stays valid."""
+        live = self._train_live and keep_train_state
         array = np.ascontiguousarray(array, dtype=np.float32)
         shape = (C.c_int64 * array.ndim)(*array.shape)
         call('xv_fcn_set_param_host', self._h, name.encode(), array.ctypes.data_as(C.c_void_p),
              shape, array.ndim)
         self._dirty = True
+        self._train_live = live       # new weights: the optimizer state starts over
 
-    def set_params(self, params):
+    def set_params(self, params, keep_train_state=False):
         for name, array in params.items():
-            self.set_param(name, array)
+            self.set_param(name, array, keep_train_state)
 
     def finalize(self):
         call('xv_fcn_finalize', self._h)
@@ -232,6 +239,7 @@ class FcnExpert(object):
         n = C.c_int64()
         call('xv_fcn_train_begin', self._h, C.byref(n))
         self.num_params = n.value
+        self._train_live = True
         return n.value
 
     def param_span(self, name):
@@ -239,22 +247,51 @@ class FcnExpert(object):
         call('xv_fcn_param_span', self._h, name.encode(), C.byref(off), C.byref(size))
         return off.value, size.value
 
+    def grad_buckets(self):
+        """[(start, stop)] ranges of the flat gradient in the order the backward pass completes
+        them (the ranges the overlapped all-reduce works on)."""
+        offsets = (C.c_int64 * 8)()
+        count = C.c_int()
+        call('xv_fcn_grad_buckets', self._h, offsets, 8, C.byref(count))
+        bounds = [offsets[i] for i in range(count.value + 1)]
+        return [(bounds[i], bounds[i + 1]) for i in range(count.value - 1, -1, -1)]
+
     def train_gradients(self, x, labels, train_encoder=True, normalize=True, grads=None,
-                        loss=None):
+                        loss=None, bucket_events=None):
         """One forward + backward pass.  Returns (grads float32 CUDA [num_params],
-        loss float64 CUDA [2] = {sum of -log p, number of valid pixels})."""
+        loss float64 CUDA [2] = {sum of -log p, number of valid pixels}).  bucket_events: list
+        of torch.cuda.Event, one per grad_buckets() entry, recorded on the current stream as
+        each bucket becomes final (needs normalize=False)."""
         n, h, w, _ = x.shape
         if grads is None:
             grads = torch.empty(self.num_params, dtype=torch.float32, device=x.device)
         if loss is None:
             loss = torch.empty(2, dtype=torch.float64, device=x.device)
-        call('xv_fcn_train_gradients', self._h, ptr(x.contiguous()), ptr(labels.contiguous()), n, h,
-             w, int(train_encoder), int(normalize), ptr(grads), ptr(loss), stream_ptr())
+        if bucket_events:
+            for e in bucket_events:
+                if not e.cuda_event:        # torch creates the handle lazily, on first record
+                    e.record()
+            arr = (C.c_void_p * len(bucket_events))(*[e.cuda_event for e in bucket_events])
+            call('xv_fcn_train_gradients_ex', self._h, ptr(x.contiguous()),
+                 ptr(labels.contiguous()), n, h, w, int(train_encoder), int(normalize),
+                 ptr(grads), ptr(loss), C.cast(arr, C.POINTER(C.c_void_p)), len(bucket_events),
+                 stream_ptr())
+        else:
+            call('xv_fcn_train_gradients', self._h, ptr(x.contiguous()), ptr(labels.contiguous()),
+                 n, h, w, int(train_encoder), int(normalize), ptr(grads), ptr(loss), stream_ptr())
         return grads, loss
 
     def adam_step(self, grads, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8):
         call('xv_fcn_adam_step', self._h, ptr(grads), C.c_float(learning_rate), C.c_float(beta1),
              C.c_float(beta2), C.c_float(epsilon), stream_ptr())
+
+    OPTIMIZERS = {'adam': 0, 'adagrad': 1, 'rmsprop': 2}
+
+    def optimizer_step(self, grads, trainer='adam', learning_rate=1e-4):
+        """One step of tf.train.{Adam,Adagrad,RMSProp}Optimizer with the TF 1.x defaults
+        (base_model.py:157-162)."""
+        call('xv_fcn_optimizer_step', self._h, ptr(grads), self.OPTIMIZERS[trainer],
+             C.c_float(learning_rate), stream_ptr())
 
     def get_params(self):
         """Current master parameters as one flat float32 numpy vector."""

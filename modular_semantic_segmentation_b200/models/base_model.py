@@ -193,10 +193,11 @@ class BaseModel(object):
                     yield {k: v[rows] for k, v in blob.items()}
         return gen_iter()
 
-    def _device_batches(self, data):
+    def _device_batches(self, data, presharded=False):
         """Yields this rank's batches as dicts of CUDA tensors.  Host batches are uploaded on
         a side stream one batch ahead, so the H2D copy of batch i+1 overlaps the kernels of
-        batch i (the reference feeds every sess.run synchronously, base_model.py:308-313)."""
+        batch i (the reference feeds every sess.run synchronously, base_model.py:308-313).
+        presharded: `data` already yields this rank's batches (the training stream)."""
         compute = torch.cuda.current_stream()
         if not hasattr(self, '_copy_stream'):
             self._copy_stream = torch.cuda.Stream()
@@ -224,11 +225,13 @@ class BaseModel(object):
             # `upload_split` = 2 (the default), or the explicit sizes of `upload_pieces`.
             split = int(self.config.get('upload_split', 2))
             explicit = self.config.get('upload_pieces')      # e.g. [4, 12]: sizes of the pieces
-            for blob in self._batches(data):
+            for blob in (data if presharded else self._batches(data)):
                 count = len(next(iter(blob.values())))
                 on_host = not all(isinstance(v, torch.Tensor) and v.is_cuda
                                   for v in blob.values())
-                bounds = upload_bounds(count, split, explicit) if on_host else None
+                # training batches are never cut: a piece would become an optimizer step
+                bounds = (upload_bounds(count, split, explicit)
+                          if on_host and not presharded else None)
                 if bounds is None:
                     yield blob
                     continue
@@ -262,7 +265,10 @@ class BaseModel(object):
             value = crop_multiple(value, batched=True)
             if key == 'labels':
                 if value.dim() == 4:        # one-hot labels of the training pipeline
-                    value = value.argmax(-1)
+                    # an all-zero row is what tf.one_hot builds for negative / void labels
+                    # (base_model.py:198-201): it must stay "ignore", not become class 0
+                    value = torch.where(value.sum(-1) > 0, value.argmax(-1),
+                                        torch.full_like(value[..., 0], -1, dtype=torch.int64))
                 out[key] = value.to(device='cuda', dtype=torch.int32, non_blocking=True)
             elif value.dtype in (torch.uint8, torch.uint16, torch.int16, torch.int32):
                 # raw sensor dtype: copy the narrow values, cast to float32 on the device
@@ -378,17 +384,16 @@ def match_weights(variables, weights, translate_prefix=False, chill_mode=False):
     import_prefix = keys[0].split('/')[0].split('_')[0] if keys else ''
 
     def translate_name(name):
-        if not translate_prefix:
+        """Name under which a variable is looked up in the file when the file was written by a
+        model with another prefix: the text before the first '_' of the variable's scope is
+        swapped for the file's prefix (base_model.py:414-428; 'forest...' scopes are exempt)."""
+        if not translate_prefix or not name.startswith(translate_prefix):
             return name
-        if not name.startswith(translate_prefix):
+        scope, sep, rest = name.partition('/')
+        first, underscore, tail = scope.partition('_')
+        if first == 'forest':
             return name
-        splitted = name.split('/')
-        further_splitted = splitted[0].split('_')
-        if further_splitted[0] == 'forest':
-            return name
-        further_splitted[0] = import_prefix
-        splitted[0] = '_'.join(further_splitted)
-        return '/'.join(splitted)
+        return import_prefix + underscore + tail + sep + rest
 
     assigned, messages = {}, []
     for var_name in variables.keys():

@@ -108,12 +108,18 @@ class BayesFusion(FusionModel):
                 self.modalities.append(key)
                 self.confusion_matrices[key] = np.asarray(matrix).astype('float32').T
         else:
-            # bayes_mix.py:143-147 reads the matrices from stored sacred runs
-            from experiments.utils import ExperimentData
+            # bayes_mix.py:143-147 reads the matrices from stored runs (file layout of
+            # experiments/utils.py:79-104; folder from config['experiment_storage_folder'] or
+            # the XVIEW_EXPERIMENT_STORAGE_FOLDER environment variable).  Unlike the reference,
+            # which leaves self.modalities empty on this path, the keys become the modalities.
+            from ..records import ExperimentData
+            folder = config.get('experiment_storage_folder')
             for key, exp_id in config['eval_experiments'].items():
-                self.confusion_matrices[key] = np.array(
-                    ExperimentData(exp_id).get_record()['info']['confusion_matrix']
-                    ['values']).astype('float32').T
+                self.modalities.append(key)
+                matrix = ExperimentData(exp_id, folder).get_record()['info']['confusion_matrix']
+                if isinstance(matrix, dict):
+                    matrix = matrix['values']
+                self.confusion_matrices[key] = np.array(matrix).astype('float32').T
         FusionModel.__init__(self, 'BayesFusion', output_dir=output_dir, **standard_config)
 
     def _build_graph(self):

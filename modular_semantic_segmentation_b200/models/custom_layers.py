@@ -28,6 +28,31 @@ def glorot_uniform(shape, rng):
     return rng.uniform(-limit, limit, size=shape).astype(np.float32)
 
 
+def softmax(inputs, temperature=1):
+    """custom_layers.py:236-245: temperature-scaled softmax over the last axis of a CUDA float32
+    tensor, on the device (xv_softmax_argmax)."""
+    scaled = inputs / temperature if temperature != 1 else inputs
+    return dev.softmax_argmax(scaled.contiguous(), want_prob=True)[0]
+
+
+def log_softmax(inputs, num_classes=None):
+    """custom_layers.py:222-233 (the DA-RNN form d - log(sum(exp(d))), d = x - max(x)): computed
+    from the device softmax as log(p) where p > 0, exact in the limit the reference takes."""
+    import torch
+    prob = softmax(inputs)
+    shifted = inputs - inputs.max(dim=-1, keepdim=True).values
+    return torch.where(prob > 0, torch.log(prob), shifted)
+
+
+def entropy(x, axis=-1):
+    """custom_layers.py:251-256: normed entropy -sum(x log clip(x, 1e-10, 1)) / log(C) of CUDA
+    float32 probabilities, through the MC-moments kernel (one "sample": the entropy of its
+    mean is the entropy of x)."""
+    if axis not in (-1, x.dim() - 1):
+        x = x.movedim(axis, -1)
+    return dev.mc_moments(x.contiguous().unsqueeze(0), want=('entropy',))['entropy']
+
+
 def conv2d(inputs, kernel, bias=None, activation=True, precision='bf16'):
     """custom_layers.py:124-139 (no batch norm): CUDA float32 NHWC in / out."""
     return dev.conv2d(inputs, kernel, bias, relu=activation, precision=precision)

@@ -66,9 +66,13 @@ class DirichletFusion(BaseModel):
         self.modalities = config['modalities']
         if 'measurement_exp' in config or 'dirichlet_params' in config:
             if 'measurement_exp' in config:
-                from experiments.utils import ExperimentData
-                measurements = np.load(ExperimentData(config["measurement_exp"])
-                                       .get_artifact("counts.npz"))
+                # dirichlet_mix.py:62-64: the fit stored by a measurement run (counts.npz)
+                import io
+                from ..records import ExperimentData
+                stored = ExperimentData(config['measurement_exp'],
+                                        config.get('experiment_storage_folder'))
+                with stored.get_artifact('counts.npz') as f:
+                    measurements = dict(np.load(io.BytesIO(f.read())))
             else:
                 measurements = config['dirichlet_params']
             self.dirichlet_params = {m: np.asarray(measurements[m]).astype('float32')
@@ -149,22 +153,24 @@ class DirichletFusion(BaseModel):
         """dirichlet_mix.py:207-257 (host, float64)."""
         num_classes = self.config['num_classes']
 
-        def dirichlet_em(measurements):
-            params = np.ones((num_classes, num_classes)).astype('float64')
-            for c in range(num_classes):
-                if class_counts[c] == 0:
-                    params[:, c] = np.ones(num_classes)
-                    continue
-                ss = (measurements[c, :] / class_counts[c]).astype('float64')
-                neg_ss = (measurements.sum(0) - measurements[c, :]) / \
-                    (class_counts.sum() - class_counts[c])
-                prior = np.ones((num_classes)).astype('float64')
-                params[:, c] = findDirichletPriors(ss, neg_ss, prior, max_iter=10000,
-                                                   delta=self.config['delta'],
-                                                   beta=self.config['beta'])
-            return params
+        total_count = class_counts.sum()
 
-        self.dirichlet_params = {m: dirichlet_em(counts[m]) for m in self.modalities}
+        def fit_columns(log_sums):
+            """Column c = concentration parameters of the expert's output given ground-truth
+            class c: maximum of the regularised likelihood of dirichletDifferentiation.py with
+            the mean log-probability inside the class as the statistic and the mean over all
+            other classes as the negative statistic.  Classes never seen keep alpha = 1."""
+            alpha = np.ones((num_classes, num_classes), np.float64)
+            everything = log_sums.sum(0)
+            for c in np.flatnonzero(np.asarray(class_counts) != 0):
+                inside = np.asarray(log_sums[c, :] / class_counts[c], np.float64)
+                outside = (everything - log_sums[c, :]) / (total_count - class_counts[c])
+                alpha[:, c] = findDirichletPriors(inside, outside, np.ones(num_classes, np.float64),
+                                                  max_iter=10000, delta=self.config['delta'],
+                                                  beta=self.config['beta'])
+            return alpha
+
+        self.dirichlet_params = {m: fit_columns(counts[m]) for m in self.modalities}
         self.class_counts = class_counts
         self._build_graph()
 

@@ -31,6 +31,14 @@ def init_fusion_fcn_variables(prefixes, num_channels, num_units, num_classes, rn
     v['fused/upscore/kernel'] = bilinear_filter_initializer((16, 16, num_units, num_units))
     v['fused/score/kernel'] = glorot_uniform((1, 1, num_units, num_classes), rng)
     v['fused/score/bias'] = np.zeros(num_classes, np.float32)
+    # fusion_fcn.py:39 calls decoder() without a batchnorm argument and decoder defaults to
+    # batchnorm=True (simple_fcn.py:91): `fused/upscore` is deconv -> BN -> ReLU and
+    # `fused/score` is conv -> BN, each with the four tf.layers.batch_normalization variables
+    for scope, channels in (('fused/upscore', num_units), ('fused/score', num_classes)):
+        v[scope + '/gamma'] = np.ones(channels, np.float32)
+        v[scope + '/beta'] = np.zeros(channels, np.float32)
+        v[scope + '/moving_mean'] = np.zeros(channels, np.float32)
+        v[scope + '/moving_variance'] = np.ones(channels, np.float32)
     return v
 
 
@@ -43,7 +51,7 @@ class _FusionFcnDevice(object):
             (m, dev.FcnExpert(num_channels[m], num_units, num_classes, precision=precision,
                               role='encoder')) for m in self.prefixes)
         self.head = dev.FcnExpert(1, num_units, num_classes, precision=precision, role='head',
-                                  head_cin=512 * len(self.prefixes))
+                                  head_cin=512 * len(self.prefixes), batchnorm='decoder')
 
     def set_variables(self, variables):
         for m, prefix in self.prefixes.items():
@@ -60,6 +68,9 @@ class _FusionFcnDevice(object):
             'upscore/kernel': variables['fused/upscore/kernel'],
             'score/kernel': variables['fused/score/kernel'],
             'score/bias': variables['fused/score/bias']})
+        self.head.set_params({'%s/%s' % (scope, leaf): variables['fused/%s/%s' % (scope, leaf)]
+                              for scope in ('upscore', 'score')
+                              for leaf in ('gamma', 'beta', 'moving_mean', 'moving_variance')})
 
     def forward(self, inputs, want=('label',), label_dtype=torch.int64):
         for m in self.prefixes:

@@ -136,57 +136,73 @@ class SimpleFCN(BaseModel):
             if empty:
                 raise UserWarning('ERROR: empty training dataset')
 
+    def make_trainer(self):
+        """The training step of this model as an object (fit() drives it; bench.py times it)."""
+        return Trainer(self)
+
     def fit(self, dataset, iterations, output=True, validation_dataset=None,
             validation_interval=100, additional_eval_datasets={}):
-        """base_model.py:179-261: `iterations` Adam steps (trainer / learning_rate from the
-        config, tf defaults beta1=0.9, beta2=0.999, eps=1e-8) on the cross-entropy of
-        simple_fcn.py:205-215.  With torch.distributed initialised every rank trains on its
-        share of each batch and the gradients are summed over ranks (one bucketed all-reduce
-        of the flat gradient vector) before the shared Adam step."""
-        from .. import sharding
-        if self.config.get('trainer', 'adam') != 'adam':
-            raise UserWarning('ERROR: only the adam trainer is available on the B200 path')
+        """base_model.py:179-261: `iterations` steps of config['trainer'] ('adam' | 'adagrad' |
+        'rmsprop', TensorFlow 1.x defaults, base_model.py:157-162) at config['learning_rate'] on
+        the cross-entropy of simple_fcn.py:205-215.  Every `validation_interval` steps the
+        validation set is scored and `loss`, `accuracy`, `IoU` (plus the mean IoU of every
+        `additional_eval_datasets` entry) are appended to `<output_dir>/summaries.jsonl` - the
+        TensorBoard summaries of base_model.py:191-251 without TensorFlow.  Batches are uploaded
+        one step ahead on a copy stream.  With torch.distributed initialised every rank trains
+        on its share of each batch; the gradient buckets are all-reduced over NCCL while the
+        backward pass is still running (Trainer.step)."""
+        import json
+        import os
         if self.config['batch_normalization']:
-            raise UserWarning('ERROR: fit() with batch normalisation is not built yet')
-        expert = self._experts[self.prefix]
-        expert.train_begin()
-        lr = float(self.config.get('learning_rate', 0.0001))
-        train_encoder = bool(self.config.get('train_encoder', True))
-        batches = self._training_batches(dataset)
-        grads = loss = None
+            raise UserWarning('ERROR: fit() with batch normalisation is not built on the B200 '
+                              'path (batch statistics in training mode)')
+        trainer = self.make_trainer()
+        batches = self._device_batches(self._training_batches(dataset), presharded=True)
+        summaries = None
+        if self.output_dir is not None:
+            os.makedirs(self.output_dir, exist_ok=True)
+            summaries = open(os.path.join(self.output_dir, 'summaries.jsonl'), 'a')
         print('INFO: Start training')
         self.loss_history = []
-        for i in range(iterations):
-            batch = self._to_device(next(batches))
-            grads, loss = expert.train_gradients(batch[self.modality], batch['labels'],
-                                                 train_encoder=train_encoder, normalize=False,
-                                                 grads=grads, loss=loss)
-            sharding.allreduce_sum_(grads)           # bucketed: one flat tensor
-            sharding.allreduce_sum_(loss)
-            dev.scale_by_count(grads, loss)
-            expert.adam_step(grads, learning_rate=lr)
-            self.global_step += 1
-            if validation_dataset is not None and i % validation_interval == 0:
-                l = loss.cpu().numpy()
-                self.loss_history.append(float(l[0] / (1e-20 + l[1])))
-                self._pull_trained_variables()
-                score, _ = self.score(validation_dataset)
-                if output:
-                    print("{:4d}: accuracy {:.2f}, IoU {:.2f}".format(
-                        i, score['total_accuracy'], score['mean_IoU']))
-                if 'abort_at_iou' in self.config and \
-                        score['mean_IoU'] > self.config['abort_at_iou']:
-                    break
-        if loss is not None:
-            l = loss.cpu().numpy()
-            self.loss = float(l[0] / (1e-20 + l[1]))
-        self._pull_trained_variables()
+        try:
+            for i in range(iterations):
+                trainer.step(next(batches))
+                self.global_step += 1
+                if validation_dataset is not None and i % validation_interval == 0:
+                    record = {'step': i, 'loss': trainer.last_loss()}
+                    self.loss_history.append(record['loss'])
+                    trainer.sync_variables()
+                    score, _ = self.score(validation_dataset)
+                    record['accuracy'] = float(score['total_accuracy'])
+                    record['IoU'] = float(score['mean_IoU'])
+                    for key, extra in additional_eval_datasets.items():
+                        record[key] = float(self.score(extra)[0]['mean_IoU'])
+                    if output:
+                        print("{:4d}: accuracy {:.2f}, IoU {:.2f}".format(
+                            i, score['total_accuracy'], score['mean_IoU']))
+                    if summaries is not None:
+                        summaries.write(json.dumps(record) + '\n')
+                        summaries.flush()
+                    if 'abort_at_iou' in self.config and \
+                            score['mean_IoU'] > self.config['abort_at_iou']:
+                        break
+        finally:
+            if summaries is not None:
+                summaries.close()
+            batches.close()
+        if iterations > 0:
+            self.loss = trainer.last_loss()
+        trainer.close()
         print('INFO: Training finished.')
 
     def _pull_trained_variables(self):
-        """Device master parameters -> self.variables (what export_weights writes)."""
+        """Device master parameters -> self.variables (what export_weights writes) and back into
+        the expert's host-side parameter store, so that a later finalize() / fit() continues
+        from the trained weights (the optimizer state on the device is kept)."""
         expert = self._experts[self.prefix]
         flat = expert.get_params()
+        head = self.prefix + '/'
+        updated = {}
         for name in list(self.variables.keys()):
             below = name.split('/', 1)[1]
             try:
@@ -194,6 +210,8 @@ class SimpleFCN(BaseModel):
             except Exception:
                 continue                               # non-trainable (bilinear kernels)
             self.variables[name] = flat[off:off + size].reshape(self.variables[name].shape).copy()
+            updated[name[len(head):]] = self.variables[name]
+        expert.set_params(updated, keep_train_state=True)
 
     def _run_batch(self, batch, fetch='prediction'):
         expert = self._experts[self.prefix]
@@ -203,3 +221,67 @@ class SimpleFCN(BaseModel):
         if fetch == 'prediction_compact':
             return expert.forward(x, want=('label',), label_dtype=torch.uint8)['label']
         return expert.forward(x, want=(fetch,))[fetch]
+
+
+class Trainer(object):
+    """One optimisation step of SimpleFCN.fit (base_model.py:153-162 + simple_fcn.py:205-215).
+
+    step(batch): forward + backward on this rank's batch (dict of CUDA tensors), sum of the
+    un-normalised gradients and of {loss sum, valid-pixel count} over the ranks, division by the
+    global pixel count, optimizer step.  Data parallel: the flat gradient is cut into the
+    buckets of `FcnExpert.grad_buckets()`; the backward pass records an event as each bucket
+    becomes final and the bucket's NCCL all-reduce is issued on a communication stream right
+    away, so that only the last (smallest) bucket's reduction is exposed."""
+
+    def __init__(self, model):
+        from .. import sharding
+        self.model = model
+        self.expert = model._experts[model.prefix]
+        self.trainer = model.config.get('trainer', 'adam')
+        if self.trainer not in dev.FcnExpert.OPTIMIZERS:
+            raise UserWarning('ERROR: unknown trainer %r' % (self.trainer,))
+        self.learning_rate = float(model.config.get('learning_rate', 0.0001))
+        self.train_encoder = bool(model.config.get('train_encoder', True))
+        if not self.expert._train_live:        # a second fit() continues: state is kept
+            self.expert.train_begin()
+        self.dist = sharding.dist_or_none()
+        self.grads = self.loss = None
+        self.buckets = self.events = self.comm = None
+        if self.dist is not None and model.config.get('overlap_allreduce', True):
+            self.buckets = self.expert.grad_buckets()
+            self.events = [torch.cuda.Event() for _ in self.buckets]
+            self.comm = torch.cuda.Stream()
+
+    def step(self, batch):
+        from .. import sharding
+        model = self.model
+        x, labels = batch[model.modality], batch['labels']
+        self.grads, self.loss = self.expert.train_gradients(
+            x, labels, train_encoder=self.train_encoder, normalize=False, grads=self.grads,
+            loss=self.loss, bucket_events=self.events)
+        if self.dist is not None:
+            compute = torch.cuda.current_stream()
+            if self.events is None:
+                sharding.allreduce_sum_(self.grads)          # one flat bucket, not overlapped
+                sharding.allreduce_sum_(self.loss)
+            else:
+                with torch.cuda.stream(self.comm):
+                    for (start, stop), event in zip(self.buckets, self.events):
+                        self.comm.wait_event(event)
+                        self.dist.all_reduce(self.grads[start:stop])
+                    self.comm.wait_stream(compute)           # the loss is written last
+                    self.dist.all_reduce(self.loss)
+                compute.wait_stream(self.comm)
+        dev.scale_by_count(self.grads, self.loss)
+        self.expert.optimizer_step(self.grads, self.trainer, self.learning_rate)
+
+    def last_loss(self):
+        """Mean cross-entropy over the valid pixels of the last step (all ranks)."""
+        l = self.loss.cpu().numpy()
+        return float(l[0] / (1e-20 + l[1]))
+
+    def sync_variables(self):
+        self.model._pull_trained_variables()
+
+    def close(self):
+        self.sync_variables()

@@ -48,12 +48,30 @@ def encode_array(array):
     return {'py/object': 'numpy.ndarray', 'dtype': str(array.dtype), 'values': array.tolist()}
 
 
+STORAGE_ENV = 'XVIEW_EXPERIMENT_STORAGE_FOLDER'
+
+
+def default_storage_folder():
+    """Where stored experiments live when the caller names no folder: the environment variable
+    XVIEW_EXPERIMENT_STORAGE_FOLDER (the role `settings.EXPERIMENT_STORAGE_FOLDER` plays at
+    experiments/utils.py:76-78)."""
+    folder = os.environ.get(STORAGE_ENV)
+    if not folder:
+        raise UserWarning('ERROR: no experiment storage folder: pass storage_folder or set %s'
+                          % STORAGE_ENV)
+    return folder
+
+
 class ExperimentData(object):
-    """Stored experiment `exp_id` below `storage_folder` (folder `<id>/` or archive `<id>.zip`)."""
+    """Stored experiment `exp_id` below `storage_folder` (folder `<id>/` or archive `<id>.zip`);
+    storage_folder defaults to default_storage_folder(), so `ExperimentData(exp_id)` works as at
+    bayes_mix.py:143-147 / dirichlet_mix.py:60-66."""
 
     _PARTS = (('info', 'info.json'), ('config', 'config.json'))
 
-    def __init__(self, exp_id, storage_folder):
+    def __init__(self, exp_id, storage_folder=None):
+        if storage_folder is None:
+            storage_folder = default_storage_folder()
         exp_id = str(exp_id)
         entries = os.listdir(storage_folder)
         if exp_id in entries:
@@ -152,8 +170,13 @@ def dump_expert_predictions(net_config, data_description, measure_set, test_set,
                 net.import_weights(starting_weights[prefix])
             predictions['measure_%s' % expert] = net.predict(measure_set)
             predictions['test_%s' % expert] = net.predict(test_set)
-    predictions['measure_gt'] = np.asarray(measure_set['labels'])
-    predictions['test_gt'] = np.asarray(test_set['labels'])
+    # predictions are cropped to multiples of 16 (crop_multiple, augmentation.py:244-262): the
+    # ground truths must describe the same pixels
+    from .input_pipeline import crop_multiple
+    predictions['measure_gt'] = np.asarray(crop_multiple(np.asarray(measure_set['labels']),
+                                                         batched=True))
+    predictions['test_gt'] = np.asarray(crop_multiple(np.asarray(test_set['labels']),
+                                                      batched=True))
     os.makedirs(save_to, exist_ok=True)
     outfile = os.path.join(save_to, 'predictions.npz')
     np.savez_compressed(outfile, **predictions)

@@ -281,7 +281,9 @@ def fusion_fcn(inputs, params, prefixes, num_units, num_classes):
     layers['score_conv5'] = conv2d(layers['concat_conv5'], params, 'fused_score_conv5')
     layers['upscore_conv5'] = deconv2d(layers['score_conv5'], params, 'fused_upscore_conv5', 2)
     layers['features'] = layers['score_conv4'] + layers['upscore_conv5']
-    layers.update(decoder(layers['features'], params, 'fused', num_units, num_classes))
+    # fusion_fcn.py:39 passes no batchnorm argument: the decoder's default batchnorm=True applies
+    layers.update(decoder(layers['features'], params, 'fused', num_units, num_classes,
+                          batchnorm=True))
     return layers
 
 
@@ -305,4 +307,14 @@ def fusion_fcn_params(prefixes, channels, num_units, num_classes, rng, gain=1.0,
     params['fused/score/kernel'] = rng.uniform(-limit, limit, size=(1, 1, num_units, num_classes)
                                                ).astype(np.float32)
     params['fused/score/bias'] = (bias_scale * rng.standard_normal(num_classes)).astype(np.float32)
+    # batch-norm variables of the decoder (non-identity statistics unless bias_scale == 0)
+    for scope, channels in (('fused/upscore', num_units), ('fused/score', num_classes)):
+        jitter = 1.0 if bias_scale else 0.0
+        params[scope + '/gamma'] = (1 + 0.2 * jitter * rng.standard_normal(channels)).astype(
+            np.float32)
+        params[scope + '/beta'] = (0.1 * jitter * rng.standard_normal(channels)).astype(np.float32)
+        params[scope + '/moving_mean'] = (0.1 * jitter * rng.standard_normal(channels)).astype(
+            np.float32)
+        params[scope + '/moving_variance'] = (1 + 0.3 * jitter * rng.random(channels)).astype(
+            np.float32)
     return params

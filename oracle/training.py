@@ -74,3 +74,25 @@ def adam_update(params, grads, m, v, step, learning_rate=1e-4, beta1=0.9, beta2=
         params[name] = (params[name] - lr_t * m[name] / (np.sqrt(v[name]) + epsilon)).astype(
             params[name].dtype)
     return params
+
+
+def adagrad_update(params, grads, acc, learning_rate=1e-4, initial_accumulator_value=0.1):
+    """tf.train.AdagradOptimizer (base_model.py:157): acc starts at 0.1; acc += g^2;
+    w -= lr * g / sqrt(acc).  Updates in place."""
+    for name, g in grads.items():
+        acc[name] = acc.get(name, initial_accumulator_value) + g * g
+        params[name] = (params[name] - learning_rate * g / np.sqrt(acc[name])).astype(
+            params[name].dtype)
+    return params
+
+
+def rmsprop_update(params, grads, ms, mom, learning_rate=1e-4, decay=0.9, momentum=0.0,
+                   epsilon=1e-10):
+    """tf.train.RMSPropOptimizer (base_model.py:159), TF 1.x defaults; the mean-square slot
+    starts at ONE: ms = decay*ms + (1-decay)*g^2; mom = momentum*mom + lr*g/sqrt(ms+eps);
+    w -= mom.  Updates in place."""
+    for name, g in grads.items():
+        ms[name] = decay * ms.get(name, 1.0) + (1 - decay) * g * g
+        mom[name] = momentum * mom.get(name, 0.0) + learning_rate * g / np.sqrt(ms[name] + epsilon)
+        params[name] = (params[name] - mom[name]).astype(params[name].dtype)
+    return params

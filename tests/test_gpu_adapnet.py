@@ -58,6 +58,15 @@ def test_adapnet_bf16_tcgen05_matches_oracle(dev, cin, nu, c, h, w):
     params['m/block_0_1/kernel'] = params['m/block_0_1/kernel'] / np.float32(hi)
     net.set_param('block_0_1/kernel', params['m/block_0_1/kernel'])
     ref = oracle.adapnet(x, params, 'm', nu, c)
+    # "trained-like" logits: the random init gives class scores of arbitrary scale; the batch norm
+    # of the last layer is rescaled so that |score| <= 3 and the plain north_star tolerance
+    # (2e-2 abs on the probabilities) is the meaningful bar
+    f = np.float32(min(1.0, 3.0 / np.abs(ref['score']).max()))
+    for leaf in ('gamma', 'beta'):
+        name = 'second_deconvolution_upconv/' + leaf
+        params['m/' + name] = params['m/' + name] * f
+        net.set_param(name, params['m/' + name])
+    ref = oracle.adapnet(x, params, 'm', nu, c)
     out = net.forward(cuda(x), want=('score', 'prob', 'label'))
     for name in LAYERS:
         got = net.layer(name)
@@ -69,8 +78,8 @@ def test_adapnet_bf16_tcgen05_matches_oracle(dev, cin, nu, c, h, w):
             name, float(err.mean() / scale), float(err.max() / scale))
     prob_ref = oracle.softmax(ref['score'])
     prob = out['prob'].cpu().numpy()
-    tol = 2e-2 * max(1.0, np.abs(ref['score']).max() / 4)
-    assert np.abs(prob - prob_ref).max() < tol
+    tol = 2e-2
+    assert np.abs(prob - prob_ref).max() < tol, float(np.abs(prob - prob_ref).max())
     label = out['label'].cpu().numpy()
     margin = np.sort(prob_ref, -1)
     decisive = (margin[..., -1] - margin[..., -2]) > 2 * tol

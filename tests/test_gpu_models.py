@@ -307,3 +307,62 @@ def test_expert_predictions_dump(tmp_path):
         assert archive['measure_rgb'].shape == (3, h, w) and archive['test_depth'].shape == (2, h, w)
         assert archive['measure_rgb'].dtype == np.int64
         np.testing.assert_array_equal(archive['test_gt'], test['labels'])
+
+
+def test_fusion_models_read_stored_experiments(tmp_path, monkeypatch):
+    """bayes_mix.py:143-147 (`eval_experiments`) and dirichlet_mix.py:60-66 (`measurement_exp`):
+    confusion matrices / Dirichlet measurements come from stored runs in the file layout of
+    experiments/utils.py:79-104."""
+    from xview.models import get_model
+    from modular_semantic_segmentation_b200 import records
+    c, n, h, w = 5, 2, 32, 32
+    rng = np.random.default_rng(31)
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    cms = {m: rng.integers(0, 60, size=(c, c)).astype(np.float64) + 150 * np.eye(c)
+           for m in ('rgb', 'depth')}
+    for i, m in enumerate(('rgb', 'depth')):
+        records.write_experiment(str(tmp_path), 100 + i, {'modality': m},
+                                 {'confusion_matrix': cms[m]}, as_zip=bool(i))
+    common = dict(data_description=_description(c), prefixes={'rgb': 'rgb', 'depth': 'depth'},
+                  expert_model='fcn', num_units=NU, num_channels={'rgb': 3, 'depth': 1},
+                  batchsize=2)
+    with get_model('bayes_fusion')(confusion_matrices=cms, **common) as net:
+        _load(net, params)
+        want = net.predict(data)
+    monkeypatch.setenv(records.STORAGE_ENV, str(tmp_path))
+    with get_model('bayes_fusion')(eval_experiments={'rgb': 100, 'depth': 101}, **common) as net:
+        assert net.modalities == ['rgb', 'depth']
+        _load(net, params)
+        np.testing.assert_array_equal(net.predict(data), want)
+    # Dirichlet measurements stored as the counts.npz artifact of a measurement run
+    fit = {m: 1.0 + rng.gamma(2.0, 2.0, size=(c, c)) for m in ('rgb', 'depth')}
+    fit['class_counts'] = rng.integers(10, 1000, size=c).astype(np.float64)
+    folder = records.write_experiment(str(tmp_path), 200, {}, {})
+    np.savez(os.path.join(folder, 'counts.npz'), **fit)
+    dcommon = dict(common, modalities=['rgb', 'depth'])
+    dcommon.pop('prefixes')
+    with get_model('dirichlet_mix')(dirichlet_params=fit, **dcommon) as net:
+        _load(net, params)
+        want = net.predict(data)
+    with get_model('dirichlet_mix')(measurement_exp=200, experiment_storage_folder=str(tmp_path),
+                                    **dcommon) as net:
+        _load(net, params)
+        np.testing.assert_array_equal(net.predict(data), want)
+
+
+def test_custom_layers_softmax_log_softmax_entropy():
+    """custom_layers.py:222-256 on the device against their numpy statements."""
+    from modular_semantic_segmentation_b200.models import custom_layers as cl
+    rng = np.random.default_rng(17)
+    x = rng.normal(0, 3, size=(2, 9, 11, 7)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    ref = oracle.softmax(x)
+    np.testing.assert_allclose(cl.softmax(xd).cpu().numpy(), ref, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(cl.softmax(xd, temperature=2.0).cpu().numpy(),
+                               oracle.softmax(x / 2), rtol=2e-6, atol=1e-7)
+    d = x - x.max(-1, keepdims=True)
+    np.testing.assert_allclose(cl.log_softmax(xd, 7).cpu().numpy(),
+                               d - np.log(np.exp(d).sum(-1, keepdims=True)), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(cl.entropy(torch.from_numpy(ref).cuda()).cpu().numpy(),
+                               oracle.normed_entropy(ref), rtol=1e-5, atol=1e-6)

@@ -131,3 +131,76 @@ def test_simple_fcn_fit_api(tmp_path):
         net2.import_weights(path, warnings=False)
         np.testing.assert_array_equal(net2.predict({'rgb': data['rgb']}), pred)
         assert net2.global_step == 12
+
+
+@pytest.mark.parametrize('trainer', ['adagrad', 'rmsprop'])
+def test_adagrad_and_rmsprop_steps_follow_the_oracle(dev, trainer):
+    """base_model.py:157-159: the other two trainers, TensorFlow 1.x defaults.  The device applies
+    its own bf16-path gradient; the update rule itself is checked by replaying the oracle's rule on
+    the device's gradients (tight), the trajectory against autograd gradients (loose)."""
+    from oracle.training import adagrad_update, rmsprop_update
+    rng = np.random.default_rng(21)
+    net, params, x, labels = _setup(dev, rng)
+    total = net.train_begin()
+    lr = 1e-3
+    names = [n for n in params if 'upscore' not in n]
+    spans = {n: net.param_span(n.split('/', 1)[1]) for n in names}
+    flat0 = net.get_params()
+    p_dev = {n: flat0[o:o + s].reshape(params[n].shape).copy() for n, (o, s) in spans.items()}
+    slot_a, slot_b = {}, {}
+    losses = []
+    for step in range(4):
+        grads, loss = net.train_gradients(cuda(x), cuda(labels))
+        l = loss.cpu().numpy()
+        losses.append(l[0] / l[1])
+        g = grads.cpu().numpy()
+        g_dev = {n: g[o:o + s].reshape(params[n].shape) for n, (o, s) in spans.items()}
+        net.optimizer_step(grads, trainer, lr)
+        if trainer == 'adagrad':
+            adagrad_update(p_dev, g_dev, slot_a, learning_rate=lr)
+        else:
+            rmsprop_update(p_dev, g_dev, slot_a, slot_b, learning_rate=lr)
+        flat = net.get_params()
+        for n, (o, s) in spans.items():
+            np.testing.assert_allclose(flat[o:o + s].reshape(params[n].shape), p_dev[n],
+                                       rtol=1e-5, atol=1e-7, err_msg='%s step %d' % (n, step))
+    assert sum(s for _, s in spans.values()) == total
+    assert losses[-1] < losses[0]
+
+
+def test_fit_twice_continues_and_writes_summaries(tmp_path):
+    """A second fit() continues from the trained weights and optimizer state (the reference keeps
+    its session); summaries.jsonl receives loss / accuracy / IoU / additional data sets every
+    validation_interval steps (base_model.py:191-251); one-hot labels with all-zero rows
+    (negative labels through tf.one_hot, base_model.py:198-201) are ignored, not class 0."""
+    import json
+    from xview.models import get_model
+    rng = np.random.default_rng(13)
+    desc = ({'rgb': np.float32, 'labels': np.int32}, {'rgb': (None, None, 3),
+                                                      'labels': (None, None)}, C)
+    labels = rng.integers(-1, C, size=(4, 32, 32)).astype(np.int32)
+    onehot = (labels[..., None] == np.arange(C)).astype(np.int32)      # -1 -> all-zero row
+    data = {'rgb': rng.uniform(0, 1, size=(4, 32, 32, 3)).astype(np.float32), 'labels': labels}
+    data_onehot = {'rgb': data['rgb'], 'labels': onehot}
+    common = dict(num_units=NU, batch_normalization=False, learning_rate=1e-3, batchsize=4, seed=5)
+    with get_model('fcn')('rgb', desc, 'rgb', output_dir=str(tmp_path), **common) as net:
+        net.fit(data, 6, validation_dataset=data, validation_interval=2, output=False,
+                additional_eval_datasets={'extra_set': data})
+        first = {k: v.copy() for k, v in net.variables.items()}
+        loss_6 = net.loss
+        net.fit(data, 6, output=False)
+        assert net.global_step == 12
+        assert net.loss < loss_6
+        twelve = {k: v.copy() for k, v in net.variables.items()}
+    with get_model('fcn')('rgb', desc, 'rgb', **common) as ref:
+        ref.fit(data_onehot, 12, output=False)       # 12 steps in one go, one-hot labels
+        for name in ('rgb/conv3_2/kernel', 'rgb/score/bias'):
+            np.testing.assert_allclose(twelve[name], ref.variables[name], rtol=0,
+                                       atol=1e-6 + 1e-3 * np.abs(ref.variables[name]).max())
+            assert not np.array_equal(first[name], twelve[name])
+    records = [json.loads(line) for line in open(tmp_path / 'summaries.jsonl')]
+    assert [r['step'] for r in records] == [0, 2, 4]
+    assert set(records[0]) == {'step', 'loss', 'accuracy', 'IoU', 'extra_set'}
+    with get_model('fcn')('rgb', desc, 'rgb', trainer='rmsprop', **common) as net:
+        net.fit(data, 3, output=False)
+        assert np.isfinite(net.loss)

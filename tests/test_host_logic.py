@@ -21,8 +21,12 @@ def built_lib():
 
 
 def test_library_exports_every_symbol_of_the_header(built_lib):
-    header = open(os.path.join(ROOT, 'include', 'xview_b200.h')).read()
-    declared = set(re.findall(r'^(?:int|const char\*)\s+(xv_[a-z0-9_]+)\s*\(', header, re.M))
+    declared = set()
+    for name in ('xview_b200.h', 'xview_b200_measure.h'):
+        header = open(os.path.join(ROOT, 'include', name)).read()
+        found = set(re.findall(r'^(?:int|const char\*)\s+(xv_[a-z0-9_]+)\s*\(', header, re.M))
+        assert found, name
+        declared |= found
     assert len(declared) >= 28
     from modular_semantic_segmentation_b200 import _abi
     assert declared == set(_abi.PROTOTYPES), declared ^ set(_abi.PROTOTYPES)
@@ -290,11 +294,12 @@ def test_dump_expert_predictions_layout(tmp_path, monkeypatch):
             self.path = path
 
         def predict(self, data):
-            return (np.asarray(data['labels']) + self.offset).astype(np.int64)
+            # the real models crop every input to multiples of 16 (crop_multiple)
+            return (np.asarray(data['labels'])[:, :16, :16] + self.offset).astype(np.int64)
 
     monkeypatch.setattr(models, 'get_model', lambda name: FakeExpert)
-    measure = {'labels': np.zeros((3, 4, 4), np.int32)}
-    test = {'labels': np.ones((2, 4, 4), np.int32)}
+    measure = {'labels': np.zeros((3, 16, 16), np.int32)}
+    test = {'labels': np.ones((2, 20, 18), np.int32)}
     out = records.dump_expert_predictions(
         {'expert_model': 'fcn', 'prefixes': {'rgb': 'p_rgb', 'depth': 'p_depth'}}, None, measure,
         test, str(tmp_path / 'out'), starting_weights={'p_rgb': 'a.npz', 'p_depth': 'b.npz'})
@@ -302,4 +307,7 @@ def test_dump_expert_predictions_layout(tmp_path, monkeypatch):
         assert sorted(archive.files) == ['measure_depth', 'measure_gt', 'measure_rgb',
                                          'test_depth', 'test_gt', 'test_rgb']
         assert (archive['measure_rgb'] == 1).all() and (archive['test_depth'] == 3).all()
-        np.testing.assert_array_equal(archive['test_gt'], test['labels'])
+        # ground truths are cropped like the predictions (same pixels on both sides)
+        np.testing.assert_array_equal(archive['test_gt'], test['labels'][:, :16, :16])
+        assert archive['test_gt'].shape == archive['test_rgb'].shape
+        np.testing.assert_array_equal(archive['measure_gt'], measure['labels'])
