@@ -211,6 +211,16 @@ int xv_softmax_argmax(const float* score, int64_t npix, int num_classes, float* 
  * labels_host: host array of `num_experts` device pointers; lut: device int32 [C^M]. */
 int xv_bayes_fuse_lut(const void* const* labels_host, int num_experts, int label_bytes,
                       const int32_t* lut, int num_classes, int64_t npix, void* out, void* stream);
+/* One step of BayesFusion.score() behind the experts (basic_fusion_model.py:21-22 argmax,
+ * bayes_mix.py:61-112 decision table, base_model.py:140-151 + :306-311 confusion matrix) as ONE
+ * kernel: takes the low-resolution class scores left by the LAST xv_fcn_forward call of each of
+ * the `num_experts` handles (bilinear decoder fast path), decodes each expert's label per pixel,
+ * looks the fused label up in lut (device int32 [C^M]) and ACCUMULATES the confusion matrix
+ * against gt_labels (device int32 [N,H,W], negative = ignore) into cm (device int64 [C,C]).
+ * fused_out (device uint8 [N,H,W]) may be NULL.  No label map touches HBM otherwise. */
+int xv_bayes_decode_score(xv_fcn* const* experts_host, int num_experts, const int32_t* lut,
+                          int num_classes, const int32_t* gt_labels, int64_t* cm,
+                          uint8_t* fused_out, void* stream);
 /* Literal Bayes fusion, bayes_mix.py:12-58: score = sum_m log_cond[m][l_m][:] + log_prior;
  * log_cond: device [M,C,C] = log(1e-20 + conditional), log_prior: device [C].
  * score (float32 [npix,C]) and label may be NULL. */

@@ -89,6 +89,7 @@ PROTOTYPES = {
     'xv_maxpool2x2': [_P, _I, _I, _I, _I, _P, _P],
     'xv_softmax_argmax': [_P, _L, _I, _P, _P, _I, _P],
     'xv_bayes_fuse_lut': [_PP, _I, _I, _P, _I, _L, _P, _P],
+    'xv_bayes_decode_score': [_PP, _I, _P, _I, _P, _P, _P, _P],
     'xv_bayes_fuse_score': [_PP, _I, _I, _P, _P, _I, _L, _P, _P, _P],
     'xv_dirichlet_fuse': [_PP, _I, _P, _P, _P, _I, _L, _P, _P, _I, _P],
     'xv_dirichlet_fuse_exact': [_PP, _I, _P, _P, _P, _I, _L, C.c_float, C.c_float, _P, _P, _I, _P,

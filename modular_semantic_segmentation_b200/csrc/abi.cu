@@ -105,6 +105,7 @@ static int make_tmap_patch(CUtensorMap* m, const void* ptr, int N, int H, int W,
 // in: bf16 [B,H,W,cin]; out: bf16 [B,H,W,cout] or, with pool, [B,H/2,W/2,cout]
 static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
                        void* out, bool pool, cudaStream_t s);
+static bool pair_kernel_applies(const ConvLayer& L, int H, int W);
 
 static int make_tmap_w(CUtensorMap* m, const void* ptr, int kdim, int cout_pad, int block_n) {
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(cout_pad)};
@@ -286,9 +287,21 @@ int get_tmap_w(xv_fcn* net, CUtensorMap* out, const void* ptr, int kdim, int cou
   return 0;
 }
 
-// in: bf16 [B,H,W,cin_gemm]; out: bf16 [B,H,W,cout] (cout % 64 == 0) or fp32 [B,H,W,cout]
+// Whether run_igemm sends this 3x3 layer to the CTA-pair kernel (the one with the fused pool).
+static bool pair_kernel_applies(const ConvLayer& L, int H, int W) {
+  int th, tw;
+  choose_tile(H, W, &th, &tw);
+  const bool halo = L.taps == 9 && !(g_debug_flags & 64) && (tw == 8 || tw == 16) &&
+                    (th + 2) * tw * 128 <= 20480;
+  return halo && L.block_n == 256 && !L.use_t && !(g_debug_flags & 128);
+}
+
+// in: bf16 [B,H,W,cin_gemm]; out: bf16 [B,H,W,cout] (cout % 64 == 0) or fp32 [B,H,W,cout].
+// pool_mode 1 / 2 (CTA-pair kernel only, see pair_kernel_applies): the epilogue also (2) or only
+// (1, `out` unused) stores the 2x2 max-pooled result into pool_out [B,H/2,W/2,cout].
 static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int H, int W,
-                     void* out, bool out_f32, cudaStream_t s) {
+                     void* out, bool out_f32, cudaStream_t s, void* pool_out = nullptr,
+                     int pool_mode = 0) {
   if (L.use_t && !out_f32 && !(g_debug_flags & 2))
     return run_igemm_t(net, L, in, B, H, W, out, false, s);
   ConvIgemmParams p;
@@ -303,7 +316,14 @@ static int run_igemm(xv_fcn* net, const ConvLayer& L, const void* in, int B, int
   // CTA-pair kernel (cta_group::2) for the 256-wide layers; debug bit7 keeps the single-CTA one
   const bool pair = p.halo && L.block_n == 256 && !(g_debug_flags & 128);
   XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, pair ? 128 : L.block_n));
-  if (!out_f32) {
+  if (pool_mode) {
+    XV_CHECK(pair && pool_out != nullptr, "fused pooling needs the CTA-pair kernel");
+    p.pool_mode = pool_mode;
+    XV_TRY(get_tmap(net, &p.tmap_pool, pool_out, B, H / 2, W / 2, L.cout, p.th / 2, p.tw / 2));
+  }
+  if (!out_f32 && pool_mode == 1) {
+    p.tmap_out = p.tmap_pool;          // never dereferenced in that mode
+  } else if (!out_f32) {
     XV_CHECK(L.cout % 64 == 0, "bf16 epilogue needs Cout % 64 == 0");
     XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, p.th, p.tw));
   } else {
@@ -566,18 +586,30 @@ struct Forward {
     return 0;
   }
 
-  // conv followed by the 2x2 max pool of simple_fcn.py:41,44,48 - fused into the conv epilogue
-  // where the transposed kernel applies (the unpooled activation is then never materialised)
-  int conv_pool(const std::string& name, const std::string& pool_name, const Act& in, Act* out) {
+  // conv followed by the 2x2 max pool of simple_fcn.py:41,44,48,58 - fused into the conv epilogue
+  // of the transposed-role kernel (conv1_2, conv2_2) or of the CTA-pair kernel (conv3_3, conv4_3).
+  // `full_out` == nullptr: the unpooled activation is not needed and, when fused, never
+  // materialised; otherwise it is stored as well (conv4_3 also feeds score_conv4).
+  int conv_pool(const std::string& name, const std::string& pool_name, const Act& in, Act* out,
+                Act* full_out = nullptr) {
     ConvLayer* L = net->conv(name);
     XV_CHECK(L != nullptr, "unknown conv layer " + name);
-    if (bf16() && L->use_t && !(g_debug_flags & 3) && !training) {
+    if (bf16() && L->use_t && !(g_debug_flags & 3) && !training && !full_out) {
       *out = make(pool_name, DType::BF16, in.B, in.H / 2, in.W / 2, L->cout);
       if (dry) return 0;
       return run_igemm_t(net, *L, in.p, in.B, in.H, in.W, out->p, true, s);
     }
+    if (bf16() && !(g_debug_flags & 1) && !training && in.H % 2 == 0 && in.W % 2 == 0 &&
+        pair_kernel_applies(*L, in.H, in.W)) {
+      if (full_out) *full_out = make(name, DType::BF16, in.B, in.H, in.W, L->cout);
+      *out = make(pool_name, DType::BF16, in.B, in.H / 2, in.W / 2, L->cout);
+      if (dry) return 0;
+      return run_igemm(net, *L, in.p, in.B, in.H, in.W, full_out ? full_out->p : nullptr, false, s,
+                       out->p, full_out ? 2 : 1);
+    }
     Act full;
     XV_TRY(conv(name, in, &full));
+    if (full_out) *full_out = full;
     return pool(pool_name, full, out);
   }
 
@@ -661,8 +693,8 @@ int Forward::run_encoder(const float* x, int N, int H, int W, Act* c43_out, Act*
   cur = t;
   XV_TRY(conv("conv3_1", cur, &t));
   XV_TRY(conv("conv3_2", t, &cur));
-  XV_TRY(conv("conv3_3", cur, &t));
-  XV_TRY(pool("pool3", t, &cur));
+  XV_TRY(conv_pool("conv3_3", "pool3", cur, &t));
+  cur = t;
   bool replicated = false;
   if (sites & XV_DROP_POOL3) {
     XV_TRY(dropout("pool3_drop", 0, true, cur, T, &t));
@@ -672,8 +704,8 @@ int Forward::run_encoder(const float* x, int N, int H, int W, Act* c43_out, Act*
   XV_TRY(conv("conv4_1", cur, &t));
   XV_TRY(conv("conv4_2", t, &cur));
   Act c43;
-  XV_TRY(conv("conv4_3", cur, &c43));
-  XV_TRY(pool("pool4", c43, &cur));
+  XV_TRY(conv_pool("conv4_3", "pool4", cur, &t, &c43));
+  cur = t;
   if (sites & XV_DROP_POOL3) {   // sic: simple_fcn.py:61 gates pool4 dropout on 'pool3'
     XV_TRY(dropout("pool4_drop", 1, true, cur, 1, &t));
     cur = t;
@@ -712,7 +744,13 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
   const int nu = net->nu;
   // upscore_conv5 + skip add (simple_fcn.py:82-85)
   fused = make("fused", DType::F32, s4.B, s4.H, s4.W, nu);
-  if (net->fast_up5) {
+  // inference with both bilinear fast paths and no dropout on the features: upscore_conv5 + skip
+  // add + the (moved) 1x1 score conv run as ONE kernel further down
+  const bool head_fused = net->fast_up5 && net->fast_up && !training &&
+                          !(sites & XV_DROP_FEATURES) && head_fused_supported(nu, net->C);
+  if (head_fused) {
+    // launched below, once `low` exists
+  } else if (net->fast_up5) {
     Act up5;
     if (training) up5 = make("upscore_conv5", DType::F32, s4.B, s4.H, s4.W, nu);
     if (!dry)
@@ -767,10 +805,17 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
     const int b_samples = lead ? N0 : B;
     const size_t lead_low = lead ? static_cast<size_t>(N0) * feat.H * feat.W * C : 0;
     if (!dry) {
-      XV_TRY(launch_score_lowres(static_cast<const float*>(feat.p),
+      if (head_fused)
+        XV_TRY(launch_head_fused(static_cast<const float*>(s5.p), static_cast<const float*>(s4.p),
+                                 static_cast<const float*>(net->g4.p),
                                  static_cast<const float*>(net->w_score_nuxc.p),
-                                 static_cast<float*>(low.p),
-                                 static_cast<size_t>(B) * feat.H * feat.W, nu, C, s));
+                                 static_cast<float*>(fused.p), static_cast<float*>(low.p), s5.B,
+                                 s5.H, s5.W, nu, C, s));
+      else
+        XV_TRY(launch_score_lowres(static_cast<const float*>(feat.p),
+                                   static_cast<const float*>(net->w_score_nuxc.p),
+                                   static_cast<float*>(low.p),
+                                   static_cast<size_t>(B) * feat.H * feat.W, nu, C, s));
       if (want_samples) {
         DecodeOut d;
         d.label_u8 = o->label_u8;
@@ -1435,6 +1480,37 @@ int xv_bayes_fuse_score(const void* const* labels, int M, int label_bytes, const
   XV_TRY(check_label_bytes(label_bytes));
   return launch_bayes_score(labels, M, label_bytes, log_cond, log_prior, C, npix, score, label,
                             XV_STREAM(stream));
+}
+
+int xv_bayes_decode_score(xv_fcn* const* experts, int M, const int32_t* lut, int C,
+                          const int32_t* gt_labels, int64_t* cm, uint8_t* fused_out,
+                          void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(experts && lut && gt_labels && cm && M >= 1 && M <= 4,
+           "xv_bayes_decode_score: bad arguments");
+  const float *low[4], *g[4], *bias[4];
+  int N = 0, h = 0, w = 0;
+  for (int m = 0; m < M; ++m) {
+    xv_fcn* e = experts[m];
+    XV_CHECK(e && e->finalized && e->fast_up && e->C == C,
+             "xv_bayes_decode_score: experts need the bilinear decoder fast path and C classes");
+    auto it = e->layers.find("score_lowres");
+    XV_CHECK(it != e->layers.end() && it->second.p != nullptr,
+             "xv_bayes_decode_score: run xv_fcn_forward on every expert first");
+    const Act& a = it->second;
+    if (m == 0) {
+      N = a.B;
+      h = a.H;
+      w = a.W;
+    }
+    XV_CHECK(a.B == N && a.H == h && a.W == w, "xv_bayes_decode_score: expert shapes differ");
+    low[m] = static_cast<const float*>(a.p);
+    g[m] = static_cast<const float*>(e->g16.p);
+    bias[m] = static_cast<const float*>(e->b_score.p);
+  }
+  return launch_decode_bayes_confusion(low, g, bias, M, lut, C, N, h, w, gt_labels,
+                                       reinterpret_cast<long long*>(cm), fused_out,
+                                       XV_STREAM(stream));
 }
 
 int xv_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m1,

@@ -31,14 +31,15 @@ constexpr int kACopies = 3;
 constexpr int kACopyBytes = 20480;                // (8 + 2) x 16 or (16 + 2) x 8 pixel rows
 constexpr int kBStages = 6;
 constexpr int kOutBufBytes = kBlockM * 128;
+constexpr int kPoolBufBytes = (kBlockM / 4) * 128;  // 32 pooled pixels x 64 channels
 constexpr int kThreads = 192;
 // BLOCK_N = output channels per tile pair (256, or 128 / 64 for the narrow layers); every CTA holds
 // BLOCK_N / 2 weight rows of a K block
 template <int BLOCK_N>
 struct PairCfg {
   static constexpr int kBHalfBytes = (BLOCK_N / 2) * 128;
-  static constexpr int kSmemBytes =
-      1024 + kACopies * kACopyBytes + kBStages * kBHalfBytes + 2 * kOutBufBytes + 256;
+  static constexpr int kSmemBytes = 1024 + kACopies * kACopyBytes + kBStages * kBHalfBytes +
+                                    2 * kOutBufBytes + 2 * kPoolBufBytes + 256;
 };
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;    // shared::cluster address -> same offset in CTA 0
 
@@ -127,7 +128,12 @@ __device__ __forceinline__ PairTile decode_pair(const ConvIgemmParams& p, int pt
   return c;
 }
 
-template <int BLOCK_N>
+// POOL: 0 = plain convolution; 1 = only the 2x2 max-pooled output is stored (conv3_3 -> pool3,
+// simple_fcn.py:48); 2 = both the full and the pooled output (conv4_3 feeds score_conv4 AND pool4,
+// simple_fcn.py:58,74).  The pool is taken on the packed bf16 results with two warp shuffles: a
+// warp's 32 TMEM lanes are 4 x 8 or 2 x 16 pixels of the tile, so the 2x2 partners of a pixel are
+// the lanes at xor 1 (x) and xor tw (y).
+template <int BLOCK_N, int POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
   constexpr int kBlockN = BLOCK_N;
@@ -139,7 +145,8 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + kACopies * kACopyBytes;
   uint8_t* smem_out = smem_b + kBStages * kBHalfBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 2 * kOutBufBytes);
+  uint8_t* smem_pool = smem_out + 2 * kOutBufBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pool + 2 * kPoolBufBytes);
   uint64_t* b_full = bars;
   uint64_t* b_empty = b_full + kBStages;
   uint64_t* a_full = b_empty + kBStages;
@@ -163,6 +170,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
     tma_prefetch_desc(&p.tmap_in);
     tma_prefetch_desc(&p.tmap_w);
     tma_prefetch_desc(&p.tmap_out);
+    if (POOL) tma_prefetch_desc(&p.tmap_pool);
     for (int s = 0; s < kBStages; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
@@ -273,6 +281,10 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
     const bool issuer = (threadIdx.x == 64);
     uint32_t acc = 0, acc_phase = 0, gchunk = 0;
     const uint32_t zero2 = 0u;
+    // pooled pixel this thread stores (the even-x, even-y pixel of every 2x2 block keeps it)
+    const int py = row / p.tw, px = row - py * p.tw;
+    const bool keeper = POOL && ((px | py) & 1) == 0;
+    const uint32_t prow = static_cast<uint32_t>((py >> 1) * (p.tw >> 1) + (px >> 1));
     for (int pt = pair_id; pt < total_pairs; pt += num_pairs) {
       const PairTile c = decode_pair(p, pt, rank, kBlockN);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -281,7 +293,8 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
 #pragma unroll 1
       for (int chunk = 0; chunk < kBlockN / 64; ++chunk, ++gchunk) {
         uint8_t* buf = smem_out + (gchunk & 1) * kOutBufBytes;
-        if (issuer) tma_store_wait_read<1>();   // the store that last used `buf` has drained
+        uint8_t* pbuf = smem_pool + (gchunk & 1) * kPoolBufBytes;
+        if (issuer) tma_store_wait_read<1>();   // the store(s) that last used `buf` have drained
         named_bar_sync(1, 128);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -310,15 +323,36 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
               if (p.relu) h = __hmax2(h, *reinterpret_cast<const __nv_bfloat162*>(&zero2));
               packed[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            const int piece = (half * 4 + j) ^ (row & 7);   // 128B swizzle
-            *reinterpret_cast<uint4*>(buf + row * 128 + piece * 16) =
-                make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (POOL != 1) {
+              const int piece = (half * 4 + j) ^ (row & 7);   // 128B swizzle
+              *reinterpret_cast<uint4*>(buf + row * 128 + piece * 16) =
+                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+            if (POOL) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&packed[e]);
+                uint32_t o = __shfl_xor_sync(0xffffffffu, packed[e], 1);
+                v = __hmax2(v, *reinterpret_cast<__nv_bfloat162*>(&o));
+                uint32_t vv = *reinterpret_cast<uint32_t*>(&v);
+                o = __shfl_xor_sync(0xffffffffu, vv, p.tw);
+                v = __hmax2(v, *reinterpret_cast<__nv_bfloat162*>(&o));
+                packed[e] = *reinterpret_cast<uint32_t*>(&v);
+              }
+              if (keeper) {
+                const uint32_t piece = static_cast<uint32_t>(half * 4 + j) ^ (prow & 7);
+                *reinterpret_cast<uint4*>(pbuf + prow * 128 + piece * 16) =
+                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              }
+            }
           }
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer) {
-          tma_store_4d(&p.tmap_out, buf, c.n0 + chunk * 64, c.x0, c.y0, c.img);
+          if (POOL != 1) tma_store_4d(&p.tmap_out, buf, c.n0 + chunk * 64, c.x0, c.y0, c.img);
+          if (POOL)
+            tma_store_4d(&p.tmap_pool, pbuf, c.n0 + chunk * 64, c.x0 >> 1, c.y0 >> 1, c.img);
           tma_store_commit();
         }
       }
@@ -349,10 +383,11 @@ conv_igemm_2cta_kernel(const __grid_constant__ ConvIgemmParams p) {
 }  // namespace
 
 // p.tmap_in box {64, tw, th + 2, 1}; p.tmap_w box {64, BLOCK_N / 2}; p.tmap_out box
-// {64, tw, th, 1}; p.n_blocks = ceil(Cout / BLOCK_N).
-template <int BLOCK_N>
+// {64, tw, th, 1}; p.n_blocks = ceil(Cout / BLOCK_N); p.pool_mode != 0: p.tmap_pool describes the
+// pooled tensor [N, H/2, W/2, Cout] with box {64, tw/2, th/2, 1}.
+template <int BLOCK_N, int POOL = 0>
 static int launch_pair(const ConvIgemmParams& p, cudaStream_t stream) {
-  auto kernel = conv_igemm_2cta_kernel<BLOCK_N>;
+  auto kernel = conv_igemm_2cta_kernel<BLOCK_N, POOL>;
   static bool configured = false;
   if (!configured) {
     XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -374,6 +409,10 @@ int launch_conv_igemm_2cta(const ConvIgemmParams& p, int block_n, cudaStream_t s
                (p.th + 2) * p.tw * 128 <= kACopyBytes,
            "conv_igemm_2cta: needs an 8x16 or 16x8 pixel tile");
   XV_CHECK(p.cin % kBlockK == 0, "conv_igemm_2cta: Cin must be a multiple of 64");
+  XV_CHECK(p.pool_mode == 0 || (block_n == 256 && p.H % 2 == 0 && p.W % 2 == 0),
+           "conv_igemm_2cta: the fused pool needs BLOCK_N = 256 and even H, W");
+  if (block_n == 256 && p.pool_mode == 1) return launch_pair<256, 1>(p, stream);
+  if (block_n == 256 && p.pool_mode == 2) return launch_pair<256, 2>(p, stream);
   if (block_n == 256) return launch_pair<256>(p, stream);
   if (block_n == 128) return launch_pair<128>(p, stream);
   if (block_n == 64) return launch_pair<64>(p, stream);

@@ -40,6 +40,10 @@ struct ConvIgemmParams {
   int patch_w;            // conv_c1_sm100.cu: floats per row of the input patch
   int halo;               // conv_igemm_t: halo variant, tmap_in box {64, 16, 18, 1}
   int w_rows;             // conv_igemm_t: rows of the weight box, 64 (Cout <= 64) or 128
+  // conv_igemm_2cta: fused 2x2 max pool in the epilogue, 1 = pooled output only, 2 = full + pooled;
+  // tmap_pool = pooled tensor [N, H/2, W/2, Cout], box {64, tw/2, th/2, 1}
+  int pool_mode;
+  CUtensorMap tmap_pool;
 };
 int conv_igemm_block_n(int cout);
 int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,
@@ -139,6 +143,11 @@ int launch_upscore2_add(const float* s5, const float* s4, const float* g_4x4xnu,
 int launch_score_lowres(const float* fused, const float* w_nuxc, float* low, size_t npix, int nu,
                         int C, cudaStream_t s);
 
+// both of the above in one pass: fused = s4 + relu(up2(s5)) (written) and low = fused x w
+bool head_fused_supported(int nu, int C);
+int launch_head_fused(const float* s5, const float* s4, const float* g_4x4xnu, const float* w_nuxc,
+                      float* fused, float* low, int N, int h, int w, int nu, int C, cudaStream_t s);
+
 struct DecodeOut {
   uint8_t* label_u8 = nullptr;    // [N,H,W]
   int64_t* label_i64 = nullptr;   // [N,H,W]
@@ -148,6 +157,12 @@ struct DecodeOut {
 // score = x8 bilinear-like upsample (shared 16x16 kernel g) of `low` + bias; softmax; argmax
 int launch_decode_upsample8(const float* low, const float* g_16x16, const float* bias, int N,
                             int h, int w, int C, const DecodeOut& out, cudaStream_t s);
+// label-only decode of M experts + decision-table lookup + confusion-matrix accumulation in one
+// pass (BayesFusion.score()); fused_out (uint8 [N,8h,8w]) may be NULL
+int launch_decode_bayes_confusion(const float* const* low, const float* const* g,
+                                  const float* const* bias, int M, const int32_t* lut, int C,
+                                  int N, int h, int w, const int32_t* gt, long long* cm,
+                                  uint8_t* fused_out, cudaStream_t s);
 // MC variant: `low` holds T sample maps [T,N,h,w,C]; accumulates population mean / variance
 // of the per-sample softmax without materialising the samples.
 int launch_decode_upsample8_mc(const float* low, const float* g_16x16, const float* bias, int T,

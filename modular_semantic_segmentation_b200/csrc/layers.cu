@@ -655,6 +655,121 @@ decode_upsample8_labels_kernel(const float* __restrict__ low, const float* __res
   if (label_u8) *reinterpret_cast<uint32_t*>(label_u8 + pix) = packed;
 }
 
+// Fused tail of BayesFusion.score(): label-only decode of up to 4 experts (same arithmetic as
+// decode_upsample8_labels_kernel, hence the same labels) -> decision-table lookup
+// (bayes_mix.py:61-112) -> confusion-matrix accumulation (base_model.py:140-151), one pass, no
+// label map in HBM unless `fused_out` asks for it.  One thread = 4 horizontally adjacent pixels.
+struct DecodeSrc {
+  const float* low[4];      // [N,h,w,C] low-resolution class scores of each expert
+  const float* bias[4];     // [C]
+  const float* g[4];        // [16,16] shared bilinear kernel
+};
+template <int C>
+__global__ void __launch_bounds__(256)
+decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ lut, int lut_size,
+                              int h, int w, const int32_t* __restrict__ gt,
+                              unsigned long long* __restrict__ cm,
+                              uint8_t* __restrict__ fused_out) {
+  extern __shared__ int32_t s_dyn[];
+  int32_t* s_lut = s_dyn;
+  unsigned int* s_cm = reinterpret_cast<unsigned int*>(s_dyn + lut_size);
+  for (int i = threadIdx.x; i < lut_size; i += 256) s_lut[i] = lut[i];
+  for (int i = threadIdx.x; i < C * C; i += 256) s_cm[i] = 0u;
+  __syncthreads();
+  const int H = 8 * h, W = 8 * w;
+  const int ox0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+  const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int img = blockIdx.z;
+  const bool live = ox0 < W && oy < H;
+  int key[4] = {-1, -1, -1, -1};
+  if (live) {
+    const int ay = (oy + 4) >> 3, ry = (oy + 4) & 7;
+    const int ax = (ox0 + 4) >> 3, rx0 = (ox0 + 4) & 7;
+    int idx[4] = {0, 0, 0, 0};
+    for (int m = 0; m < M; ++m) {
+      const float* __restrict__ low = src.low[m];
+      const float* __restrict__ g = src.g[m];
+      const float* __restrict__ bias = src.bias[m];
+      float s[4][C];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < C; ++c) s[i][c] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int iy = ay - a, ky = ry + 8 * a;
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int ix = ax - b;
+          if (ix < 0 || ix >= w) continue;
+          const float4 wg = __ldg(reinterpret_cast<const float4*>(g + ky * 16 + rx0 + 8 * b));
+          const float wgt[4] = {wg.x, wg.y, wg.z, wg.w};
+          const float* lp = low + ((static_cast<size_t>(img) * h + iy) * w + ix) * C;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float v = __ldg(lp + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[i][c] = fmaf(wgt[i], v, s[i][c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int best = 0;
+        float bestv = s[i][0] + __ldg(bias);
+#pragma unroll
+        for (int c = 1; c < C; ++c) {
+          const float v = s[i][c] + __ldg(bias + c);
+          if (v > bestv) {
+            bestv = v;
+            best = c;
+          }
+        }
+        idx[i] = idx[i] * C + best;
+      }
+    }
+    const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox0;
+    const int4 lv = __ldg(reinterpret_cast<const int4*>(gt + pix));
+    const int l[4] = {lv.x, lv.y, lv.z, lv.w};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int fused = s_lut[idx[i]];
+      packed |= static_cast<uint32_t>(fused & 0xff) << (8 * i);
+      if (l[i] >= 0 && l[i] < C) key[i] = l[i] * C + fused;
+    }
+    if (fused_out) *reinterpret_cast<uint32_t*>(fused_out + pix) = packed;
+  }
+  // warp-aggregated shared-memory histogram (same scheme as confusion_kernel in fusion.cu)
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int key0 = __shfl_sync(0xffffffffu, key[j], 0);
+    if (__all_sync(0xffffffffu, key[j] == key0)) {
+      if (lane == 0 && key0 >= 0) atomicAdd(&s_cm[key0], 32u);
+    } else {
+      const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
+      if (key[j] >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&s_cm[key[j]], __popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += 256)
+    if (s_cm[i]) atomicAdd(cm + i, static_cast<unsigned long long>(s_cm[i]));
+}
+
+template <int C>
+int decode_bayes_dispatch(const DecodeSrc& src, int M, const int32_t* lut, int lut_size, int N,
+                          int h, int w, const int32_t* gt, long long* cm, uint8_t* fused_out,
+                          cudaStream_t s) {
+  dim3 grid(div_up(8 * w, 256), div_up(8 * h, 4), N);
+  decode_bayes_confusion_kernel<C><<<grid, 256, (lut_size + C * C) * sizeof(int32_t), s>>>(
+      src, M, lut, lut_size, h, w, gt, reinterpret_cast<unsigned long long*>(cm), fused_out);
+  XV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 template <int C>
 int decode_dispatch(bool mc, const float* low, const float* g, const float* bias, int T, int N,
                     int h, int w, const DecodeOut& out, float* mean_prob, float* var_prob,
@@ -844,6 +959,106 @@ int launch_upscore2_add(const float* s5, const float* s4, const float* g, float*
   count_launch();
   return 0;
 }
+// Fused head tail (simple_fcn.py:82-85 + the 1x1 score conv moved below the upsampling, DESIGN.md
+// 4.2): fused = s4 + relu(up2(s5)) and low = fused x W[nu, C] in one pass over the 1/8-resolution
+// pixels.  Four threads share a pixel (nu / 4 channels each as float4 pieces); `fused` is written
+// too (small, and fit() / the layer diagnostics read it).
+template <int C>
+__global__ void __launch_bounds__(256)
+head_fused_kernel(const float4* __restrict__ s5, const float4* __restrict__ s4,
+                  const float* __restrict__ g, const float* __restrict__ w,
+                  float4* __restrict__ fused, float* __restrict__ low, int N, int h, int wd,
+                  int nu) {
+  extern __shared__ float s_hw[];
+  float* s_w = s_hw;                       // [nu][C]
+  float* s_g = s_hw + nu * C;              // [16][nu]
+  for (int i = threadIdx.x; i < nu * C; i += 256) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < 16 * nu; i += 256) s_g[i] = g[i];
+  __syncthreads();
+  const int nu4 = nu >> 2;
+  const int part = threadIdx.x & 3;
+  const int ho = 2 * h, wo = 2 * wd;
+  const size_t npix = static_cast<size_t>(N) * ho * wo;
+  const size_t quads = static_cast<size_t>(gridDim.x) * 64;
+  const size_t iters = (npix + quads - 1) / quads;       // uniform trip count per warp
+  for (size_t it = 0; it < iters; ++it) {
+    const size_t p = it * quads + blockIdx.x * 64 + (threadIdx.x >> 2);
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    if (p < npix) {
+      const int ox = static_cast<int>(p % wo);
+      const size_t t = p / wo;
+      const int oy = static_cast<int>(t % ho);
+      const size_t img = t / ho;
+      // oy = 2*iy - 1 + ky  ->  ky in {(oy+1)%2, (oy+1)%2 + 2}; same for x
+      int ky[2], iy[2], kx[2], ix[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        ky[a] = ((oy + 1) & 1) + 2 * a;
+        iy[a] = (oy + 1 - ky[a]) >= 0 ? (oy + 1 - ky[a]) / 2 : -1;
+        if (iy[a] >= h) iy[a] = -1;
+        kx[a] = ((ox + 1) & 1) + 2 * a;
+        ix[a] = (ox + 1 - kx[a]) >= 0 ? (ox + 1 - kx[a]) / 2 : -1;
+        if (ix[a] >= wd) ix[a] = -1;
+      }
+      for (int u4 = part; u4 < nu4; u4 += 4) {
+        float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (iy[a] < 0) continue;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (ix[b] < 0) continue;
+            const float4 v = __ldg(s5 + ((img * h + iy[a]) * wd + ix[b]) * nu4 + u4);
+            const float* gr = s_g + (ky[a] * 4 + kx[b]) * nu + u4 * 4;
+            up[0] = fmaf(gr[0], v.x, up[0]);
+            up[1] = fmaf(gr[1], v.y, up[1]);
+            up[2] = fmaf(gr[2], v.z, up[2]);
+            up[3] = fmaf(gr[3], v.w, up[3]);
+          }
+        }
+        const float4 a4 = __ldg(s4 + p * nu4 + u4);
+        const float4 f = make_float4(a4.x + fmaxf(up[0], 0.f), a4.y + fmaxf(up[1], 0.f),
+                                     a4.z + fmaxf(up[2], 0.f), a4.w + fmaxf(up[3], 0.f));
+        fused[p * nu4 + u4] = f;
+        const float* wr = s_w + u4 * 4 * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          acc[c] = fmaf(f.x, wr[c], acc[c]);
+          acc[c] = fmaf(f.y, wr[C + c], acc[c]);
+          acc[c] = fmaf(f.z, wr[2 * C + c], acc[c]);
+          acc[c] = fmaf(f.w, wr[3 * C + c], acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+    }
+    if (p < npix && part == 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) low[p * C + c] = acc[c];
+    }
+  }
+}
+
+template <int C>
+int head_fused_dispatch(const float* s5, const float* s4, const float* g, const float* w,
+                        float* fused, float* low, int N, int h, int wd, int nu, cudaStream_t s) {
+  const size_t npix = static_cast<size_t>(N) * 4 * h * wd;
+  const size_t blocks = (npix + 63) / 64;
+  const size_t cap = static_cast<size_t>(device_info().num_sms) * 8;
+  head_fused_kernel<C><<<static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap), 256,
+                         (nu * C + 16 * nu) * sizeof(float), s>>>(
+      reinterpret_cast<const float4*>(s5), reinterpret_cast<const float4*>(s4), g, w,
+      reinterpret_cast<float4*>(fused), low, N, h, wd, nu);
+  XV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 template <int C>
 int score_lowres_v4_dispatch(const float* fused, const float* w, float* low, size_t npix, int nu,
                              cudaStream_t s) {
@@ -857,6 +1072,16 @@ int score_lowres_v4_dispatch(const float* fused, const float* w, float* low, siz
   return 0;
 }
 
+bool head_fused_supported(int nu, int C) {
+  return nu % 4 == 0 && C >= 2 && C <= kMaxClasses && (nu * C + 16 * nu) * 4 <= 48 * 1024;
+}
+int launch_head_fused(const float* s5, const float* s4, const float* g_4x4xnu, const float* w_nuxc,
+                      float* fused, float* low, int N, int h, int w, int nu, int C,
+                      cudaStream_t s) {
+  XV_CHECK(head_fused_supported(nu, C), "head_fused: unsupported num_units / num_classes");
+  XV_DISPATCH_C(C, (head_fused_dispatch<kC>(s5, s4, g_4x4xnu, w_nuxc, fused, low, N, h, w, nu, s)));
+  return 0;
+}
 int launch_score_lowres(const float* fused, const float* w, float* low, size_t npix, int nu, int C,
                         cudaStream_t s) {
   if (nu % 16 == 0 && nu * C * 4 <= 40 * 1024) {
@@ -871,6 +1096,24 @@ int launch_decode_upsample8(const float* low, const float* g, const float* bias,
                             int w, int C, const DecodeOut& out, cudaStream_t s) {
   XV_DISPATCH_C(C, (decode_dispatch<kC>(false, low, g, bias, 1, N, h, w, out, nullptr, nullptr,
                                         nullptr, s)));
+}
+int launch_decode_bayes_confusion(const float* const* low, const float* const* g,
+                                  const float* const* bias, int M, const int32_t* lut, int C,
+                                  int N, int h, int w, const int32_t* gt, long long* cm,
+                                  uint8_t* fused_out, cudaStream_t s) {
+  XV_CHECK(M >= 1 && M <= 4, "decode_bayes_confusion: 1..4 experts");
+  XV_CHECK((8 * w) % 4 == 0, "decode_bayes_confusion: width must be a multiple of 4");
+  int lut_size = 1;
+  for (int m = 0; m < M; ++m) lut_size *= C;
+  XV_CHECK((lut_size + C * C) * 4 <= 48 * 1024, "decode_bayes_confusion: decision table too large");
+  DecodeSrc src;
+  for (int m = 0; m < 4; ++m) {
+    src.low[m] = m < M ? low[m] : nullptr;
+    src.g[m] = m < M ? g[m] : nullptr;
+    src.bias[m] = m < M ? bias[m] : nullptr;
+  }
+  XV_DISPATCH_C(C, (decode_bayes_dispatch<kC>(src, M, lut, lut_size, N, h, w, gt, cm, fused_out, s)));
+  return 0;
 }
 int launch_decode_upsample8_mc(const float* low, const float* g, const float* bias, int T, int N,
                                int h, int w, int C, float* mean_prob, float* var_prob,

@@ -381,6 +381,21 @@ def bayes_fuse_lut(labels, lut, num_classes):
     return out
 
 
+def bayes_decode_score(experts, lut, num_classes, gt_labels, cm, want_fused=False):
+    """One kernel behind the experts' last forward calls: per-expert label decode -> decision
+    table -> confusion-matrix accumulation into cm (xv_bayes_decode_score).  experts: FcnExpert
+    handles whose forward() ran on the batch; gt_labels int32 CUDA [N,H,W]; returns the fused
+    uint8 label map if `want_fused`, else None."""
+    init()
+    assert gt_labels.dtype == torch.int32 and cm.dtype == torch.int64
+    handles = (C.c_void_p * len(experts))(*[e._h for e in experts])
+    fused = (torch.empty(gt_labels.shape, dtype=torch.uint8, device=gt_labels.device)
+             if want_fused else None)
+    call('xv_bayes_decode_score', C.cast(handles, C.POINTER(C.c_void_p)), len(experts), ptr(lut),
+         num_classes, ptr(gt_labels.contiguous()), ptr(cm), ptr(fused), stream_ptr())
+    return fused
+
+
 def bayes_fuse_score(labels, log_cond, log_prior, want_score=True):
     """log_cond float32 CUDA [M,C,C], log_prior float32 CUDA [C]."""
     init()

@@ -309,8 +309,7 @@ class BaseModel(object):
         cm = self._cm_device
         cm.zero_()
         for batch in self._device_batches(data):
-            prediction = self._run_batch(batch, 'prediction_compact')
-            dev.confusion_accumulate(prediction, batch['labels'].contiguous(), cm)
+            self._score_batch(batch, cm)
         sharding.allreduce_sum_(cm)
         confusion_matrix = cm.cpu().numpy().astype(np.float64)
         measures = measures_from_confusion_matrix(confusion_matrix)
@@ -321,9 +320,14 @@ class BaseModel(object):
         tensors): experts -> fusion -> confusion-matrix accumulation, no host transfer and no
         synchronisation.  Returns the int64 device matrix being accumulated."""
         cm = self._cm_device if confusion_matrix is None else confusion_matrix
-        prediction = self._run_batch(batch, 'prediction_compact')
-        dev.confusion_accumulate(prediction, batch['labels'], cm)
+        self._score_batch(batch, cm)
         return cm
+
+    def _score_batch(self, batch, cm):
+        """One batch of score(): prediction + confusion-matrix accumulation into `cm` (device
+        int64).  Models may override it with a fused path (BayesFusion does)."""
+        prediction = self._run_batch(batch, 'prediction_compact')
+        dev.confusion_accumulate(prediction, batch['labels'].contiguous(), cm)
 
     def load_weights(self, filepath):
         """base_model.py:333-339 restores a TensorFlow checkpoint; only the npz route exists

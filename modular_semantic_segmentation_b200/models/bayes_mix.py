@@ -138,3 +138,22 @@ class BayesFusion(FusionModel):
         if fetch == 'fused_score':
             return dev.bayes_fuse_score(labels, self._log_cond, self._log_prior)[0]
         return dev.bayes_fuse_lut(labels, self._lut, self.config['num_classes'])
+
+    def _score_batch(self, batch, cm):
+        """score() step with the tail fused into one kernel: each expert runs up to its
+        low-resolution class scores, then label decode + decision table + confusion matrix
+        happen in a single pass (no label map in HBM).  Needs the bilinear decoder fast path of
+        the FCN experts; anything else takes the generic route."""
+        if self.config.get('fused_score_tail', True) and not getattr(self, '_no_fused_tail', False) \
+                and self.config['expert_model'] == 'fcn' and len(self.modalities) <= 4 \
+                and self.config.get('precision', 'bf16') == 'bf16':
+            experts = [self._experts[self._expert_prefix(m)] for m in self.modalities]
+            for m, expert in zip(self.modalities, experts):
+                expert.forward(batch[m], want=())
+            try:
+                dev.bayes_decode_score(experts, self._lut, self.config['num_classes'],
+                                       batch['labels'], cm)
+                return
+            except dev._abi.XViewError:
+                self._no_fused_tail = True      # e.g. non-bilinear upscore kernels were imported
+        FusionModel._score_batch(self, batch, cm)

@@ -49,7 +49,8 @@ def test_fcn_fp32_validation_mode_matches_oracle(dev, cin, h, w):
 @pytest.mark.parametrize('cin,h,w', [(3, 64, 96), (1, 96, 64), (3, 48, 80)])
 def test_fcn_bf16_tcgen05_matches_oracle(dev, cin, h, w, fused_pool):
     """Probabilities within 2e-2 abs of the fp32 oracle (north_star bf16 tolerance).  With
-    pooling fused into the conv epilogue conv1_2 / conv2_2 are never materialised."""
+    pooling fused into the conv epilogues conv1_2 / conv2_2 / conv3_3 are never materialised
+    (conv4_3 is: it also feeds score_conv4)."""
     dev.set_debug_flags(0 if fused_pool else 1)
     rng = np.random.default_rng(10 + cin)
     net, params = _net(dev, 'bf16', cin, rng)
@@ -62,7 +63,7 @@ def test_fcn_bf16_tcgen05_matches_oracle(dev, cin, h, w, fused_pool):
     out = net.forward(cuda(x), want=('score', 'prob', 'label'))
     report = []
     for name in LAYERS:
-        if fused_pool and name in ('conv1_2', 'conv2_2'):
+        if fused_pool and name in ('conv1_2', 'conv2_2', 'conv3_3'):
             with pytest.raises(Exception):
                 net.layer(name)
             continue

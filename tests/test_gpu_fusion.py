@@ -62,9 +62,13 @@ def test_bayes_fusion_bit_exact(dev, exp868, prior, label_dtype):
 
 
 def _dirichlet_tables(params, sigma, prior):
+    """alpha - 1, lbeta(alpha) and log(1e-20 + prior) in float32, built like the product's
+    dirichlet_tables and oracle.dirichlet_fusion_f32 build them: the normaliser is evaluated in
+    float64 on the float32 concentrations and rounded once."""
     alpha = [(np.float32(sigma) * p.astype('float32')) for p in params]
     am1 = np.stack([a - np.float32(1) for a in alpha]).astype(np.float32)
-    lognorm = np.stack([oracle.dirichlet_log_norm(a).astype(np.float32) for a in alpha])
+    lognorm = np.stack([oracle.dirichlet_log_norm(a.astype(np.float64)).astype(np.float32)
+                        for a in alpha])
     logprior = np.log(np.float32(1e-20) + np.asarray(prior, np.float32)).astype(np.float32)
     return am1, lognorm, logprior
 
@@ -128,11 +132,11 @@ def test_dirichlet_fusion_exact_mode_is_bit_exact_at_full_size(dev):
     tables = [cuda(t) for t in _dirichlet_tables(params, 1.0, prior)]
     dp = [cuda(p) for p in probs]
     redone = torch.zeros(1, dtype=torch.int64, device='cuda')
+    score, label_all = dev.dirichlet_fuse(dp, *tables, want_score=True, exact=True)
+    np.testing.assert_array_equal(score.cpu().numpy(), ref)
+    np.testing.assert_array_equal(label_all.cpu().numpy(), ref_label)
     _, label = dev.dirichlet_fuse(dp, *tables, exact=True, num_exact=redone)
     np.testing.assert_array_equal(label.cpu().numpy(), ref_label)
-    score, label_all = dev.dirichlet_fuse(dp, *tables, want_score=True, exact=True)
-    np.testing.assert_array_equal(label_all.cpu().numpy(), ref_label)
-    np.testing.assert_array_equal(score.cpu().numpy(), ref)
     _, fast = dev.dirichlet_fuse(dp, *tables, label_dtype=torch.uint8)
     npix = ref_label.size
     _flip_report('dirichlet C=12 16x768x384', fast.cpu().numpy(), ref_label, int(redone.item()), npix)
@@ -169,11 +173,11 @@ def test_dirichlet_fusion_exact_mode_on_adversarial_near_ties(dev, c):
     tables = [cuda(t) for t in _dirichlet_tables(params, 1.0, prior)]
     dp = [cuda(p) for p in probs]
     redone = torch.zeros(1, dtype=torch.int64, device='cuda')
+    score, _ = dev.dirichlet_fuse(dp, *tables, want_score=True, exact=True)
+    np.testing.assert_array_equal(score.cpu().numpy(), ref)
     for dtype in (torch.int64, torch.uint8):
         _, label = dev.dirichlet_fuse(dp, *tables, exact=True, label_dtype=dtype, num_exact=redone)
         np.testing.assert_array_equal(label.cpu().numpy().astype(np.int64), ref_label)
-    score, _ = dev.dirichlet_fuse(dp, *tables, want_score=True, exact=True)
-    np.testing.assert_array_equal(score.cpu().numpy(), ref)
     # the construction really produces ties: classes 0 and 2 have identical scores everywhere
     np.testing.assert_array_equal(ref[..., 0], ref[..., 2])
     assert not (ref_label == 2).any()

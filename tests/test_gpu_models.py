@@ -366,3 +366,44 @@ def test_custom_layers_softmax_log_softmax_entropy():
                                d - np.log(np.exp(d).sum(-1, keepdims=True)), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(cl.entropy(torch.from_numpy(ref).cuda()).cpu().numpy(),
                                oracle.normed_entropy(ref), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('c,h,w', [(6, 48, 64), (13, 32, 80)])
+def test_bayes_score_fused_tail_equals_generic_route(c, h, w):
+    """BayesFusion.score() runs decode + decision table + confusion matrix as one kernel
+    (xv_bayes_decode_score); the generic route (expert labels -> xv_bayes_fuse_lut ->
+    xv_confusion_accumulate) must give the identical matrix, and both the oracle's count."""
+    from xview.models import get_model
+    from modular_semantic_segmentation_b200 import device as dev
+    rng = np.random.default_rng(c)
+    n = 3
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    cms = {m: rng.integers(0, 60, size=(c, c)).astype(np.float64) + 150 * np.eye(c)
+           for m in ('rgb', 'depth')}
+    common = dict(confusion_matrices=cms, data_description=_description(c),
+                  prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn', num_units=NU,
+                  num_channels={'rgb': 3, 'depth': 1}, batchsize=2)
+    with get_model('bayes_fusion')(**common) as net:
+        _load(net, params)
+        before = dev.launch_count()
+        _, cm_fused = net.score(data)
+        launches_fused = dev.launch_count() - before
+        pred = net.predict(data)
+        # the kernel can also return the fused labels it counted
+        experts = [net._experts[m] for m in net.modalities]
+        batch = net._to_device({k: v[:2] for k, v in data.items()})
+        for m, e in zip(net.modalities, experts):
+            e.forward(batch[m], want=())
+        scratch = torch.zeros((c, c), dtype=torch.int64, device='cuda')
+        fused = dev.bayes_decode_score(experts, net._lut, c, batch['labels'], scratch,
+                                       want_fused=True)
+        np.testing.assert_array_equal(fused.cpu().numpy(), pred[:2])
+    with get_model('bayes_fusion')(fused_score_tail=False, **common) as net:
+        _load(net, params)
+        before = dev.launch_count()
+        _, cm_generic = net.score(data)
+        launches_generic = dev.launch_count() - before
+    np.testing.assert_array_equal(cm_fused, cm_generic)
+    np.testing.assert_array_equal(cm_fused, oracle.confusion_matrix(data['labels'], pred, c))
+    assert launches_fused < launches_generic
