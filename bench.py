@@ -523,6 +523,32 @@ def run_gpu(args):
     want_px = sum(labelled[i % n_sets] for i in range(args.steps))
     assert int(cm.sum().item()) == want_px, (int(cm.sum().item()), want_px)
 
+    # ---------------- the same K steps replayed from captured CUDA graphs (one graph per input
+    # set): launch gaps between the ~33 kernels of a step disappear.  Reported beside `value`,
+    # which stays the eager loop the per-kernel roofline events belong to.
+    graph_info = None
+    try:
+        graphs = [net.capture_score_step(dev_sets[i], cm) for i in range(n_sets)]
+        for i in range(warmup):
+            graphs[i % n_sets][0].replay()
+        barrier()
+        cm.zero_()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            graphs[i % n_sets][0].replay()
+        g1.record()
+        barrier()
+        graph_ms = max_over_ranks(g0.elapsed_time(g1))
+        assert int(cm.sum().item()) == want_px
+        graph_info = {'value': world * BATCH * args.steps / (graph_ms * 1e-3),
+                      'ms_per_step': graph_ms / args.steps,
+                      'kernels_per_graph': int(graphs[0][1])}
+        del graphs
+    except Exception as err:                      # capture is an optimisation, never a requirement
+        graph_info = {'unavailable': str(err)[:200]}
+        torch.cuda.synchronize()
+
     # ---------------- end to end through the public API with host buffers (e2e)
     # each rank scores its own batch-16 shard (shard_images=False: the dict a rank passes IS
     # its shard); score() still all-reduces the confusion matrix over ranks at its end
@@ -627,7 +653,7 @@ def run_gpu(args):
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-        'data': 'synthetic', 'soak_s': round(soak_s, 2),
+        'data': 'synthetic', 'soak_s': round(soak_s, 2), 'cuda_graph': graph_info,
         'config': {'workload': WORKLOAD, 'global_batch': world * BATCH,
                    'parallelism': 'images sharded over %d GPU(s), no data-path collective' % world,
                    'l2': 'inputs rotate over %d sets (%.0f MB) and every step streams >2 GB of '

@@ -1198,16 +1198,17 @@ int xv_fcn_finalize(xv_fcn* net) {
   }
   // Fast decoder paths exist in the bf16 production mode only; the fp32 validation mode keeps
   // the reference op order (dense transposed convolutions).
-  net->fast_up5 = net->fast_up = false;
+  net->fast_up5 = net->fast_up = net->diag_up5 = net->diag_up = false;
   if (net->precision == XV_PRECISION_BF16) {
-    if (!net->bn_all() && deconv_is_diagonal(*w5, 4, nu)) {
+    if (deconv_is_diagonal(*w5, 4, nu)) {
       std::vector<float> g(16 * nu);
       for (int t = 0; t < 16; ++t)
         for (int u = 0; u < nu; ++u) g[t * nu + u] = w5->data[(static_cast<size_t>(t) * nu + u) * nu + u];
       XV_TRY(net->g4.upload(g));
-      net->fast_up5 = true;
+      net->diag_up5 = true;
+      net->fast_up5 = !net->bn_all();
     }
-    if (!net->bn_decoder() && deconv_is_diagonal(*w16, 16, nu)) {
+    if (deconv_is_diagonal(*w16, 16, nu)) {
       // the 1x1 score conv commutes with the upsampling only if every channel shares one
       // non-negative 16x16 kernel (then ReLU after it is the identity on non-negative input)
       bool shared = true;
@@ -1220,7 +1221,8 @@ int xv_fcn_finalize(xv_fcn* net) {
       }
       if (shared) {
         XV_TRY(net->g16.upload(g));
-        net->fast_up = true;
+        net->diag_up = true;
+        net->fast_up = !net->bn_decoder();
       }
     }
   }
@@ -1610,6 +1612,17 @@ struct TrainLayer {
   int k, cin, cout;
   size_t w_off, b_off;               // offsets into the flat parameter / gradient buffers
   std::unique_ptr<ConvLayer> bwd;    // data-gradient conv (flipped + transposed weights)
+  // batch-norm training: the forward conv with the RAW weights, no ReLU (the inference layer of
+  // the same name carries the folded moving statistics)
+  std::unique_ptr<ConvLayer> fwd;
+};
+
+// batch-norm variables of one scope inside the flat vector (gamma / beta are trained; the moving
+// statistics ride along with zero gradients and are updated by the forward pass)
+struct BnParam {
+  std::string name;
+  int C;
+  size_t g_off, b_off, mm_off, mv_off;
 };
 
 struct TrainState {
@@ -1618,6 +1631,8 @@ struct TrainState {
   DevBuf master, m, v;               // fp32 flat
   DevBuf loss;                       // double[2]: sum of -log p, #valid pixels
   int64_t step = 0;
+  bool bn = false;                   // batch_normalization=True: batch statistics in training
+  std::vector<BnParam> bns;
   int opt_kind = XV_OPT_ADAM;        // whose slot values m / v currently hold
   // gradient buckets for the overlapped all-reduce: suffixes of the flat vector in the order
   // the backward pass completes them (conv5_x + heads, conv4_x, conv3_x, conv1_x + conv2_x)
@@ -1632,10 +1647,18 @@ static TrainLayer* find_layer(TrainState* ts, const std::string& n) {
     if (l.name == n) return &l;
   return nullptr;
 }
+static BnParam* find_bn(TrainState* ts, const std::string& n) {
+  for (auto& b : ts->bns)
+    if (b.name == n) return &b;
+  return nullptr;
+}
 
 // master fp32 -> bf16 operand copies (forward + data-gradient) and padded biases of one layer
 static int repack_layer(xv_fcn* net, TrainState* ts, TrainLayer& tl, cudaStream_t s) {
-  ConvLayer* L = net->conv(tl.name);
+  // batch-norm training: the raw weights go to the layer's own forward copy; the final score conv
+  // reads its fp32 master values directly
+  if (ts->bn && tl.name == "score") return 0;
+  ConvLayer* L = ts->bn ? tl.fwd.get() : net->conv(tl.name);
   const float* w = static_cast<const float*>(ts->master.p) + tl.w_off;
   const float* b = static_cast<const float*>(ts->master.p) + tl.b_off;
   if (tl.name == "score") {
@@ -1857,17 +1880,259 @@ int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, in
   return bucket_done(3);
 }
 
+// ------------------------------------------------------------------ fit() with batch norm
+// One training step of the batch-normalised expert (simple_fcn.py:201-215 with batchnorm=True,
+// is_training=True): every conv / transposed conv -> batch norm on batch statistics -> ReLU; the
+// final score conv -> batch norm without activation.  Encoder tensors are bf16 (pre-norm z and
+// post-ReLU y are both kept for the backward pass), heads and decoder fp32.  The decoder runs at
+// full resolution because its batch statistics are taken there (upscore: [N,H,W,num_units]).
+struct BnTrain {
+  xv_fcn* net;
+  TrainState* ts;
+  Arena* arena;
+  cudaStream_t s;
+  bool dry;
+  float* grads;
+
+  struct Rec {          // what the backward pass needs from one normalised layer
+    Act z, y;
+    float *mean = nullptr, *rstd = nullptr;
+  };
+
+  float* master() { return static_cast<float*>(ts->master.p); }
+  Act make(DType dt, int B, int H, int W, int C) {
+    Act a;
+    a.dt = dt;
+    a.B = B;
+    a.H = H;
+    a.W = W;
+    a.C = C;
+    a.p = arena->alloc(a.elems() * (dt == DType::F32 ? 4 : 2));
+    return a;
+  }
+  template <typename T>
+  T* scratch(size_t n) { return static_cast<T*>(arena->alloc(n * sizeof(T))); }
+  static size_t npix(const Act& a) { return static_cast<size_t>(a.B) * a.H * a.W; }
+
+  int bn_fwd(const std::string& name, const Act& z, int relu, const float* bias_extra, Rec* r) {
+    BnParam* bp = find_bn(ts, name);
+    XV_CHECK(bp != nullptr && bp->C == z.C, "no batch-norm variables for " + name);
+    r->z = z;
+    r->y = make(z.dt, z.B, z.H, z.W, z.C);
+    r->mean = scratch<float>(z.C);
+    r->rstd = scratch<float>(z.C);
+    double* sums = scratch<double>(2 * z.C);
+    if (dry) return 0;
+    const bool bf = z.dt == DType::BF16;
+    XV_TRY(launch_bn_stats(z.p, bf, npix(z), z.C, sums, s));
+    XV_TRY(launch_bn_finalize(sums, npix(z), z.C, 1e-3f, 0.99f, bias_extra, r->mean, r->rstd,
+                              master() + bp->mm_off, master() + bp->mv_off, s));
+    return launch_bn_apply(z.p, bf, r->mean, r->rstd, master() + bp->g_off, master() + bp->b_off,
+                           npix(z), z.C, relu, r->y.p, s);
+  }
+  // g: gradient wrt the layer output (same dtype / shape as r.y); mask: apply the ReLU mask of r.y
+  int bn_bwd(const std::string& name, const Rec& r, const void* g, bool mask, Act* dz,
+             __nv_bfloat16* dz_pad = nullptr, int c_pad = 0) {
+    BnParam* bp = find_bn(ts, name);
+    *dz = make(r.z.dt, r.z.B, r.z.H, r.z.W, r.z.C);
+    double* sums = scratch<double>(2 * r.z.C);
+    if (dry) return 0;
+    return launch_bn_backward(g, mask ? r.y.p : nullptr, r.z.p, r.z.dt == DType::BF16, r.mean,
+                              r.rstd, master() + bp->g_off, npix(r.z), r.z.C, sums, dz->p, dz_pad,
+                              c_pad, grads + bp->g_off, grads + bp->b_off, s);
+  }
+  int bucket_done(int b) {
+    if (dry || b >= static_cast<int>(ts->bucket_events.size()) || !ts->bucket_events[b]) return 0;
+    XV_CUDA(cudaEventRecord(ts->bucket_events[b], s));
+    return 0;
+  }
+  // 1x1 head: weight gradient + data gradient from dz (fp32) and its padded bf16 copy
+  int head_bwd(const std::string& name, const Rec& r, const Act& x, const Act& g_out, Act* dx) {
+    TrainLayer* tl = find_layer(ts, name);
+    const int c_pad = tl->bwd->cin_gemm;
+    Act dz16 = make(DType::BF16, r.z.B, r.z.H, r.z.W, c_pad);
+    Act dz;
+    XV_TRY(bn_bwd(name, r, g_out.p, true, &dz, static_cast<__nv_bfloat16*>(dz16.p), c_pad));
+    *dx = make(DType::BF16, r.z.B, r.z.H, r.z.W, tl->cin);
+    if (dry) return 0;
+    XV_TRY(launch_outer_sum_bf16(static_cast<const __nv_bfloat16*>(x.p),
+                                 static_cast<const float*>(dz.p), grads + tl->w_off, npix(r.z),
+                                 tl->cin, tl->cout, s));
+    return run_igemm(net, *tl->bwd, dz16.p, r.z.B, r.z.H, r.z.W, dx->p, false, s);
+  }
+
+  int run(const float* x, const int32_t* labels, int N, int H, int W, int train_encoder);
+};
+
+int BnTrain::run(const float* x, const int32_t* labels, int N, int H, int W, int train_encoder) {
+  const int nu = net->nu, C = net->C;
+  Rec rec[13];
+  Act input[13], pooled[13];
+  bool has_pool[13];
+  // ---------------------------------------------------------------- forward, encoder
+  Act cur;
+  int h = H, w = W;
+  for (int i = 0; i < 13; ++i) {
+    TrainLayer* tl = find_layer(ts, kConvNames[i]);
+    Act z = make(DType::BF16, N, h, w, tl->cout);
+    input[i] = cur;
+    if (!dry) {
+      if (i == 0)
+        XV_TRY(run_igemm_c1(net, *tl->fwd, x, N, h, w, z.p, s));
+      else
+        XV_TRY(run_igemm(net, *tl->fwd, cur.p, N, h, w, z.p, false, s));
+    }
+    XV_TRY(bn_fwd(kConvNames[i], z, 1, nullptr, &rec[i]));
+    cur = rec[i].y;
+    has_pool[i] = (i == 1 || i == 3 || i == 6 || i == 9);
+    if (has_pool[i]) {
+      pooled[i] = make(DType::BF16, N, h / 2, w / 2, tl->cout);
+      if (!dry)
+        XV_TRY(launch_maxpool_bf16(static_cast<const __nv_bfloat16*>(cur.p),
+                                   static_cast<__nv_bfloat16*>(pooled[i].p), N, h, w, tl->cout, s));
+      cur = pooled[i];
+      h /= 2;
+      w /= 2;
+    }
+  }
+  const int h8 = H / 8, w8 = W / 8, h16 = H / 16, w16 = W / 16;
+  const Act c43 = rec[9].y, c53 = rec[12].y;
+  // ---------------------------------------------------------------- forward, heads + decoder
+  Rec r4, r5, rup5, rup, rsc;
+  TrainLayer* t4 = find_layer(ts, "score_conv4");
+  TrainLayer* t5 = find_layer(ts, "score_conv5");
+  TrainLayer* tsc = find_layer(ts, "score");
+  Act s4z = make(DType::F32, N, h8, w8, nu), s5z = make(DType::F32, N, h16, w16, nu);
+  if (!dry) {
+    XV_TRY(run_igemm(net, *t4->fwd, c43.p, N, h8, w8, s4z.p, true, s));
+    XV_TRY(run_igemm(net, *t5->fwd, c53.p, N, h16, w16, s5z.p, true, s));
+  }
+  XV_TRY(bn_fwd("score_conv4", s4z, 1, nullptr, &r4));
+  XV_TRY(bn_fwd("score_conv5", s5z, 1, nullptr, &r5));
+  Act up5z = make(DType::F32, N, h8, w8, nu);
+  if (!dry)
+    XV_TRY(launch_upsample_diag(static_cast<const float*>(r5.y.p),
+                                static_cast<const float*>(net->g4.p), true, N, h16, w16, nu, 4, 2,
+                                static_cast<float*>(up5z.p), s));
+  XV_TRY(bn_fwd("upscore_conv5", up5z, 1, nullptr, &rup5));
+  Act fused = make(DType::F32, N, h8, w8, nu);
+  if (!dry)
+    XV_TRY(launch_add_f32(static_cast<const float*>(r4.y.p), static_cast<const float*>(rup5.y.p),
+                          static_cast<float*>(fused.p), fused.elems(), s));
+  Act upz = make(DType::F32, N, H, W, nu);
+  if (!dry)
+    XV_TRY(launch_upsample_diag(static_cast<const float*>(fused.p),
+                                static_cast<const float*>(net->g16.p), false, N, h8, w8, nu, 16, 8,
+                                static_cast<float*>(upz.p), s));
+  XV_TRY(bn_fwd("upscore", upz, 1, nullptr, &rup));
+  // score conv: the bias is left out of z (batch norm cancels it), it only enters the moving mean
+  Act scz = make(DType::F32, N, H, W, C);
+  const size_t full = static_cast<size_t>(N) * H * W;
+  if (!dry)
+    XV_TRY(launch_score_lowres(static_cast<const float*>(rup.y.p), master() + tsc->w_off,
+                               static_cast<float*>(scz.p), full, nu, C, s));
+  XV_TRY(bn_fwd("score", scz, 0, master() + tsc->b_off, &rsc));
+  // ---------------------------------------------------------------- loss + backward, decoder
+  float* dbias_scratch = scratch<float>(C);
+  Act dscz, dup = make(DType::F32, N, H, W, nu), dupz;
+  if (!dry) {
+    XV_CUDA(cudaMemsetAsync(dbias_scratch, 0, C * sizeof(float), s));
+    XV_TRY(launch_ce_grad(static_cast<float*>(rsc.y.p), labels, static_cast<int64_t>(full), C,
+                          static_cast<double*>(ts->loss.p), dbias_scratch, s));
+  }
+  XV_TRY(bn_bwd("score", rsc, rsc.y.p, false, &dscz));          // rsc.y now holds dL/dscore
+  if (!dry)
+    XV_TRY(launch_score_bwd(static_cast<const float*>(dscz.p), static_cast<const float*>(rup.y.p),
+                            master() + tsc->w_off, static_cast<float*>(dup.p), grads + tsc->w_off,
+                            full, nu, C, s));
+  XV_TRY(bn_bwd("upscore", rup, dup.p, true, &dupz));
+  Act dfused = make(DType::F32, N, h8, w8, nu);
+  if (!dry)
+    XV_TRY(launch_upsample_diag_transpose(static_cast<const float*>(dupz.p),
+                                          static_cast<const float*>(net->g16.p), false, N, h8, w8,
+                                          nu, 16, 8, static_cast<float*>(dfused.p), s));
+  Act dup5z, ds5 = make(DType::F32, N, h16, w16, nu);
+  XV_TRY(bn_bwd("upscore_conv5", rup5, dfused.p, true, &dup5z));
+  if (!dry)
+    XV_TRY(launch_upsample_diag_transpose(static_cast<const float*>(dup5z.p),
+                                          static_cast<const float*>(net->g4.p), true, N, h16, w16,
+                                          nu, 4, 2, static_cast<float*>(ds5.p), s));
+  Act d43a, d53;
+  XV_TRY(head_bwd("score_conv4", r4, c43, dfused, &d43a));
+  XV_TRY(head_bwd("score_conv5", r5, c53, ds5, &d53));
+  if (!train_encoder) {
+    for (int b = 0; b < 4; ++b) XV_TRY(bucket_done(b));
+    return 0;
+  }
+  // ---------------------------------------------------------------- backward, encoder
+  Act da = d53;           // gradient wrt the output y of layer i (or wrt its pooled map)
+  for (int i = 12; i >= 0; --i) {
+    TrainLayer* tl = find_layer(ts, kConvNames[i]);
+    const Rec& r = rec[i];
+    Act dz;
+    if (has_pool[i]) {
+      // route the pooled gradient to the argmax positions and apply the ReLU mask (+ the second
+      // gradient source of conv4_3: its score_conv4 branch)
+      Act ghat = make(DType::BF16, r.y.B, r.y.H, r.y.W, r.y.C);
+      if (!dry)
+        XV_TRY(launch_pool_relu_bwd_bf16(
+            static_cast<const __nv_bfloat16*>(da.p), static_cast<const __nv_bfloat16*>(r.y.p),
+            static_cast<const __nv_bfloat16*>(pooled[i].p),
+            i == 9 ? static_cast<const __nv_bfloat16*>(d43a.p) : nullptr,
+            static_cast<__nv_bfloat16*>(ghat.p), r.y.B, r.y.H, r.y.W, r.y.C, nullptr, s));
+      XV_TRY(bn_bwd(kConvNames[i], r, ghat.p, false, &dz));
+    } else {
+      XV_TRY(bn_bwd(kConvNames[i], r, da.p, true, &dz));
+    }
+    const int lh = r.z.H, lw = r.z.W;
+    Act dx;
+    if (i > 0) dx = make(DType::BF16, N, lh, lw, tl->cin);
+    if (!dry) {
+      if (i == 0) {
+        XV_TRY(launch_conv_wgrad_c1(x, static_cast<const __nv_bfloat16*>(dz.p), grads + tl->w_off,
+                                    N, lh, lw, tl->cin, tl->cout, s));
+      } else {
+        if (tl->cin % 64 == 0 && !(g_debug_flags & 8))
+          XV_TRY(run_wgrad_tc(net, input[i].p, dz.p, grads + tl->w_off, N, lh, lw, tl->cin,
+                              tl->cout, s));
+        else
+          XV_TRY(launch_conv_wgrad(static_cast<const __nv_bfloat16*>(input[i].p),
+                                   static_cast<const __nv_bfloat16*>(dz.p), grads + tl->w_off, N,
+                                   lh, lw, tl->cin, tl->cout, s));
+        XV_TRY(run_igemm(net, *tl->bwd, dz.p, N, lh, lw, dx.p, false, s));
+      }
+    }
+    da = dx;
+    if (i == 10) XV_TRY(bucket_done(0));
+    if (i == 7) XV_TRY(bucket_done(1));
+    if (i == 4) XV_TRY(bucket_done(2));
+  }
+  return bucket_done(3);
+}
+
 }  // namespace xv
 
 extern "C" {
 
 int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out) {
   XV_CHECK(net && net->finalized, "xv_fcn_train_begin: finalize the expert first");
-  XV_CHECK(net->precision == XV_PRECISION_BF16 && !net->batchnorm,
-           "fit() runs on the bf16 path without batch normalisation");
-  XV_CHECK(net->fast_up5 && net->fast_up,
+  XV_CHECK(net->precision == XV_PRECISION_BF16 && (net->batchnorm == 0 || net->batchnorm == 1),
+           "fit() runs on the bf16 path (batch norm on every layer or on none)");
+  XV_CHECK(net->diag_up5 && net->diag_up,
            "fit() needs the (non-trainable) bilinear transposed-conv kernels");
   std::unique_ptr<TrainState> ts(new TrainState());
+  ts->bn = net->bn_all();
+  auto add_bn = [&](const std::string& name, int c) {
+    BnParam b;
+    b.name = name;
+    b.C = c;
+    b.g_off = ts->total;
+    b.b_off = ts->total + c;
+    b.mm_off = ts->total + 2 * static_cast<size_t>(c);
+    b.mv_off = ts->total + 3 * static_cast<size_t>(c);
+    ts->total += 4 * static_cast<size_t>(c);
+    ts->bns.push_back(b);
+  };
   auto add = [&](const std::string& name, int k, int cin, int cout, bool need_bwd) -> int {
     TrainLayer tl;
     tl.name = name;
@@ -1878,6 +2143,22 @@ int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out) {
     ts->total += static_cast<size_t>(k) * k * cin * cout;
     tl.b_off = ts->total;
     ts->total += cout;
+    if (ts->bn) {
+      add_bn(name, cout);
+      if (name != "score") {
+        const HostParam *w, *b;
+        XV_TRY(get_param(net, name + "/kernel", {k, k, cin, cout}, &w));
+        XV_TRY(get_param(net, name + "/bias", {cout}, &b));
+        tl.fwd.reset(new ConvLayer());
+        tl.fwd->name = name + "_train";
+        tl.fwd->k = k;
+        tl.fwd->cin = cin;
+        tl.fwd->cout = cout;
+        tl.fwd->relu = 0;
+        const std::vector<float> ones(cout, 1.f), zeros(cout, 0.f);
+        XV_TRY(pack_conv(net, tl.fwd.get(), w->data.data(), b->data.data(), ones, zeros, false));
+      }
+    }
     if (need_bwd) {
       // data-gradient conv: Cin' = Cout (padded to 64 for the 1x1 heads), Cout' = Cin, no bias/ReLU
       tl.bwd.reset(new ConvLayer());
@@ -1910,6 +2191,10 @@ int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out) {
   XV_TRY(add("score_conv4", 1, 512, net->nu, true));
   XV_TRY(add("score_conv5", 1, 512, net->nu, true));
   XV_TRY(add("score", 1, net->nu, net->C, false));
+  if (ts->bn) {     // the two bilinear transposed convs: fixed kernels, trained batch norm
+    add_bn("upscore_conv5", net->nu);
+    add_bn("upscore", net->nu);
+  }
   // the 1x1 heads' data-gradient operand has K = padded nu: kdim of bwd = cin (padded)
   std::vector<float> flat(ts->total, 0.f);
   for (auto& tl : ts->layers) {
@@ -1918,6 +2203,15 @@ int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out) {
     XV_TRY(get_param(net, tl.name + "/bias", {tl.cout}, &b));
     std::copy(w->data.begin(), w->data.end(), flat.begin() + tl.w_off);
     std::copy(b->data.begin(), b->data.end(), flat.begin() + tl.b_off);
+  }
+  for (auto& bp : ts->bns) {
+    const char* leaves[4] = {"/gamma", "/beta", "/moving_mean", "/moving_variance"};
+    const size_t offs[4] = {bp.g_off, bp.b_off, bp.mm_off, bp.mv_off};
+    for (int i = 0; i < 4; ++i) {
+      const HostParam* v;
+      XV_TRY(get_param(net, bp.name + leaves[i], {bp.C}, &v));
+      std::copy(v->data.begin(), v->data.end(), flat.begin() + offs[i]);
+    }
   }
   ts->bucket_off = {0, find_layer(ts.get(), "conv3_1")->w_off,
                     find_layer(ts.get(), "conv4_1")->w_off,
@@ -1941,9 +2235,18 @@ int xv_fcn_param_span(xv_fcn* net, const char* name, int64_t* offset, int64_t* s
   std::string n(name);
   const size_t slash = n.rfind('/');
   XV_CHECK(slash != std::string::npos, "parameter name must look like 'conv1_1/kernel'");
-  TrainLayer* tl = find_layer(it->second.get(), n.substr(0, slash));
-  XV_CHECK(tl != nullptr, "not a trainable parameter: " + n);
-  const bool is_w = n.substr(slash + 1) == "kernel";
+  const std::string scope = n.substr(0, slash), leaf = n.substr(slash + 1);
+  if (leaf == "gamma" || leaf == "beta" || leaf == "moving_mean" || leaf == "moving_variance") {
+    BnParam* bp = find_bn(it->second.get(), scope);
+    XV_CHECK(bp != nullptr, "not a batch-norm variable of this training state: " + n);
+    *offset = static_cast<int64_t>(leaf == "gamma" ? bp->g_off : leaf == "beta" ? bp->b_off
+                                   : leaf == "moving_mean" ? bp->mm_off : bp->mv_off);
+    *size = bp->C;
+    return 0;
+  }
+  TrainLayer* tl = find_layer(it->second.get(), scope);
+  XV_CHECK(tl != nullptr && (leaf == "kernel" || leaf == "bias"), "not a trainable parameter: " + n);
+  const bool is_w = leaf == "kernel";
   *offset = static_cast<int64_t>(is_w ? tl->w_off : tl->b_off);
   *size = is_w ? static_cast<int64_t>(tl->k) * tl->k * tl->cin * tl->cout : tl->cout;
   return 0;
@@ -1987,6 +2290,24 @@ int xv_fcn_train_gradients_ex(xv_fcn* net, const float* x, const int32_t* labels
            "bucket events need un-normalised gradients (scale after the all-reduce)");
   for (int i = 0; i < num_events; ++i)
     ts->bucket_events.push_back(reinterpret_cast<cudaEvent_t>(bucket_events_host[i]));
+  if (ts->bn) {
+    Arena dry_arena;
+    BnTrain plan{net, ts, &dry_arena, s, true, grads};
+    XV_TRY(plan.run(x, labels, n, h, w, train_encoder));
+    XV_TRY(net->arena_buf.ensure(dry_arena.off + 1024));
+    Arena real_arena;
+    real_arena.base = static_cast<char*>(net->arena_buf.p);
+    XV_CUDA(cudaMemsetAsync(grads, 0, ts->total * sizeof(float), s));
+    XV_CUDA(cudaMemsetAsync(ts->loss.p, 0, 2 * sizeof(double), s));
+    BnTrain real{net, ts, &real_arena, s, false, grads};
+    XV_TRY(real.run(x, labels, n, h, w, train_encoder));
+    if (normalize)
+      XV_TRY(launch_scale_by_count(grads, ts->total, static_cast<const double*>(ts->loss.p), s));
+    if (loss_out)
+      XV_CUDA(cudaMemcpyAsync(loss_out, ts->loss.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice,
+                              s));
+    return 0;
+  }
   xv_fcn_outputs none;
   std::memset(&none, 0, sizeof(none));
   Forward plan{net, Arena(), s, true, 1, nullptr};

@@ -1,0 +1,50 @@
+// argmax(softmax(score)) without evaluating the softmax (basic_fusion_model.py:21-22).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace xv {
+
+// Label of one pixel = first index of the maximum of p_c = fl(fl(expf(s_c - mx)) / sum), i.e.
+// exactly what the probability-writing kernels return, computed from the scores alone:
+//  * p is a non-decreasing function of s, so a class AFTER the first score maximum can never win
+//    (ties go to the lower index);
+//  * a class BEFORE it wins only if its probability rounds to the same float as the maximum's.
+//    With e_best = expf(0) = 1 that needs expf(s_c - mx) >= 1 - 3 ulp; expf is within 2 ulp, so
+//    s_c - mx >= -4.8e-7 is necessary.  Only then (practically never) is the softmax evaluated,
+//    with the same operation order as the kernels that write probabilities.
+template <int C>
+__device__ __forceinline__ int argmax_of_softmax(const float (&s)[C]) {
+  float mx = s[0];
+  int best = 0;
+#pragma unroll
+  for (int c = 1; c < C; ++c) {
+    if (s[c] > mx) {
+      mx = s[c];
+      best = c;
+    }
+  }
+  bool close = false;
+#pragma unroll
+  for (int c = 0; c < C - 1; ++c) close = close || (c < best && s[c] - mx >= -4.8e-7f);
+  if (!close) return best;
+  float e[C];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    e[c] = expf(s[c] - mx);
+    sum += e[c];
+  }
+  int b = 0;
+  float bv = -1.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float pr = e[c] / sum;
+    if (pr > bv) {
+      bv = pr;
+      b = c;
+    }
+  }
+  return b;
+}
+
+}  // namespace xv

@@ -10,6 +10,7 @@
 //   MC moments          xview/models/variance_mix.py:62-66, bayesian_fcn.py:48-57
 //   sufficient stats    xview/models/dirichlet_mix.py:142-163
 //   confusion matrix    xview/models/base_model.py:140-151
+#include "argmax.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -192,7 +193,10 @@ softmax_argmax_kernel(const float* __restrict__ score, int64_t npix, float* __re
     px_load<C>(score, base, cnt, slice, v);
     const bool live = lane < cnt;
     int best = 0;
-    if (live) {
+    if (live && prob == nullptr) {
+      // label only: the argmax of the softmax follows from the scores (argmax.cuh)
+      best = argmax_of_softmax<C>(v);
+    } else if (live) {
       float mx = v[0];
 #pragma unroll
       for (int c = 1; c < C; ++c) mx = fmaxf(mx, v[c]);
@@ -205,6 +209,8 @@ softmax_argmax_kernel(const float* __restrict__ score, int64_t npix, float* __re
 #pragma unroll
       for (int c = 0; c < C; ++c) v[c] = v[c] / sum;
       best = argmax_first<C>(v);
+    }
+    if (live) {
       if (label64) label64[base + lane] = best;
       if (label8) label8[base + lane] = static_cast<uint8_t>(best);
     }

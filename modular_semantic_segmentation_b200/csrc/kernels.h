@@ -241,6 +241,30 @@ int launch_fill_f32(float* x, size_t n, float value, cudaStream_t s);
 int launch_pack_weights(const float* w, __nv_bfloat16* fwd, __nv_bfloat16* bwd, int taps, int cin,
                         int cout, int fwd_kdim, int bwd_kdim, int c1_layout, cudaStream_t s);
 
+// ------------------------------------------------------------- bn_train.cu
+// batch normalisation on batch statistics (training mode); sums: device double[2*C] scratch
+int launch_bn_stats(const void* z, bool bf16, size_t npix, int C, double* sums, cudaStream_t s);
+int launch_bn_finalize(const double* sums, size_t npix, int C, float eps, float momentum,
+                       const float* bias_extra, float* mean, float* rstd, float* moving_mean,
+                       float* moving_var, cudaStream_t s);
+int launch_bn_apply(const void* z, bool bf16, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, size_t npix, int C, int relu, void* y,
+                    cudaStream_t s);
+// g: gradient wrt the layer output; y_mask != NULL: masked by (y_mask > 0) (ReLU) on the fly.
+// Writes dz (same dtype as z), dgamma[C], dbeta[C] and optionally (fp32 only) dz as bf16 padded
+// to c_pad channels.
+int launch_bn_backward(const void* g, const void* y_mask, const void* z, bool bf16,
+                       const float* mean, const float* rstd, const float* gamma, size_t npix,
+                       int C, double* sums, void* dz, __nv_bfloat16* dz_pad, int c_pad,
+                       float* dgamma, float* dbeta, cudaStream_t s);
+// channel-diagonal transposed convolution (k = 2 * stride, 'same') and its transpose, fp32 NHWC
+int launch_upsample_diag(const float* in, const float* g, bool per_channel, int N, int h, int w,
+                         int C, int k, int stride, float* out, cudaStream_t s);
+int launch_upsample_diag_transpose(const float* dout, const float* g, bool per_channel, int N,
+                                   int h, int w, int C, int k, int stride, float* din,
+                                   cudaStream_t s);
+int launch_add_f32_inplace(float* a, const float* b, size_t n, cudaStream_t s);
+
 constexpr int kMaxClasses = 24;
 
 }  // namespace xv

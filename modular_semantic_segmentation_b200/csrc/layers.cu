@@ -3,6 +3,7 @@
 // generic fp32 "validation mode" layers that follow the reference op order literally.
 //
 // Reference: xview/models/simple_fcn.py:10-134, xview/models/custom_layers.py:8-25,71-139.
+#include "argmax.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -468,8 +469,8 @@ score_lowres_v4_kernel(const float4* __restrict__ fused, const float* __restrict
 // Decoder tail: 16x16 stride-8 upsampling of the low-res class scores + bias + softmax +
 // argmax in one pass; block = 16x16 output pixels, the <= 4x4 contributing low-res pixels
 // are staged in shared memory.  T > 1: loop over MC samples and accumulate moments.
-// SOFTMAX == false: labels (and raw scores) only - the argmax is taken on the scores, the
-// exponentials are skipped.
+// SOFTMAX == false: labels (and raw scores) only - the argmax of the softmax is derived from the
+// scores (argmax.cuh), the exponentials are evaluated only on near-ties.
 template <int C, bool MC, bool SOFTMAX = true>
 __global__ void __launch_bounds__(256)
 decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__ g,
@@ -536,15 +537,7 @@ decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__
       for (int c = 0; c < C; ++c) out.score[pix * C + c] = s[c];
     }
     if (!MC && !SOFTMAX) {
-      int best = 0;
-      float bestv = s[0];
-#pragma unroll
-      for (int c = 1; c < C; ++c) {
-        if (s[c] > bestv) {
-          bestv = s[c];
-          best = c;
-        }
-      }
+      const int best = argmax_of_softmax<C>(s);
       if (out.label_u8) out.label_u8[pix] = static_cast<uint8_t>(best);
       if (out.label_i64) out.label_i64[pix] = best;
       continue;
@@ -637,18 +630,14 @@ decode_upsample8_labels_kernel(const float* __restrict__ low, const float* __res
   }
   uint32_t packed = 0;
   const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox0;
+  float b[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) b[c] = __ldg(bias + c);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int best = 0;
-    float bestv = s[i][0] + __ldg(bias);
 #pragma unroll
-    for (int c = 1; c < C; ++c) {
-      const float v = s[i][c] + __ldg(bias + c);
-      if (v > bestv) {
-        bestv = v;
-        best = c;
-      }
-    }
+    for (int c = 0; c < C; ++c) s[i][c] += b[c];
+    const int best = argmax_of_softmax<C>(s[i]);
     packed |= static_cast<uint32_t>(best) << (8 * i);
     if (label_i64) label_i64[pix + i] = best;
   }
@@ -667,7 +656,7 @@ struct DecodeSrc {
 template <int C>
 __global__ void __launch_bounds__(256)
 decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ lut, int lut_size,
-                              int h, int w, const int32_t* __restrict__ gt,
+                              int N, int h, int w, const int32_t* __restrict__ gt,
                               unsigned long long* __restrict__ cm,
                               uint8_t* __restrict__ fused_out) {
   extern __shared__ int32_t s_dyn[];
@@ -677,9 +666,18 @@ decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ 
   for (int i = threadIdx.x; i < C * C; i += 256) s_cm[i] = 0u;
   __syncthreads();
   const int H = 8 * h, W = 8 * w;
-  const int ox0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-  const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
-  const int img = blockIdx.z;
+  const int lane = threadIdx.x & 31;
+  // few, fat blocks (each ends with C*C global atomics on the same addresses): a block walks
+  // over many 256 x 4 pixel tiles and keeps its histogram in shared memory
+  const int tiles_x = (W + 255) / 256, tiles_y = (H + 3) / 4;
+  const int total = tiles_x * tiles_y * N;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  const int bxi = tile % tiles_x;
+  const int rest = tile / tiles_x;
+  const int byi = rest % tiles_y;
+  const int img = rest / tiles_y;
+  const int ox0 = (bxi * 64 + (threadIdx.x & 63)) * 4;
+  const int oy = byi * 4 + (threadIdx.x >> 6);
   const bool live = ox0 < W && oy < H;
   int key[4] = {-1, -1, -1, -1};
   if (live) {
@@ -716,17 +714,9 @@ decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ 
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        int best = 0;
-        float bestv = s[i][0] + __ldg(bias);
 #pragma unroll
-        for (int c = 1; c < C; ++c) {
-          const float v = s[i][c] + __ldg(bias + c);
-          if (v > bestv) {
-            bestv = v;
-            best = c;
-          }
-        }
-        idx[i] = idx[i] * C + best;
+        for (int c = 0; c < C; ++c) s[i][c] += __ldg(bias + c);
+        idx[i] = idx[i] * C + argmax_of_softmax<C>(s[i]);
       }
     }
     const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox0;
@@ -742,7 +732,6 @@ decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ 
     if (fused_out) *reinterpret_cast<uint32_t*>(fused_out + pix) = packed;
   }
   // warp-aggregated shared-memory histogram (same scheme as confusion_kernel in fusion.cu)
-  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int key0 = __shfl_sync(0xffffffffu, key[j], 0);
@@ -753,6 +742,7 @@ decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ 
       if (key[j] >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&s_cm[key[j]], __popc(peers));
     }
   }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < C * C; i += 256)
     if (s_cm[i]) atomicAdd(cm + i, static_cast<unsigned long long>(s_cm[i]));
@@ -762,9 +752,11 @@ template <int C>
 int decode_bayes_dispatch(const DecodeSrc& src, int M, const int32_t* lut, int lut_size, int N,
                           int h, int w, const int32_t* gt, long long* cm, uint8_t* fused_out,
                           cudaStream_t s) {
-  dim3 grid(div_up(8 * w, 256), div_up(8 * h, 4), N);
+  const long long tiles = static_cast<long long>(div_up(8 * w, 256)) * div_up(8 * h, 4) * N;
+  const long long cap = static_cast<long long>(device_info().num_sms) * 3;   // resident blocks
+  const int grid = static_cast<int>(tiles < cap ? tiles : cap);
   decode_bayes_confusion_kernel<C><<<grid, 256, (lut_size + C * C) * sizeof(int32_t), s>>>(
-      src, M, lut, lut_size, h, w, gt, reinterpret_cast<unsigned long long*>(cm), fused_out);
+      src, M, lut, lut_size, N, h, w, gt, reinterpret_cast<unsigned long long*>(cm), fused_out);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

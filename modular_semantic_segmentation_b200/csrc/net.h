@@ -105,6 +105,9 @@ struct xv_fcn {
   std::vector<std::unique_ptr<ConvLayer>> convs;   // conv1_1..conv5_3, score_conv4, score_conv5, score
   // decoder
   bool fast_up5 = false, fast_up = false;
+  // the loaded transposed-conv kernels are channel-diagonal (g4 / g16 hold the diagonals); the
+  // fast inference paths additionally need the layer to be free of batch norm
+  bool diag_up5 = false, diag_up = false;
   DevBuf g4, g16, w_score_nuxc, b_score;           // fast paths
   DevBuf w_up5, w_up, up5_scale, up5_shift, up_scale, up_shift;   // generic paths
   DevBuf arena_buf;

@@ -60,6 +60,18 @@ def upload_bounds(count, split=2, explicit=None):
     return None
 
 
+def _nbytes(value):
+    if isinstance(value, torch.Tensor):
+        return value.numel() * value.element_size()
+    return getattr(value, 'nbytes', 0)
+
+
+def upload_order(batch):
+    """Keys of a host batch in the order they are copied to the device: image arrays by
+    ascending size, labels last (they are needed last)."""
+    return sorted(batch, key=lambda k: (k == 'labels', _nbytes(batch[k])))
+
+
 class _DeviceBatch(dict):
     """Batch of CUDA tensors whose uploads may still be in flight on the copy stream: reading an
     entry makes the compute stream wait for that entry's copy only."""
@@ -209,9 +221,10 @@ class BaseModel(object):
             copy.wait_stream(compute)          # never overwrite buffers the kernels still read
             tensors, events = {}, {}
             with torch.cuda.stream(copy):
-                # images first, labels last; one event per array, so the first expert starts as
-                # soon as ITS modality has arrived (see _DeviceBatch)
-                for key in sorted(host_batch, key=lambda k: k == 'labels'):
+                # smallest image array first (nothing can hide the first copy), labels last; one
+                # event per array, so an expert starts as soon as ITS modality has arrived (see
+                # _DeviceBatch and FusionModel._arrival_order)
+                for key in upload_order(host_batch):
                     tensors.update(self._to_device({key: host_batch[key]}))
                     events[key] = torch.cuda.Event()
                     events[key].record(copy)
@@ -243,6 +256,11 @@ class BaseModel(object):
             pending = upload(next(it))
         except StopIteration:
             return
+        # The host may run at most `depth` batches ahead of the device: without a bound a long
+        # data set is enqueued in one go, every upload allocates fresh device buffers (the
+        # previous ones are still in flight) and the caching allocator falls back to cudaMalloc.
+        in_flight = []
+        depth = int(self.config.get('upload_depth', 3))
         while pending is not None:
             dev_batch, event = pending
             try:
@@ -251,9 +269,14 @@ class BaseModel(object):
                 nxt = None
             if event is not None:
                 compute.wait_event(event)
+            if len(in_flight) >= depth:
+                in_flight.pop(0).synchronize()
             # issue the next upload before the caller launches this batch's kernels
             pending = upload(nxt) if nxt is not None else None
             yield dev_batch
+            done = torch.cuda.Event()
+            done.record(compute)              # the caller has enqueued this batch's kernels
+            in_flight.append(done)
 
     @staticmethod
     def _to_device(batch):
@@ -322,6 +345,31 @@ class BaseModel(object):
         cm = self._cm_device if confusion_matrix is None else confusion_matrix
         self._score_batch(batch, cm)
         return cm
+
+    def capture_score_step(self, batch, confusion_matrix=None):
+        """CUDA-graph form of score_batch_on_device for a batch that stays at the same device
+        addresses (a resident evaluation set that is scored repeatedly): captures experts ->
+        fusion -> confusion-matrix accumulation once and returns a callable that replays the
+        whole step as ONE graph launch on the current stream.  The two warm-up passes and the
+        capture itself do not change `confusion_matrix`'s meaning: it is zeroed afterwards."""
+        cm = self._cm_device if confusion_matrix is None else confusion_matrix
+        current = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(current)
+        with torch.cuda.stream(side):
+            for _ in range(2):                 # sizes the arenas / descriptor caches
+                self._score_batch(batch, cm)
+        current.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        launches = dev.launch_count()
+        with torch.cuda.graph(graph):
+            self._score_batch(batch, cm)
+        launches = dev.launch_count() - launches
+        torch.cuda.synchronize()
+        cm.zero_()
+        self._graphs = getattr(self, '_graphs', []) + [graph]      # keep the pools alive
+        return graph, launches
 
     def _score_batch(self, batch, cm):
         """One batch of score(): prediction + confusion-matrix accumulation into `cm` (device

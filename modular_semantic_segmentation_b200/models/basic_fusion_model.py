@@ -43,9 +43,18 @@ class FusionModel(BaseModel):
             self._register_expert(self._expert_prefix(m), expert, variables)
         self.prediction = 'prediction'
 
+    def _arrival_order(self, batch):
+        """Modalities in the order their arrays reach the device (smallest first, see
+        base_model.upload_order): the expert of the first one starts while the others are still
+        being copied.  The fusion rules index experts by `self.modalities`, so the order in
+        which the experts RUN does not matter for the result."""
+        from .base_model import _nbytes
+        return sorted(self.modalities, key=lambda m: _nbytes(dict.__getitem__(batch, m))
+                      if isinstance(batch, dict) else 0)
+
     def _expert_outputs(self, batch, wants, label_dtype):
         outputs = {}
-        for m in self.modalities:
+        for m in self._arrival_order(batch):
             expert = self._experts[self._expert_prefix(m)]
             out = expert.forward(batch[m], want=wants, label_dtype=label_dtype)
             if 'label' in out:

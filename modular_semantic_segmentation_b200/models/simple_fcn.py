@@ -150,12 +150,12 @@ class SimpleFCN(BaseModel):
         TensorBoard summaries of base_model.py:191-251 without TensorFlow.  Batches are uploaded
         one step ahead on a copy stream.  With torch.distributed initialised every rank trains
         on its share of each batch; the gradient buckets are all-reduced over NCCL while the
-        backward pass is still running (Trainer.step)."""
+        backward pass is still running (Trainer.step).  With batch_normalization=True every layer
+        normalises with the statistics of the rank's own batch (as the reference's replicas
+        would: no synchronised batch norm) and the moving statistics are updated every step
+        (the UPDATE_OPS dependency of base_model.py:155-156)."""
         import json
         import os
-        if self.config['batch_normalization']:
-            raise UserWarning('ERROR: fit() with batch normalisation is not built on the B200 '
-                              'path (batch statistics in training mode)')
         trainer = self.make_trainer()
         batches = self._device_batches(self._training_batches(dataset), presharded=True)
         summaries = None

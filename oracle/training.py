@@ -15,10 +15,35 @@ import torch.nn.functional as F
 from .fcn import CONV_LAYERS
 
 
-def _conv(x, p, scope, relu=True):
+class _Bf16Both(torch.autograd.Function):
+    """Value rounded to bfloat16 on the way forward, gradient rounded to bfloat16 on the way
+    back: what happens to an activation the device stores in bf16 (and to the data gradient it
+    stores in bf16 for the layer below)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().to(g.dtype)
+
+
+def _bf16_forward_only(w):
+    """bf16 operand copy of an fp32 master weight: rounded in the forward and data-gradient
+    passes, while its own gradient stays fp32 (straight-through)."""
+    return w + (w.detach().bfloat16().to(w.dtype) - w.detach())
+
+
+def _conv(x, p, scope, relu=True, emulate_bf16=False, store_bf16=True):
     w = p[scope + '/kernel']
+    if emulate_bf16:
+        w = _bf16_forward_only(w)
     y = F.conv2d(x, w.permute(3, 2, 0, 1), p[scope + '/bias'], padding=(w.shape[0] - 1) // 2)
-    return F.relu(y) if relu else y
+    y = F.relu(y) if relu else y
+    if emulate_bf16 and store_bf16:
+        y = _Bf16Both.apply(y)
+    return y
 
 
 def _deconv(x, p, scope, stride):
@@ -29,9 +54,13 @@ def _deconv(x, p, scope, stride):
 
 
 def loss_and_grads(params, prefix, x, labels, num_classes, dtype=torch.float32,
-                   train_encoder=True):
+                   train_encoder=True, emulate_bf16=False):
     """Returns (loss, {variable name: gradient}) for one batch.  x NHWC, labels [N,H,W] int;
-    labels outside [0, C) contribute nothing (all-zero one-hot row)."""
+    labels outside [0, C) contribute nothing (all-zero one-hot row).
+    emulate_bf16: same graph with the device's storage precision restated - bf16 operand copies
+    of the weights, encoder activations and their data gradients rounded to bf16, fp32 heads and
+    decoder - so that the device's backward pass can be checked against
+    autograd much more tightly than against the pure fp32 graph."""
     p = {}
     for name, value in params.items():
         t = torch.tensor(np.asarray(value), dtype=dtype)
@@ -45,12 +74,14 @@ def loss_and_grads(params, prefix, x, labels, num_classes, dtype=torch.float32,
     h = torch.tensor(np.asarray(x), dtype=dtype).permute(0, 3, 1, 2)
     acts = {}
     for name, _ in CONV_LAYERS:
-        h = _conv(h, p, s(name))
+        h = _conv(h, p, s(name), emulate_bf16=emulate_bf16)
         acts[name] = h
         if name in ('conv1_2', 'conv2_2', 'conv3_3', 'conv4_3'):
             h = F.max_pool2d(h, 2)
-    score4 = _conv(acts['conv4_3'], p, s('score_conv4'))
-    score5 = _conv(acts['conv5_3'], p, s('score_conv5'))
+    score4 = _conv(acts['conv4_3'], p, s('score_conv4'), emulate_bf16=emulate_bf16,
+                   store_bf16=False)
+    score5 = _conv(acts['conv5_3'], p, s('score_conv5'), emulate_bf16=emulate_bf16,
+                   store_bf16=False)
     fused = score4 + _deconv(score5, p, s('upscore_conv5'), 2)
     up = _deconv(fused, p, s('upscore'), 8)
     score = _conv(up, p, s('score'), relu=False).permute(0, 2, 3, 1)      # NHWC
@@ -96,3 +127,88 @@ def rmsprop_update(params, grads, ms, mom, learning_rate=1e-4, decay=0.9, moment
         mom[name] = momentum * mom.get(name, 0.0) + learning_rate * g / np.sqrt(ms[name] + epsilon)
         params[name] = (params[name] - mom[name]).astype(params[name].dtype)
     return params
+
+
+
+# ------------------------------------------------------------------ batch norm in training mode
+BN_EPS = 1e-3        # tf.layers.batch_normalization defaults
+BN_MOMENTUM = 0.99
+BN_SCOPES = [n for n, _ in CONV_LAYERS] + ['score_conv4', 'score_conv5', 'upscore_conv5',
+                                          'upscore', 'score']
+
+
+def _bn_train(z, p, scope, stats):
+    """tf.layers.batch_normalization(training=True) on an NCHW tensor: normalise with the
+    statistics of the batch (biased variance), y = gamma * (z - mean) / sqrt(var + 1e-3) + beta;
+    the batch mean / biased variance are recorded for the moving-average update."""
+    mean = z.mean(dim=(0, 2, 3))
+    var = z.var(dim=(0, 2, 3), unbiased=False)
+    stats[scope] = (mean.detach().numpy().copy(), var.detach().numpy().copy(),
+                    z.shape[0] * z.shape[2] * z.shape[3])
+    zhat = (z - mean[None, :, None, None]) * torch.rsqrt(var + BN_EPS)[None, :, None, None]
+    return zhat * p[scope + '/gamma'][None, :, None, None] + p[scope + '/beta'][None, :, None, None]
+
+
+def loss_and_grads_bn(params, prefix, x, labels, num_classes, dtype=torch.float32):
+    """Training graph of simple_fcn.py:201-215 with batchnorm=True, is_training=True: every
+    conv / transposed conv is followed by batch normalisation on batch statistics, then ReLU
+    (custom_layers.py:112-119,127-136); the final score conv has batch norm but no activation.
+    Returns (loss, gradients incl. gamma / beta, {scope: (batch mean, biased batch variance,
+    count)})."""
+    p = {}
+    for name, value in params.items():
+        t = torch.tensor(np.asarray(value), dtype=dtype)
+        parts = name.split('/')
+        trainable = not (parts[-2] in ('upscore_conv5', 'upscore') and parts[-1] == 'kernel')
+        trainable = trainable and parts[-1] not in ('moving_mean', 'moving_variance')
+        t.requires_grad_(trainable)
+        p[name] = t
+    s = lambda n: prefix + '/' + n
+    stats = {}
+
+    def conv_bn(h, scope, relu=True):
+        w = p[s(scope) + '/kernel']
+        z = F.conv2d(h, w.permute(3, 2, 0, 1), p[s(scope) + '/bias'],
+                     padding=(w.shape[0] - 1) // 2)
+        y = _bn_train(z, p, s(scope), stats)
+        return F.relu(y) if relu else y
+
+    def deconv_bn(h, scope, stride):
+        w = p[s(scope) + '/kernel']
+        k = w.shape[0]
+        z = F.conv_transpose2d(h, w.permute(3, 2, 0, 1), stride=stride,
+                               padding=(k - stride) // 2)
+        return F.relu(_bn_train(z, p, s(scope), stats))
+
+    h = torch.tensor(np.asarray(x), dtype=dtype).permute(0, 3, 1, 2)
+    acts = {}
+    for name, _ in CONV_LAYERS:
+        h = conv_bn(h, name)
+        acts[name] = h
+        if name in ('conv1_2', 'conv2_2', 'conv3_3', 'conv4_3'):
+            h = F.max_pool2d(h, 2)
+    score4 = conv_bn(acts['conv4_3'], 'score_conv4')
+    score5 = conv_bn(acts['conv5_3'], 'score_conv5')
+    fused = score4 + deconv_bn(score5, 'upscore_conv5', 2)
+    up = deconv_bn(fused, 'upscore', 8)
+    score = conv_bn(up, 'score', relu=False).permute(0, 2, 3, 1)
+    logp = F.log_softmax(score, dim=-1)
+    lab = torch.tensor(np.asarray(labels), dtype=torch.int64)
+    valid = (lab >= 0) & (lab < num_classes)
+    picked = torch.gather(logp, -1, lab.clamp(0, num_classes - 1)[..., None])[..., 0]
+    loss = -(picked * valid).sum() / (1e-20 + valid.sum())
+    loss.backward()
+    grads = {n: t.grad.numpy() for n, t in p.items() if t.requires_grad and t.grad is not None}
+    stats = {k[len(prefix) + 1:]: v for k, v in stats.items()}
+    return float(loss.detach()), grads, stats
+
+
+def moving_average_update(moving_mean, moving_variance, batch_mean, batch_variance, count,
+                          momentum=BN_MOMENTUM):
+    """Update ops of tf.layers.batch_normalization (base_model.py:155-156 runs them with every
+    training step): moving = momentum * moving + (1 - momentum) * batch statistic.  The fused TF
+    kernel feeds the UNBIASED batch variance (Bessel-corrected) into the moving variance;
+    documented assumption (no TensorFlow in the image)."""
+    unbiased = batch_variance * (count / max(count - 1, 1))
+    return (momentum * moving_mean + (1 - momentum) * batch_mean,
+            momentum * moving_variance + (1 - momentum) * unbiased)

@@ -182,7 +182,7 @@ def test_config2_bayes_fusion_matches_oracle_at_full_size(h, w):
     mIoU within 0.1 point."""
     from xview.models import get_model
     rng = np.random.default_rng(h + 1)
-    n = 1
+    n = 3          # a single frame leaves ~0.1 point of sampling noise on the mean IoU
     data = _data(rng, n, h, w)
     params = _trained_like(rng)
     cms = _cms(rng)

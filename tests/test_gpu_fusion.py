@@ -32,6 +32,40 @@ def test_softmax_argmax(dev, c, npix):
     assert (lt.cpu().numpy() == 1).all()
 
 
+@pytest.mark.parametrize('c', [12, 13, 3])
+def test_label_only_argmax_equals_argmax_of_probabilities_on_near_ties(dev, c):
+    """Label-only kernels derive argmax(softmax(score)) from the scores (csrc/argmax.cuh) and
+    evaluate the softmax only on near-ties: on scores whose top classes differ by 0, 1, 2, 4 or 8
+    ulps (in either index order) the labels must equal the argmax of the probabilities the
+    probability-writing kernel returns, and follow tf.argmax's first-index rule on exact ties."""
+    rng = np.random.default_rng(500 + c)
+    npix = 40000
+    score = rng.normal(0, 2, size=(npix, c)).astype(np.float32)
+    top = score.max(-1)
+    first = rng.integers(0, c, size=npix)
+    second = (first + rng.integers(1, c, size=npix)) % c
+    ulps = rng.choice([0, 1, 2, 4, 8], size=npix)
+    rows = np.arange(npix)
+    score[rows, first] = top
+    near = top.copy()
+    for _ in range(8):
+        step = ulps > 0
+        near[step] = np.nextafter(near[step], np.float32(-np.inf))
+        ulps = np.maximum(ulps - 1, 0)
+    score[rows, second] = near
+    d = cuda(score)
+    prob, label_full = dev.softmax_argmax(d)
+    _, label_only = dev.softmax_argmax(d, want_prob=False, label_dtype=torch.uint8)
+    _, label_only64 = dev.softmax_argmax(d, want_prob=False)
+    want = prob.cpu().numpy().argmax(-1)
+    np.testing.assert_array_equal(label_full.cpu().numpy(), want)
+    np.testing.assert_array_equal(label_only.cpu().numpy().astype(np.int64), want)
+    np.testing.assert_array_equal(label_only64.cpu().numpy(), want)
+    # the construction exercises both outcomes: the earlier near-tied class wins sometimes
+    earlier = (second < first)
+    assert (want[earlier] == second[earlier]).any() and (want[earlier] == first[earlier]).any()
+
+
 @pytest.mark.parametrize('prior', ['data', 'uniform', 0.3])
 @pytest.mark.parametrize('label_dtype', [torch.int64, torch.uint8])
 def test_bayes_fusion_bit_exact(dev, exp868, prior, label_dtype):

@@ -53,6 +53,33 @@ def test_gradients_match_autograd(dev, cin):
     print('\n'.join(report))
 
 
+@pytest.mark.parametrize('cin', [3, 1])
+def test_gradients_match_bf16_emulating_autograd_tightly(dev, cin):
+    """The same comparison against autograd on the graph that restates the device's storage
+    precision (bf16 weights / activations / data gradients, fp32 heads): what is left is
+    accumulation order and double rounding, so every gradient tensor must agree to a few percent
+    in relative L2 norm and to cosine > 0.999."""
+    rng = np.random.default_rng(140 + cin)
+    net, params, x, labels = _setup(dev, rng, cin)
+    net.train_begin()
+    grads = net.train_gradients(cuda(x), cuda(labels))[0].cpu().numpy()
+    _, ref = loss_and_grads(params, 'm', x, labels, C, emulate_bf16=True)
+    report = []
+    worst = 0.0
+    for name, g_ref in ref.items():
+        off, size = net.param_span(name.split('/', 1)[1])
+        g = grads[off:off + size].reshape(g_ref.shape)
+        denom = np.linalg.norm(g_ref) + 1e-12
+        rel = np.linalg.norm(g - g_ref) / denom
+        cos = float((g * g_ref).sum() / (np.linalg.norm(g) * denom + 1e-20))
+        report.append('%s rel=%.4f cos=%.5f' % (name, rel, cos))
+        worst = max(worst, rel)
+    print('\n'.join(report))
+    for line in report:
+        rel, cos = float(line.split('rel=')[1].split()[0]), float(line.split('cos=')[1])
+        assert rel < 5e-2 and cos > 0.999, line
+
+
 def test_tensor_core_weight_gradient_equals_cuda_core_reference(dev):
     """Same bf16 operands, fp32 accumulation: the tcgen05 wgrad kernel and the CUDA-core kernel
     must agree to accumulation-order noise."""
@@ -214,3 +241,91 @@ def test_fit_twice_continues_and_writes_summaries(tmp_path):
     with get_model('fcn')('rgb', desc, 'rgb', trainer='rmsprop', **common) as net:
         net.fit(data, 3, output=False)
         assert np.isfinite(net.loss)
+
+
+def _setup_bn(dev, rng, cin=3, n=2, h=32, w=48):
+    params = oracle.glorot_fcn_params('m', cin, NU, C, rng, gain=1.45, bias_scale=0.05,
+                                      batchnorm=True)
+    net = dev.FcnExpert(cin, NU, C, batchnorm=True, precision='bf16')
+    net.set_params({k.split('/', 1)[1]: v for k, v in params.items()})
+    x = rng.uniform(0, 1, size=(n, h, w, cin)).astype(np.float32)
+    labels = rng.integers(-1, C, size=(n, h, w)).astype(np.int32)
+    return net, params, x, labels
+
+
+@pytest.mark.parametrize('cin', [3, 1])
+def test_batchnorm_training_gradients_and_moving_statistics(dev, cin):
+    """fit() with batch_normalization=True (custom_layers.py:112-119,127-136 in training mode):
+    loss, every gradient tensor (kernels, gamma, beta) and the moving-average update against torch
+    autograd on the same graph (oracle.training.loss_and_grads_bn)."""
+    from oracle.training import loss_and_grads_bn, moving_average_update
+    rng = np.random.default_rng(60 + cin)
+    net, params, x, labels = _setup_bn(dev, rng, cin)
+    total = net.train_begin()
+    grads, loss = net.train_gradients(cuda(x), cuda(labels))
+    grads = grads.cpu().numpy()
+    loss = loss.cpu().numpy()
+    ref_loss, ref, stats = loss_and_grads_bn(params, 'm', x, labels, C)
+    assert loss[1] == (labels >= 0).sum()
+    assert abs(loss[0] / loss[1] - ref_loss) < 3e-2 * abs(ref_loss), (loss[0] / loss[1], ref_loss)
+    report = []
+    for name, g_ref in ref.items():
+        off, size = net.param_span(name.split('/', 1)[1])
+        g = grads[off:off + size].reshape(g_ref.shape)
+        denom = np.linalg.norm(g_ref) + 1e-12
+        rel = np.linalg.norm(g - g_ref) / denom
+        cos = float((g * g_ref).sum() / (np.linalg.norm(g) * denom + 1e-20))
+        report.append((name, rel, cos))
+    print('\n'.join('%s rel=%.3f cos=%.4f' % r for r in report))
+    for name, rel, cos in report:
+        if name.endswith('/bias'):
+            continue            # batch norm cancels the bias: its true gradient is zero
+        assert cos > 0.97 and rel < 0.25, (name, rel, cos)
+    # conv biases: exactly zero on the device, numerically ~0 in autograd
+    for name, g_ref in ref.items():
+        if name.endswith('/bias'):
+            off, size = net.param_span(name.split('/', 1)[1])
+            assert not grads[off:off + size].any()
+            assert np.abs(g_ref).max() < 1e-3 * max(np.abs(ref[name[:-4] + 'kernel']).max(), 1e-6)
+    # moving statistics after this one step
+    flat = net.get_params()
+    for scope, (mean, var, count) in stats.items():
+        mm_ref, mv_ref = moving_average_update(params['m/%s/moving_mean' % scope],
+                                               params['m/%s/moving_variance' % scope], mean, var,
+                                               count)
+        off, size = net.param_span(scope + '/moving_mean')
+        np.testing.assert_allclose(flat[off:off + size], mm_ref, rtol=0,
+                                   atol=2e-3 * max(np.abs(mean).max(), 1e-3), err_msg=scope)
+        off, size = net.param_span(scope + '/moving_variance')
+        np.testing.assert_allclose(flat[off:off + size], mv_ref, rtol=2e-3, atol=1e-5,
+                                   err_msg=scope)
+    assert sum(net.param_span(n.split('/', 1)[1])[1] for n in params
+               if 'upscore' not in n or not n.endswith('kernel')) == total
+
+
+def test_simple_fcn_fit_with_batch_normalization(tmp_path):
+    """SimpleFCN.fit() with batch_normalization=True: the loss falls, gamma / beta / moving
+    statistics change, and a fresh model importing the exported weights predicts the same
+    (test-time graph: batch norm on the moving statistics, folded into the convolutions)."""
+    from xview.models import get_model
+    rng = np.random.default_rng(23)
+    desc = ({'rgb': np.float32, 'labels': np.int32}, {'rgb': (None, None, 3),
+                                                      'labels': (None, None)}, C)
+    data = {'rgb': rng.uniform(0, 1, size=(4, 32, 32, 3)).astype(np.float32),
+            'labels': rng.integers(0, C, size=(4, 32, 32)).astype(np.int32)}
+    common = dict(num_units=NU, batch_normalization=True, learning_rate=1e-3, batchsize=4, seed=5)
+    with get_model('fcn')('rgb', desc, 'rgb', output_dir=str(tmp_path), **common) as net:
+        before = {k: v.copy() for k, v in net.variables.items()}
+        net.fit(data, 10, validation_dataset=data, validation_interval=3, output=False)
+        assert net.loss_history[-1] < net.loss_history[0]
+        for leaf in ('gamma', 'beta', 'moving_mean', 'moving_variance'):
+            name = 'rgb/conv2_1/' + leaf
+            assert not np.array_equal(net.variables[name], before[name]), name
+        assert not np.array_equal(net.variables['rgb/upscore/gamma'], before['rgb/upscore/gamma'])
+        np.testing.assert_array_equal(net.variables['rgb/upscore/kernel'],
+                                      before['rgb/upscore/kernel'])
+        path = net.export_weights()
+        pred = net.predict({'rgb': data['rgb']})
+    with get_model('fcn')('rgb', desc, 'rgb', num_units=NU, batch_normalization=True) as net2:
+        net2.import_weights(path, warnings=False)
+        np.testing.assert_array_equal(net2.predict({'rgb': data['rgb']}), pred)

@@ -234,6 +234,14 @@ def test_adapnet_variable_layout_matches_oracle():
     assert up.shape == (16, 16, 14, 20) and up[:, :, 3, 3].max() > 0 and up[:, :, 3, 4].max() == 0
 
 
+def test_upload_order_smallest_image_first_labels_last():
+    from modular_semantic_segmentation_b200.models.base_model import upload_order
+    batch = {'rgb': np.zeros((2, 16, 16, 3), np.float32), 'labels': np.zeros((2, 16, 16), np.int32),
+             'depth': np.zeros((2, 16, 16, 1), np.float32)}
+    assert upload_order(batch) == ['depth', 'rgb', 'labels']
+    assert upload_order({'labels': batch['labels'], 'rgb': batch['rgb']}) == ['rgb', 'labels']
+
+
 def test_upload_bounds():
     from modular_semantic_segmentation_b200.models.base_model import upload_bounds
     assert upload_bounds(16) == [0, 4, 16]            # a quarter first, then the rest
