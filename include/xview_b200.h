@@ -202,6 +202,19 @@ int xv_conv2d(const float* x, const float* w_hwio_host, const float* bias_host, 
 int xv_deconv2d(const float* x, const float* w_khkwoi_host, int n, int h, int w, int cin,
                 int cout, int k, int stride, int relu, float* out, void* stream);
 int xv_maxpool2x2(const float* x, int n, int h, int w, int c, float* out, void* stream);
+/* tf.layers.batch_normalization(training=True) as custom_layers.py:116,132-134 applies it after a
+ * convolution: x [N,H,W,c] float32 -> y = [relu](gamma * (x - mean) / sqrt(var + 1e-3) + beta) with
+ * the statistics of the batch; mean_out / var_out (device float32 [c], biased variance) may be
+ * NULL; moving_mean / moving_var (device float32 [c], may be NULL) are updated in place with
+ * momentum 0.99 (Bessel-corrected variance). */
+int xv_batchnorm_train(const float* x, const float* gamma, const float* beta, int n, int h, int w,
+                       int c, int relu, float* y, float* mean_out, float* var_out,
+                       float* moving_mean, float* moving_var, void* stream);
+/* Its backward pass: dy = gradient wrt y, y = the forward output (ReLU mask if relu != 0) ->
+ * dx [N,H,W,c], dgamma [c], dbeta [c] (all device float32, OVERWRITTEN). */
+int xv_batchnorm_train_backward(const float* x, const float* y, const float* dy,
+                                const float* gamma, int n, int h, int w, int c, int relu,
+                                float* dx, float* dgamma, float* dbeta, void* stream);
 
 /* ---- per-pixel fusion stage ---------------------------------------------------------- */
 /* tf.nn.softmax + tf.argmax, basic_fusion_model.py:21-22.  prob / label may be NULL. */

@@ -87,6 +87,8 @@ PROTOTYPES = {
     'xv_conv2d': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'xv_deconv2d': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'xv_maxpool2x2': [_P, _I, _I, _I, _I, _P, _P],
+    'xv_batchnorm_train': [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    'xv_batchnorm_train_backward': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     'xv_softmax_argmax': [_P, _L, _I, _P, _P, _I, _P],
     'xv_bayes_fuse_lut': [_PP, _I, _I, _P, _I, _L, _P, _P],
     'xv_bayes_decode_score': [_PP, _I, _P, _I, _P, _P, _P, _P],

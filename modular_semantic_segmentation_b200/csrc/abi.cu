@@ -837,6 +837,28 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
     return 0;
   }
 
+  // batch-normalised decoder on a bilinear upscore kernel (fusion_fcn's head, batchnorm=True
+  // experts): one fused pass, the upsampled num_units-channel tensor is never materialised
+  if (bf16() && net->diag_up && net->bn_decoder() && !want_moments && !training &&
+      decode_bn_supported(nu, C)) {
+    ConvLayer* L = net->conv("score");
+    if (!dry && want_samples) {
+      DecodeOut d;
+      d.label_u8 = o->label_u8;
+      d.label_i64 = o->label_i64;
+      d.prob = o->prob;
+      d.score = o->score;
+      const int b_samples = lead ? N0 : B;
+      XV_TRY(launch_decode_bn_upsample8(
+          static_cast<const float*>(feat.p), static_cast<const float*>(net->g16.p),
+          static_cast<const float*>(net->up_scale.p), static_cast<const float*>(net->up_shift.p),
+          static_cast<const float*>(net->w_score_nuxc.p), static_cast<const float*>(net->b_score.p),
+          static_cast<const float*>(L->bn_scale.p), static_cast<const float*>(L->bn_shift.p),
+          b_samples, feat.H, feat.W, nu, C, d, s));
+    }
+    return 0;
+  }
+
   // generic decoder, reference op order: upscore (dense transposed conv) -> [BN] -> ReLU ->
   // 1x1 score -> softmax -> argmax (simple_fcn.py:129-133, basic_fusion_model.py:21-22)
   Act up = make("upscore", DType::F32, B, Hf, Wf, nu);
@@ -1366,6 +1388,58 @@ int xv_maxpool2x2(const float* x, int n, int h, int w, int c, float* out, void* 
 
 // Timing harness for one tensor-core conv layer on synthetic bf16 data (not a reference
 // entry point; used by tools/conv_bench.py to study the kernel in isolation).
+int xv_batchnorm_train(const float* x, const float* gamma, const float* beta, int n, int h, int w,
+                       int c, int relu, float* y, float* mean_out, float* var_out,
+                       float* moving_mean, float* moving_var, void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(x && gamma && beta && y && n > 0 && h > 0 && w > 0 && c > 0, "xv_batchnorm_train: bad arguments");
+  XV_CHECK((moving_mean == nullptr) == (moving_var == nullptr),
+           "xv_batchnorm_train: pass both moving statistics or none");
+  cudaStream_t s = XV_STREAM(stream);
+  const size_t npix = static_cast<size_t>(n) * h * w;
+  DevBuf scratch;
+  XV_TRY(scratch.ensure(2 * c * sizeof(double) + 2 * c * sizeof(float)));
+  double* sums = static_cast<double*>(scratch.p);
+  float* mean = reinterpret_cast<float*>(sums + 2 * c);
+  float* rstd = mean + c;
+  XV_TRY(launch_bn_stats(x, false, npix, c, sums, s));
+  XV_TRY(launch_bn_finalize(sums, npix, c, 1e-3f, 0.99f, nullptr, mean, rstd, moving_mean,
+                            moving_var, s));
+  XV_TRY(launch_bn_apply(x, false, mean, rstd, gamma, beta, npix, c, relu, y, s));
+  if (mean_out) XV_CUDA(cudaMemcpyAsync(mean_out, mean, c * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (var_out) {
+    // var = 1 / rstd^2 - eps, recomputed on the host side of the scratch to keep one code path
+    std::vector<float> r(c);
+    XV_CUDA(cudaMemcpyAsync(r.data(), rstd, c * sizeof(float), cudaMemcpyDeviceToHost, s));
+    XV_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < c; ++i) r[i] = 1.f / (r[i] * r[i]) - 1e-3f;
+    XV_CUDA(cudaMemcpyAsync(var_out, r.data(), c * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  XV_CUDA(cudaStreamSynchronize(s));      // the scratch buffer dies with this call
+  return 0;
+}
+
+int xv_batchnorm_train_backward(const float* x, const float* y, const float* dy,
+                                const float* gamma, int n, int h, int w, int c, int relu,
+                                float* dx, float* dgamma, float* dbeta, void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(x && dy && gamma && dx && dgamma && dbeta && (y || !relu),
+           "xv_batchnorm_train_backward: bad arguments");
+  cudaStream_t s = XV_STREAM(stream);
+  const size_t npix = static_cast<size_t>(n) * h * w;
+  DevBuf scratch;
+  XV_TRY(scratch.ensure(2 * c * sizeof(double) + 2 * c * sizeof(float)));
+  double* sums = static_cast<double*>(scratch.p);
+  float* mean = reinterpret_cast<float*>(sums + 2 * c);
+  float* rstd = mean + c;
+  XV_TRY(launch_bn_stats(x, false, npix, c, sums, s));
+  XV_TRY(launch_bn_finalize(sums, npix, c, 1e-3f, 0.99f, nullptr, mean, rstd, nullptr, nullptr, s));
+  XV_TRY(launch_bn_backward(dy, relu ? y : nullptr, x, false, mean, rstd, gamma, npix, c, sums, dx,
+                            nullptr, 0, dgamma, dbeta, s));
+  XV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
 int xv_bench_conv_igemm(int n, int h, int w, int cin, int cout, int k, int iters, int flags,
                         float* ms_out) {
   XV_TRY(ensure_init());

@@ -157,6 +157,13 @@ struct DecodeOut {
 // score = x8 bilinear-like upsample (shared 16x16 kernel g) of `low` + bias; softmax; argmax
 int launch_decode_upsample8(const float* low, const float* g_16x16, const float* bias, int N,
                             int h, int w, int C, const DecodeOut& out, cudaStream_t s);
+// batch-normalised decoder in one pass: upscore = relu(up_scale * up8(feat) + up_shift),
+// score = sc_scale * (upscore x w + bias) + sc_shift, softmax, argmax
+bool decode_bn_supported(int nu, int C);
+int launch_decode_bn_upsample8(const float* feat, const float* g_16x16, const float* up_scale,
+                               const float* up_shift, const float* w_nuxc, const float* bias,
+                               const float* sc_scale, const float* sc_shift, int N, int h, int w,
+                               int nu, int C, const DecodeOut& out, cudaStream_t s);
 // label-only decode of M experts + decision-table lookup + confusion-matrix accumulation in one
 // pass (BayesFusion.score()); fused_out (uint8 [N,8h,8w]) may be NULL
 int launch_decode_bayes_confusion(const float* const* low, const float* const* g,

@@ -644,6 +644,124 @@ decode_upsample8_labels_kernel(const float* __restrict__ low, const float* __res
   if (label_u8) *reinterpret_cast<uint32_t*>(label_u8 + pix) = packed;
 }
 
+// Decoder tail with batch norm (decoder(batchnorm=True), simple_fcn.py:115-133, as fusion_fcn.py:39
+// builds it): upscore = relu(BN(bilinear x8 upsampling)) per feature channel, score = BN(1x1 conv),
+// softmax, argmax - in one pass from the 1/8-resolution features.  The ReLU sits between the
+// upsampling and the 1x1 conv, so the conv cannot move below the upsampling as in the plain
+// decoder; the upsampled num_units-channel tensor still never exists in memory: a block handles
+// 16 x 16 output pixels from the <= 4 x 4 feature cells it touches.
+template <int C>
+__global__ void __launch_bounds__(256)
+decode_bn_upsample8_kernel(const float* __restrict__ feat, const float* __restrict__ g,
+                           const float* __restrict__ up_scale, const float* __restrict__ up_shift,
+                           const float* __restrict__ w, const float* __restrict__ bias,
+                           const float* __restrict__ sc_scale, const float* __restrict__ sc_shift,
+                           int h, int wd, int nu, DecodeOut out) {
+  extern __shared__ float s_dyn_f[];
+  float* s_feat = s_dyn_f;                 // [16 cells][nu]
+  float* s_w = s_feat + 16 * nu;           // [nu][C]
+  float* s_aff = s_w + nu * C;             // [2][nu] scale, shift of the upscore batch norm
+  __shared__ float s_g[256];
+  const int H = 8 * h, W = 8 * wd;
+  const int bx = blockIdx.x * 16, by = blockIdx.y * 16;
+  const int img = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int ox = bx + tx, oy = by + ty;
+  s_g[threadIdx.x] = g[threadIdx.x];
+  const int iy0 = (by + 4) / 8 - 1, ix0 = (bx + 4) / 8 - 1;
+  for (int i = threadIdx.x; i < 16 * nu; i += 256) {
+    const int u = i % nu, cell = i / nu;
+    const int iy = iy0 + cell / 4, ix = ix0 + cell % 4;
+    float v = 0.f;
+    if (iy >= 0 && iy < h && ix >= 0 && ix < wd)
+      v = __ldg(feat + ((static_cast<size_t>(img) * h + iy) * wd + ix) * nu + u);
+    s_feat[i] = v;
+  }
+  for (int i = threadIdx.x; i < nu * C; i += 256) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < nu; i += 256) {
+    s_aff[i] = up_scale[i];
+    s_aff[nu + i] = up_shift[i];
+  }
+  __syncthreads();
+  if (ox >= W || oy >= H) return;
+  const int ay = (oy + 4) >> 3, ry = (oy + 4) & 7;
+  const int ax = (ox + 4) >> 3, rx = (ox + 4) & 7;
+  float wgt[4];
+  int cell[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int iy = ay - a, ix = ax - b;
+      const bool in = iy >= 0 && iy < h && ix >= 0 && ix < wd;
+      wgt[a * 2 + b] = in ? s_g[(ry + 8 * a) * 16 + rx + 8 * b] : 0.f;
+      cell[a * 2 + b] = in ? ((iy - iy0) * 4 + (ix - ix0)) * nu : 0;
+    }
+  }
+  float sc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) sc[c] = 0.f;
+  for (int u = 0; u < nu; ++u) {
+    float v = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v = fmaf(wgt[t], s_feat[cell[t] + u], v);
+    v = fmaxf(fmaf(v, s_aff[u], s_aff[nu + u]), 0.f);
+    const float* wr = s_w + u * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) sc[c] = fmaf(v, wr[c], sc[c]);
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    sc[c] = fmaf(sc[c] + __ldg(bias + c), __ldg(sc_scale + c), __ldg(sc_shift + c));
+    mx = fmaxf(mx, sc[c]);
+  }
+  const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox;
+  if (out.score) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) out.score[pix * C + c] = sc[c];
+  }
+  if (!out.prob) {
+    const int best = argmax_of_softmax<C>(sc);
+    if (out.label_u8) out.label_u8[pix] = static_cast<uint8_t>(best);
+    if (out.label_i64) out.label_i64[pix] = best;
+    return;
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    sc[c] = expf(sc[c] - mx);
+    sum += sc[c];
+  }
+  int best = 0;
+  float bestv = -1.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float pr = sc[c] / sum;
+    out.prob[pix * C + c] = pr;
+    if (pr > bestv) {
+      bestv = pr;
+      best = c;
+    }
+  }
+  if (out.label_u8) out.label_u8[pix] = static_cast<uint8_t>(best);
+  if (out.label_i64) out.label_i64[pix] = best;
+}
+
+template <int C>
+int decode_bn_dispatch(const float* feat, const float* g, const float* up_scale,
+                       const float* up_shift, const float* w, const float* bias,
+                       const float* sc_scale, const float* sc_shift, int N, int h, int wd, int nu,
+                       const DecodeOut& out, cudaStream_t s) {
+  dim3 grid(div_up(8 * wd, 16), div_up(8 * h, 16), N);
+  const size_t smem = (16 * nu + nu * C + 2 * nu) * sizeof(float);
+  decode_bn_upsample8_kernel<C><<<grid, 256, smem, s>>>(feat, g, up_scale, up_shift, w, bias,
+                                                        sc_scale, sc_shift, h, wd, nu, out);
+  XV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 // Fused tail of BayesFusion.score(): label-only decode of up to 4 experts (same arithmetic as
 // decode_upsample8_labels_kernel, hence the same labels) -> decision-table lookup
 // (bayes_mix.py:61-112) -> confusion-matrix accumulation (base_model.py:140-151), one pass, no
@@ -1088,6 +1206,18 @@ int launch_decode_upsample8(const float* low, const float* g, const float* bias,
                             int w, int C, const DecodeOut& out, cudaStream_t s) {
   XV_DISPATCH_C(C, (decode_dispatch<kC>(false, low, g, bias, 1, N, h, w, out, nullptr, nullptr,
                                         nullptr, s)));
+}
+bool decode_bn_supported(int nu, int C) {
+  return C >= 2 && C <= kMaxClasses && (16 * nu + nu * C + 2 * nu) * 4 <= 48 * 1024;
+}
+int launch_decode_bn_upsample8(const float* feat, const float* g_16x16, const float* up_scale,
+                               const float* up_shift, const float* w_nuxc, const float* bias,
+                               const float* sc_scale, const float* sc_shift, int N, int h, int w,
+                               int nu, int C, const DecodeOut& out, cudaStream_t s) {
+  XV_CHECK(decode_bn_supported(nu, C), "decode_bn: unsupported num_units / num_classes");
+  XV_DISPATCH_C(C, (decode_bn_dispatch<kC>(feat, g_16x16, up_scale, up_shift, w_nuxc, bias,
+                                           sc_scale, sc_shift, N, h, w, nu, out, s)));
+  return 0;
 }
 int launch_decode_bayes_confusion(const float* const* low, const float* const* g,
                                   const float* const* bias, int M, const int32_t* lut, int C,

@@ -350,6 +350,32 @@ def deconv2d(x, kernel, stride, relu=True):
     return out
 
 
+def batchnorm_train(x, gamma, beta, relu=True, moving_mean=None, moving_var=None):
+    """tf.layers.batch_normalization(training=True) (+ ReLU) on a float32 CUDA NHWC tensor.
+    Returns (y, batch mean, biased batch variance); the optional moving statistics (float32
+    CUDA [c]) are updated in place."""
+    init()
+    n, h, w, c = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    var = torch.empty(c, dtype=torch.float32, device=x.device)
+    call('xv_batchnorm_train', ptr(x.contiguous()), ptr(gamma), ptr(beta), n, h, w, c, int(relu),
+         ptr(y), ptr(mean), ptr(var), ptr(moving_mean), ptr(moving_var), stream_ptr())
+    return y, mean, var
+
+
+def batchnorm_train_backward(x, y, dy, gamma, relu=True):
+    """Backward of batchnorm_train: returns (dx, dgamma, dbeta)."""
+    init()
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    call('xv_batchnorm_train_backward', ptr(x.contiguous()), ptr(y), ptr(dy.contiguous()),
+         ptr(gamma), n, h, w, c, int(relu), ptr(dx), ptr(dgamma), ptr(dbeta), stream_ptr())
+    return dx, dgamma, dbeta
+
+
 def maxpool2x2(x):
     init()
     n, h, w, c = x.shape

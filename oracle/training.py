@@ -149,12 +149,15 @@ def _bn_train(z, p, scope, stats):
     return zhat * p[scope + '/gamma'][None, :, None, None] + p[scope + '/beta'][None, :, None, None]
 
 
-def loss_and_grads_bn(params, prefix, x, labels, num_classes, dtype=torch.float32):
+def loss_and_grads_bn(params, prefix, x, labels, num_classes, dtype=torch.float32,
+                      emulate_bf16=False):
     """Training graph of simple_fcn.py:201-215 with batchnorm=True, is_training=True: every
     conv / transposed conv is followed by batch normalisation on batch statistics, then ReLU
     (custom_layers.py:112-119,127-136); the final score conv has batch norm but no activation.
     Returns (loss, gradients incl. gamma / beta, {scope: (batch mean, biased batch variance,
-    count)})."""
+    count)}).  emulate_bf16: the device's storage precision restated (bf16 operand copies of the
+    encoder / head weights, encoder pre-norm outputs z and activations y and their gradients
+    rounded to bf16; fp32 heads and decoder)."""
     p = {}
     for name, value in params.items():
         t = torch.tensor(np.asarray(value), dtype=dtype)
@@ -166,12 +169,19 @@ def loss_and_grads_bn(params, prefix, x, labels, num_classes, dtype=torch.float3
     s = lambda n: prefix + '/' + n
     stats = {}
 
-    def conv_bn(h, scope, relu=True):
+    def conv_bn(h, scope, relu=True, q_weights=False, q_acts=False):
         w = p[s(scope) + '/kernel']
+        if emulate_bf16 and q_weights:
+            w = _bf16_forward_only(w)
         z = F.conv2d(h, w.permute(3, 2, 0, 1), p[s(scope) + '/bias'],
                      padding=(w.shape[0] - 1) // 2)
+        if emulate_bf16 and q_acts:
+            z = _Bf16Both.apply(z)
         y = _bn_train(z, p, s(scope), stats)
-        return F.relu(y) if relu else y
+        y = F.relu(y) if relu else y
+        if emulate_bf16 and q_acts:
+            y = _Bf16Both.apply(y)
+        return y
 
     def deconv_bn(h, scope, stride):
         w = p[s(scope) + '/kernel']
@@ -183,12 +193,12 @@ def loss_and_grads_bn(params, prefix, x, labels, num_classes, dtype=torch.float3
     h = torch.tensor(np.asarray(x), dtype=dtype).permute(0, 3, 1, 2)
     acts = {}
     for name, _ in CONV_LAYERS:
-        h = conv_bn(h, name)
+        h = conv_bn(h, name, q_weights=True, q_acts=True)
         acts[name] = h
         if name in ('conv1_2', 'conv2_2', 'conv3_3', 'conv4_3'):
             h = F.max_pool2d(h, 2)
-    score4 = conv_bn(acts['conv4_3'], 'score_conv4')
-    score5 = conv_bn(acts['conv5_3'], 'score_conv5')
+    score4 = conv_bn(acts['conv4_3'], 'score_conv4', q_weights=True)
+    score5 = conv_bn(acts['conv5_3'], 'score_conv5', q_weights=True)
     fused = score4 + deconv_bn(score5, 'upscore_conv5', 2)
     up = deconv_bn(fused, 'upscore', 8)
     score = conv_bn(up, 'score', relu=False).permute(0, 2, 3, 1)

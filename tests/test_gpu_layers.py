@@ -117,3 +117,47 @@ def test_maxpool(dev):
     rng = np.random.default_rng(0)
     x = rng.standard_normal((2, 8, 12, 10)).astype(np.float32)
     np.testing.assert_array_equal(dev.maxpool2x2(cuda(x)).cpu().numpy(), oracle.max_pool2x2(x))
+
+
+@pytest.mark.parametrize('n,h,w,c,relu', [(2, 9, 13, 64, True), (3, 16, 8, 5, False),
+                                          (1, 24, 24, 320, True)])
+def test_batchnorm_training_layer(dev, n, h, w, c, relu):
+    """tf.layers.batch_normalization(training=True) + ReLU (custom_layers.py:116,132-134): forward,
+    batch statistics, moving-average update and the full backward pass against torch autograd."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n * 100 + c)
+    x = (rng.standard_normal((n, h, w, c)) * rng.uniform(0.5, 3, size=c) +
+         rng.uniform(-2, 2, size=c)).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, size=c).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, size=c).astype(np.float32)
+    dy = rng.standard_normal((n, h, w, c)).astype(np.float32)
+    mm0 = rng.standard_normal(c).astype(np.float32)
+    mv0 = rng.uniform(0.5, 2, size=c).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    gt = torch.tensor(gamma, dtype=torch.float64, requires_grad=True)
+    bt = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+    mean = xt.mean(dim=(0, 1, 2))
+    var = xt.var(dim=(0, 1, 2), unbiased=False)
+    yt = (xt - mean) * torch.rsqrt(var + 1e-3) * gt + bt
+    if relu:
+        yt = F.relu(yt)
+    (yt * torch.tensor(dy, dtype=torch.float64)).sum().backward()
+    mm, mv = cuda(mm0), cuda(mv0)
+    y, bmean, bvar = dev.batchnorm_train(cuda(x), cuda(gamma), cuda(beta), relu=relu,
+                                         moving_mean=mm, moving_var=mv)
+    np.testing.assert_allclose(y.cpu().numpy(), yt.detach().numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(bmean.cpu().numpy(), mean.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(bvar.cpu().numpy(), var.detach().numpy(), rtol=1e-4, atol=1e-6)
+    count = n * h * w
+    np.testing.assert_allclose(mm.cpu().numpy(), 0.99 * mm0 + 0.01 * mean.detach().numpy(),
+                               rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mv.cpu().numpy(),
+                               0.99 * mv0 + 0.01 * var.detach().numpy() * count / (count - 1),
+                               rtol=1e-5, atol=1e-6)
+    dx, dgamma, dbeta = dev.batchnorm_train_backward(cuda(x), y, cuda(dy), cuda(gamma), relu=relu)
+    scale = np.abs(xt.grad.numpy()).max()
+    np.testing.assert_allclose(dx.cpu().numpy(), xt.grad.numpy(), rtol=0, atol=2e-5 * scale)
+    np.testing.assert_allclose(dgamma.cpu().numpy(), gt.grad.numpy(), rtol=1e-4,
+                               atol=1e-4 * np.abs(gt.grad.numpy()).max())
+    np.testing.assert_allclose(dbeta.cpu().numpy(), bt.grad.numpy(), rtol=1e-4,
+                               atol=1e-4 * np.abs(bt.grad.numpy()).max())
