@@ -1754,13 +1754,16 @@ static int repack_layer(xv_fcn* net, TrainState* ts, TrainLayer& tl, cudaStream_
 }
 
 // tensor-core weight gradient; the split of the pixel tiles over CTAs is chosen to fill whole waves
+// dy: bf16 [B,H,W,dy_channels] (dy_channels = 0: == cout; the 1x1 heads pass their gradient
+// zero-padded to 64 channels); taps = 9 (3x3) or 1 (1x1)
 static int run_wgrad_tc(xv_fcn* net, const void* x, const void* dy, float* dw, int B, int H, int W,
-                        int cin, int cout, cudaStream_t s) {
+                        int cin, int cout, cudaStream_t s, int taps = 9, int dy_channels = 0) {
   ConvWgradParams p;
   std::memset(&p, 0, sizeof(p));
   choose_tile(H, W, &p.th, &p.tw);
   XV_TRY(get_tmap(net, &p.tmap_x, x, B, H, W, cin, p.th, p.tw));
-  XV_TRY(get_tmap(net, &p.tmap_dy, dy, B, H, W, cout, p.th, p.tw));
+  XV_TRY(get_tmap(net, &p.tmap_dy, dy, B, H, W, dy_channels ? dy_channels : cout, p.th, p.tw));
+  p.taps = taps;
   p.dw = dw;
   p.N = B;
   p.H = H;
@@ -1770,7 +1773,7 @@ static int run_wgrad_tc(xv_fcn* net, const void* x, const void* dy, float* dw, i
   p.tiles_x = div_up(W, p.tw);
   p.tiles_y = div_up(H, p.th);
   p.m_blocks = div_up(cout, 128);
-  p.total_atoms = 9 * cin / 64;
+  p.total_atoms = taps * cin / 64;
   p.n_groups = div_up(p.total_atoms, 4);
   const int base = p.m_blocks * p.n_groups;
   const int tiles = B * p.tiles_x * p.tiles_y;
@@ -1863,9 +1866,14 @@ struct Backward {
                                 static_cast<float*>(dpre.p),
                                 static_cast<__nv_bfloat16*>(dpre16.p), npix, nu, nu_pad, s));
     XV_TRY(launch_bias_grad_f32(static_cast<const float*>(dpre.p), grads + tl->b_off, npix, nu, s));
-    XV_TRY(launch_outer_sum_bf16(static_cast<const __nv_bfloat16*>(x.p),
-                                 static_cast<const float*>(dpre.p), grads + tl->w_off, npix, tl->cin,
-                                 nu, s));
+    // weight gradient [512, nu] = x^T . dpre on the tensor cores (K = pixels), from the bf16 copy
+    if (tl->cin % 64 == 0 && !(g_debug_flags & 8))
+      XV_TRY(run_wgrad_tc(net, x.p, dpre16.p, grads + tl->w_off, y.B, y.H, y.W, tl->cin, nu, s, 1,
+                          nu_pad));
+    else
+      XV_TRY(launch_outer_sum_bf16(static_cast<const __nv_bfloat16*>(x.p),
+                                   static_cast<const float*>(dpre.p), grads + tl->w_off, npix,
+                                   tl->cin, nu, s));
     return run_igemm(net, *tl->bwd, dpre16.p, y.B, y.H, y.W, dx->p, false, s);
   }
 
@@ -2029,9 +2037,13 @@ struct BnTrain {
     XV_TRY(bn_bwd(name, r, g_out.p, true, &dz, static_cast<__nv_bfloat16*>(dz16.p), c_pad));
     *dx = make(DType::BF16, r.z.B, r.z.H, r.z.W, tl->cin);
     if (dry) return 0;
-    XV_TRY(launch_outer_sum_bf16(static_cast<const __nv_bfloat16*>(x.p),
-                                 static_cast<const float*>(dz.p), grads + tl->w_off, npix(r.z),
-                                 tl->cin, tl->cout, s));
+    if (tl->cin % 64 == 0 && !(g_debug_flags & 8))
+      XV_TRY(run_wgrad_tc(net, x.p, dz16.p, grads + tl->w_off, r.z.B, r.z.H, r.z.W, tl->cin,
+                          tl->cout, s, 1, c_pad));
+    else
+      XV_TRY(launch_outer_sum_bf16(static_cast<const __nv_bfloat16*>(x.p),
+                                   static_cast<const float*>(dz.p), grads + tl->w_off, npix(r.z),
+                                   tl->cin, tl->cout, s));
     return run_igemm(net, *tl->bwd, dz16.p, r.z.B, r.z.H, r.z.W, dx->p, false, s);
   }
 

@@ -1,5 +1,5 @@
-// Tensor-core weight gradient of the 3x3 convolutions (fit(), base_model.py:153-162 applied to
-// the conv kernels of simple_fcn.py:39-67):
+// Tensor-core weight gradient of the 3x3 convolutions and (taps = 1) of the 1x1 heads (fit(),
+// base_model.py:153-162 applied to the conv kernels of simple_fcn.py:39-79):
 //
 //     dW[tap][ci][co] = sum over pixels p   x[p + shift(tap)][ci] * dy[p][co]
 //
@@ -97,8 +97,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ ConvWgradParams p) {
         for (int a = 0; a < n_atoms; ++a) {
           const int atom = atom0 + a;
           const int tap = atom / cin_chunks, cc = atom - tap * cin_chunks;
-          tma_load_4d(base + (2 + a) * kBoxBytes, &p.tmap_x, &full_bar[stage], cc * 64,
-                      x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+          const int sx = p.taps == 1 ? 0 : tap % 3 - 1, sy = p.taps == 1 ? 0 : tap / 3 - 1;
+          tma_load_4d(base + (2 + a) * kBoxBytes, &p.tmap_x, &full_bar[stage], cc * 64, x0 + sx,
+                      y0 + sy, img);
         }
       }
       __syncwarp();
@@ -173,6 +174,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ ConvWgradParams p) {
 int launch_conv_wgrad_tc(const ConvWgradParams& p, cudaStream_t stream) {
   XV_CHECK(p.cin % 64 == 0, "conv_wgrad_tc: Cin must be a multiple of 64");
   XV_CHECK(p.th * p.tw == 128, "conv_wgrad_tc: tile must hold 128 pixels");
+  XV_CHECK(p.taps == 9 || p.taps == 1, "conv_wgrad_tc: 3x3 or 1x1 filters");
   static bool configured = false;
   if (!configured) {
     XV_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -75,7 +75,8 @@ struct ConvWgradParams {
   int N, H, W, cin, cout;
   int th, tw, tiles_x, tiles_y;
   int m_blocks;           // ceil(Cout / 128)
-  int total_atoms;        // 9 * Cin / 64  ((tap, 64-channel chunk) pairs)
+  int taps;               // 9 (3x3 'same') or 1 (1x1)
+  int total_atoms;        // taps * Cin / 64  ((tap, 64-channel chunk) pairs)
   int n_groups;           // ceil(total_atoms / 4)
   int k_splits;           // pixel tiles are dealt round-robin to k_splits CTAs
 };

@@ -425,40 +425,57 @@ conv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
 }
 
 // conv1_1 weight gradient (raw fp32 input, CIN <= 3): thread = (output channel, pixel lane) keeps
-// the 9*CIN partial sums of its channel in registers over a contiguous pixel range; the input
-// neighbourhood loads are warp-uniform broadcasts, the dy loads are coalesced over channels.
+// the 9*CIN partial sums of its channel in registers over whole image rows (no per-pixel index
+// arithmetic); the input neighbourhood loads are warp-uniform broadcasts, the dy loads are
+// coalesced over channels.  The pixel lanes of a block are summed in shared memory first and few
+// blocks are launched: the 9*CIN*Cout global atomics all hit the same 576..1728 addresses (the
+// first version spent most of its 3 ms serialising 2.7 M of them).
 template <int CIN>
 __global__ void __launch_bounds__(kThreads)
 conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                      float* __restrict__ dw, int N, int H, int W, int cout) {
   constexpr int K = 9 * CIN;
+  extern __shared__ float s_part[];                        // [K][cout]
   const int lanes = kThreads / cout;                       // cout = 64 -> 4 pixel lanes
   const int co = threadIdx.x % cout, lane = threadIdx.x / cout;
-  const size_t npix = static_cast<size_t>(N) * H * W;
-  const size_t per_block = (npix + gridDim.x - 1) / gridDim.x;
-  const size_t p0 = blockIdx.x * per_block;
-  const size_t p1 = p0 + per_block < npix ? p0 + per_block : npix;
+  for (int i = threadIdx.x; i < K * cout; i += kThreads) s_part[i] = 0.f;
+  __syncthreads();
+  const int rows = N * H;
+  const int per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per_block;
+  const int r1 = r0 + per_block < rows ? r0 + per_block : rows;
   float acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.f;
   if (lane < lanes) {
-    for (size_t p = p0 + lane; p < p1; p += lanes) {
-      const float d = __bfloat162float(dy[p * cout + co]);
-      const int px = static_cast<int>(p % W);
-      const int py = static_cast<int>((p / W) % H);
-      const size_t img = p / (static_cast<size_t>(W) * H);
+    for (int r = r0; r < r1; ++r) {
+      const int py = r % H;
+      const float* xrow = x + static_cast<size_t>(r) * W * CIN;     // row r of the stacked images
+      const __nv_bfloat16* dyrow = dy + static_cast<size_t>(r) * W * cout + co;
+      const bool up = py > 0, down = py + 1 < H;
+      for (int px = lane; px < W; px += lanes) {
+        const float d = __bfloat162float(dyrow[static_cast<size_t>(px) * cout]);
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const float* src = x + ((img * H + yy) * W + xx) * CIN;
+        for (int ty = 0; ty < 3; ++ty) {
+          if ((ty == 0 && !up) || (ty == 2 && !down)) continue;
+          const float* src = xrow + (static_cast<ptrdiff_t>(ty) - 1) * W * CIN + px * CIN;
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) acc[tap * CIN + ci] = fmaf(__ldg(src + ci), d, acc[tap * CIN + ci]);
+          for (int tx = 0; tx < 3; ++tx) {
+            const int xx = px + tx - 1;
+            if (xx < 0 || xx >= W) continue;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+              acc[(ty * 3 + tx) * CIN + ci] =
+                  fmaf(__ldg(src + (tx - 1) * CIN + ci), d, acc[(ty * 3 + tx) * CIN + ci]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) atomicAdd(dw + k * cout + co, acc[k]);
+    for (int k = 0; k < K; ++k) atomicAdd(&s_part[k * cout + co], acc[k]);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * cout; i += kThreads) atomicAdd(dw + i, s_part[i]);
 }
 
 // ------------------------------------------------------------------ optimizer + re-packing
@@ -625,10 +642,12 @@ int launch_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
 int launch_conv_wgrad_c1(const float* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W,
                          int cin, int cout, cudaStream_t s) {
   XV_CHECK(cout <= kThreads && cin >= 1 && cin <= 3, "conv_wgrad_c1: Cin <= 3, Cout <= 256");
-  const int grid = device_info().num_sms * 8;
-  if (cin == 1) conv_wgrad_c1_kernel<1><<<grid, kThreads, 0, s>>>(x, dy, dw, N, H, W, cout);
-  if (cin == 2) conv_wgrad_c1_kernel<2><<<grid, kThreads, 0, s>>>(x, dy, dw, N, H, W, cout);
-  if (cin == 3) conv_wgrad_c1_kernel<3><<<grid, kThreads, 0, s>>>(x, dy, dw, N, H, W, cout);
+  int grid = device_info().num_sms * 4;
+  if (grid > N * H) grid = N * H;
+  const size_t smem = static_cast<size_t>(9) * cin * cout * sizeof(float);
+  if (cin == 1) conv_wgrad_c1_kernel<1><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
+  if (cin == 2) conv_wgrad_c1_kernel<2><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
+  if (cin == 3) conv_wgrad_c1_kernel<3><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
   XV_LAUNCHED();
 }
 int launch_scale_by_count(float* g, size_t n, const double* loss, cudaStream_t s) {

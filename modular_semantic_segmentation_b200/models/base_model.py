@@ -238,13 +238,18 @@ class BaseModel(object):
             # `upload_split` = 2 (the default), or the explicit sizes of `upload_pieces`.
             split = int(self.config.get('upload_split', 2))
             explicit = self.config.get('upload_pieces')      # e.g. [4, 12]: sizes of the pieces
+            first = True
             for blob in (data if presharded else self._batches(data)):
                 count = len(next(iter(blob.values())))
                 on_host = not all(isinstance(v, torch.Tensor) and v.is_cuda
                                   for v in blob.values())
-                # training batches are never cut: a piece would become an optimizer step
+                # Only the FIRST batch of a data set is cut (nothing else can hide its copy);
+                # the upload of every later batch already overlaps the kernels of the batch
+                # before it, and a piece costs ~0.5 ms of small-batch inefficiency.  Training
+                # batches are never cut: a piece would become an optimizer step.
                 bounds = (upload_bounds(count, split, explicit)
-                          if on_host and not presharded else None)
+                          if on_host and first and not presharded else None)
+                first = False
                 if bounds is None:
                     yield blob
                     continue

@@ -2,6 +2,7 @@
 pooling) against the oracle, through the C ABI."""
 import numpy as np
 import pytest
+import torch
 
 import oracle
 from util import bf16_round, cuda
