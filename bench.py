@@ -566,10 +566,10 @@ def run_gpu(args):
 
     # one score() call over the whole data set (K x 16 frames, batchsize 16): the reference's
     # API shape (base_model.py:294-313); uploads of batch i+1 overlap the kernels of batch i
-    def dataset():
-        for i in range(args.steps):
+    def dataset(count=args.steps):
+        for i in range(count):
             yield host_sets[i % n_sets]
-    net.score(host_sets[0])
+    net.score(dataset(2 * n_sets))            # untimed: sizes the allocator for run-ahead uploads
     barrier()
     t0 = time.perf_counter()
     _, cm_ds = net.score(dataset())
@@ -593,9 +593,10 @@ def run_gpu(args):
     raw_s = max_over_ranks(time.perf_counter() - t0)
     assert np.array_equal(cm_raw, cm_host)
 
-    def raw_dataset():
-        for i in range(args.steps):
+    def raw_dataset(count=args.steps):
+        for i in range(count):
             yield raw_sets[i % n_sets]
+    net.score(raw_dataset(2 * n_sets))
     barrier()
     t0 = time.perf_counter()
     _, cm_raw_ds = net.score(raw_dataset())

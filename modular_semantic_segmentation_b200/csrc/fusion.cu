@@ -97,13 +97,25 @@ struct WarpStage {
   static constexpr bool kUse = (C % 2) != 0;
   static constexpr int kFloats = kUse ? (kPix / 32) * 32 * C : 1;
 };
+// Full warps move their 32 * C floats (128 * C bytes, 16-byte aligned because the chunk starts at a
+// multiple of 32 pixels) as float4 pieces; the ragged last chunk falls back to scalar accesses.
 template <int C>
 __device__ __forceinline__ void warp_load(const float* __restrict__ g, int64_t base, int cnt,
                                           float* __restrict__ slice, float (&v)[C]) {
   const int lane = threadIdx.x & 31;
   const float* p = g + base * C;
   __syncwarp();
-  for (int i = lane; i < cnt * C; i += 32) slice[i] = __ldg(p + i);
+  if (cnt == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    float4* s4 = reinterpret_cast<float4*>(slice);
+#pragma unroll
+    for (int i = 0; i < (8 * C + 31) / 32; ++i) {
+      const int j = lane + 32 * i;
+      if (j < 8 * C) s4[j] = __ldg(p4 + j);
+    }
+  } else {
+    for (int i = lane; i < cnt * C; i += 32) slice[i] = __ldg(p + i);
+  }
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < C; ++k) v[k] = lane < cnt ? slice[lane * C + k] : 0.f;
@@ -117,7 +129,17 @@ __device__ __forceinline__ void warp_store(float* __restrict__ g, int64_t base, 
 #pragma unroll
   for (int k = 0; k < C; ++k) slice[lane * C + k] = v[k];
   __syncwarp();
-  for (int i = lane; i < cnt * C; i += 32) p[i] = slice[i];
+  if (cnt == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* s4 = reinterpret_cast<const float4*>(slice);
+#pragma unroll
+    for (int i = 0; i < (8 * C + 31) / 32; ++i) {
+      const int j = lane + 32 * i;
+      if (j < 8 * C) p4[j] = s4[j];
+    }
+  } else {
+    for (int i = lane; i < cnt * C; i += 32) p[i] = slice[i];
+  }
 }
 
 // Pixel access used by every kernel below: direct vector access for even C, warp staging for
@@ -185,7 +207,7 @@ template <int C>
 __global__ void __launch_bounds__(kPix)
 softmax_argmax_kernel(const float* __restrict__ score, int64_t npix, float* __restrict__ prob,
                       int64_t* __restrict__ label64, uint8_t* __restrict__ label8) {
-  __shared__ float s_stage[WarpStage<C>::kFloats];
+  __shared__ __align__(16) float s_stage[WarpStage<C>::kFloats];
   float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
   const int lane = threadIdx.x & 31;
   XV_WARP_LOOP(base, cnt, npix) {
@@ -367,7 +389,7 @@ dirichlet_fuse_kernel(PtrPack probs, int M, const float* __restrict__ alpha_m1,
   }
   for (int i = threadIdx.x; i < M * C; i += kPix) s_norm[i] = lognorm[i];
   for (int i = threadIdx.x; i < C; i += kPix) s_prior[i] = logprior[i];
-  __shared__ float s_stage[WarpStage<C>::kFloats];
+  __shared__ __align__(16) float s_stage[WarpStage<C>::kFloats];
   float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
   const int lane = threadIdx.x & 31;
   const bool exact = exact_amax >= 0.f;
@@ -456,7 +478,7 @@ template <int C, bool VAR>
 __global__ void __launch_bounds__(kPix)
 mean_fuse_kernel(PtrPack probs, PtrPack vars, int M, int64_t npix, float* __restrict__ score,
                  void* __restrict__ label_out, int label_bytes) {
-  __shared__ float s_stage[WarpStage<C>::kFloats];
+  __shared__ __align__(16) float s_stage[WarpStage<C>::kFloats];
   float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
   const int lane = threadIdx.x & 31;
   XV_WARP_LOOP(base, cnt, npix) {
@@ -503,7 +525,7 @@ mc_moments_kernel(const float* __restrict__ samples, int T, int64_t npix, float*
                   float* __restrict__ sum_var) {
   const float inv_logc = 1.f / logf(static_cast<float>(C));
   const bool want_ce = cond_entropy != nullptr;
-  __shared__ float s_stage[WarpStage<C>::kFloats];
+  __shared__ __align__(16) float s_stage[WarpStage<C>::kFloats];
   float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
   const int lane = threadIdx.x & 31;
   XV_WARP_LOOP(base, cnt, npix) {
@@ -559,7 +581,7 @@ suffstats_kernel(const float* __restrict__ prob, const int32_t* __restrict__ lab
   for (int i = threadIdx.x; i < C * C; i += kPix) s_S[i] = 0.0;
   for (int i = threadIdx.x; i < C; i += kPix) s_n[i] = 0u;
   __syncthreads();
-  __shared__ float s_stage[WarpStage<C>::kFloats];
+  __shared__ __align__(16) float s_stage[WarpStage<C>::kFloats];
   float* slice = s_stage + (WarpStage<C>::kUse ? (threadIdx.x >> 5) * 32 * C : 0);
   const int lane = threadIdx.x & 31;
   XV_WARP_LOOP(base, cnt, npix) {

@@ -424,37 +424,53 @@ conv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
       atomicAdd(dw + (static_cast<size_t>(t) * cin + ci0 + ci) * cout + co0 + cog * 8 + j, acc[t][j]);
 }
 
-// conv1_1 weight gradient (raw fp32 input, CIN <= 3): thread = (output channel, pixel lane) keeps
-// the 9*CIN partial sums of its channel in registers over whole image rows (no per-pixel index
-// arithmetic); the input neighbourhood loads are warp-uniform broadcasts, the dy loads are
-// coalesced over channels.  The pixel lanes of a block are summed in shared memory first and few
-// blocks are launched: the 9*CIN*Cout global atomics all hit the same 576..1728 addresses (the
-// first version spent most of its 3 ms serialising 2.7 M of them).
-template <int CIN>
+// conv1_1 weight gradient (raw fp32 input, CIN <= 3):  dW[tap][ci][co] = sum_p x[p + tap][ci] * dy[p][co].
+// Thread = (group of CH output channels, pixel lane): one 16-byte (CH = 8) or 8-byte (CH = 4) dy
+// load and 9*CIN input loads feed 9*CIN*CH FMAs, so the kernel is FMA-bound instead of load-bound
+// (the one-channel-per-thread version issued ten loads per nine FMAs and took 1.9 - 3 ms at batch
+// 16).  Whole image rows per block (no per-pixel index arithmetic); the pixel lanes of a block are
+// summed in shared memory and few blocks are launched, because the 9*CIN*Cout global atomics all
+// hit the same addresses.
+template <int CIN, int CH>
 __global__ void __launch_bounds__(kThreads)
 conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                      float* __restrict__ dw, int N, int H, int W, int cout) {
   constexpr int K = 9 * CIN;
   extern __shared__ float s_part[];                        // [K][cout]
-  const int lanes = kThreads / cout;                       // cout = 64 -> 4 pixel lanes
-  const int co = threadIdx.x % cout, lane = threadIdx.x / cout;
+  const int groups = cout / CH;                            // channel groups per pixel
+  const int lanes = kThreads / groups;                     // pixel lanes per block
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
   for (int i = threadIdx.x; i < K * cout; i += kThreads) s_part[i] = 0.f;
   __syncthreads();
   const int rows = N * H;
   const int per_block = (rows + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * per_block;
   const int r1 = r0 + per_block < rows ? r0 + per_block : rows;
-  float acc[K];
+  float acc[K][CH];
 #pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < CH; ++j) acc[k][j] = 0.f;
   if (lane < lanes) {
     for (int r = r0; r < r1; ++r) {
       const int py = r % H;
       const float* xrow = x + static_cast<size_t>(r) * W * CIN;     // row r of the stacked images
-      const __nv_bfloat16* dyrow = dy + static_cast<size_t>(r) * W * cout + co;
+      const __nv_bfloat16* dyrow = dy + static_cast<size_t>(r) * W * cout + g * CH;
       const bool up = py > 0, down = py + 1 < H;
       for (int px = lane; px < W; px += lanes) {
-        const float d = __bfloat162float(dyrow[static_cast<size_t>(px) * cout]);
+        float d[CH];
+        if constexpr (CH == 8) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(dyrow + static_cast<size_t>(px) * cout));
+          unpack8(v, d);
+        } else {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(dyrow + static_cast<size_t>(px) * cout));
+          const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+          d[0] = __bfloat162float(a.x);
+          d[1] = __bfloat162float(a.y);
+          d[2] = __bfloat162float(b.x);
+          d[3] = __bfloat162float(b.y);
+        }
 #pragma unroll
         for (int ty = 0; ty < 3; ++ty) {
           if ((ty == 0 && !up) || (ty == 2 && !down)) continue;
@@ -464,15 +480,20 @@ conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
             const int xx = px + tx - 1;
             if (xx < 0 || xx >= W) continue;
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci)
-              acc[(ty * 3 + tx) * CIN + ci] =
-                  fmaf(__ldg(src + (tx - 1) * CIN + ci), d, acc[(ty * 3 + tx) * CIN + ci]);
+            for (int ci = 0; ci < CIN; ++ci) {
+              const float xv = __ldg(src + (tx - 1) * CIN + ci);
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                acc[(ty * 3 + tx) * CIN + ci][j] = fmaf(xv, d[j], acc[(ty * 3 + tx) * CIN + ci][j]);
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) atomicAdd(&s_part[k * cout + co], acc[k]);
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < CH; ++j) atomicAdd(&s_part[k * cout + g * CH + j], acc[k][j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K * cout; i += kThreads) atomicAdd(dw + i, s_part[i]);
@@ -641,13 +662,15 @@ int launch_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
 }
 int launch_conv_wgrad_c1(const float* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W,
                          int cin, int cout, cudaStream_t s) {
-  XV_CHECK(cout <= kThreads && cin >= 1 && cin <= 3, "conv_wgrad_c1: Cin <= 3, Cout <= 256");
+  XV_CHECK(cout % 8 == 0 && cout <= 256 && cin >= 1 && cin <= 3,
+           "conv_wgrad_c1: Cin <= 3, Cout a multiple of 8 and <= 256");
+  XV_CHECK((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "conv_wgrad_c1: dy must be 16-byte aligned");
   int grid = device_info().num_sms * 4;
   if (grid > N * H) grid = N * H;
   const size_t smem = static_cast<size_t>(9) * cin * cout * sizeof(float);
-  if (cin == 1) conv_wgrad_c1_kernel<1><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
-  if (cin == 2) conv_wgrad_c1_kernel<2><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
-  if (cin == 3) conv_wgrad_c1_kernel<3><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
+  if (cin == 1) conv_wgrad_c1_kernel<1, 8><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
+  if (cin == 2) conv_wgrad_c1_kernel<2, 4><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
+  if (cin == 3) conv_wgrad_c1_kernel<3, 4><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
   XV_LAUNCHED();
 }
 int launch_scale_by_count(float* g, size_t n, const double* loss, cudaStream_t s) {

@@ -110,12 +110,23 @@ class DirichletFusion(BaseModel):
         if num_samples <= 1:
             return [self._experts[m].forward(batch[m], want=('prob',))['prob']
                     for m in self.modalities]
-        from .variance_mix import mc_dropout_seed
-        return [self._experts[m].forward(batch[m], want=('mean_prob',), dropout={
-            'rate': self.config.get('dropout_rate', 0.5),
-            'layers': list(self.config.get('dropout_layers', ['pool3'])),
-            'num_samples': num_samples, 'seed': mc_dropout_seed(self, i)})['mean_prob']
-                for i, m in enumerate(self.modalities)]
+        from .variance_mix import mc_dropout_seed, split_samples_over_ranks
+        split = split_samples_over_ranks(self)
+        means = []
+        for i, m in enumerate(self.modalities):
+            cfg = {'rate': self.config.get('dropout_rate', 0.5),
+                   'layers': list(self.config.get('dropout_layers', ['pool3'])),
+                   'num_samples': num_samples, 'seed': mc_dropout_seed(self, i)}
+            if split is None:
+                means.append(self._experts[m].forward(batch[m], want=('mean_prob',),
+                                                      dropout=cfg)['mean_prob'])
+            else:       # samples split over the ranks (batch-1 latency mode), moments merged
+                cfg.update(num_samples=split[0], seed=cfg['seed'] + 7919 * (split[1] + 1))
+                out = self._experts[m].forward(batch[m], want=('mean_prob', 'var_prob'),
+                                               dropout=cfg)
+                sharding.combine_moments_(out['mean_prob'], out['var_prob'], split[0])
+                means.append(out['mean_prob'])
+        return means
 
     def _run_batch(self, batch, fetch='prediction'):
         if self._tables is None:

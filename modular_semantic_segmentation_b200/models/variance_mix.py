@@ -2,6 +2,7 @@
 shipped (pre-refactor BaseModel signature); the working statement is
 experiments/timing.py:180-233, which this class follows."""
 from .. import device as dev
+from .. import sharding
 from .basic_fusion_model import FusionModel
 
 
@@ -23,6 +24,24 @@ def mc_dropout_seed(model, stream_index):
     return (base * 1000003 + calls * 8191 + stream_index) & 0xFFFFFFFFFFFFFFFF
 
 
+def split_samples_over_ranks(model):
+    """(samples of this rank, rank) if the model is configured to split its MC-dropout SAMPLES
+    over the ranks instead of the images (`split_samples=True`, `shard_images=False`: every rank
+    sees every image - the batch-1 latency mode of SURVEY.md section 8e), else None.  Every rank
+    needs at least two samples (moments of a single sample are degenerate)."""
+    if not model.config.get('split_samples', False):
+        return None
+    rank, world = sharding.rank_world()
+    if world == 1:
+        return None
+    if model.config.get('shard_images', True):
+        raise UserWarning('ERROR: split_samples=True needs shard_images=False')
+    mine = sharding.samples_for_rank(int(model.config['num_samples']), rank, world)
+    if mine < 2:
+        raise UserWarning('ERROR: split_samples needs at least 2 MC samples per rank')
+    return mine, rank
+
+
 class VarianceFusion(FusionModel):
     """variance_mix.py:18-83: MC-dropout (dropout after pool3, `num_samples` samples sharing
     one weight load) gives the per-pixel variance, a dropout-free pass gives the
@@ -41,16 +60,25 @@ class VarianceFusion(FusionModel):
         import torch
         label_dtype = torch.uint8 if fetch == 'prediction_compact' else torch.int64
         probs, variances = [], []
+        split = split_samples_over_ranks(self)
         for i, m in enumerate(self.modalities):
             expert = self._experts[self._expert_prefix(m)]
             # one call: the dropout-free pass (probabilities, variance_mix.py:68-69) rides along
             # as a leading sample of the MC batch, so conv1_1..pool3 run once for both
-            out = expert.forward(batch[m], want=('prob', 'mean_var'), dropout={
-                'rate': self.config['dropout_rate'], 'layers': ['pool3'],
-                'num_samples': self.config['num_samples'], 'with_deterministic': True,
-                'seed': mc_dropout_seed(self, i)})
+            cfg = {'rate': self.config['dropout_rate'], 'layers': ['pool3'],
+                   'num_samples': self.config['num_samples'], 'with_deterministic': True,
+                   'seed': mc_dropout_seed(self, i)}
+            if split is None:
+                out = expert.forward(batch[m], want=('prob', 'mean_var'), dropout=cfg)
+                variances.append(out['mean_var'])
+            else:
+                # batch-1 latency mode: this rank draws its share of the samples, the per-rank
+                # moments are merged over NCCL (every rank ends with the full result)
+                cfg.update(num_samples=split[0], seed=cfg['seed'] + 7919 * (split[1] + 1))
+                out = expert.forward(batch[m], want=('prob', 'mean_prob', 'var_prob'), dropout=cfg)
+                sharding.combine_moments_(out['mean_prob'], out['var_prob'], split[0])
+                variances.append(out['var_prob'].mean(-1))
             probs.append(out['prob'])
-            variances.append(out['mean_var'])
         score, label = dev.variance_fuse(probs, variances, want_score=(fetch == 'fused_score'),
                                          label_dtype=label_dtype)
         return score if fetch == 'fused_score' else label

@@ -72,3 +72,40 @@ def gather_interleaved(local, like_device):
         if counts[r]:
             out[r:total:world] = bufs[r][:counts[r]]
     return out
+
+
+def samples_for_rank(num_samples, rank, world):
+    """How many of `num_samples` MC-dropout samples `rank` draws when the samples (not the
+    images) are split over the ranks: the first `num_samples % world` ranks take one more."""
+    return num_samples // world + (1 if rank < num_samples % world else 0)
+
+
+def combine_moments_(mean, var, local_samples, extra=()):
+    """Merge per-rank population moments of MC-dropout samples into the moments of all samples
+    ("split the T MC samples across GPUs and allreduce first/second
+    moments").  mean / var: this rank's population mean and variance over its `local_samples`
+    samples (tensors of equal shape, modified in place); `extra`: further tensors whose
+    sample-weighted average is wanted (e.g. a mean-over-classes variance is NOT one of them - it
+    is derived from `var` afterwards).  Returns the total number of samples.
+
+        mean = sum_r t_r mean_r / T,   var = sum_r t_r (var_r + mean_r^2) / T - mean^2
+    """
+    dist = dist_or_none()
+    if dist is None:
+        return local_samples
+    t = float(local_samples)
+    second = (var + mean * mean) * t
+    mean.mul_(t)
+    total = torch.tensor([t], dtype=torch.float64, device=mean.device)
+    dist.all_reduce(mean)
+    dist.all_reduce(second)
+    dist.all_reduce(total)
+    total_t = float(total.item())
+    mean.div_(total_t)
+    var.copy_(second / total_t - mean * mean)
+    var.clamp_(min=0)
+    for tensor in extra:
+        tensor.mul_(t)
+        dist.all_reduce(tensor)
+        tensor.div_(total_t)
+    return int(round(total_t))

@@ -39,9 +39,23 @@ with get_model('fcn')('rgb', fdesc, 'rgb', num_units=8, batch_normalization=Fals
     trained = fnet.variables['rgb/conv4_2/kernel'].copy()
     trained_head = fnet.variables['rgb/score/kernel'].copy()
     final_loss = fnet.loss
+# batch-1 latency mode: the T MC-dropout samples (not the images) are split over the ranks and the
+# per-rank moments merged over NCCL; every rank must end with the same fused labels
+split_ok = True
+if world > 1:
+    with get_model('variance_fusion')(data_description=desc, prefixes={'rgb': 'rgb', 'depth': 'depth'},
+                                      expert_model='fcn', num_units=8,
+                                      num_channels={'rgb': 3, 'depth': 1}, batchsize=1,
+                                      num_samples=7, dropout_rate=0.3, seed=4, shard_images=False,
+                                      split_samples=True, deterministic_dropout=True) as vnet:
+        vpred = vnet.predict({'rgb': data['rgb'][:2], 'depth': data['depth'][:2]})
+    mine = torch.from_numpy(vpred).cuda()
+    both = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    split_ok = bool(all(torch.equal(b, both[0]) for b in both)) and vpred.shape == (2, 32, 48)
 if rank == 0:
     np.savez(os.environ['XV_OUT'], cm=cm, pred=pred, miou=measures['mean_IoU'], trained=trained,
-             trained_head=trained_head, final_loss=final_loss)
+             trained_head=trained_head, final_loss=final_loss, split_ok=split_ok)
 dist.destroy_process_group()
 '''
 
@@ -81,6 +95,7 @@ def test_two_gpu_score_and_predict_equal_single_gpu(tmp_path):
     np.testing.assert_array_equal(results[2]['pred'], results[1]['pred'])
     assert results[2]['miou'] == results[1]['miou']
     assert results[1]['pred'].shape == (n, h, w)
+    assert bool(results[2]['split_ok'])          # MC samples split over the ranks, merged moments
     # 2-rank data-parallel training follows the 1-rank trajectory (same global batches; the
     # gradient sums differ only by fp32 accumulation order)
     np.testing.assert_allclose(results[2]['final_loss'], results[1]['final_loss'], rtol=2e-2)

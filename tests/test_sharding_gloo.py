@@ -92,3 +92,34 @@ def test_two_rank_dirichlet_fit_statistics_and_empty_rank(tmp_path):
     world = 2
     mp.spawn(_fit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ('ok%d' % r)).exists() for r in range(world))
+
+
+def _moments_worker(rank, world, port, out_dir):
+    """MC samples split over the ranks (batch-1 latency mode): every rank draws its share of the
+    T samples, the per-rank population moments are merged by all-reduce."""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from modular_semantic_segmentation_b200 import sharding
+    rng = np.random.default_rng(2)
+    t_total, c = 7, 5                                    # uneven: 4 + 3 samples
+    samples = rng.random((t_total, 3, 4, 6, c))
+    counts = [sharding.samples_for_rank(t_total, r, world) for r in range(world)]
+    assert counts == [4, 3] and sum(counts) == t_total
+    lo = sum(counts[:rank])
+    mine = samples[lo:lo + counts[rank]]
+    mean = torch.from_numpy(mine.mean(0))
+    var = torch.from_numpy(mine.var(0))
+    total = sharding.combine_moments_(mean, var, counts[rank])
+    assert total == t_total
+    np.testing.assert_allclose(mean.numpy(), samples.mean(0), rtol=1e-12)
+    np.testing.assert_allclose(var.numpy(), samples.var(0), rtol=1e-9, atol=1e-15)
+    open(os.path.join(out_dir, 'ok%d' % rank), 'w').write('ok')
+    dist.destroy_process_group()
+
+
+def test_two_rank_mc_sample_split_moments(tmp_path):
+    world = 2
+    mp.spawn(_moments_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ('ok%d' % r)).exists() for r in range(world))
