@@ -259,6 +259,18 @@ int xv_dirichlet_fuse_exact(const float* const* probs_host, int num_experts, con
                             const float* log_norm, const float* log_prior, int num_classes,
                             int64_t npix, float abs_alpha_m1_max, float abs_norm_max, float* score,
                             void* label, int label_bytes, int64_t* num_exact, void* stream);
+/* One step of DirichletFusion behind its two experts as ONE kernel: the decoder tail of both
+ * (x8 upsampling + bias + softmax, simple_fcn.py:129-133 / basic_fusion_model.py:21) from the
+ * low-resolution class scores left by the LAST xv_fcn_forward call of each handle, Dirichlet fusion
+ * (dirichlet_mix.py:14-36,100-113; abs_alpha_m1_max >= 0: bit-exact argmax as in
+ * xv_dirichlet_fuse_exact, < 0: fast arithmetic), then the fused label (label, may be NULL) and / or
+ * the confusion matrix ACCUMULATED against gt_labels into cm (base_model.py:140-151; both NULL or
+ * both set).  Labels are identical to xv_fcn_forward(prob) + xv_dirichlet_fuse_exact. */
+int xv_dirichlet_decode_score(xv_fcn* const* experts_host, int num_experts, const float* alpha_m1,
+                              const float* log_norm, const float* log_prior, int num_classes,
+                              float abs_alpha_m1_max, float abs_norm_max, const int32_t* gt_labels,
+                              int64_t* cm, void* label, int label_bytes, int64_t* num_exact,
+                              void* stream);
 /* average_mix.py:18-21; every sum and quotient individually rounded (bit-exact vs float32 numpy) */
 int xv_average_fuse(const float* const* probs_host, int num_experts, int num_classes,
                     int64_t npix, float* score, void* label, int label_bytes, void* stream);

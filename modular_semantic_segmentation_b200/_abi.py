@@ -96,6 +96,8 @@ PROTOTYPES = {
     'xv_dirichlet_fuse': [_PP, _I, _P, _P, _P, _I, _L, _P, _P, _I, _P],
     'xv_dirichlet_fuse_exact': [_PP, _I, _P, _P, _P, _I, _L, C.c_float, C.c_float, _P, _P, _I, _P,
                                 _P],
+    'xv_dirichlet_decode_score': [_PP, _I, _P, _P, _P, _I, C.c_float, C.c_float, _P, _P, _P, _I,
+                                  _P, _P],
     'xv_average_fuse': [_PP, _I, _I, _L, _P, _P, _I, _P],
     'xv_variance_fuse': [_PP, _PP, _I, _I, _L, _P, _P, _I, _P],
     'xv_mc_moments': [_P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P],

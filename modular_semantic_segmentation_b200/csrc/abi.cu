@@ -1589,6 +1589,43 @@ int xv_bayes_decode_score(xv_fcn* const* experts, int M, const int32_t* lut, int
                                        XV_STREAM(stream));
 }
 
+int xv_dirichlet_decode_score(xv_fcn* const* experts, int M, const float* alpha_m1,
+                              const float* log_norm, const float* log_prior, int C,
+                              float abs_alpha_m1_max, float abs_norm_max, const int32_t* gt_labels,
+                              int64_t* cm, void* label, int label_bytes, int64_t* num_exact,
+                              void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(experts && alpha_m1 && log_norm && log_prior && M == 2,
+           "xv_dirichlet_decode_score: two experts and their tables are needed");
+  if (label) XV_TRY(check_label_bytes(label_bytes));
+  XV_CHECK(label != nullptr || cm != nullptr, "xv_dirichlet_decode_score: nothing to compute");
+  const float *low[2], *g[2], *bias[2];
+  int N = 0, h = 0, w = 0;
+  for (int m = 0; m < M; ++m) {
+    xv_fcn* e = experts[m];
+    XV_CHECK(e && e->finalized && e->fast_up && e->C == C,
+             "xv_dirichlet_decode_score: experts need the bilinear decoder fast path and C classes");
+    auto it = e->layers.find("score_lowres");
+    XV_CHECK(it != e->layers.end() && it->second.p != nullptr,
+             "xv_dirichlet_decode_score: run xv_fcn_forward on every expert first");
+    const Act& a = it->second;
+    if (m == 0) {
+      N = a.B;
+      h = a.H;
+      w = a.W;
+    }
+    XV_CHECK(a.B == N && a.H == h && a.W == w, "xv_dirichlet_decode_score: expert shapes differ");
+    low[m] = static_cast<const float*>(a.p);
+    g[m] = static_cast<const float*>(e->g16.p);
+    bias[m] = static_cast<const float*>(e->b_score.p);
+  }
+  return launch_decode_dirichlet(low, g, bias, M, alpha_m1, log_norm, log_prior, abs_alpha_m1_max,
+                                 abs_norm_max, C, N, h, w, gt_labels,
+                                 reinterpret_cast<long long*>(cm), label, label_bytes,
+                                 reinterpret_cast<unsigned long long*>(num_exact),
+                                 XV_STREAM(stream));
+}
+
 int xv_dirichlet_fuse(const float* const* probs, int M, const float* alpha_m1,
                       const float* log_norm, const float* log_prior, int C, int64_t npix,
                       float* score, void* label, int label_bytes, void* stream) {

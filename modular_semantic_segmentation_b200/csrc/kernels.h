@@ -204,6 +204,17 @@ int launch_suffstats(const float* prob, const int32_t* labels, int64_t npix, int
 int launch_confusion(const void* pred, int pred_bytes, const int32_t* labels, int64_t npix, int C,
                      long long* cm /*[C,C] +=*/, cudaStream_t s);
 
+// ------------------------------------------------------------- decode_dirichlet.cu
+// fused tail of DirichletFusion for two experts: x8 decode + softmax of both -> Dirichlet fusion
+// (fast form, exact re-evaluation of near-ties when exact_amax >= 0) -> label_out (may be NULL)
+// and / or confusion-matrix accumulation against gt into cm (both NULL or both set)
+int launch_decode_dirichlet(const float* const* low, const float* const* g,
+                            const float* const* bias, int M, const float* alpha_m1,
+                            const float* lognorm, const float* logprior, float exact_amax,
+                            float exact_tail, int C, int N, int h, int w, const int32_t* gt,
+                            long long* cm, void* label_out, int label_bytes,
+                            unsigned long long* n_exact, cudaStream_t s);
+
 // ------------------------------------------------------------- mc_dirichlet.cu
 int launch_dirichlet_fit_samples(const float* samples, int T, int64_t npix, int C, float tol,
                                  int maxiter, float* alpha, int* iters, cudaStream_t s);

@@ -588,6 +588,32 @@ decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__
   }
 }
 
+// the C class scores of one low-resolution cell: 16-byte loads where the row is 16-byte aligned
+// (C % 4 == 0; the map itself comes from an arena slot aligned to 1 KB)
+template <int C>
+__device__ __forceinline__ void load_cell(const float* __restrict__ lp, float (&v)[C]) {
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(lp) + q);
+      v[4 * q] = t.x;
+      v[4 * q + 1] = t.y;
+      v[4 * q + 2] = t.z;
+      v[4 * q + 3] = t.w;
+    }
+  } else if constexpr (C % 2 == 0) {
+#pragma unroll
+    for (int q = 0; q < C / 2; ++q) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(lp) + q);
+      v[2 * q] = t.x;
+      v[2 * q + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __ldg(lp + c);
+  }
+}
+
 // Label-only decode (what score() asks for).  One thread = 4 horizontally adjacent output pixels:
 // they share their four low-resolution cells ((ox + 4) >> 3 is constant over an aligned group of
 // 4), so the cells are read once per group - the one-pixel-per-thread version was bound by L1
@@ -620,11 +646,12 @@ decode_upsample8_labels_kernel(const float* __restrict__ low, const float* __res
       const float4 wg = __ldg(reinterpret_cast<const float4*>(g + ky * 16 + rx0 + 8 * b));
       const float wgt[4] = {wg.x, wg.y, wg.z, wg.w};
       const float* lp = low + ((static_cast<size_t>(img) * h + iy) * w + ix) * C;
+      float cellv[C];
+      load_cell<C>(lp, cellv);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float v = __ldg(lp + c);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i][c] = fmaf(wgt[i], v, s[i][c]);
+        for (int i = 0; i < 4; ++i) s[i][c] = fmaf(wgt[i], cellv[c], s[i][c]);
       }
     }
   }
@@ -822,11 +849,12 @@ decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ 
           const float4 wg = __ldg(reinterpret_cast<const float4*>(g + ky * 16 + rx0 + 8 * b));
           const float wgt[4] = {wg.x, wg.y, wg.z, wg.w};
           const float* lp = low + ((static_cast<size_t>(img) * h + iy) * w + ix) * C;
+          float cellv[C];
+          load_cell<C>(lp, cellv);
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const float v = __ldg(lp + c);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) s[i][c] = fmaf(wgt[i], v, s[i][c]);
+            for (int i = 0; i < 4; ++i) s[i][c] = fmaf(wgt[i], cellv[c], s[i][c]);
           }
         }
       }

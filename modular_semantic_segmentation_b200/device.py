@@ -192,6 +192,7 @@ class FcnExpert(object):
                 o.mean_var = out['mean_var'].data_ptr()
         call('xv_fcn_forward', self._h, ptr(x), n, h, w, C.byref(cfg) if cfg is not None else None,
              C.byref(o), stream_ptr())
+        self._last_forward_shape = (b, h, w)
         if keep_alive:
             torch.cuda.current_stream().synchronize()
         return out
@@ -468,6 +469,27 @@ def dirichlet_fuse(probs, alpha_m1, log_norm, log_prior, want_score=False,
              c, npix, ptr(score), ptr(label), _label_bytes(label), stream_ptr())
     del keep
     return score, label
+
+
+def dirichlet_decode_score(experts, alpha_m1, log_norm, log_prior, num_classes, magnitudes,
+                           gt_labels=None, cm=None, want_label=True, label_dtype=torch.int64,
+                           exact=True, num_exact=None):
+    """One kernel behind the two experts' last forward calls: decoder tail (x8 upsampling +
+    softmax) of both -> Dirichlet fusion (bit-exact argmax if `exact`) -> fused labels and / or
+    confusion-matrix accumulation into cm (xv_dirichlet_decode_score).  No probability tensor is
+    written.  Returns the label map (or None)."""
+    init()
+    handles = (C.c_void_p * len(experts))(*[e._h for e in experts])
+    label = None
+    if want_label:
+        n, h, w = experts[0]._last_forward_shape
+        label = torch.empty((n, h, w), dtype=label_dtype, device=alpha_m1.device)
+    amax, tail = magnitudes if exact else (-1.0, 0.0)
+    call('xv_dirichlet_decode_score', C.cast(handles, C.POINTER(C.c_void_p)), len(experts),
+         ptr(alpha_m1), ptr(log_norm), ptr(log_prior), num_classes, C.c_float(amax),
+         C.c_float(tail), ptr(gt_labels), ptr(cm), ptr(label),
+         _label_bytes(label) if label is not None else 8, ptr(num_exact), stream_ptr())
+    return label
 
 
 def average_fuse(probs, want_score=False, label_dtype=torch.int64):

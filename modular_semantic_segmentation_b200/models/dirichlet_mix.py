@@ -128,10 +128,45 @@ class DirichletFusion(BaseModel):
                 means.append(out['mean_prob'])
         return means
 
+    def _fused_tail_applies(self):
+        """The one-kernel tail (decode of both experts + Dirichlet fusion [+ confusion matrix],
+        xv_dirichlet_decode_score) covers the reference's own configuration: two FCN experts,
+        dropout-free softmax outputs, up to 16 classes."""
+        return (self.config.get('fused_score_tail', True) and
+                not getattr(self, '_no_fused_tail', False) and
+                self.config['expert_model'] == 'fcn' and len(self.modalities) == 2 and
+                self.config.get('precision', 'bf16') == 'bf16' and
+                int(self.config.get('num_samples', 1)) <= 1 and self.config['num_classes'] <= 16)
+
+    def _fused_tail(self, batch, cm, want_label, label_dtype=torch.int64):
+        experts = [self._experts[m] for m in self.modalities]
+        for m in sorted(self.modalities, key=lambda k: dict.__getitem__(batch, k).numel()):
+            self._experts[m].forward(batch[m], want=())
+        try:
+            return True, dev.dirichlet_decode_score(
+                experts, *self._tables, self.config['num_classes'], self._magnitudes,
+                gt_labels=batch['labels'].contiguous() if cm is not None else None, cm=cm,
+                want_label=want_label, label_dtype=label_dtype,
+                exact=bool(self.config.get('exact_fusion', True)))
+        except dev._abi.XViewError:
+            self._no_fused_tail = True      # e.g. non-bilinear upscore kernels were imported
+            return False, None
+
+    def _score_batch(self, batch, cm):
+        if self._tables is not None and self._fused_tail_applies():
+            done, _ = self._fused_tail(batch, cm, want_label=False)
+            if done:
+                return
+        BaseModel._score_batch(self, batch, cm)
+
     def _run_batch(self, batch, fetch='prediction'):
         if self._tables is None:
             raise UserWarning('ERROR: DirichletFusion has to be fitted before inference')
         label_dtype = torch.uint8 if fetch == 'prediction_compact' else torch.int64
+        if fetch in ('prediction', 'prediction_compact') and self._fused_tail_applies():
+            done, label = self._fused_tail(batch, None, want_label=True, label_dtype=label_dtype)
+            if done:
+                return label
         self.probs = dict(zip(self.modalities, self._probs(batch)))
         # `exact_fusion` (default True): bit-exact argmax of the fixed-order float32 rule; the
         # fast arithmetic is kept for pixels whose decision margin exceeds the error bound

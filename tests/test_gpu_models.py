@@ -407,3 +407,44 @@ def test_bayes_score_fused_tail_equals_generic_route(c, h, w):
     np.testing.assert_array_equal(cm_fused, cm_generic)
     np.testing.assert_array_equal(cm_fused, oracle.confusion_matrix(data['labels'], pred, c))
     assert launches_fused < launches_generic
+
+
+@pytest.mark.parametrize('c,h,w', [(12, 48, 64), (5, 32, 80)])
+def test_dirichlet_fused_tail_equals_generic_route(c, h, w):
+    """DirichletFusion runs decode + softmax of both experts + Dirichlet fusion (+ confusion
+    matrix) as one kernel (xv_dirichlet_decode_score); labels and matrices must be identical to
+    the generic route (expert probabilities in HBM -> xv_dirichlet_fuse_exact ->
+    xv_confusion_accumulate) and to the float32 oracle applied to the device's probabilities."""
+    from xview.models import get_model
+    from modular_semantic_segmentation_b200 import device as dev
+    rng = np.random.default_rng(100 + c)
+    n = 3
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    fit = {m: 1.0 + rng.gamma(2.0, 2.0, size=(c, c)) + 3 * np.eye(c) for m in ('rgb', 'depth')}
+    fit['class_counts'] = rng.integers(10, 1000, size=c).astype(np.float64)
+    common = dict(data_description=_description(c), modalities=['rgb', 'depth'], expert_model='fcn',
+                  num_units=NU, num_channels={'rgb': 3, 'depth': 1}, batchsize=2,
+                  dirichlet_params=fit)
+    with get_model('dirichlet_mix')(**common) as net:
+        _load(net, params)
+        before = dev.launch_count()
+        _, cm_fused = net.score(data)
+        launches_fused = dev.launch_count() - before
+        pred_fused = net.predict(data)
+    with get_model('dirichlet_mix')(fused_score_tail=False, **common) as net:
+        _load(net, params)
+        before = dev.launch_count()
+        _, cm_generic = net.score(data)
+        launches_generic = dev.launch_count() - before
+        pred_generic = net.predict(data)
+        probs = [net._experts[m].forward(torch.from_numpy(data[m]).cuda(),
+                                         want=('prob',))['prob'].cpu().numpy()
+                 for m in ('rgb', 'depth')]
+    np.testing.assert_array_equal(pred_fused, pred_generic)
+    np.testing.assert_array_equal(cm_fused, cm_generic)
+    np.testing.assert_array_equal(cm_fused, oracle.confusion_matrix(data['labels'], pred_fused, c))
+    ref = oracle.dirichlet_fusion_f32(probs, [fit['rgb'], fit['depth']],
+                                      oracle.dirichlet_prior(fit['class_counts']))
+    np.testing.assert_array_equal(pred_fused, oracle.argmax_first(ref))
+    assert launches_fused < launches_generic
