@@ -448,3 +448,30 @@ def test_dirichlet_fused_tail_equals_generic_route(c, h, w):
                                       oracle.dirichlet_prior(fit['class_counts']))
     np.testing.assert_array_equal(pred_fused, oracle.argmax_first(ref))
     assert launches_fused < launches_generic
+
+
+def test_cuda_graph_score_step_equals_eager():
+    """BaseModel.capture_score_step: the whole score() step of a device-resident batch replayed
+    from one CUDA graph accumulates the same confusion matrix as the eager launches."""
+    from xview.models import get_model
+    c, n, h, w = 6, 4, 48, 64
+    rng = np.random.default_rng(41)
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    cms = {m: rng.integers(0, 60, size=(c, c)).astype(np.float64) + 150 * np.eye(c)
+           for m in ('rgb', 'depth')}
+    with get_model('bayes_fusion')(
+            confusion_matrices=cms, data_description=_description(c),
+            prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn', num_units=NU,
+            num_channels={'rgb': 3, 'depth': 1}, batchsize=n) as net:
+        _load(net, params)
+        batch = net._to_device(data)
+        eager = torch.zeros((c, c), dtype=torch.int64, device='cuda')
+        net.score_batch_on_device(batch, eager)
+        cm = torch.zeros((c, c), dtype=torch.int64, device='cuda')
+        graph, kernels = net.capture_score_step(batch, cm)
+        assert kernels == 33 and int(cm.sum()) == 0          # capture leaves the matrix empty
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(cm.cpu().numpy(), 3 * eager.cpu().numpy())
