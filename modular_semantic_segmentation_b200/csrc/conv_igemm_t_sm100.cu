@@ -313,24 +313,68 @@ conv_igemm_t_kernel(const __grid_constant__ ConvIgemmParams p) {
           tma_store_commit();
         }
       } else {
+        // Un-pooled output: the accumulator (lanes = channels, columns = pixels) has to reach the
+        // pixel-major staging rows (128 B = 64 channels per pixel).  tcgen05.ld.16x256b hands
+        // every thread the mma-style fragment (row t/4 [+8], columns 2(t%4), +1 of each 8-column
+        // group), which is exactly what stmatrix.trans wants: one stmatrix.x4 writes four 8x8
+        // bf16 blocks as 16-byte pieces of eight pixel rows - 16 store instructions per warp and
+        // 128-pixel half instead of the 128 two-byte scatter stores of the first version (the
+        // shared-memory port is this kernel's bottleneck: tensor pipe 65 % on conv2_1).
+        const bool warp_live = (n0 + q * 32) < p.cout;      // Cout % 64 == 0: uniform per warp
+        float fb[2][2];
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const int c = n0 + q * 32 + hs * 16 + (lane >> 2) + rh * 8;
+            fb[hs][rh] = c < p.cout ? __ldg(p.bias + c) : 0.f;
+          }
+        const int mi = lane >> 3, rr = lane & 7;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {    // 128 pixels = 8 tile rows at a time
           if (issuer) tma_store_wait_read<0>();
           named_bar_sync(1, 128);
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_row + (half * 4 + j) * 32, r);
-            tmem_ld_wait();
-            if (live) {
+          for (int blk = 0; blk < 2; ++blk) {     // 64 pixels per fragment load
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float v = __uint_as_float(r[i]) + bias;
-                if (p.relu) v = fmaxf(v, 0.f);
-                const uint32_t row = static_cast<uint32_t>(j * 32 + i);
-                *reinterpret_cast<__nv_bfloat16*>(my_chunk + row * 128 +
-                                                  ((ch_piece ^ (row & 7)) << 4) + ch_off) =
-                    __float2bfloat16_rn(v);
+            for (int hs = 0; hs < 2; ++hs) {      // lanes 0-15 / 16-31 of this warp's quarter
+              uint32_t r[32];
+              tmem_ld_16x256b_x8(t_row + (static_cast<uint32_t>(hs * 16) << 16) + half * 128 +
+                                     blk * 64,
+                                 r);
+              tmem_ld_wait();
+              if (warp_live) {
+                const int chgrp = q * 32 + hs * 16 + (mi & 1) * 8;      // channels of "my" block
+                uint8_t* chunk = staging + (chgrp >> 6) * 16384;
+                const uint32_t piece = static_cast<uint32_t>((chgrp & 63) >> 3);
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                  uint32_t m[4];
+#pragma unroll
+                  for (int u = 0; u < 2; ++u) {
+                    const int rep = i + u;
+                    float v0 = __uint_as_float(r[4 * rep]) + fb[hs][0];
+                    float v1 = __uint_as_float(r[4 * rep + 1]) + fb[hs][0];
+                    float v2 = __uint_as_float(r[4 * rep + 2]) + fb[hs][1];
+                    float v3 = __uint_as_float(r[4 * rep + 3]) + fb[hs][1];
+                    if (p.relu) {
+                      v0 = fmaxf(v0, 0.f);
+                      v1 = fmaxf(v1, 0.f);
+                      v2 = fmaxf(v2, 0.f);
+                      v3 = fmaxf(v3, 0.f);
+                    }
+                    m[2 * u] = pack_bf16x2(v0, v1);
+                    m[2 * u + 1] = pack_bf16x2(v2, v3);
+                  }
+                  const uint32_t row = static_cast<uint32_t>(blk * 64 + (i + (mi >> 1)) * 8 + rr);
+                  const uint32_t addr =
+                      smem_u32(chunk) + row * 128 + ((piece ^ (row & 7)) << 4);
+                  asm volatile(
+                      "stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(
+                          addr),
+                      "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3])
+                      : "memory");
+                }
               }
             }
           }
