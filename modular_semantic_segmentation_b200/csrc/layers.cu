@@ -8,6 +8,8 @@
 #include "kernels.h"
 
 namespace xv {
+int debug_flags();   // abi.cu; bit 8: scalar dropout kernel, bit 9: per-sample-barrier MC decode
+
 
 namespace {
 
@@ -212,6 +214,55 @@ __global__ void dropout_kernel(const T* __restrict__ in, T* __restrict__ out, si
         out[i] = static_cast<T>(kept ? v / keep : 0.f);
       }
     }
+  }
+}
+
+// bf16, 8 elements per thread.  nvec = n / 8 vectors per copy, total = vectors of the whole output,
+// pass_vecs = leading vectors copied through; element j of the dropout region belongs to Philox
+// group j / 4 exactly as in dropout_kernel.
+__global__ void dropout_bf16x8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                      size_t nvec, size_t total, float rate,
+                                      const uint8_t* __restrict__ ext_mask, uint64_t seed,
+                                      uint64_t offset, size_t pass_vecs) {
+  const float inv_keep = 1.f / (1.f - rate);
+  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 x = __ldg(in + v % nvec);
+    if (v < pass_vecs) {
+      out[v] = x;
+      continue;
+    }
+    const size_t j = v - pass_vecs;              // vector index inside the dropout region
+    bool kept[8];
+    if (ext_mask != nullptr) {
+      const uint2 m = __ldg(reinterpret_cast<const uint2*>(ext_mask) + j);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kept[e] = (((e < 4 ? m.x : m.y) >> (8 * (e & 3))) & 0xffu) != 0;
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t c = 2 * j + h + offset;
+        const uint4 rnd = philox4x32_10(
+            make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0x58564231u, 0u),
+            make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+        kept[4 * h] = u01(rnd.x) >= rate;
+        kept[4 * h + 1] = u01(rnd.y) >= rate;
+        kept[4 * h + 2] = u01(rnd.z) >= rate;
+        kept[4 * h + 3] = u01(rnd.w) >= rate;
+      }
+    }
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+      // same arithmetic as the scalar kernel: kept ? v / keep : 0, rounded to bf16
+      const float a = kept[2 * q] ? __bfloat162float(t.x) / (1.f - rate) : 0.f;
+      const float b = kept[2 * q + 1] ? __bfloat162float(t.y) / (1.f - rate) : 0.f;
+      o[q] = pack_bf16x2(a, b);
+    }
+    (void)inv_keep;
+    out[v] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -588,6 +639,122 @@ decode_upsample8_kernel(const float* __restrict__ low, const float* __restrict__
   }
 }
 
+// MC-dropout decode: mean / population variance over the T per-sample softmax outputs of a pixel
+// (variance_mix.py:62-66) without materialising the samples.  The low-resolution cells of
+// kTB samples are staged per barrier pair (the generic kernel above synchronises twice per
+// sample, which made this pass latency-bound: 1.3 ms per modality for 8 frames x 20 samples), the
+// softmax uses ex2.approx and one reciprocal per sample - the moments are statistics over random
+// masks, their consumers compare them at 1e-4 - and the Welford update stays in registers.
+template <int C>
+__global__ void __launch_bounds__(256)
+decode_upsample8_mc_kernel(const float* __restrict__ low, const float* __restrict__ g,
+                           const float* __restrict__ bias, int T, int N, int h, int w,
+                           float* __restrict__ mean_prob, float* __restrict__ var_prob,
+                           float* __restrict__ mean_var) {
+  constexpr int kTB = 8;
+  __shared__ float s_low[kTB][16 * C];
+  __shared__ float s_g[256];
+  __shared__ float s_b[C];
+  const int H = 8 * h, W = 8 * w;
+  const int bx = blockIdx.x * 16, by = blockIdx.y * 16;
+  const int img = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int ox = bx + tx, oy = by + ty;
+  const bool valid = ox < W && oy < H;
+  s_g[threadIdx.x] = g[threadIdx.x];
+  if (threadIdx.x < C) s_b[threadIdx.x] = bias[threadIdx.x];
+  const int iy0 = (by + 4) / 8 - 1, ix0 = (bx + 4) / 8 - 1;
+  const int ay = (oy + 4) >> 3, ry = (oy + 4) & 7;
+  const int ax = (ox + 4) >> 3, rx = (ox + 4) & 7;
+  float wgt[4];
+  int cell[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int iy = ay - a, ix = ax - b;
+      const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
+      wgt[a * 2 + b] = 0.f;
+      cell[a * 2 + b] = in ? ((iy - iy0) * 4 + (ix - ix0)) * C : 0;
+      if (in) cell[a * 2 + b] |= 0x40000000;      // mark: weight read after the barrier
+    }
+  float mean[C], m2[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) mean[c] = m2[c] = 0.f;
+  for (int t0 = 0; t0 < T; t0 += kTB) {
+    const int tb = T - t0 < kTB ? T - t0 : kTB;
+    __syncthreads();
+    for (int i = threadIdx.x; i < tb * 16 * C; i += 256) {
+      const int tt = i / (16 * C), rem = i - tt * 16 * C;
+      const int c = rem % C, cl = rem / C;
+      const int iy = iy0 + cl / 4, ix = ix0 + cl % 4;
+      float v = 0.f;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+        v = __ldg(low + (((static_cast<size_t>(t0 + tt) * N + img) * h + iy) * w + ix) * C + c);
+      s_low[tt][rem] = v;
+    }
+    __syncthreads();
+    if (t0 == 0) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+          if (cell[a * 2 + b] & 0x40000000) {
+            wgt[a * 2 + b] = s_g[(ry + 8 * a) * 16 + rx + 8 * b];
+            cell[a * 2 + b] &= 0x3fffffff;
+          }
+    }
+    if (!valid) continue;
+    for (int tt = 0; tt < tb; ++tt) {
+      float s[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) s[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* lp = s_low[tt] + cell[k];
+#pragma unroll
+        for (int c = 0; c < C; ++c) s[c] = fmaf(wgt[k], lp[c], s[c]);
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        s[c] += s_b[c];
+        mx = fmaxf(mx, s[c]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        s[c] = __expf(s[c] - mx);
+        sum += s[c];
+      }
+      const float inv = 1.f / sum;
+      const float inv_n = 1.f / static_cast<float>(t0 + tt + 1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float pr = s[c] * inv;
+        const float d = pr - mean[c];
+        mean[c] = fmaf(d, inv_n, mean[c]);
+        m2[c] = fmaf(d, pr - mean[c], m2[c]);
+      }
+    }
+  }
+  if (valid) {
+    const size_t pix = (static_cast<size_t>(img) * H + oy) * W + ox;
+    const float inv_t = 1.f / static_cast<float>(T);
+    float mv = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      // explicit roundings: the result must not depend on which outputs were asked for (the
+      // compiler otherwise contracts v into an fma only in the variant that does not store it)
+      const float v = __fmul_rn(m2[c], inv_t);
+      if (mean_prob) mean_prob[pix * C + c] = mean[c];
+      if (var_prob) var_prob[pix * C + c] = v;
+      mv = __fadd_rn(mv, v);
+    }
+    if (mean_var) mean_var[pix] = mv / static_cast<float>(C);
+  }
+}
+
 // the C class scores of one low-resolution cell: 16-byte loads where the row is 16-byte aligned
 // (C % 4 == 0; the map itself comes from an arena slot aligned to 1 KB)
 template <int C>
@@ -917,9 +1084,12 @@ int decode_dispatch(bool mc, const float* low, const float* g, const float* bias
     dim3 lgrid(div_up(8 * w, 256), div_up(8 * h, 4), N);
     decode_upsample8_labels_kernel<C><<<lgrid, 256, 0, s>>>(low, g, bias, h, w, out.label_u8,
                                                             out.label_i64);
-  } else if (mc)
+  } else if (mc && (debug_flags() & 512))
     decode_upsample8_kernel<C, true><<<grid, 256, 0, s>>>(low, g, bias, T, N, h, w, out,
                                                            mean_prob, var_prob, mean_var);
+  else if (mc)
+    decode_upsample8_mc_kernel<C><<<grid, 256, 0, s>>>(low, g, bias, T, N, h, w, mean_prob,
+                                                       var_prob, mean_var);
   else if (out.prob)
     decode_upsample8_kernel<C, false><<<grid, 256, 0, s>>>(low, g, bias, 1, N, h, w, out,
                                                             nullptr, nullptr, nullptr);
@@ -1025,6 +1195,20 @@ int launch_maxpool_f32(const float* in, float* out, int N, int H, int W, int C, 
 }
 int launch_dropout_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, int replicate,
                         const DropoutSpec& d, cudaStream_t s) {
+  // fast path: 16-byte accesses, 8 elements (two Philox groups) per thread; same masks as the
+  // scalar kernel (the Philox counter is the index of a group of four elements)
+  if (!(debug_flags() & 256) && n % 8 == 0 && d.pass_elems % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      (d.ext_mask == nullptr || (reinterpret_cast<uintptr_t>(d.ext_mask) & 7) == 0)) {
+    const size_t vecs = n * replicate / 8;
+    dropout_bf16x8_kernel<<<grid_for(vecs), kThreads, 0, s>>>(
+        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n / 8, vecs, d.rate,
+        d.ext_mask, d.seed, d.offset, d.pass_elems / 8);
+    XV_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const size_t groups = (n * replicate + 3) / 4 + 1;
   dropout_kernel<__nv_bfloat16><<<grid_for(groups), kThreads, 0, s>>>(
       in, out, n, replicate, d.rate, d.ext_mask, d.seed, d.offset, d.pass_elems);

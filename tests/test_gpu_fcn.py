@@ -192,6 +192,35 @@ def test_mc_dropout_with_dropout_free_leading_sample(dev, precision):
     assert torch.equal(philox['prob'], plain['prob'])
 
 
+def test_vector_dropout_and_staged_mc_decode_match_their_scalar_variants(dev):
+    """The 8-elements-per-thread dropout kernel draws the same Philox / external masks as the
+    scalar kernel (debug flag 256), bit for bit, also behind a dropout-free leading sample; the
+    MC decode that stages eight samples per barrier (ex2.approx softmax) stays within 1e-6 of
+    the per-sample-barrier kernel (flag 512) and does not depend on the outputs asked for."""
+    rng = np.random.default_rng(31)
+    t, n, h, w, rate = 11, 2, 32, 48, 0.5
+    net, _ = _net(dev, 'bf16', 3, rng)
+    x = cuda(rng.uniform(0, 1, size=(n, h, w, 3)).astype(np.float32))
+    want = ('prob', 'mean_prob', 'var_prob', 'mean_var')
+    for cfg in ({'rate': rate, 'layers': ['pool3', 'pool4'], 'num_samples': t, 'seed': 5},
+                {'rate': rate, 'layers': ['pool3'], 'num_samples': t, 'seed': 6,
+                 'with_deterministic': True},
+                {'rate': rate, 'layers': ['pool4'], 'num_samples': t,
+                 'masks': _masks(rng, t, n, h, w, rate, ['pool4'])}):
+        new = {k: v.clone() for k, v in net.forward(x, want=want, dropout=cfg).items()}
+        only = net.forward(x, want=('mean_var',), dropout=cfg)['mean_var'].clone()
+        assert torch.equal(only, new['mean_var'])
+        dev.set_debug_flags(256)
+        scalar = {k: v.clone() for k, v in net.forward(x, want=want, dropout=cfg).items()}
+        dev.set_debug_flags(512)
+        slow = {k: v.clone() for k, v in net.forward(x, want=want, dropout=cfg).items()}
+        dev.set_debug_flags(0)
+        for key in want:
+            assert torch.equal(scalar[key], new[key]), key
+            assert (slow[key] - new[key]).abs().max().item() < 1e-6, key
+        assert torch.equal(slow['prob'], new['prob'])
+
+
 def test_fused_philox_dropout_statistics(dev):
     """Without external masks the fused Philox generator must drop ~rate of the units,
     independently per sample, and be reproducible for a fixed seed."""
