@@ -33,7 +33,7 @@ struct IgemmSample {
 static bool g_profile = false;
 static std::vector<IgemmSample> g_samples;
 
-static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients
+static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients, bit10: conv1_2 without the row-pair kernel
 
 static DeviceInfo g_dev;
 const DeviceInfo& device_info() { return g_dev; }
@@ -266,6 +266,35 @@ int get_tmap_ex(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, in
   return 0;
 }
 
+// Every second row of a bf16 [N,H,W,C] activation (parity 0: rows 0, 2, ..; 1: rows 1, 3, ..)
+// viewed as (C, W, rows, N), box {64, 16, 17, 1}: the operand patches of the row-pair kernel.
+static int get_tmap_rows2(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W,
+                          int C, int parity) {
+  const std::array<long long, 9> key = {static_cast<long long>(reinterpret_cast<uintptr_t>(ptr)),
+                                        N, H, W, C, -2, parity, 17, 16};
+  if (net) {
+    auto it = net->tmaps.find(key);
+    if (it != net->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  const cuuint64_t px = static_cast<cuuint64_t>(C) * 2;
+  const char* base = static_cast<const char*>(ptr) + (parity ? px * W : 0);
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
+                        static_cast<cuuint64_t>((H + 1 - parity) / 2), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {px, 2 * px * W, px * W * H};
+  cuuint32_t box[4] = {64, 16, 17, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(row parity) failed: " + std::to_string(r));
+  if (net) cache_tmap(net, key, *out);
+  return 0;
+}
+
 int get_tmap(xv_fcn* net, CUtensorMap* out, const void* ptr, int N, int H, int W, int C, int th,
              int tw) {
   return get_tmap_ex(net, out, ptr, N, H, W, C, C, 1, th, tw);
@@ -362,6 +391,36 @@ static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, i
                        void* out, bool pool, cudaStream_t s) {
   ConvIgemmParams p;
   std::memset(&p, 0, sizeof(p));
+  // conv1_2 + pool1: both halves of the 128 accumulator lanes carry an output row
+  // (conv_igemm_rowpair_sm100.cu); debug bit10 keeps the half-empty transposed-role kernel
+  if (pool && L.taps == 9 && L.cin_gemm == 64 && L.cout <= 64 && H % 2 == 0 && W % 2 == 0 &&
+      !(g_debug_flags & (64 | 1024))) {
+    XV_TRY(get_tmap_rows2(net, &p.tmap_in_par[0], in, B, H, W, 64, 0));
+    XV_TRY(get_tmap_rows2(net, &p.tmap_in_par[1], in, B, H, W, 64, 1));
+    XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 64));
+    XV_TRY(get_tmap(net, &p.tmap_out, out, B, H / 2, W / 2, L.cout, 16, 8));
+    p.bias = static_cast<const float*>(L.bias_pad.p);
+    p.N = B;
+    p.H = H;
+    p.W = W;
+    p.cin = 64;
+    p.cout = L.cout;
+    p.tiles_x = div_up(W, 16);
+    p.tiles_y = div_up(H, 32);
+    p.n_blocks = 1;
+    p.relu = L.relu;
+    if (!g_profile) return launch_conv_igemm_rowpair(p, s);
+    IgemmSample smp;
+    XV_CUDA(cudaEventCreate(&smp.e0));
+    XV_CUDA(cudaEventCreate(&smp.e1));
+    smp.flops = 2.0 * B * H * W * static_cast<double>(L.cout) * L.k * L.k * L.cin;
+    smp.block_n = 0;
+    XV_CUDA(cudaEventRecord(smp.e0, s));
+    const int rc = launch_conv_igemm_rowpair(p, s);
+    XV_CUDA(cudaEventRecord(smp.e1, s));
+    g_samples.push_back(smp);
+    return rc;
+  }
   p.th = p.tw = 16;
   // debug bit6: previous variant (nine shifted 16x16 tiles per channel chunk instead of three
   // column-shifted 18x16 patches)

@@ -107,6 +107,34 @@ def test_fcn_kernel_variants_agree(dev, cin):
         assert (alt['label'] == base['label']).float().mean().item() > 0.99
 
 
+@pytest.mark.parametrize('n,h,w', [(2, 64, 48), (1, 48, 32), (3, 80, 16), (1, 128, 16)])
+def test_conv1_2_row_pair_kernel_matches_the_half_empty_one(dev, n, h, w):
+    """conv1_2 + pool1 through the row-pair kernel (accumulator lanes 64..127 carry the next
+    output row) against the transposed-role kernel it replaces (debug bit10) and against an fp64
+    convolution of the same bf16 operands: same products, another summation order - at most one
+    bf16 ulp apart, and only rarely.  Heights that are not a multiple of the 32-row tile included."""
+    rng = np.random.default_rng(h + w)
+    net, params = _net(dev, 'bf16', 3, rng)
+    x = cuda(rng.uniform(0, 1, size=(n, h, w, 3)).astype(np.float32))
+    net.forward(x, want=('label',))
+    new, c11 = net.layer('pool1'), net.layer('conv1_1')
+    dev.set_debug_flags(1024)
+    net.forward(x, want=('label',))
+    old = net.layer('pool1')
+    dev.set_debug_flags(0)
+    assert new.shape == old.shape == (n, h // 2, w // 2, 64)
+    ulp = 2.0 ** -7 * np.maximum(np.abs(old), 2.0 ** -126)
+    assert (np.abs(new - old) <= ulp).all()
+    assert (new == old).mean() > 0.98
+    # exact reference from the stored bf16 conv1_1 activation and bf16-rounded weights
+    wq = torch.from_numpy(params['m/conv1_2/kernel']).bfloat16().double()      # HWIO
+    ref = torch.nn.functional.conv2d(torch.from_numpy(c11).double().permute(0, 3, 1, 2),
+                                     wq.permute(3, 2, 0, 1), padding=1)
+    ref = torch.relu(ref + torch.from_numpy(params['m/conv1_2/bias']).double()[None, :, None, None])
+    ref = torch.nn.functional.max_pool2d(ref, 2).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(new, ref, rtol=2.0 ** -7, atol=1e-6)
+
+
 def test_fcn_batchnorm_fp32(dev):
     rng = np.random.default_rng(5)
     net, params = _net(dev, 'fp32', 3, rng, batchnorm=True)
@@ -202,11 +230,11 @@ def test_vector_dropout_and_staged_mc_decode_match_their_scalar_variants(dev):
     net, _ = _net(dev, 'bf16', 3, rng)
     x = cuda(rng.uniform(0, 1, size=(n, h, w, 3)).astype(np.float32))
     want = ('prob', 'mean_prob', 'var_prob', 'mean_var')
-    for cfg in ({'rate': rate, 'layers': ['pool3', 'pool4'], 'num_samples': t, 'seed': 5},
+    for cfg in ({'rate': rate, 'layers': ['pool3', 'conv5_3'], 'num_samples': t, 'seed': 5},
                 {'rate': rate, 'layers': ['pool3'], 'num_samples': t, 'seed': 6,
                  'with_deterministic': True},
-                {'rate': rate, 'layers': ['pool4'], 'num_samples': t,
-                 'masks': _masks(rng, t, n, h, w, rate, ['pool4'])}):
+                {'rate': rate, 'layers': ['conv4_3'], 'num_samples': t,
+                 'masks': _masks(rng, t, n, h, w, rate, ['conv4_3'])}):
         new = {k: v.clone() for k, v in net.forward(x, want=want, dropout=cfg).items()}
         only = net.forward(x, want=('mean_var',), dropout=cfg)['mean_var'].clone()
         assert torch.equal(only, new['mean_var'])
