@@ -14,18 +14,18 @@ namespace xv {
 //    with the same operation order as the kernels that write probabilities.
 template <int C>
 __device__ __forceinline__ int argmax_of_softmax(const float (&s)[C]) {
-  float mx = s[0];
+  // one pass: `before` is the largest score in front of the running maximum (the value the
+  // maximum had when it was last replaced), which is all the tie test needs
+  float mx = s[0], before = -INFINITY;
   int best = 0;
 #pragma unroll
   for (int c = 1; c < C; ++c) {
-    if (s[c] > mx) {
-      mx = s[c];
-      best = c;
-    }
+    const bool up = s[c] > mx;
+    before = up ? mx : before;
+    best = up ? c : best;
+    mx = up ? s[c] : mx;
   }
-  bool close = false;
-#pragma unroll
-  for (int c = 0; c < C - 1; ++c) close = close || (c < best && s[c] - mx >= -4.8e-7f);
+  const bool close = before - mx >= -4.8e-7f;
   if (!close) return best;
   float e[C];
   float sum = 0.f;

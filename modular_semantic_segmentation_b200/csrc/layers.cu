@@ -966,7 +966,7 @@ struct DecodeSrc {
   const float* g[4];        // [16,16] shared bilinear kernel
 };
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 decode_bayes_confusion_kernel(DecodeSrc src, int M, const int32_t* __restrict__ lut, int lut_size,
                               int N, int h, int w, const int32_t* __restrict__ gt,
                               unsigned long long* __restrict__ cm,
