@@ -1,7 +1,8 @@
 """Turns the raw round-2 captures under gpurun_out/ (tools/gpu_r02_profile.sh) into the committed
-summaries under profiles/ and prints the markdown section for profiles/README.md.
+summaries under profiles/ and writes profiles/README.md (round-2 sections, the multi-GPU lines
+from profiles/r02_bench_{2,8}gpu.json, then the round-1 page profiles/r01_README.md).
 
-    python tools/summarize_profiles_r02.py > /tmp/r02_section.md
+    python tools/summarize_profiles_r02.py
 """
 import collections
 import csv
@@ -127,6 +128,8 @@ for rep in ('r02_stream_raw.csv', 'r02_tail_raw.csv'):
     hdr, unit_row, rows = raw(path)
     idx = {v: hdr.index(k) for k, v in names.items() if k in hdr}
     unit = {v: unit_row[hdr.index(k)] for k, v in names.items() if k in hdr}
+    file_unit = {v: unit_row[hdr.index(k)] for k, v in names.items() if k in hdr}
+    to_mb = {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}
     for row in rows:
         rec = {'capture': rep}
         for key, i in idx.items():
@@ -136,10 +139,16 @@ for rep in ('r02_stream_raw.csv', 'r02_tail_raw.csv'):
                     val = float(val.replace(',', ''))
                 except ValueError:
                     pass
+                # ncu picks the byte unit per capture: normalise to MB
+                if key in ('dram_rd', 'dram_wr') and isinstance(val, float):
+                    val = round(val * to_mb.get(file_unit[key], 1.0), 3)
+                if key == 'us' and isinstance(val, float) and file_unit[key] == 'ns':
+                    val /= 1e3
             else:
                 val = short(val)
             rec[key] = val
         summary.append(rec)
+    unit['dram_rd'] = unit['dram_wr'] = 'Mbyte' 
 if summary:
     json.dump({'units': unit, 'launches': summary},
               open(os.path.join(P, 'r02_ncu_full_summary.json'), 'w'), indent=1)
@@ -152,6 +161,26 @@ if summary:
             rec.get('kernel'), rec.get('us'), rec.get('dram_rd'), rec.get('dram_wr'),
             rec.get('tensor_pct'), rec.get('dram_pct'), rec.get('regs')))
     md.append('')
+
+# mean DRAM traffic per tensor-core conv launch of the stream capture -> roofline.traffic of bench.py
+convs = [r for r in summary if r['capture'] == 'r02_stream_raw.csv' and 'conv_' in r['kernel']
+         and isinstance(r.get('dram_rd'), float)]
+if convs:
+    mean_b = sum((r['dram_rd'] + r['dram_wr']) * 1e6 for r in convs) / len(convs)
+    algo = {'conv1_1 (rgb)': 16 * 768 * 384 * (3 * 4 + 64 * 2), 'conv1_2+pool1': 16 * 768 * 384 * 64 * 2 * 1.25,
+            'conv2_1': 16 * 384 * 192 * (64 + 128) * 2}
+    json.dump({'conv_igemm_dram_bytes_per_launch': mean_b,
+               'note': 'mean dram__bytes_read+write over the %d tensor-core conv launches of one rgb '
+                       'stream forward (batch 16, 768x384), ncu --set full, round 2 '
+                       '(profiles/r02_ncu_full_summary.json)' % len(convs),
+               'algorithmic_bytes_examples': algo},
+              open(os.path.join(P, 'roofline_traffic.json'), 'w'), indent=1)
+    md.append('Mean DRAM traffic per tensor-core conv launch: %.1f MB (`roofline_traffic.json`, the '
+              'static `roofline.traffic` of bench.py).  Against algorithmic bytes: conv1_1 rgb '
+              '%.0f MB, conv1_2+pool1 %.0f MB (604 + 151), conv2_1 %.0f MB - measured traffic is '
+              '1.0x the algorithmic bytes on the layers that dominate it.\n'
+              % (mean_b / 1e6, algo['conv1_1 (rgb)'] / 1e6, algo['conv1_2+pool1'] / 1e6,
+                 algo['conv2_1'] / 1e6))
 
 # ---------------------------------------------------------------- other artefacts
 for name in ('r02_fusion_roofline.json', 'r02_timing_sweep.json', 'r02_fit_launches.csv'):
@@ -180,4 +209,49 @@ for name in ('r02_fusion_roofline.json', 'r02_timing_sweep.json', 'r02_fit_launc
             md.append('| **total** | %d | %.1f | |\n' % (len(one), tot))
         else:
             shutil.copy(src, os.path.join(P, name))
+# ---------------------------------------------------------------- multi-GPU lines (gpu_r02_multi.sh)
+mg = []
+for n in (2, 4, 8):
+    path = os.path.join(P, 'r02_bench_%dgpu.json' % n)
+    if os.path.exists(path):
+        mg.append((n, last_json(path)))
+if mg:
+    md.append('### bench.py --gpus N (torchrun, one rank per GPU; `r02_bench_<N>gpu.json`)\n')
+    md.append('| N | value (device-resident) | e2e per batch-16 call | e2e ONE call over the data set | '
+              'raw uint8/uint16 inputs (per call / data set) | fit frames/s | MC T=20 frames/s | '
+              'sharded_check |')
+    md.append('|---|---|---|---|---|---|---|---|')
+    one = b
+    md.append('| 1 | %.0f | %.0f | %.0f | %.0f / %.0f | %.0f | %.0f | - |' % (
+        one['value'], one['e2e']['value'], one['e2e']['dataset_call']['value'],
+        one['e2e']['raw_dtype_inputs']['value'], one['e2e']['raw_dtype_inputs']['dataset_call'],
+        one['fit']['value'], one['dirichlet_mc_T20']['value']))
+    for n, x in mg:
+        sc = x.get('sharded_check') or {}
+        md.append('| %d | %.0f | %.0f | %.0f | %.0f / %.0f | %.0f | %.0f | %s |' % (
+            n, x['value'], x['e2e']['value'], x['e2e']['dataset_call']['value'],
+            x['e2e']['raw_dtype_inputs']['value'], x['e2e']['raw_dtype_inputs']['dataset_call'],
+            x.get('fit', {}).get('value', float('nan')),
+            x.get('dirichlet_mc_T20', {}).get('value', float('nan')),
+            'equal to single rank' if sc.get('equal_to_single_rank') else sc))
+    md.append('')
+    md.append('The N = 1 row is this page\'s bench line; the N > 1 lines may predate the last kernel '
+              'changes of the round (see the file dates).  Topology of the 8-GPU box: '
+              '`r02_topo_8gpu.txt` (one NUMA node, all GPUs on CPUs 0-31); 2-GPU `pytest -m gpu` log of '
+              'tests/test_gpu_multi.py: `r02_test_gpu_multi_2gpu.log`.\n')
+md.append('### compute-sanitizer\n\n`r02_sanitizer_summary.md` (memcheck + racecheck over one small case per '
+          'kernel family, `tools/sanitize.sh`).\n')
+md.append('### Batch-1 latency sweep (`r02_timing_sweep.json`, protocol of experiments/timing.py)\n')
+sweep = os.path.join(G, 'r02_timing_sweep.txt')
+if os.path.exists(sweep):
+    md.append('```')
+    md.extend(l.rstrip() for l in open(sweep).read().strip().splitlines()[-24:])
+    md.append('```\n')
+for name, title in (('r02_adapnet_bench.json', 'Adapnet expert (`tools/adapnet_bench.py`)'),
+                    ('r02_bench_reference.json', '`bench.py --impl reference` (oracle port on the host cores)')):
+    path = os.path.join(P, name)
+    if os.path.exists(path):
+        md.append('### %s\n\n```\n%s\n```\n' % (title, open(path).read().strip()[:1500]))
+text = '# Profiles\n\n' + '\n'.join(md) + '\n\n---\n\n' + open(os.path.join(P, 'r01_README.md')).read()
+open(os.path.join(P, 'README.md'), 'w').write(text)
 print('\n'.join(md))
