@@ -47,4 +47,13 @@ __device__ __forceinline__ int argmax_of_softmax(const float (&s)[C]) {
   return b;
 }
 
+// Natural log of a NORMAL positive float on the MUFU: lg2.approx.ftz * ln 2.  Same values as
+// __logf for normal inputs, without its subnormal rescue (five extra ALU instructions per call);
+// the Dirichlet kernels only call it on 1e-20 + p with p >= 0.
+__device__ __forceinline__ float fast_log_normal(float x) {
+  float t;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t * 0.693147180559945309f;
+}
+
 }  // namespace xv

@@ -183,7 +183,7 @@ decode_dirichlet_kernel(DirSrc src, const float* __restrict__ alpha_m1,
         const float inv = 1.f / sum;
 #pragma unroll
         for (int k = 0; k < C; ++k) {
-          lx[k] = __logf(1e-20f + p[m][k] * inv);
+          lx[k] = fast_log_normal(1e-20f + p[m][k] * inv);
           lmax = fmaxf(lmax, fabsf(lx[k]));
         }
         unsigned long long ll2[CP / 2];

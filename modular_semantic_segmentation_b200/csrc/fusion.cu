@@ -436,7 +436,7 @@ dirichlet_fuse_kernel(PtrPack probs, int M, const float* __restrict__ alpha_m1,
         const float inv = 1.f / sum;
 #pragma unroll
         for (int k = 0; k < C; ++k) {
-          lx[k] = __logf(1e-20f + lx[k] * inv);
+          lx[k] = fast_log_normal(1e-20f + lx[k] * inv);
           if (exact) lmax = fmaxf(lmax, fabsf(lx[k]));
         }
         // packed fp32 FMAs (fma.rn.f32x2, sm_100): one broadcast LDS.128 feeds two 2-wide FMAs
