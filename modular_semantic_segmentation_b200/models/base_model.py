@@ -331,9 +331,18 @@ class BaseModel(object):
             out = self._run_batch(batch, fetch)
             ret.append(out)
         local = torch.cat(ret) if ret else None
-        if _dist() is not None:
+        # every rank evaluated its share of the images (its rows of the caller's dict, or with
+        # shard_images=False the whole dict it was handed): interleave the shares back together.
+        # Not so when the ranks split the MC SAMPLES of the same images (split_samples).
+        if _dist() is not None and not self._same_images_on_every_rank():
             local = sharding.gather_interleaved(local, 'cuda')
         return local.cpu().numpy()
+
+    def _same_images_on_every_rank(self):
+        """True when the ranks cooperate on the SAME images (`split_samples`: each draws a share
+        of the MC-dropout samples and the moments are merged inside the batch) - then every rank
+        already ends with the complete result and nothing is gathered or reduced afterwards."""
+        return bool(self.config.get('split_samples', False))
 
     def _has_output(self, attr):
         return attr in getattr(self, 'output_attrs', ('prediction',))
@@ -345,7 +354,8 @@ class BaseModel(object):
         cm.zero_()
         for batch in self._device_batches(data):
             self._score_batch(batch, cm)
-        sharding.allreduce_sum_(cm)
+        if not self._same_images_on_every_rank():
+            sharding.allreduce_sum_(cm)
         confusion_matrix = cm.cpu().numpy().astype(np.float64)
         measures = measures_from_confusion_matrix(confusion_matrix)
         return measures, confusion_matrix

@@ -190,9 +190,10 @@ class DirichletFusion(BaseModel):
             labels = batch['labels'].contiguous()
             for i, (m, prob) in enumerate(zip(self.modalities, self._probs(batch))):
                 dev.dirichlet_suffstats(prob, labels, stats[m], counts if i == 0 else scratch)
-        for m in self.modalities:
-            sharding.allreduce_sum_(stats[m])
-        sharding.allreduce_sum_(counts)
+        if not self._same_images_on_every_rank():
+            for m in self.modalities:
+                sharding.allreduce_sum_(stats[m])
+            sharding.allreduce_sum_(counts)
         return {m: s.cpu().numpy() for m, s in stats.items()}, counts.cpu().numpy()
 
     def _fit_sufficient_statistic(self, counts, class_counts):

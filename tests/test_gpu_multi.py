@@ -30,6 +30,14 @@ with get_model('bayes_fusion')(confusion_matrices=cms, data_description=desc,
                                seed=3) as net:
     measures, cm = net.score(data)
     pred = net.predict({'rgb': data['rgb'], 'depth': data['depth']})
+# shard_images=False: the dict a rank passes IS its share (here every rank passes all images, so
+# the all-reduced matrix counts every image `world` times)
+with get_model('bayes_fusion')(confusion_matrices=cms, data_description=desc,
+                               prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn',
+                               num_units=8, num_channels={'rgb': 3, 'depth': 1}, batchsize=2,
+                               seed=3, shard_images=False) as net2:
+    _, cm_rep = net2.score(data)
+replica_ok = bool(np.array_equal(cm_rep, world * cm))
 # data-parallel fit(): every rank trains on its share of each batch, gradients are summed
 fdesc = ({'rgb': np.float32, 'labels': np.int32}, {'rgb': (None, None, 3), 'labels': (None, None)}, c)
 train = {'rgb': data['rgb'][:6] / 255.0, 'labels': np.clip(data['labels'][:6], 0, None)}
@@ -41,7 +49,7 @@ with get_model('fcn')('rgb', fdesc, 'rgb', num_units=8, batch_normalization=Fals
     final_loss = fnet.loss
 # batch-1 latency mode: the T MC-dropout samples (not the images) are split over the ranks and the
 # per-rank moments merged over NCCL; every rank must end with the same fused labels
-split_ok = True
+split_ok, split_shape = True, (2, 32, 48)
 if world > 1:
     with get_model('variance_fusion')(data_description=desc, prefixes={'rgb': 'rgb', 'depth': 'depth'},
                                       expert_model='fcn', num_units=8,
@@ -52,10 +60,12 @@ if world > 1:
     mine = torch.from_numpy(vpred).cuda()
     both = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(both, mine)
-    split_ok = bool(all(torch.equal(b, both[0]) for b in both)) and vpred.shape == (2, 32, 48)
+    split_ok = bool(all(torch.equal(b, both[0]) for b in both))
+    split_shape = tuple(vpred.shape)
 if rank == 0:
     np.savez(os.environ['XV_OUT'], cm=cm, pred=pred, miou=measures['mean_IoU'], trained=trained,
-             trained_head=trained_head, final_loss=final_loss, split_ok=split_ok)
+             trained_head=trained_head, final_loss=final_loss, split_ok=split_ok,
+             split_shape=np.asarray(split_shape), replica_ok=replica_ok)
 dist.destroy_process_group()
 '''
 
@@ -95,7 +105,10 @@ def test_two_gpu_score_and_predict_equal_single_gpu(tmp_path):
     np.testing.assert_array_equal(results[2]['pred'], results[1]['pred'])
     assert results[2]['miou'] == results[1]['miou']
     assert results[1]['pred'].shape == (n, h, w)
-    assert bool(results[2]['split_ok'])          # MC samples split over the ranks, merged moments
+    # MC samples split over the ranks, merged moments: every rank ends with the same label maps
+    assert tuple(results[2]['split_shape']) == (2, h, w)
+    assert bool(results[2]['split_ok'])
+    assert bool(results[2]['replica_ok']) and bool(results[1]['replica_ok'])
     # 2-rank data-parallel training follows the 1-rank trajectory (same global batches; the
     # gradient sums differ only by fp32 accumulation order)
     np.testing.assert_allclose(results[2]['final_loss'], results[1]['final_loss'], rtol=2e-2)
