@@ -16,5 +16,5 @@ run() {   # tool family
   local rc=$?
   echo "$1 $2: rc=$rc $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$log" | tail -1)" | tee -a "$OUT/summary.txt"
 }
-for fam in conv2cta convt conv1 fcn wgrad fusion confusion; do run memcheck "$fam"; done
-for fam in conv2cta convt conv1 wgrad fusion confusion; do run racecheck "$fam"; done
+for fam in ${FAMILIES_MEM:-conv2cta convt conv1 fcn tails wgrad fusion confusion}; do run memcheck "$fam"; done
+for fam in ${FAMILIES_RACE:-conv2cta convt conv1 tails wgrad fusion confusion}; do run racecheck "$fam"; done

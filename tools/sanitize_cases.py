@@ -4,7 +4,8 @@
 
 Families: conv2cta (CTA-pair cta_group::2 kernel, odd last tile pair), convt (transposed-role
 kernel with and without the fused pool), conv1 (conv1_1 operand packing), fcn (whole expert incl.
-decoder, MC dropout), wgrad (training step: tensor-core weight gradient, pool/ReLU backward,
+decoder, MC dropout), tails (row-pair conv1_2 + pool1, staged MC decode, vector dropout, fused
+Bayes / Dirichlet score tails), wgrad (training step: tensor-core weight gradient, pool/ReLU backward,
 optimizers), fusion (softmax, Bayes, Dirichlet fast + exact, average, variance, moments,
 sufficient statistics), confusion.  Shapes are tiny so that the ~50x slowdown of the tools stays
 in seconds; every case still covers ragged tiles."""
@@ -57,6 +58,35 @@ def fcn():
               dropout={'rate': 0.3, 'layers': ['pool3', 'conv4_3', 'features'], 'num_samples': 3,
                        'seed': 1, 'with_deterministic': True})
     e.close()
+
+
+def tails():
+    """Round-2 kernels: row-pair conv1_2 + pool1 (height not a multiple of its 32-row tile),
+    8-element dropout + staged MC decode (T > 8: two staging chunks), the fused Bayes and
+    Dirichlet score tails."""
+    c = 5
+    experts = [expert(3, 8, c), expert(1, 8, c)]
+    g = torch.Generator(device='cuda').manual_seed(2)
+    xs = [torch.rand((2, 48, 32, 3), device='cuda', generator=g),
+          torch.rand((2, 48, 32, 1), device='cuda', generator=g)]
+    gt = torch.randint(-1, c, (2, 48, 32), device='cuda', generator=g, dtype=torch.int32)
+    cm = torch.zeros((c, c), dtype=torch.int64, device='cuda')
+    for e, x in zip(experts, xs):
+        e.forward(x, want=('mean_prob', 'var_prob', 'mean_var'),
+                  dropout={'rate': 0.5, 'layers': ['pool3'], 'num_samples': 11, 'seed': 3})
+        e.forward(x, want=())
+    lut = torch.randint(0, c, (c, c), device='cuda', generator=g, dtype=torch.int32)
+    dev.bayes_decode_score(experts, lut, c, gt, cm, want_fused=True)
+    am1 = torch.rand((2, c, c), device='cuda', generator=g) * 3
+    norm = torch.rand((2, c), device='cuda', generator=g)
+    prior = torch.log(torch.full((c,), 1.0 / c, device='cuda'))
+    mags = dev.dirichlet_table_magnitudes(am1, norm, prior)
+    dev.dirichlet_decode_score(experts, am1, norm, prior, c, mags, gt_labels=gt, cm=cm)
+    dev.dirichlet_decode_score(experts, am1, norm, prior, c, mags, exact=False,
+                               label_dtype=torch.uint8)
+    assert int(cm.sum()) == 2 * int((gt >= 0).sum())
+    for e in experts:
+        e.close()
 
 
 def wgrad():
@@ -112,7 +142,8 @@ def confusion():
         assert int(cm.sum()) == 2 * int((gt >= 0).sum())
 
 
-FAMILIES = {'conv2cta': conv2cta, 'convt': convt, 'conv1': conv1, 'fcn': fcn, 'wgrad': wgrad,
+FAMILIES = {'conv2cta': conv2cta, 'convt': convt, 'conv1': conv1, 'fcn': fcn, 'tails': tails,
+            'wgrad': wgrad,
             'fusion': fusion, 'confusion': confusion}
 
 if __name__ == '__main__':
