@@ -338,6 +338,48 @@ class BaseModel(object):
             local = sharding.gather_interleaved(local, 'cuda')
         return local.cpu().numpy()
 
+    # Small batches leave most of the 148 SMs idle in the deep layers (one 768x384 frame is nine
+    # 128-pixel tiles in conv5_x), and the experts are independent until the fusion rule: up to
+    # this many pixels per modality they run concurrently, each on its own CUDA stream
+    # (config `overlap_experts`: True / False / None = by size).
+    OVERLAP_MAX_PIXELS = 4 * 768 * 384
+
+    def _overlap_experts(self, batch):
+        choice = self.config.get('overlap_experts')
+        if choice is not None:
+            return bool(choice) and len(self.modalities) > 1
+        if len(self.modalities) < 2 or not isinstance(batch, dict):
+            return False
+        x = dict.__getitem__(batch, self.modalities[0])
+        return x.shape[0] * x.shape[1] * x.shape[2] <= self.OVERLAP_MAX_PIXELS
+
+    def _run_experts(self, batch, fn, order=None):
+        """{modality: fn(modality, input)} for every modality, experts in arrival order.  Below
+        OVERLAP_MAX_PIXELS each call is enqueued on a side stream forked from the current one
+        and joined before returning, so the caller keeps its single-stream view."""
+        if order is None:      # smallest upload first (see upload_order)
+            order = sorted(self.modalities, key=lambda m: _nbytes(dict.__getitem__(batch, m))
+                           if isinstance(batch, dict) else 0)
+        order = list(order)
+        if not self._overlap_experts(batch):
+            return {m: fn(m, batch[m]) for m in order}
+        current = torch.cuda.current_stream()
+        if not hasattr(self, '_side_streams'):
+            self._side_streams = {}
+        outputs, used = {}, []
+        for m in order:
+            x = batch[m]                   # the current stream waits for this modality's upload
+            side = self._side_streams.get(m)
+            if side is None:
+                side = self._side_streams[m] = torch.cuda.Stream()
+            side.wait_stream(current)
+            with torch.cuda.stream(side):
+                outputs[m] = fn(m, x)
+            used.append(side)
+        for side in used:
+            current.wait_stream(side)
+        return outputs
+
     def _same_images_on_every_rank(self):
         """True when the ranks cooperate on the SAME images (`split_samples`: each draws a share
         of the MC-dropout samples and the moments are merged inside the batch) - then every rank

@@ -53,14 +53,13 @@ class FusionModel(BaseModel):
                       if isinstance(batch, dict) else 0)
 
     def _expert_outputs(self, batch, wants, label_dtype):
-        outputs = {}
-        for m in self._arrival_order(batch):
-            expert = self._experts[self._expert_prefix(m)]
-            out = expert.forward(batch[m], want=wants, label_dtype=label_dtype)
+        def run(m, x):
+            out = self._experts[self._expert_prefix(m)].forward(x, want=wants,
+                                                                label_dtype=label_dtype)
             if 'label' in out:
                 out['classification'] = out['label']
-            outputs[m] = out
-        return outputs
+            return out
+        return self._run_experts(batch, run)
 
     def _fusion(self, expert_outputs, fetch, label_dtype):
         raise NotImplementedError

@@ -148,8 +148,8 @@ class BayesFusion(FusionModel):
                 and self.config['expert_model'] == 'fcn' and len(self.modalities) <= 4 \
                 and self.config.get('precision', 'bf16') == 'bf16':
             experts = [self._experts[self._expert_prefix(m)] for m in self.modalities]
-            for m in self._arrival_order(batch):
-                self._experts[self._expert_prefix(m)].forward(batch[m], want=())
+            self._run_experts(batch, lambda m, x: self._experts[self._expert_prefix(m)].forward(
+                x, want=()))
             try:
                 dev.bayes_decode_score(experts, self._lut, self.config['num_classes'],
                                        batch['labels'], cm)

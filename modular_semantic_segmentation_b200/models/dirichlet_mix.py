@@ -108,8 +108,9 @@ class DirichletFusion(BaseModel):
         weight load; otherwise the dropout-free softmax of dirichlet_mix.py:98."""
         num_samples = int(self.config.get('num_samples', 1))
         if num_samples <= 1:
-            return [self._experts[m].forward(batch[m], want=('prob',))['prob']
-                    for m in self.modalities]
+            outs = self._run_experts(
+                batch, lambda m, x: self._experts[m].forward(x, want=('prob',))['prob'])
+            return [outs[m] for m in self.modalities]
         from .variance_mix import mc_dropout_seed, split_samples_over_ranks
         split = split_samples_over_ranks(self)
         means = []
@@ -140,8 +141,7 @@ class DirichletFusion(BaseModel):
 
     def _fused_tail(self, batch, cm, want_label, label_dtype=torch.int64):
         experts = [self._experts[m] for m in self.modalities]
-        for m in sorted(self.modalities, key=lambda k: dict.__getitem__(batch, k).numel()):
-            self._experts[m].forward(batch[m], want=())
+        self._run_experts(batch, lambda m, x: self._experts[m].forward(x, want=()))
         try:
             return True, dev.dirichlet_decode_score(
                 experts, *self._tables, self.config['num_classes'], self._magnitudes,

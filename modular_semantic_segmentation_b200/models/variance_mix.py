@@ -61,15 +61,22 @@ class VarianceFusion(FusionModel):
         label_dtype = torch.uint8 if fetch == 'prediction_compact' else torch.int64
         probs, variances = [], []
         split = split_samples_over_ranks(self)
+        cfgs = {}
         for i, m in enumerate(self.modalities):
-            expert = self._experts[self._expert_prefix(m)]
             # one call: the dropout-free pass (probabilities, variance_mix.py:68-69) rides along
             # as a leading sample of the MC batch, so conv1_1..pool3 run once for both
-            cfg = {'rate': self.config['dropout_rate'], 'layers': ['pool3'],
-                   'num_samples': self.config['num_samples'], 'with_deterministic': True,
-                   'seed': mc_dropout_seed(self, i)}
+            cfgs[m] = {'rate': self.config['dropout_rate'], 'layers': ['pool3'],
+                       'num_samples': self.config['num_samples'], 'with_deterministic': True,
+                       'seed': mc_dropout_seed(self, i)}
+        if split is None:
+            outs = self._run_experts(
+                batch, lambda m, x: self._experts[self._expert_prefix(m)].forward(
+                    x, want=('prob', 'mean_var'), dropout=cfgs[m]), order=self.modalities)
+        for i, m in enumerate(self.modalities):
+            expert = self._experts[self._expert_prefix(m)]
+            cfg = cfgs[m]
             if split is None:
-                out = expert.forward(batch[m], want=('prob', 'mean_var'), dropout=cfg)
+                out = outs[m]
                 variances.append(out['mean_var'])
             else:
                 # batch-1 latency mode: this rank draws its share of the samples, the per-rank

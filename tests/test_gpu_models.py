@@ -475,3 +475,44 @@ def test_cuda_graph_score_step_equals_eager():
             graph.replay()
         torch.cuda.synchronize()
         np.testing.assert_array_equal(cm.cpu().numpy(), 3 * eager.cpu().numpy())
+
+
+@pytest.mark.parametrize('model', ['bayes_fusion', 'dirichlet_mix', 'average_fusion',
+                                   'variance_fusion'])
+def test_concurrent_experts_equal_sequential_experts(model):
+    """Small batches run the experts of the modalities on separate CUDA streams (forked from and
+    joined to the caller's stream, `overlap_experts`); results are those of the sequential
+    schedule bit for bit, through predict(), score() and repeated calls."""
+    from xview.models import get_model
+    c, n, h, w = 6, 3, 48, 64
+    rng = np.random.default_rng(5)
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    extra = {}
+    if model == 'bayes_fusion':
+        extra['confusion_matrices'] = {m: rng.integers(0, 60, size=(c, c)).astype(np.float64) +
+                                       150 * np.eye(c) for m in ('rgb', 'depth')}
+    if model == 'dirichlet_mix':
+        extra['dirichlet_params'] = {m: 1.0 + rng.gamma(2.0, 2.0, size=(c, c)) + 4.0 * np.eye(c)
+                                     for m in ('rgb', 'depth')}
+        extra['dirichlet_params']['class_counts'] = rng.integers(100, 1000, size=c).astype(np.float64)
+        extra['modalities'] = ['rgb', 'depth']
+    else:
+        extra['prefixes'] = {'rgb': 'rgb', 'depth': 'depth'}
+    if model == 'variance_fusion':
+        extra.update(num_samples=5, dropout_rate=0.4, deterministic_dropout=True, seed=3)
+    results = {}
+    for overlap in (False, True):
+        with get_model(model)(data_description=_description(c), expert_model='fcn', num_units=NU,
+                              num_channels={'rgb': 3, 'depth': 1}, batchsize=2,
+                              overlap_experts=overlap, **extra) as net:
+            _load(net, params)
+            preds = [net.predict({'rgb': data['rgb'], 'depth': data['depth']}) for _ in range(3)]
+            cms = [net.score(data)[1] for _ in range(2)]
+        for p in preds[1:]:
+            np.testing.assert_array_equal(p, preds[0])
+        np.testing.assert_array_equal(cms[0], cms[1])
+        results[overlap] = (preds[0], cms[0])
+    np.testing.assert_array_equal(results[True][0], results[False][0])
+    np.testing.assert_array_equal(results[True][1], results[False][1])
+    assert results[True][1].sum() == (data['labels'] >= 0).sum()
