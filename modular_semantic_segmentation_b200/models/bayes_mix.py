@@ -133,6 +133,25 @@ class BayesFusion(FusionModel):
         self._log_cond = dev.to_device(log_cond)
         self._log_prior = dev.to_device(log_prior)
 
+    def get_insight(self, batch):
+        """What experiments/bayes_fusion.py:57-61 (`collect_data`) asks of the model - the
+        reference calls this method without defining it; the four entries are the tensors the
+        command stores: per-expert softmax probabilities [M,N,H,W,C], the log-likelihood rows
+        log(1e-20 + p(output | class)) selected by each expert's decision and the conditionals
+        themselves (second and third return value of bayes_fusion, bayes_mix.py:30-58), both
+        [M,N,H,W,C], and the fused prediction [N,H,W] - as numpy arrays."""
+        batch = self._to_device({k: v for k, v in batch.items() if k != 'labels'})
+        outputs = self._expert_outputs(batch, ('prob', 'label'), torch.int64)
+        labels = [outputs[m]['classification'] for m in self.modalities]
+        fused = dev.bayes_fuse_lut(labels, self._lut, self.config['num_classes'])
+        cond = torch.from_numpy(np.stack(self.conditionals).astype(np.float32)).cuda()
+        log_cond = self._log_cond.reshape(cond.shape)
+        picked = [(log_cond[i][lab], cond[i][lab]) for i, lab in enumerate(labels)]
+        return (torch.stack([outputs[m]['prob'] for m in self.modalities]).cpu().numpy(),
+                torch.stack([p[0] for p in picked]).cpu().numpy(),
+                torch.stack([p[1] for p in picked]).cpu().numpy(),
+                fused.cpu().numpy())
+
     def _fusion(self, expert_outputs, fetch, label_dtype):
         labels = [expert_outputs[m]['classification'] for m in self.modalities]
         if fetch == 'fused_score':

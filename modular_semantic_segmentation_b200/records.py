@@ -181,3 +181,23 @@ def dump_expert_predictions(net_config, data_description, measure_set, test_set,
     outfile = os.path.join(save_to, 'predictions.npz')
     np.savez_compressed(outfile, **predictions)
     return outfile
+
+
+def dump_bayes_insight(net, batches, save_to):
+    """experiments/bayes_fusion.py:47-69 (`collect_data`): run `net.get_insight` over the
+    batches and store predictions.npz, likelihoods.npz, conditionals.npz and probs.npz, one
+    positional array (arr_0, arr_1, ...) per batch as np.savez_compressed(path, *list) does.
+    Returns the four paths."""
+    collected = {'probs': [], 'likelihoods': [], 'conditionals': [], 'predictions': []}
+    for batch in batches:
+        insight = net.get_insight(batch)
+        collected['probs'].append(insight[0])
+        collected['likelihoods'].append(insight[1])
+        collected['conditionals'].append(insight[2])
+        collected['predictions'].append(insight[3])
+    os.makedirs(save_to, exist_ok=True)
+    paths = []
+    for name in ('predictions', 'likelihoods', 'conditionals', 'probs'):
+        paths.append(os.path.join(save_to, name + '.npz'))
+        np.savez_compressed(paths[-1], *collected[name])
+    return paths

@@ -516,3 +516,43 @@ def test_concurrent_experts_equal_sequential_experts(model):
     np.testing.assert_array_equal(results[True][0], results[False][0])
     np.testing.assert_array_equal(results[True][1], results[False][1])
     assert results[True][1].sum() == (data['labels'] >= 0).sum()
+
+
+def test_bayes_fusion_insight_dump(tmp_path):
+    """experiments/bayes_fusion.py:47-69 (`collect_data`): get_insight returns the experts'
+    probabilities, the log-likelihood rows and conditionals bayes_fusion selects for their
+    decisions (bit-equal to the oracle's float32 rule on the same decisions) and the fused
+    prediction; records.dump_bayes_insight stores them the way the command does."""
+    from xview.models import get_model
+    from modular_semantic_segmentation_b200 import records
+    c, n, h, w = 6, 3, 32, 48
+    rng = np.random.default_rng(12)
+    data = _data(rng, n, h, w, c)
+    params = _trained_like(rng, c)
+    cms = {m: rng.integers(0, 60, size=(c, c)).astype(np.float64) + 150 * np.eye(c)
+           for m in ('rgb', 'depth')}
+    with get_model('bayes_fusion')(
+            confusion_matrices=cms, data_description=_description(c),
+            prefixes={'rgb': 'rgb', 'depth': 'depth'}, expert_model='fcn', num_units=NU,
+            num_channels={'rgb': 3, 'depth': 1}, batchsize=2) as net:
+        _load(net, params)
+        probs, likelihoods, conditionals, prediction = net.get_insight(data)
+        fused = net.predict(data)
+        batches = [{k: v[i:i + 2] for k, v in data.items()} for i in (0, 2)]
+        paths = records.dump_bayes_insight(net, batches, str(tmp_path / 'insight'))
+    assert probs.shape == likelihoods.shape == conditionals.shape == (2, n, h, w, c)
+    np.testing.assert_allclose(probs.sum(-1), 1.0, atol=1e-5)
+    np.testing.assert_array_equal(prediction, fused)
+    decisions = [probs[i].argmax(-1) for i in range(2)]
+    tables = [cms[m].astype('float32').T for m in ('rgb', 'depth')]
+    ref_score, ref_ll, ref_cond = oracle.bayes_fusion(decisions, tables, 'data')
+    for i in range(2):
+        np.testing.assert_array_equal(likelihoods[i], ref_ll[i].astype(np.float32))
+        np.testing.assert_array_equal(conditionals[i], ref_cond[i].astype(np.float32))
+    np.testing.assert_array_equal(prediction, oracle.argmax_first(ref_score))
+    assert [os.path.basename(p) for p in paths] == ['predictions.npz', 'likelihoods.npz',
+                                                    'conditionals.npz', 'probs.npz']
+    stored = np.load(paths[0])
+    assert sorted(stored.files) == ['arr_0', 'arr_1']
+    np.testing.assert_array_equal(np.concatenate([stored['arr_0'], stored['arr_1']]), fused)
+    assert np.load(paths[3])['arr_1'].shape == (2, 1, h, w, c)

@@ -319,3 +319,23 @@ def test_dump_expert_predictions_layout(tmp_path, monkeypatch):
         np.testing.assert_array_equal(archive['test_gt'], test['labels'][:, :16, :16])
         assert archive['test_gt'].shape == archive['test_rgb'].shape
         np.testing.assert_array_equal(archive['measure_gt'], measure['labels'])
+
+
+def test_bayes_insight_dump_layout(tmp_path):
+    """records.dump_bayes_insight: four archives with one positional array per batch, the layout
+    np.savez_compressed(path, *list) gives experiments/bayes_fusion.py:62-69."""
+    from modular_semantic_segmentation_b200 import records
+
+    class Stub(object):
+        def get_insight(self, batch):
+            n = len(batch['rgb'])
+            return (np.full((2, n, 4, 4, 3), 1 / 3.0), np.zeros((2, n, 4, 4, 3)),
+                    np.ones((2, n, 4, 4, 3)), np.arange(n * 16).reshape(n, 4, 4))
+
+    batches = [{'rgb': np.zeros((2, 4, 4, 3))}, {'rgb': np.zeros((1, 4, 4, 3))}]
+    paths = records.dump_bayes_insight(Stub(), batches, str(tmp_path / 'out'))
+    assert [os.path.basename(p) for p in paths] == ['predictions.npz', 'likelihoods.npz',
+                                                    'conditionals.npz', 'probs.npz']
+    predictions = np.load(paths[0])
+    assert predictions.files == ['arr_0', 'arr_1'] and predictions['arr_1'].shape == (1, 4, 4)
+    assert np.load(paths[3])['arr_0'].shape == (2, 2, 4, 4, 3)
