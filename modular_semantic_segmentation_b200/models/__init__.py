@@ -6,6 +6,7 @@ from .average_mix import AverageFusion
 from .variance_mix import VarianceFusion
 from .fusion_fcn import FusionFCN
 from .adapnet import Adapnet
+from .bayesian_fcn import BayesianFCN
 
 
 def get_model(name):
@@ -14,6 +15,8 @@ def get_model(name):
         return SimpleFCN
     elif name == 'adapnet':
         return Adapnet
+    elif name == 'bayesian_fcn':     # not in the reference's factory (its class cannot be built)
+        return BayesianFCN
     elif name == 'fusion_fcn':
         return FusionFCN
     elif name in ['bayes_mix', 'bayes_fusion']:

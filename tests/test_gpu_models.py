@@ -556,3 +556,41 @@ def test_bayes_fusion_insight_dump(tmp_path):
     assert sorted(stored.files) == ['arr_0', 'arr_1']
     np.testing.assert_array_equal(np.concatenate([stored['arr_0'], stored['arr_1']]), fused)
     assert np.load(paths[3])['arr_1'].shape == (2, 1, h, w, c)
+
+
+def test_bayesian_fcn_sampling_uncertainty():
+    """bayesian_fcn.py:9-57: mean and uncertainty measures of the MC-dropout samples against the
+    oracle's restatement evaluated on the very same samples (fixed Philox seed), through the
+    function and through the model class."""
+    from xview.models import get_model
+    from xview.models.bayesian_fcn import sampling_uncertainty
+    c, n, h, w, t = 6, 2, 32, 48, 7
+    rng = np.random.default_rng(21)
+    data = _data(rng, n, h, w, c)
+    params = {k: v for k, v in _trained_like(rng, c).items() if k.startswith('rgb/')}
+    layers = ['pool3', 'pool4', 'conv5_3', 'features']
+    with get_model('bayesian_fcn')('rgb', _description(c), 'rgb', num_units=NU, num_samples=t,
+                                   dropout_rate=0.3, dropout_layers=layers, batchsize=n,
+                                   deterministic_dropout=True, seed=2) as net:
+        _load(net, params)
+        expert = net._experts['rgb']
+        x = torch.from_numpy(data['rgb']).cuda()
+        from xview.models.variance_mix import mc_dropout_seed
+        seed = mc_dropout_seed(net, 0)
+        samples = expert.forward(x, want=('prob',), dropout={
+            'rate': 0.3, 'layers': ['pool3', 'conv5_3', 'features'], 'num_samples': t,
+            'seed': seed})['prob'].cpu().numpy().reshape(t, n, h, w, c)
+        mean, unc = sampling_uncertainty(x, expert, t, c, dropout_rate=0.3, dropout_layers=layers,
+                                         seed=seed)
+        mean, unc = mean.cpu().numpy(), {k: v.cpu().numpy() for k, v in unc.items()}
+        pred = net.predict({'rgb': data['rgb']})
+        entropy = net.predict({'rgb': data['rgb']}, output_attr='entropy')
+        measures, cm = net.score(data)
+    assert samples.shape == (t, n, h, w, c) and np.abs(samples[0] - samples[1]).max() > 1e-4
+    ref_mean, ref_unc = oracle.sampling_uncertainty(samples.astype(np.float64))
+    np.testing.assert_allclose(mean, ref_mean, atol=1e-6)
+    for key in ('entropy', 'cond_entropy', 'variance'):
+        np.testing.assert_allclose(unc[key], ref_unc[key], atol=2e-6, err_msg=key)
+    np.testing.assert_array_equal(pred, mean.argmax(-1))
+    np.testing.assert_array_equal(entropy, unc['entropy'])
+    np.testing.assert_array_equal(cm, oracle.confusion_matrix(data['labels'], pred, c))

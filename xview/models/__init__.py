@@ -4,13 +4,13 @@ import sys
 
 from modular_semantic_segmentation_b200 import models as _impl
 from modular_semantic_segmentation_b200.models import (Adapnet, AverageFusion, BayesFusion,
-                                                       DirichletFusion, FusionFCN, SimpleFCN,
-                                                       VarianceFusion, get_model)
+                                                       BayesianFCN, DirichletFusion, FusionFCN,
+                                                       SimpleFCN, VarianceFusion, get_model)
 
 # make `xview.models.simple_fcn`, `xview.models.bayes_mix`, ... importable as in the reference
 for _name in ('base_model', 'simple_fcn', 'basic_fusion_model', 'bayes_mix', 'dirichlet_mix',
               'average_mix', 'variance_mix', 'custom_layers', 'dirichletDifferentiation',
-              'fusion_fcn', 'adapnet'):
+              'fusion_fcn', 'adapnet', 'bayesian_fcn'):
     __import__('modular_semantic_segmentation_b200.models.' + _name)
     sys.modules[__name__ + '.' + _name] = getattr(_impl, _name)
     globals()[_name] = getattr(_impl, _name)
