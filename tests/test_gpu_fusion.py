@@ -365,3 +365,8 @@ def test_dirichlet_uncertainty_fusion(dev):
     scale = np.abs(ref).max()
     np.testing.assert_allclose(score.cpu().numpy(), ref, rtol=0, atol=1e-4 * scale)
     assert_labels_match(label.cpu().numpy(), ref, 2e-4 * scale)
+    # the reference-named entry point (uncertainty_dirichlet_mix.py:18) over the same kernel
+    from xview.models.uncertainty_dirichlet_mix import dirichlet_uncertainty_fusion
+    again = dirichlet_uncertainty_fusion([cuda(p) for p in probs], cond,
+                                         [cuda(v) for v in variances], prior)
+    assert torch.equal(again, score)
