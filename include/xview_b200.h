@@ -198,6 +198,15 @@ int xv_fcn_train_end(xv_fcn* net);
 int xv_conv2d(const float* x, const float* w_hwio_host, const float* bias_host, int n, int h,
               int w, int cin, int cout, int k, int relu, int precision, float* out,
               void* stream);
+/* Gradient of the loss wrt the 3x3 kernel of such a layer, as the minimize() of
+ * base_model.py:157-162 differentiates custom_layers.py:131: x [N,H,W,cin] layer input, dy
+ * [N,H,W,cout] gradient wrt the pre-activation output (device float32, rounded to bf16 like the
+ * activations fit() keeps) -> dw [3,3,cin,cout] (device float32, OVERWRITTEN), fp32
+ * accumulation.  use_tensor_cores != 0: the tcgen05 kernel of fit() (cin % 64 == 0), else the
+ * CUDA-core reference kernel (cin % 32 == 0); cout % 64 == 0.  The data gradient of the layer
+ * is xv_conv2d itself on the flipped, transposed kernel. */
+int xv_conv2d_weight_gradient(const float* x, const float* dy, int n, int h, int w, int cin,
+                              int cout, int use_tensor_cores, float* dw, void* stream);
 /* conv2d_transpose 'same', no bias: x [N,h,w,cin] -> out [N,h*stride,w*stride,cout] */
 int xv_deconv2d(const float* x, const float* w_khkwoi_host, int n, int h, int w, int cin,
                 int cout, int k, int stride, int relu, float* out, void* stream);

@@ -85,6 +85,7 @@ PROTOTYPES = {
     'xv_fcn_get_params_host': [_P, _P, _L, _P],
     'xv_fcn_train_end': [_P],
     'xv_conv2d': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    'xv_conv2d_weight_gradient': [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     'xv_deconv2d': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'xv_maxpool2x2': [_P, _I, _I, _I, _I, _P, _P],
     'xv_batchnorm_train': [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],

@@ -2296,6 +2296,33 @@ int BnTrain::run(const float* x, const int32_t* labels, int N, int H, int W, int
 
 extern "C" {
 
+// Weight gradient of ONE 3x3 'same' convolution layer, the kernels fit() uses:
+// dw[tap][ci][co] = sum_p bf16(x)[p + shift(tap)][ci] * bf16(dy)[p][co], fp32 accumulation.
+int xv_conv2d_weight_gradient(const float* x, const float* dy, int n, int h, int w, int cin,
+                              int cout, int use_tensor_cores, float* dw, void* stream) {
+  XV_TRY(ensure_init());
+  XV_CHECK(x && dy && dw, "xv_conv2d_weight_gradient: NULL argument");
+  XV_CHECK(cout % 64 == 0, "xv_conv2d_weight_gradient: Cout % 64 == 0 required");
+  XV_CHECK(use_tensor_cores ? cin % 64 == 0 : cin % 32 == 0,
+           "xv_conv2d_weight_gradient: Cin % 64 (tensor cores) / % 32 (CUDA cores) required");
+  cudaStream_t s = XV_STREAM(stream);
+  const size_t npix = static_cast<size_t>(n) * h * w;
+  DevBuf x16, dy16;
+  XV_TRY(x16.ensure(npix * cin * 2));
+  XV_TRY(dy16.ensure(npix * cout * 2));
+  XV_TRY(launch_f32_to_bf16(x, static_cast<__nv_bfloat16*>(x16.p), npix * cin, s));
+  XV_TRY(launch_f32_to_bf16(dy, static_cast<__nv_bfloat16*>(dy16.p), npix * cout, s));
+  XV_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(9) * cin * cout * sizeof(float), s));
+  if (use_tensor_cores)
+    XV_TRY(run_wgrad_tc(nullptr, x16.p, dy16.p, dw, n, h, w, cin, cout, s, 9, 0));
+  else
+    XV_TRY(launch_conv_wgrad(static_cast<const __nv_bfloat16*>(x16.p),
+                             static_cast<const __nv_bfloat16*>(dy16.p), dw, n, h, w, cin, cout, s));
+  XV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+
 int xv_fcn_train_begin(xv_fcn* net, int64_t* num_params_out) {
   XV_CHECK(net && net->finalized, "xv_fcn_train_begin: finalize the expert first");
   XV_CHECK(net->precision == XV_PRECISION_BF16 && (net->batchnorm == 0 || net->batchnorm == 1),

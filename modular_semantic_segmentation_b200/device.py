@@ -339,6 +339,18 @@ def conv2d(x, kernel, bias=None, relu=True, precision='bf16'):
     return out
 
 
+def conv2d_weight_gradient(x, dy, tensor_cores=True):
+    """Gradient wrt the 3x3 kernel of a 'same' convolution (the kernels fit() uses): x
+    [N,H,W,cin], dy [N,H,W,cout] CUDA float32 (rounded to bf16 inside) -> dw [3,3,cin,cout]."""
+    init()
+    n, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    dw = torch.empty((3, 3, cin, cout), dtype=torch.float32, device=x.device)
+    call('xv_conv2d_weight_gradient', ptr(x.contiguous()), ptr(dy.contiguous()), n, h, w, cin, cout,
+         1 if tensor_cores else 0, ptr(dw), stream_ptr())
+    return dw
+
+
 def deconv2d(x, kernel, stride, relu=True):
     """custom_layers.py:71-121 without batch norm; kernel numpy [kh,kw,Cout,Cin]."""
     init()

@@ -347,3 +347,32 @@ def test_simple_fcn_fit_with_batch_normalization(tmp_path):
     with get_model('fcn')('rgb', desc, 'rgb', num_units=NU, batch_normalization=True) as net2:
         net2.import_weights(path, warnings=False)
         np.testing.assert_array_equal(net2.predict({'rgb': data['rgb']}), pred)
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(2, 32, 48, 64, 64), (1, 48, 32, 64, 128),
+                                            (2, 16, 32, 128, 256), (1, 16, 16, 512, 512)])
+def test_conv_layer_gradients_within_1e3_of_float64(dev, n, h, w, cin, cout):
+    """The backward kernels of one 3x3 layer on their own, away from the chaos of a deep
+    random net: weight gradient (tcgen05 kernel and CUDA-core reference, xv_conv2d_weight_gradient)
+    and data gradient (the forward conv kernels on the flipped, transposed filter - exactly what
+    fit() launches) against float64 autograd of the SAME bf16-rounded operands.  fp32
+    accumulation: 1e-3 of the largest entry for dW; dX is stored as bf16 (2^-8 relative)."""
+    rng = np.random.default_rng(cin + cout + h)
+    bf = lambda a: torch.from_numpy(a).bfloat16().float()          # noqa: E731
+    x = bf(rng.standard_normal((n, h, w, cin)).astype(np.float32))
+    dy = bf(rng.standard_normal((n, h, w, cout)).astype(np.float32))
+    kern = bf((rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32))
+    # float64 reference
+    xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = kern.double().permute(3, 2, 0, 1).requires_grad_(True)
+    out = torch.nn.functional.conv2d(xr, wr, padding=1)
+    out.backward(dy.double().permute(0, 3, 1, 2))
+    dw_ref = wr.grad.permute(2, 3, 1, 0).numpy()                    # -> HWIO
+    dx_ref = xr.grad.permute(0, 2, 3, 1).numpy()
+    for tensor_cores in (True, False):
+        dw = dev.conv2d_weight_gradient(x.cuda(), dy.cuda(), tensor_cores=tensor_cores)
+        np.testing.assert_allclose(dw.cpu().numpy(), dw_ref, rtol=0,
+                                   atol=1e-3 * np.abs(dw_ref).max(), err_msg=str(tensor_cores))
+    flipped = np.ascontiguousarray(kern.numpy()[::-1, ::-1].transpose(0, 1, 3, 2))
+    dx = dev.conv2d(dy.cuda(), flipped, None, relu=False, precision='bf16').cpu().numpy()
+    np.testing.assert_allclose(dx, dx_ref, rtol=2.0 ** -8, atol=1e-3 * np.abs(dx_ref).max())
