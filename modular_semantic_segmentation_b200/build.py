@@ -49,7 +49,8 @@ def build(force=False, verbose=False):
         with open(os.path.join(HERE, 'build', src + '.ptxas.log'), 'w') as f:
             f.write(out)
     if relink:
-        cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
+        cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + \
+              ['-cudart', 'static']
         subprocess.check_call(cmd)
     return LIB
 
