@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libxview_b200.so')
 SOURCES = ['abi.cu', 'conv_igemm_sm100.cu', 'conv_igemm_t_sm100.cu', 'layers.cu', 'fusion.cu',
            'mc_dirichlet.cu', 'train.cu', 'bn_train.cu', 'decode_dirichlet.cu',
-           'conv_wgrad_sm100.cu', 'adapnet.cu', 'adapnet_kernels.cu',
+           'conv_wgrad_sm100.cu', 'conv_wgrad_2cta_sm100.cu', 'adapnet.cu', 'adapnet_kernels.cu',
            'conv_c1_sm100.cu', 'conv_igemm_2cta_sm100.cu', 'conv_igemm_rowpair_sm100.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

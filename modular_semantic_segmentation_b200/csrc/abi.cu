@@ -1868,12 +1868,16 @@ static int run_wgrad_tc(xv_fcn* net, const void* x, const void* dy, float* dw, i
   p.cout = cout;
   p.tiles_x = div_up(W, p.tw);
   p.tiles_y = div_up(H, p.th);
-  p.m_blocks = div_up(cout, 128);
+  // CTA pairs (M = 256 per MMA, the x operand split over the pair) where the shapes allow it;
+  // debug bit11 keeps the single-CTA kernel
+  const bool pair = taps == 9 && cin % 128 == 0 && cout % 256 == 0 && dy_channels == 0 &&
+                    !(g_debug_flags & 2048);
+  p.m_blocks = pair ? cout / 256 : div_up(cout, 128);
   p.total_atoms = taps * cin / 64;
   p.n_groups = div_up(p.total_atoms, 4);
   const int base = p.m_blocks * p.n_groups;
   const int tiles = B * p.tiles_x * p.tiles_y;
-  const int sms = g_dev.num_sms;
+  const int sms = pair ? g_dev.num_sms / 2 : g_dev.num_sms;      // schedulable CTAs / clusters
   int best_k = 1;
   double best_cost = 1e30;
   for (int k = 1; k <= 64 && k <= tiles; ++k) {
@@ -1885,7 +1889,7 @@ static int run_wgrad_tc(xv_fcn* net, const void* x, const void* dy, float* dw, i
     }
   }
   p.k_splits = best_k;
-  return launch_conv_wgrad_tc(p, s);
+  return pair ? launch_conv_wgrad_2cta(p, s) : launch_conv_wgrad_tc(p, s);
 }
 
 struct Backward {

@@ -85,6 +85,9 @@ struct ConvWgradParams {
   int k_splits;           // pixel tiles are dealt round-robin to k_splits CTAs
 };
 int launch_conv_wgrad_tc(const ConvWgradParams& p, cudaStream_t stream);
+// conv_wgrad_2cta_sm100.cu: the same for Cout % 256 == 0, Cin % 128 == 0 on CTA pairs
+// (cta_group::2, M = 256); m_blocks = Cout / 256
+int launch_conv_wgrad_2cta(const ConvWgradParams& p, cudaStream_t stream);
 
 // ------------------------------------------------------------- layers.cu
 int launch_im2col_c1(const float* x, __nv_bfloat16* out, int N, int H, int W, int cin,
