@@ -451,21 +451,58 @@ conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
   for (int k = 0; k < K; ++k)
 #pragma unroll
     for (int j = 0; j < CH; ++j) acc[k][j] = 0.f;
-  if (lane < lanes) {
-    for (int r = r0; r < r1; ++r) {
-      const int py = r % H;
-      const float* xrow = x + static_cast<size_t>(r) * W * CIN;     // row r of the stacked images
-      const __nv_bfloat16* dyrow = dy + static_cast<size_t>(r) * W * cout + g * CH;
-      const bool up = py > 0, down = py + 1 < H;
-      for (int px = lane; px < W; px += lanes) {
+  // the three input rows a gradient row needs live in shared memory (a rotating window over the
+  // block's rows): the 9 * CIN input reads per pixel are LDS instead of L1-hitting LDG, whose
+  // latency the two resident blocks per SM (72+ accumulators per thread) could not hide
+  float* s_x = s_part + K * cout;                          // [3][W * CIN], slot = row mod 3
+  const int row_elems = W * CIN;
+  auto stage_row = [&](int r) {                            // row r of the stacked images, or zeros
+    float* dst = s_x + ((r % 3 + 3) % 3) * row_elems;
+    const bool in = r >= 0 && r < rows;
+    for (int i = threadIdx.x; i < row_elems; i += kThreads)
+      dst[i] = in ? __ldg(x + static_cast<size_t>(r) * row_elems + i) : 0.f;
+  };
+  if (r0 < r1) {
+    stage_row(r0 - 1);
+    stage_row(r0);
+  }
+  // kU pixels per step, their dy vectors loaded up front: one 16-byte load in flight per thread
+  // left the kernel bound by memory latency (0.62 ms for 604 MB at batch 16; 8 per step costs a
+  // resident block)
+  constexpr int kU = 4;
+  for (int r = r0; r < r1; ++r) {
+    stage_row(r + 1);
+    __syncthreads();
+    const int py = r % H;
+    const __nv_bfloat16* dyrow = dy + static_cast<size_t>(r) * W * cout + g * CH;
+    const bool up = py > 0, down = py + 1 < H;
+    for (int px0 = lane; lane < lanes && px0 < W; px0 += lanes * kU) {
+      uint4 raw[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int px = px0 + u * lanes;
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (px < W) {
+          if constexpr (CH == 8) {
+            raw[u] = __ldg(reinterpret_cast<const uint4*>(dyrow + static_cast<size_t>(px) * cout));
+          } else {
+            const uint2 v =
+                __ldg(reinterpret_cast<const uint2*>(dyrow + static_cast<size_t>(px) * cout));
+            raw[u].x = v.x;
+            raw[u].y = v.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int px = px0 + u * lanes;
+        if (px >= W) break;
         float d[CH];
         if constexpr (CH == 8) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(dyrow + static_cast<size_t>(px) * cout));
-          unpack8(v, d);
+          unpack8(raw[u], d);
         } else {
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(dyrow + static_cast<size_t>(px) * cout));
-          const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
-          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+          const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw[u].x);
+          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw[u].y);
           d[0] = __bfloat162float(a.x);
           d[1] = __bfloat162float(a.y);
           d[2] = __bfloat162float(b.x);
@@ -474,14 +511,14 @@ conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
 #pragma unroll
         for (int ty = 0; ty < 3; ++ty) {
           if ((ty == 0 && !up) || (ty == 2 && !down)) continue;
-          const float* src = xrow + (static_cast<ptrdiff_t>(ty) - 1) * W * CIN + px * CIN;
+          const float* src = s_x + ((r + ty - 1) % 3 + 3) % 3 * row_elems + px * CIN;
 #pragma unroll
           for (int tx = 0; tx < 3; ++tx) {
             const int xx = px + tx - 1;
             if (xx < 0 || xx >= W) continue;
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci) {
-              const float xv = __ldg(src + (tx - 1) * CIN + ci);
+              const float xv = src[(tx - 1) * CIN + ci];
 #pragma unroll
               for (int j = 0; j < CH; ++j)
                 acc[(ty * 3 + tx) * CIN + ci][j] = fmaf(xv, d[j], acc[(ty * 3 + tx) * CIN + ci][j]);
@@ -490,6 +527,9 @@ conv_wgrad_c1_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
         }
       }
     }
+    __syncthreads();              // row r - 1's slot is overwritten by the next stage_row
+  }
+  if (lane < lanes) {
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -667,7 +707,18 @@ int launch_conv_wgrad_c1(const float* x, const __nv_bfloat16* dy, float* dw, int
   XV_CHECK((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "conv_wgrad_c1: dy must be 16-byte aligned");
   int grid = device_info().num_sms * 4;
   if (grid > N * H) grid = N * H;
-  const size_t smem = static_cast<size_t>(9) * cin * cout * sizeof(float);
+  const size_t smem = (static_cast<size_t>(9) * cin * cout + static_cast<size_t>(3) * W * cin) *
+                      sizeof(float);
+  XV_CHECK(smem <= 200 * 1024, "conv_wgrad_c1: image too wide for the staged input rows");
+  if (smem > 48 * 1024) {      // beyond the default limit: opt in (idempotent, cheap)
+    const int bytes = static_cast<int>(smem);
+    XV_CUDA(cudaFuncSetAttribute(conv_wgrad_c1_kernel<1, 8>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    XV_CUDA(cudaFuncSetAttribute(conv_wgrad_c1_kernel<2, 4>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    XV_CUDA(cudaFuncSetAttribute(conv_wgrad_c1_kernel<3, 4>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
   if (cin == 1) conv_wgrad_c1_kernel<1, 8><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
   if (cin == 2) conv_wgrad_c1_kernel<2, 4><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
   if (cin == 3) conv_wgrad_c1_kernel<3, 4><<<grid, kThreads, smem, s>>>(x, dy, dw, N, H, W, cout);
