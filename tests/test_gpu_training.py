@@ -350,7 +350,8 @@ def test_simple_fcn_fit_with_batch_normalization(tmp_path):
 
 
 @pytest.mark.parametrize('n,h,w,cin,cout', [(2, 32, 48, 64, 64), (1, 48, 32, 64, 128),
-                                            (2, 16, 32, 128, 256), (1, 16, 16, 512, 512)])
+                                            (2, 16, 32, 128, 256), (1, 16, 16, 512, 512),
+                                            (3, 24, 40, 128, 256), (1, 40, 24, 256, 512)])
 def test_conv_layer_gradients_within_1e3_of_float64(dev, n, h, w, cin, cout):
     """The backward kernels of one 3x3 layer on their own, away from the chaos of a deep
     random net: weight gradient (tcgen05 kernel and CUDA-core reference, xv_conv2d_weight_gradient)
