@@ -23,7 +23,9 @@ extern "C" {
  * bit7 = single-CTA MMAs for the Cout >= 256 layers instead of the CTA-pair (cta_group::2)
  * kernel, bit8 = scalar (4 elements per thread) dropout kernel, bit9 = MC decode with two
  * barriers per sample instead of the eight-sample staging, bit10 = conv1_2 + pool1 on the
- * transposed-role kernel instead of the row-pair kernel.  0 = production behaviour. */
+ * transposed-role kernel instead of the row-pair kernel, bit11 = single-CTA weight-gradient
+ * kernel for every layer, bit12 = fit() loss head as decode + ce_grad + upsample8_transpose.
+ * 0 = production behaviour. */
 int xv_set_debug_flags(int flags);
 /* Number of kernels this library has launched since it was loaded. */
 int xv_launch_count(int64_t* out);

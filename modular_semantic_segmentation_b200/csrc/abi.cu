@@ -33,7 +33,7 @@ struct IgemmSample {
 static bool g_profile = false;
 static std::vector<IgemmSample> g_samples;
 
-static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients, bit10: conv1_2 without the row-pair kernel
+static int g_debug_flags = 0;   // bit0: no pool fusion, bit1: no transposed kernel, bit2: conv1_1 via im2col buffer, bit3: CUDA-core weight gradients, bit10: conv1_2 without the row-pair kernel, bit11: single-CTA weight gradients, bit12: three-kernel loss head
 
 static DeviceInfo g_dev;
 const DeviceInfo& device_info() { return g_dev; }
@@ -855,9 +855,13 @@ int Forward::run_head(Act c43, Act c53, bool replicated, const xv_fcn_outputs* o
     Act low = make("score_lowres", DType::F32, B, feat.H, feat.W, C);
     xv_fcn_outputs train_out;
     if (training) {
-      Act sc = make("train_score", DType::F32, B, Hf, Wf, C);
+      // fit(): the loss head works on the low-resolution scores (loss_lowres_grad_kernel); the
+      // full-resolution score tensor only exists for the three-kernel form behind debug bit12
       std::memset(&train_out, 0, sizeof(train_out));
-      train_out.score = static_cast<float*>(sc.p);
+      if (g_debug_flags & 4096) {
+        Act sc = make("train_score", DType::F32, B, Hf, Wf, C);
+        train_out.score = static_cast<float*>(sc.p);
+      }
       o = &train_out;
     }
     const bool want_samples = o->score || o->prob || o->label_i64 || o->label_u8;
@@ -1991,7 +1995,9 @@ int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, in
   const int nu = net->nu, C = net->C;
   const int h8 = H / 8, w8 = W / 8, h16 = H / 16, w16 = W / 16;
   TrainLayer* tscore = find_layer(ts, "score");
-  Act score = layer("train_score"), low = layer("score_lowres"), fused = layer("fused");
+  const bool fused_loss = !(g_debug_flags & 4096);
+  Act low = layer("score_lowres"), fused = layer("fused");
+  Act score = fused_loss ? low : layer("train_score");
   Act up5 = layer("upscore_conv5"), s4 = layer("score_conv4"), s5 = layer("score_conv5");
   const size_t npix = static_cast<size_t>(N) * H * W;
   const size_t nlow = static_cast<size_t>(N) * h8 * w8;
@@ -2000,11 +2006,19 @@ int Backward::run(const float* x, const int32_t* labels, int N, int H, int W, in
   Act dfused = make(DType::F32, N, h8, w8, nu);
   Act ds5 = make(DType::F32, N, h16, w16, nu);
   if (!dry) {
-    XV_TRY(launch_ce_grad(static_cast<float*>(score.p), labels, static_cast<int64_t>(npix), C,
-                          static_cast<double*>(ts->loss.p), grads + tscore->b_off, s));
-    XV_TRY(launch_upsample8_transpose(static_cast<const float*>(score.p),
-                                      static_cast<const float*>(net->g16.p),
-                                      static_cast<float*>(dlow.p), N, h8, w8, C, s));
+    if (fused_loss) {
+      XV_TRY(launch_loss_lowres_grad(static_cast<const float*>(low.p),
+                                     static_cast<const float*>(net->g16.p),
+                                     static_cast<const float*>(net->b_score.p), labels, N, h8, w8,
+                                     C, static_cast<float*>(dlow.p),
+                                     static_cast<double*>(ts->loss.p), grads + tscore->b_off, s));
+    } else {
+      XV_TRY(launch_ce_grad(static_cast<float*>(score.p), labels, static_cast<int64_t>(npix), C,
+                            static_cast<double*>(ts->loss.p), grads + tscore->b_off, s));
+      XV_TRY(launch_upsample8_transpose(static_cast<const float*>(score.p),
+                                        static_cast<const float*>(net->g16.p),
+                                        static_cast<float*>(dlow.p), N, h8, w8, C, s));
+    }
     XV_TRY(launch_score_bwd(static_cast<const float*>(dlow.p), static_cast<const float*>(fused.p),
                             static_cast<const float*>(net->w_score_nuxc.p),
                             static_cast<float*>(dfused.p), grads + tscore->w_off, nlow, nu, C, s));

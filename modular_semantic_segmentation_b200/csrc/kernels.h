@@ -234,6 +234,11 @@ int launch_reduce_max(const float* x, int64_t n, float* out, cudaStream_t s);
 // ------------------------------------------------------------- train.cu
 int launch_ce_grad(float* score, const int32_t* labels, int64_t npix, int C, double* loss,
                    float* dbias, cudaStream_t s);
+// decode + softmax - onehot + loss + transposed x8 upsampling in one pass (bilinear fast path);
+// dlow [N,h,w,C] is overwritten, loss[0..1] / dbias[C] are accumulated into
+int launch_loss_lowres_grad(const float* low, const float* g_16x16, const float* bias,
+                            const int32_t* labels, int N, int h, int w, int C, float* dlow,
+                            double* loss, float* dbias, cudaStream_t s);
 int launch_upsample8_transpose(const float* dscore, const float* g, float* dlow, int N, int h,
                                int w, int C, cudaStream_t s);
 int launch_score_bwd(const float* dlow, const float* fused, const float* w, float* dfused,

@@ -377,3 +377,32 @@ def test_conv_layer_gradients_within_1e3_of_float64(dev, n, h, w, cin, cout):
     flipped = np.ascontiguousarray(kern.numpy()[::-1, ::-1].transpose(0, 1, 3, 2))
     dx = dev.conv2d(dy.cuda(), flipped, None, relu=False, precision='bf16').cpu().numpy()
     np.testing.assert_allclose(dx, dx_ref, rtol=2.0 ** -8, atol=1e-3 * np.abs(dx_ref).max())
+
+
+@pytest.mark.parametrize('n,h,w', [(2, 32, 48), (1, 48, 80), (3, 16, 16)])
+def test_fused_loss_head_equals_three_kernel_form(dev, n, h, w):
+    """loss_lowres_grad_kernel (decode + softmax - onehot + loss + transposed upsampling from the
+    1/8-resolution scores, nothing at full resolution in HBM) against the decode / ce_grad /
+    upsample8_transpose sequence it replaces (debug bit12): same loss, same gradients up to the
+    order of the float32 sums."""
+    rng = np.random.default_rng(h * w)
+    net, params, x, labels = _setup(dev, rng, n=n, h=h, w=w)
+    labels[0, :5] = -1                                   # unlabelled pixels
+    net.train_begin()
+    g_new, loss_new = net.train_gradients(cuda(x), cuda(labels))
+    g_new = g_new.cpu().numpy()
+    dev.set_debug_flags(4096)
+    g_old, loss_old = net.train_gradients(cuda(x), cuda(labels))
+    dev.set_debug_flags(0)
+    g_old = g_old.cpu().numpy()
+    loss_new, loss_old = loss_new.cpu().numpy(), loss_old.cpu().numpy()     # {sum -log p, #valid}
+    assert loss_new[1] == loss_old[1] == (labels >= 0).sum()
+    assert abs(loss_new[0] - loss_old[0]) <= 1e-5 * abs(loss_old[0])
+    for name in ('score/kernel', 'score/bias', 'score_conv4/kernel', 'conv5_3/kernel',
+                 'conv3_1/kernel', 'conv1_1/kernel'):
+        off, size = net.param_span(name)
+        a, b = g_new[off:off + size], g_old[off:off + size]
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-3 * np.abs(b).max() + 1e-12, err_msg=name)
+    off, size = net.param_span('score/bias')
+    np.testing.assert_allclose(g_new[off:off + size], g_old[off:off + size], rtol=1e-4, atol=1e-7)
+    net.close()
