@@ -224,7 +224,13 @@ __global__ void dropout_bf16x8_kernel(const uint4* __restrict__ in, uint4* __res
                                       size_t nvec, size_t total, float rate,
                                       const uint8_t* __restrict__ ext_mask, uint64_t seed,
                                       uint64_t offset, size_t pass_vecs) {
-  const float inv_keep = 1.f / (1.f - rate);
+  // x / keep as tf.nn.dropout computes it; when keep is a power of two (rate 0.5, the usual MC
+  // setting) the product with 1 / keep is the same float and saves eight divisions per thread
+  const float keep = 1.f - rate;
+  const float inv_keep = 1.f / keep;
+  int expo;
+  const bool pow2 = frexpf(keep, &expo) == 0.5f;
+  const uint32_t thresh = rate <= 0.f ? 0u : static_cast<uint32_t>(ceilf(rate * 16777216.f));
   for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < total;
        v += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const uint4 x = __ldg(in + v % nvec);
@@ -245,10 +251,11 @@ __global__ void dropout_bf16x8_kernel(const uint4* __restrict__ in, uint4* __res
         const uint4 rnd = philox4x32_10(
             make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0x58564231u, 0u),
             make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-        kept[4 * h] = u01(rnd.x) >= rate;
-        kept[4 * h + 1] = u01(rnd.y) >= rate;
-        kept[4 * h + 2] = u01(rnd.z) >= rate;
-        kept[4 * h + 3] = u01(rnd.w) >= rate;
+        // u01(r) >= rate  <=>  (r >> 8) >= ceil(rate * 2^24): both sides are exact
+        kept[4 * h] = (rnd.x >> 8) >= thresh;
+        kept[4 * h + 1] = (rnd.y >> 8) >= thresh;
+        kept[4 * h + 2] = (rnd.z >> 8) >= thresh;
+        kept[4 * h + 3] = (rnd.w >> 8) >= thresh;
       }
     }
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
@@ -257,11 +264,11 @@ __global__ void dropout_bf16x8_kernel(const uint4* __restrict__ in, uint4* __res
     for (int q = 0; q < 4; ++q) {
       const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
       // same arithmetic as the scalar kernel: kept ? v / keep : 0, rounded to bf16
-      const float a = kept[2 * q] ? __bfloat162float(t.x) / (1.f - rate) : 0.f;
-      const float b = kept[2 * q + 1] ? __bfloat162float(t.y) / (1.f - rate) : 0.f;
+      const float fa = __bfloat162float(t.x), fb = __bfloat162float(t.y);
+      const float a = kept[2 * q] ? (pow2 ? fa * inv_keep : fa / keep) : 0.f;
+      const float b = kept[2 * q + 1] ? (pow2 ? fb * inv_keep : fb / keep) : 0.f;
       o[q] = pack_bf16x2(a, b);
     }
-    (void)inv_keep;
     out[v] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
