@@ -1853,6 +1853,37 @@ static int repack_layer(xv_fcn* net, TrainState* ts, TrainLayer& tl, cudaStream_
   return 0;
 }
 
+// all layers after an optimizer step: one launch for every conv kernel + bias (pack_all_kernel),
+// the final score layer's fp32 copies separately
+static int repack_all(xv_fcn* net, TrainState* ts, cudaStream_t s) {
+  PackAllParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (auto& tl : ts->layers) {
+    if (tl.name == "score" || p.num_layers == 20) {
+      XV_TRY(repack_layer(net, ts, tl, s));
+      continue;
+    }
+    ConvLayer* L = ts->bn ? tl.fwd.get() : net->conv(tl.name);
+    PackLayer& d = p.layer[p.num_layers++];
+    d.w = static_cast<const float*>(ts->master.p) + tl.w_off;
+    d.b = static_cast<const float*>(ts->master.p) + tl.b_off;
+    d.fwd = static_cast<__nv_bfloat16*>(L->w_packed.p);
+    d.bwd = tl.bwd ? static_cast<__nv_bfloat16*>(tl.bwd->w_packed.p) : nullptr;
+    d.bias_pad = static_cast<float*>(L->bias_pad.p);
+    d.taps = tl.k * tl.k;
+    d.cin = tl.cin;
+    d.cout = tl.cout;
+    d.fwd_kdim = L->kdim;
+    d.bwd_kdim = tl.bwd ? tl.bwd->kdim : 0;
+    d.c1_layout = (L->taps == 1 && L->k == 3) ? 1 : 0;
+    d.first = p.total;
+    d.elems = static_cast<unsigned long long>(d.taps) * d.cin * d.cout;
+    p.total += d.elems;
+  }
+  if (p.num_layers > 0) XV_TRY(launch_pack_all(p, s));
+  return 0;
+}
+
 // tensor-core weight gradient; the split of the pixel tiles over CTAs is chosen to fill whole waves
 // dy: bf16 [B,H,W,dy_channels] (dy_channels = 0: == cout; the 1x1 heads pass their gradient
 // zero-padded to 64 channels); taps = 9 (3x3) or 1 (1x1)
@@ -2585,7 +2616,7 @@ int xv_fcn_adam_step(xv_fcn* net, const float* grads, float learning_rate, float
                                         (1.0 - std::pow(beta1, t)));
   XV_TRY(launch_adam(static_cast<float*>(ts->master.p), grads, static_cast<float*>(ts->m.p),
                      static_cast<float*>(ts->v.p), ts->total, lr_t, beta1, beta2, epsilon, s));
-  for (auto& tl : ts->layers) XV_TRY(repack_layer(net, ts, tl, s));
+  XV_TRY(repack_all(net, ts, s));
   return 0;
 }
 
@@ -2615,7 +2646,7 @@ int xv_fcn_optimizer_step(xv_fcn* net, const float* grads, int kind, float learn
   else
     XV_TRY(launch_rmsprop(static_cast<float*>(ts->master.p), grads, v, m, ts->total,
                           learning_rate, 0.9f, 0.f, 1e-10f, s));
-  for (auto& tl : ts->layers) XV_TRY(repack_layer(net, ts, tl, s));
+  XV_TRY(repack_all(net, ts, s));
   return 0;
 }
 

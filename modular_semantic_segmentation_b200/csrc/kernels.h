@@ -269,6 +269,22 @@ int launch_adagrad(float* w, const float* g, float* acc, size_t n, float lr, cud
 int launch_rmsprop(float* w, const float* g, float* ms, float* mom, size_t n, float lr,
                    float decay, float momentum, float eps, cudaStream_t s);
 int launch_fill_f32(float* x, size_t n, float value, cudaStream_t s);
+// every conv layer of a network re-packed in one launch (see launch_pack_weights for the layouts)
+struct PackLayer {
+  const float* w;          // fp32 HWIO master kernel
+  const float* b;          // fp32 master bias [cout]
+  __nv_bfloat16* fwd;      // forward operand rows
+  __nv_bfloat16* bwd;      // data-gradient operand rows (may be NULL)
+  float* bias_pad;         // padded bias of the forward layer
+  unsigned long long first, elems;   // range of this layer in the concatenated element index
+  int taps, cin, cout, fwd_kdim, bwd_kdim, c1_layout;
+};
+struct PackAllParams {
+  PackLayer layer[20];
+  int num_layers;
+  unsigned long long total;
+};
+int launch_pack_all(const PackAllParams& p, cudaStream_t s);
 int launch_pack_weights(const float* w, __nv_bfloat16* fwd, __nv_bfloat16* bwd, int taps, int cin,
                         int cout, int fwd_kdim, int bwd_kdim, int c1_layout, cudaStream_t s);
 

@@ -932,6 +932,38 @@ int launch_adam(float* w, const float* g, float* m, float* v, size_t n, float lr
   adam_kernel<<<grid_for(n), kThreads, 0, s>>>(w, g, m, v, n, lr_t, b1, b2, eps);
   XV_LAUNCHED();
 }
+// All layers of a network in ONE launch (after every optimizer step: 15 pack launches + 15 bias
+// copies per step otherwise).  Element i of the concatenated HWIO kernels belongs to the layer
+// whose [first, first + elems) range holds it; the biases ride along at the front of the grid.
+__global__ void pack_all_kernel(const __grid_constant__ PackAllParams p) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  for (int l = 0; l < p.num_layers; ++l)
+    for (size_t j = tid; j < static_cast<size_t>(p.layer[l].cout); j += stride)
+      p.layer[l].bias_pad[j] = p.layer[l].b[j];
+  int l = 0;
+  for (size_t i = tid; i < p.total; i += stride) {
+    while (i >= p.layer[l].first + p.layer[l].elems) ++l;      // i grows: l only moves forward
+    const PackLayer& d = p.layer[l];
+    const size_t k = i - d.first;
+    const int co = static_cast<int>(k % d.cout);
+    const int ci = static_cast<int>((k / d.cout) % d.cin);
+    const int t = static_cast<int>(k / (static_cast<size_t>(d.cout) * d.cin));
+    const __nv_bfloat16 q = __float2bfloat16_rn(d.w[k]);
+    if (d.c1_layout) {
+      d.fwd[static_cast<size_t>(co) * 64 + t * d.cin + ci] = q;
+      d.fwd[static_cast<size_t>(co) * 64 + 9 * d.cin + t * d.cin + ci] = q;
+    } else {
+      d.fwd[static_cast<size_t>(co) * d.fwd_kdim + t * d.cin + ci] = q;
+    }
+    if (d.bwd) d.bwd[static_cast<size_t>(ci) * d.bwd_kdim + (d.taps - 1 - t) * d.cout + co] = q;
+  }
+}
+
+int launch_pack_all(const PackAllParams& p, cudaStream_t s) {
+  pack_all_kernel<<<grid_for(p.total), kThreads, 0, s>>>(p);
+  XV_LAUNCHED();
+}
 int launch_pack_weights(const float* w, __nv_bfloat16* fwd, __nv_bfloat16* bwd, int taps, int cin,
                         int cout, int fwd_kdim, int bwd_kdim, int c1_layout, cudaStream_t s) {
   pack_weights_kernel<<<grid_for(static_cast<size_t>(taps) * cin * cout), kThreads, 0, s>>>(
