@@ -25,22 +25,22 @@ from ..sharding import dist_or_none as _dist
 
 
 def measures_from_confusion_matrix(confusion_matrix):
-    """The float64 measures of base_model.py:315-329 (class 0 = void is excluded from
-    total_accuracy and mean_IoU)."""
-    confusion_matrix = np.asarray(confusion_matrix, dtype=np.float64)
+    """The measures score() reports, in float64 and with the operation order of
+    base_model.py:315-329 (they are pinned bit for bit by tests/golden/exp868.npz): rows are
+    ground truth, columns predictions; class 0 (void) counts for neither total_accuracy nor
+    mean_IoU; classes that never occur give nan and are skipped by the means."""
+    cm = np.asarray(confusion_matrix, dtype=np.float64)
+    hits = np.diag(cm)
+    per_truth, per_prediction = cm.sum(1), cm.sum(0)
     with np.errstate(divide='ignore', invalid='ignore'):
-        measures = {}
-        measures['confusion_matrix'] = confusion_matrix
-        diag = np.diag(confusion_matrix)
-        measures['recall'] = diag / confusion_matrix.sum(1)
-        measures['precision'] = diag / confusion_matrix.sum(0)
-        measures['F1'] = 2 * measures['precision'] * measures['recall'] / \
-            (measures['precision'] + measures['recall'])
-        measures['mean_F1'] = np.nanmean(measures['F1'])
-        measures['total_accuracy'] = diag[1:].sum() / confusion_matrix[1:, :].sum()
-        measures['IoU'] = diag / (confusion_matrix.sum(1) + confusion_matrix.sum(0) - diag)
-        measures['mean_IoU'] = np.nanmean(measures['IoU'][1:])
-    return measures
+        recall = hits / per_truth
+        precision = hits / per_prediction
+        f1 = 2 * precision * recall / (precision + recall)
+        iou = hits / (per_truth + per_prediction - hits)
+        accuracy = hits[1:].sum() / cm[1:, :].sum()
+    return {'confusion_matrix': cm, 'recall': recall, 'precision': precision, 'F1': f1,
+            'mean_F1': np.nanmean(f1), 'total_accuracy': accuracy, 'IoU': iou,
+            'mean_IoU': np.nanmean(iou[1:])}
 
 
 def upload_bounds(count, split=2, explicit=None):

@@ -77,19 +77,20 @@ def bayes_decision_table(confusion_matrices, class_prior='data'):
 
 
 def bayes_decision_matrix(confusion_matrices, class_prior='data'):
-    """bayes_mix.py:61-112 verbatim semantics (float64 log-likelihood buffer)."""
-    num_classes = confusion_matrices[0].shape[0]
-    num_experts = len(confusion_matrices)
-    combos = np.array(list(product(*(range(num_classes) for _ in range(num_experts)))))
-    log_likelihoods = np.zeros((combos.shape[0], num_experts, num_classes))
-    for i_expert in range(num_experts):
-        conditional = _conditional(np.asarray(confusion_matrices[i_expert]))
-        with np.errstate(divide='ignore'):
-            log_likelihoods[:, i_expert, :] = np.log(1e-20 + conditional[combos[:, i_expert]])
-    prior = _prior(np.asarray(confusion_matrices[-1]), class_prior)
+    """The fused decision for every combination of expert outputs, with the arithmetic of
+    bayes_mix.py:61-112: per-expert log(1e-20 + conditional) rows gathered into a FLOAT64
+    buffer [combinations, experts, classes] (whatever dtype the matrices have), summed over the
+    experts, plus log(prior), argmax.  Returns an array of shape [C] * num_experts."""
+    experts = [np.asarray(m) for m in confusion_matrices]
+    num_classes, num_experts = experts[0].shape[0], len(experts)
+    # row i: expert i's output in every combination, last expert varying fastest
+    outputs = np.indices((num_classes,) * num_experts).reshape(num_experts, -1)
+    gathered = np.zeros((outputs.shape[1], num_experts, num_classes))
     with np.errstate(divide='ignore'):
-        fused = np.argmax(log_likelihoods.sum(1) + np.log(prior), axis=1)
-    return fused.reshape([num_classes for _ in range(num_experts)])
+        for i, matrix in enumerate(experts):
+            gathered[:, i, :] = np.log(1e-20 + _conditional(matrix)[outputs[i]])
+        score = gathered.sum(1) + np.log(_prior(experts[-1], class_prior))
+    return np.argmax(score, axis=1).reshape((num_classes,) * num_experts)
 
 
 class BayesFusion(FusionModel):
