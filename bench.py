@@ -92,9 +92,11 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.rows = []            # (time, sm_mhz, sm_max_mhz, [reasons])
+        self.smi_rows = []
         self.proc = None
         self._stop = False
         self.source = None
+        self._index = index
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -110,33 +112,41 @@ class ClockSampler(object):
             self.source = 'nvml'
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-            return
         except Exception:
             self.source = None
+        # nvidia-smi runs beside NVML as a second witness (a box was seen where the NVML thread
+        # delivered nothing during the timed region); its rows are used when NVML has none
+        self.smi_rows = []
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '50'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.source = 'nvidia-smi'
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            self.smi_thread = threading.Thread(target=self._read, daemon=True)
+            self.smi_thread.start()
+            if self.source is None:
+                self.source = 'nvidia-smi'
         except OSError:
             self.proc = None
+        self._index = index
 
     def _poll(self):
         nv = self._nvml
         while not self._stop:
             try:
                 mhz = float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
-                self.rows.append((time.time(), mhz, self._max,
-                                  [name for name, bit in self.REASONS if mask & bit]))
-            except Exception:
-                pass
+                reasons = ['reasons_unavailable']
+                for query in ('nvmlDeviceGetCurrentClocksEventReasons',
+                              'nvmlDeviceGetCurrentClocksThrottleReasons'):
+                    try:
+                        mask = int(getattr(nv, query)(self._handle))
+                        reasons = [name for name, bit in self.REASONS if mask & bit]
+                        break
+                    except Exception:
+                        continue
+                self.rows.append((time.time(), mhz, self._max, reasons))
+            except Exception as err:
+                self.last_error = repr(err)[:120]
             time.sleep(0.01)
 
     def _read(self):
@@ -144,9 +154,9 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(',')]
             try:
-                self.rows.append((time.time(), float(parts[0]), float(parts[1]),
-                                  [n for n, f in zip(names, parts[3:7])
-                                   if f.lower().startswith('active')]))
+                self.smi_rows.append((time.time(), float(parts[0]), float(parts[1]),
+                                      [n for n, f in zip(names, parts[3:7])
+                                       if f.lower().startswith('active')]))
             except (ValueError, IndexError):
                 continue
 
@@ -158,17 +168,36 @@ class ClockSampler(object):
         self._stop = True
         if self.proc is not None:
             self.proc.terminate()
-        inside = [r for r in self.rows if t0 <= r[0] <= t1]
-        if len(inside) < 5:       # widen slightly rather than report too few samples
-            inside = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+
+        def window(rows):
+            inside = [r for r in rows if t0 <= r[0] <= t1]
+            if len(inside) < 5:   # widen slightly rather than report too few samples
+                inside = [r for r in rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+            return inside
+        source = self.source
+        inside = window(self.rows)
+        if not inside and self.smi_rows:
+            inside, source = window(self.smi_rows), 'nvidia-smi'
         if not inside:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'], 'samples': 0,
-                    'source': self.source}
+            # last resort: one synchronous query right after the region (says so in `source`)
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self._index),
+                                      '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=10).stdout
+                parts = [p.strip() for p in out.strip().splitlines()[0].split(',')]
+                names = [n for n, _ in self.REASONS]
+                inside = [(t1, float(parts[0]), float(parts[1]),
+                           [n for n, f in zip(names, parts[3:7]) if f.lower().startswith('active')])]
+                source = 'nvidia-smi, one query right after the timed region'
+            except Exception:
+                return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'],
+                        'samples': 0, 'source': self.source,
+                        'error': getattr(self, 'last_error', None)}
         reasons = sorted({name for r in inside for name in r[3]})
         return {'sm_mhz': float(np.median([r[1] for r in inside])),
                 'sm_min_mhz': float(min(r[1] for r in inside)),
                 'sm_max_mhz': float(max(r[2] for r in inside)),
-                'reasons': reasons, 'samples': len(inside), 'source': self.source}
+                'reasons': reasons, 'samples': len(inside), 'source': source}
 
 
 # ------------------------------------------------------------------------------- CPU arm
