@@ -663,10 +663,19 @@ def run_gpu(args):
     peak_tf, peak_tf_burst, peak_gbs, peak_kind = _peaks()
     extra = {}
     if not args.no_extras:
-        extra['dirichlet_mc_T20'] = dirichlet_mc_bench(world, rank)
-        extra['fit'] = fit_bench(world, rank)
+        # secondary figures must never cost the headline line: a failure is reported in place
+        # (single rank; with several ranks a rank that fails inside a collective cannot be
+        # rescued here and the launcher's timeout applies)
+        def guarded(fn, *fn_args):
+            try:
+                return fn(*fn_args)
+            except Exception as err:          # noqa: BLE001
+                torch.cuda.synchronize()
+                return {'unavailable': repr(err)[:200]}
+        extra['dirichlet_mc_T20'] = guarded(dirichlet_mc_bench, world, rank)
+        extra['fit'] = guarded(fit_bench, world, rank)
         if rank == 0:
-            extra['fusion_hbm'] = fusion_hbm_rows(peak_gbs)
+            extra['fusion_hbm'] = guarded(fusion_hbm_rows, peak_gbs)
             extra['fusion_hbm']['_peak_gbs'] = peak_gbs
     barrier()
 
