@@ -339,3 +339,44 @@ def test_bayes_insight_dump_layout(tmp_path):
     predictions = np.load(paths[0])
     assert predictions.files == ['arr_0', 'arr_1'] and predictions['arr_1'].shape == (1, 4, 4)
     assert np.load(paths[3])['arr_0'].shape == (2, 2, 4, 4, 3)
+
+
+def test_clock_sampler_prefers_nvml_rows_and_falls_back_to_nvidia_smi_rows():
+    """bench.ClockSampler.stop: samples inside the timed region, NVML first, the nvidia-smi
+    witness when NVML delivered nothing (seen on one box), widened by 50 ms when fewer than five
+    fall inside."""
+    import bench
+    sampler = bench.ClockSampler.__new__(bench.ClockSampler)
+    sampler.proc, sampler._stop, sampler.source, sampler._index = None, False, 'nvml', 0
+    t0 = 1000.0
+    sampler.rows = [(t0 + 0.01 * i, 1500.0 + i, 1965.0, ['sw_power_cap']) for i in range(10)]
+    sampler.smi_rows = [(t0 + 0.02, 1400.0, 1965.0, [])]
+    got = sampler.stop(t0, t0 + 0.1)
+    assert got['source'] == 'nvml' and got['samples'] == 10 and got['reasons'] == ['sw_power_cap']
+    assert got['sm_mhz'] == 1504.5 and got['sm_min_mhz'] == 1500.0 and got['sm_max_mhz'] == 1965.0
+    sampler.rows = []
+    got = sampler.stop(t0, t0 + 0.1)
+    assert got['source'] == 'nvidia-smi' and got['samples'] == 1 and got['sm_mhz'] == 1400.0
+    sampler.smi_rows = [(t0 - 0.03, 1300.0, 1965.0, ['hw_slowdown'])]       # only in the margin
+    got = sampler.stop(t0, t0 + 0.1)
+    assert got['samples'] == 1 and got['reasons'] == ['hw_slowdown']
+
+
+def test_small_batches_overlap_their_experts():
+    """BaseModel._overlap_experts: by size (at most four 768x384 frames) unless the config
+    decides; never for a single modality."""
+    from modular_semantic_segmentation_b200.models.base_model import BaseModel
+    model = BaseModel.__new__(BaseModel)
+    model.modalities = ['rgb', 'depth']
+    model.config = {}
+    small = {'rgb': np.zeros((4, 768, 384, 3), np.float32), 'depth': np.zeros((4, 768, 384, 1), np.float32)}
+    large = {'rgb': np.zeros((5, 768, 384, 3), np.uint8), 'depth': np.zeros((5, 768, 384, 1), np.uint8)}
+    assert model._overlap_experts(small) and not model._overlap_experts(large)
+    model.config = {'overlap_experts': True}
+    assert model._overlap_experts(large)
+    model.config = {'overlap_experts': False}
+    assert not model._overlap_experts(small)
+    model.config, model.modalities = {'overlap_experts': True}, ['rgb']
+    assert not model._overlap_experts(small)
+    model.config = {'split_samples': True}
+    assert model._same_images_on_every_rank()
