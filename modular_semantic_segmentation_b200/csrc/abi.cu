@@ -393,12 +393,17 @@ static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, i
   std::memset(&p, 0, sizeof(p));
   // conv1_2 + pool1: both halves of the 128 accumulator lanes carry an output row
   // (conv_igemm_rowpair_sm100.cu); debug bit10 keeps the half-empty transposed-role kernel
-  if (pool && L.taps == 9 && L.cin_gemm == 64 && L.cout <= 64 && H % 2 == 0 && W % 2 == 0 &&
+  const bool rowpair_pool = pool && L.cout <= 64 && H % 2 == 0 && W % 2 == 0;
+  const bool rowpair_full = !pool && L.cout == 64;      // fit() forward / data gradient of conv1_2
+  if ((rowpair_pool || rowpair_full) && L.taps == 9 && L.cin_gemm == 64 &&
       !(g_debug_flags & (64 | 1024))) {
     XV_TRY(get_tmap_rows2(net, &p.tmap_in_par[0], in, B, H, W, 64, 0));
     XV_TRY(get_tmap_rows2(net, &p.tmap_in_par[1], in, B, H, W, 64, 1));
     XV_TRY(get_tmap_w(net, &p.tmap_w, L.w_packed.p, L.kdim, L.cout_pad, 64));
-    XV_TRY(get_tmap(net, &p.tmap_out, out, B, H / 2, W / 2, L.cout, 16, 8));
+    if (pool)
+      XV_TRY(get_tmap(net, &p.tmap_out, out, B, H / 2, W / 2, L.cout, 16, 8));
+    else
+      XV_TRY(get_tmap(net, &p.tmap_out, out, B, H, W, L.cout, 8, 16));
     p.bias = static_cast<const float*>(L.bias_pad.p);
     p.N = B;
     p.H = H;
@@ -409,14 +414,14 @@ static int run_igemm_t(xv_fcn* net, const ConvLayer& L, const void* in, int B, i
     p.tiles_y = div_up(H, 32);
     p.n_blocks = 1;
     p.relu = L.relu;
-    if (!g_profile) return launch_conv_igemm_rowpair(p, s);
+    if (!g_profile) return launch_conv_igemm_rowpair(p, pool, s);
     IgemmSample smp;
     XV_CUDA(cudaEventCreate(&smp.e0));
     XV_CUDA(cudaEventCreate(&smp.e1));
     smp.flops = 2.0 * B * H * W * static_cast<double>(L.cout) * L.k * L.k * L.cin;
     smp.block_n = 0;
     XV_CUDA(cudaEventRecord(smp.e0, s));
-    const int rc = launch_conv_igemm_rowpair(p, s);
+    const int rc = launch_conv_igemm_rowpair(p, pool, s);
     XV_CUDA(cudaEventRecord(smp.e1, s));
     g_samples.push_back(smp);
     return rc;

@@ -1,6 +1,6 @@
-// Row-pair variant of the transposed-role 3x3 convolution for Cin = 64, Cout <= 64 followed by
-// the 2x2 max pool: conv1_2 + pool1 of simple_fcn.py:40-41 (inference; only the pooled tensor
-// is stored).
+// Row-pair variant of the transposed-role 3x3 convolution for Cin = 64, Cout <= 64: conv1_2 of
+// simple_fcn.py:40-41, either with the 2x2 max pool fused (inference: only pool1 is stored) or
+// with the full activation as output (fit(): forward and data gradient of conv1_2).
 //
 // Why: with the output channels on the M axis (conv_igemm_t_sm100.cu) a 64-channel layer fills
 // half of the 128 accumulator lanes, so half of every tcgen05.mma multiplies zeros - conv1_2 ran
@@ -50,6 +50,9 @@ constexpr int kSmemBytes =
     1024 + kWBlocks * kWBlock + kRing * kPatchBytes + kStagingBytes + kXchgBytes + 256;
 static_assert(kSmemBytes <= 227 * 1024, "row-pair conv: shared memory budget");
 
+// POOL: only the 2x2 max-pooled tensor is stored (inference, conv1_2 -> pool1); !POOL: the full
+// activation (fit() forward / data gradient, or a caller that wants conv1_2 itself).
+template <bool POOL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_rowpair_kernel(const __grid_constant__ ConvIgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -198,6 +201,77 @@ conv_igemm_rowpair_kernel(const __grid_constant__ ConvIgemmParams p) {
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kPixels;
+      if constexpr (!POOL) {
+        // Un-pooled output, 8 image rows (4 row pairs = 64 accumulator columns) per round through
+        // the 16 KB staging buffer: tcgen05.ld.16x256b hands every thread the mma-style fragment
+        // and stmatrix.x4.trans writes four 8-channel x 8-pixel blocks as 16-byte pieces of eight
+        // pixel rows (as in conv_igemm_t_sm100.cu); the staging row of accumulator column
+        // (pair ip, pixel x) is (2 ip + half) * 16 + x.
+        float fb[2][2];
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const int c = (q & 1) * 32 + hs * 16 + (lane >> 2) + rh * 8;
+            fb[hs][rh] = c < p.cout ? __ldg(p.bias + c) : 0.f;
+          }
+        const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll 1
+        for (int round = 0; round < 4; ++round) {
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs) {
+            uint32_t r[32];
+            tmem_ld_16x256b_x8(t_row + (static_cast<uint32_t>(hs * 16) << 16) + round * 64, r);
+            tmem_ld_wait();
+            const uint32_t piece =
+                static_cast<uint32_t>(((q & 1) * 32 + hs * 16 + (mi & 1) * 8) >> 3);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              uint32_t m[4];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int rep = i + u;
+                float v0 = __uint_as_float(r[4 * rep]) + fb[hs][0];
+                float v1 = __uint_as_float(r[4 * rep + 1]) + fb[hs][0];
+                float v2 = __uint_as_float(r[4 * rep + 2]) + fb[hs][1];
+                float v3 = __uint_as_float(r[4 * rep + 3]) + fb[hs][1];
+                if (p.relu) {
+                  v0 = fmaxf(v0, 0.f);
+                  v1 = fmaxf(v1, 0.f);
+                  v2 = fmaxf(v2, 0.f);
+                  v3 = fmaxf(v3, 0.f);
+                }
+                m[2 * u] = pack_bf16x2(v0, v1);
+                m[2 * u + 1] = pack_bf16x2(v2, v3);
+              }
+              const int grp = i + (mi >> 1);                     // 8-column group of the round
+              const uint32_t srow =
+                  static_cast<uint32_t>((2 * (grp >> 1) + half) * 16 + (grp & 1) * 8 + rr);
+              const uint32_t addr = smem_u32(staging) + srow * 128 + ((piece ^ (srow & 7)) << 4);
+              asm volatile(
+                  "stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(
+                      addr),
+                  "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3])
+                  : "memory");
+            }
+          }
+          if (round == 3) {
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_4d(&p.tmap_out, staging, 0, x0, y0 + round * 8, img);
+            tma_store_commit();
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       if (issuer) tma_store_wait_read<0>();
       named_bar_sync(1, 128);
 #pragma unroll 1
@@ -266,24 +340,31 @@ conv_igemm_rowpair_kernel(const __grid_constant__ ConvIgemmParams p) {
 
 }  // namespace
 
-// Params: N, H (even), W (even), cin = 64, cout <= 64, tiles_y = ceil(H / 32), tiles_x =
-// ceil(W / 16); tmap_in_par[0] / [1]: the even / odd input rows, box {64, 16, 17, 1}; tmap_w box
-// {64, 64}; tmap_out: the pooled output [N, H/2, W/2, Cout], box {64, 8, 16, 1}.
-int launch_conv_igemm_rowpair(const ConvIgemmParams& p, cudaStream_t stream) {
-  XV_CHECK(p.cin == 64 && p.cout <= 64, "conv_igemm_rowpair: Cin = 64 and Cout <= 64 only");
-  XV_CHECK(p.H % 2 == 0 && p.W % 2 == 0, "conv_igemm_rowpair: pooling needs even H, W");
+// Params: N, H, W, cin = 64, cout <= 64, tiles_y = ceil(H / 32), tiles_x = ceil(W / 16);
+// tmap_in_par[0] / [1]: the even / odd input rows, box {64, 16, 17, 1}; tmap_w box {64, 64};
+// pool: H, W even, tmap_out = the pooled output [N, H/2, W/2, Cout], box {64, 8, 16, 1};
+// !pool: tmap_out = the full output [N, H, W, Cout], box {64, 16, 8, 1}.
+template <bool POOL>
+static int launch_rowpair(const ConvIgemmParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    XV_CUDA(cudaFuncSetAttribute(conv_igemm_rowpair_kernel,
+    XV_CUDA(cudaFuncSetAttribute(conv_igemm_rowpair_kernel<POOL>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   const int total_tiles = p.N * p.tiles_y * p.tiles_x;
   const int grid = total_tiles < device_info().num_sms ? total_tiles : device_info().num_sms;
-  conv_igemm_rowpair_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  conv_igemm_rowpair_kernel<POOL><<<grid, kThreads, kSmemBytes, stream>>>(p);
   XV_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+int launch_conv_igemm_rowpair(const ConvIgemmParams& p, bool pool, cudaStream_t stream) {
+  XV_CHECK(p.cin == 64 && p.cout <= 64, "conv_igemm_rowpair: Cin = 64 and Cout <= 64 only");
+  XV_CHECK(!pool || (p.H % 2 == 0 && p.W % 2 == 0), "conv_igemm_rowpair: pooling needs even H, W");
+  XV_CHECK(pool || p.cout == 64, "conv_igemm_rowpair: the un-pooled epilogue needs Cout = 64");
+  return pool ? launch_rowpair<true>(p, stream) : launch_rowpair<false>(p, stream);
 }
 
 }  // namespace xv

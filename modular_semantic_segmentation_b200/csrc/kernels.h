@@ -48,7 +48,8 @@ struct ConvIgemmParams {
 // conv_igemm_rowpair_sm100.cu: 3x3 conv (Cin = 64, Cout <= 64) + bias + ReLU + 2x2 max pool, both
 // halves of the accumulator lanes in use; tmap_in_par[0/1] = even / odd input rows, box
 // {64, 16, 17, 1}; tmap_w box {64, 64}; tmap_out = pooled output, box {64, 8, 16, 1}
-int launch_conv_igemm_rowpair(const ConvIgemmParams& p, cudaStream_t stream);
+// pool == false: the full activation instead (tmap_out box {64, 16, 8, 1} on [N, H, W, 64]).
+int launch_conv_igemm_rowpair(const ConvIgemmParams& p, bool pool, cudaStream_t stream);
 int conv_igemm_block_n(int cout);
 int launch_conv_igemm(const ConvIgemmParams& p, int block_n, int taps, bool out_f32,
                       cudaStream_t stream);

@@ -29,7 +29,9 @@ BF16_CASES = [
     (1, 16, 8, 64, 64, 3),        # exactly one 128-pixel tile
     (1, 16, 16, 64, 64, 3),       # exactly one 256-pixel tile of the transposed-role kernel
     (2, 40, 24, 128, 128, 3),     # transposed-role kernel, ragged 16x16 tiles, 2 K chunks
-    (2, 32, 48, 64, 64, 3),       # conv1_2-like
+    (2, 32, 48, 64, 64, 3),       # conv1_2-like: un-pooled row-pair kernel, one 32-row tile
+    (1, 41, 23, 64, 64, 3),       # same, odd height and width: ragged 32 x 16 tiles
+    (3, 80, 40, 64, 64, 3),       # same, three row tiles with a ragged last one
     (1, 24, 40, 64, 128, 3),      # ragged tiles in both directions
     (1, 16, 24, 128, 256, 3),     # BLOCK_N = 256
     (2, 8, 16, 256, 512, 3),      # two N blocks
