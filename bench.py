@@ -727,6 +727,10 @@ def run_gpu(args):
                      'kernel_share_of_step': conv_ms / ms,
                      'peak_source': 'frac: bf16_tflops_sustained, frac_burst: bf16_tflops; %s'
                                     % peak_kind,
+                     'frac_note': 'both the achieved rate and the sustained peak are power-capped '
+                                  'figures (see clocks): frac slightly above 1 means this box '
+                                  'throttles less than the one the peak was measured on; '
+                                  'frac_burst is against the un-throttled cuBLAS figure',
                      'whole_step_tflops': GFLOP_PER_FRAME * BATCH * args.steps / ms},
     }
     if sharded_check is not None:
