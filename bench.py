@@ -82,7 +82,8 @@ def _peaks():
 
 class ClockSampler(object):
     """SM clock + throttle reasons sampled during the timed region: NVML polled every 10 ms from
-    a thread (a 20-step timed region lasts ~0.1 s), nvidia-smi -lms as the fallback."""
+    a thread (a 20-step timed region lasts ~0.1 s); nvidia-smi -lms when NVML is unavailable, one
+    nvidia-smi query right after the region when NVML delivered nothing inside it."""
 
     REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40),
                ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
@@ -114,20 +115,21 @@ class ClockSampler(object):
             self.thread.start()
         except Exception:
             self.source = None
-        # nvidia-smi runs beside NVML as a second witness (a box was seen where the NVML thread
-        # delivered nothing during the timed region); its rows are used when NVML has none
+        # nvidia-smi -lms only when NVML is unavailable (a second poller would add driver queries
+        # to the timed region for nothing); if NVML is there but delivers no sample in the window
+        # - seen on one box - stop() falls back to one query right after the region
         self.smi_rows = []
-        try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '20'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.smi_thread = threading.Thread(target=self._read, daemon=True)
-            self.smi_thread.start()
-            if self.source is None:
+        if self.source is None:
+            try:
+                self.proc = subprocess.Popen(
+                    ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
+                     '--format=csv,noheader,nounits', '-lms', '50'],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.smi_thread = threading.Thread(target=self._read, daemon=True)
+                self.smi_thread.start()
                 self.source = 'nvidia-smi'
-        except OSError:
-            self.proc = None
+            except OSError:
+                self.proc = None
         self._index = index
 
     def _poll(self):
@@ -518,6 +520,9 @@ def run_gpu(args):
     for i in range(warmup):
         device_step(i)
     barrier()
+    # the clock sampler runs from the soak on: the soak is the same step under the same load, so
+    # its samples (hundreds) back the few that fall into the ~0.1 s timed region
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     # untimed soak of the same step: clocks / power settle before anything is timed
     t_soak = time.time()
     i = 0
@@ -529,8 +534,6 @@ def run_gpu(args):
     soak_s = time.time() - t_soak
     barrier()
     cm.zero_()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.03)
     launches0 = dev.launch_count()
     dev.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -546,6 +549,14 @@ def run_gpu(args):
     dev.profile_enable(False)
     launches = dev.launch_count() - launches0
     clocks = sampler.stop(t_start, t_end) if sampler else None
+    if clocks is not None and sampler.source is not None:
+        during_soak = [r for r in (sampler.rows or sampler.smi_rows)
+                       if t_soak + 0.5 * soak_s <= r[0] < t_start]
+        if during_soak:
+            clocks['soak'] = {'sm_mhz': float(np.median([r[1] for r in during_soak])),
+                              'samples': len(during_soak),
+                              'reasons': sorted({n for r in during_soak for n in r[3]}),
+                              'window': 'second half of the untimed soak (same step, same load)'}
     ms = max_over_ranks(ms)
     value = world * BATCH * args.steps / (ms * 1e-3)
     # checksum of the device-resident loop: every labelled pixel was counted exactly once
